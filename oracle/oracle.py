@@ -1,0 +1,297 @@
+"""ctypes binding of oracle/libhnsw_oracle.so — TEST INFRASTRUCTURE ONLY.
+
+The oracle is the CPU restatement of the reference's arithmetic (see hnsw_oracle.c header).  It may
+be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs,
+and by nothing under hnsw_clj_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libhnsw_oracle.so")
+
+COSINE, L2, IP = 0, 1, 2
+GAUSSIAN, UNIFORM, UNIT, CLUSTERED = 0, 1, 2, 3
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "hnsw_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _declare(_lib)
+    return _lib
+
+
+_p = C.c_void_p
+_i64, _i32, _f64, _int = C.c_int64, C.c_int32, C.c_double, C.c_int
+
+
+def _declare(L):
+    for name in ("orc_cosine_distance_ultra", "orc_cosine_distance_direct", "orc_euclidean_distance", "orc_dot"):
+        f = getattr(L, name)
+        f.restype, f.argtypes = _f64, [_p, _p, _i64]
+    L.orc_norm.restype, L.orc_norm.argtypes = _f64, [_p, _i64]
+    L.orc_row_norms_f32.restype, L.orc_row_norms_f32.argtypes = None, [_p, _i64, _i64, _p]
+    L.orc_rng_init.restype, L.orc_rng_init.argtypes = None, [_p, _i64]
+    L.orc_rng_next_int.restype, L.orc_rng_next_int.argtypes = _i32, [_p]
+    L.orc_rng_next_int_bound.restype, L.orc_rng_next_int_bound.argtypes = _i32, [_p, _i32]
+    L.orc_rng_next_double.restype, L.orc_rng_next_double.argtypes = _f64, [_p]
+    L.orc_rng_next_gaussian.restype, L.orc_rng_next_gaussian.argtypes = _f64, [_p]
+    L.orc_rng_sizeof.restype, L.orc_rng_sizeof.argtypes = _i64, []
+    L.orc_gen_dataset.restype, L.orc_gen_dataset.argtypes = None, [_i64, _i64, _int, _i32, _f64, _i64, _p]
+    L.orc_exact_knn_f32.restype = None
+    L.orc_exact_knn_f32.argtypes = [_p, _i64, _i64, _p, _i64, _i64, _int, _p, _p, _int]
+    L.orc_recall.restype, L.orc_recall.argtypes = _f64, [_p, _p, _i64, _i64]
+    L.orc_kmeanspp_init.restype = None
+    L.orc_kmeanspp_init.argtypes = [_p, _i64, _i64, _i32, _int, _i64, _p, _int]
+    L.orc_kmeanspp_init_literal.restype = None
+    L.orc_kmeanspp_init_literal.argtypes = [_p, _i64, _i64, _i32, _int, _i64, _p]
+    L.orc_assign.restype, L.orc_assign.argtypes = None, [_p, _i64, _i64, _p, _i32, _int, _p, _int]
+    L.orc_update_centroids.restype, L.orc_update_centroids.argtypes = None, [_p, _i64, _i64, _p, _i32, _p]
+    L.orc_kmeans.restype = None
+    L.orc_kmeans.argtypes = [_p, _i64, _i64, _i32, _i32, _int, _i64, _p, _p, _p, _int]
+    L.orc_build_lists.restype, L.orc_build_lists.argtypes = None, [_p, _i64, _i32, _p, _p]
+    L.orc_ivf_search.restype = None
+    L.orc_ivf_search.argtypes = [_p, _i64, _i64, _p, _i32, _p, _p, _p, _p, _i64, _i64, _i32, _int, _p, _p, _p, _int]
+    L.orc_hnsw_create.restype, L.orc_hnsw_create.argtypes = _p, [_p, _i64, _i64, _int, _i32, _i32, _i64]
+    L.orc_hnsw_free.restype, L.orc_hnsw_free.argtypes = None, [_p]
+    L.orc_hnsw_build.restype, L.orc_hnsw_build.argtypes = None, [_p]
+    L.orc_hnsw_entry.restype, L.orc_hnsw_entry.argtypes = _i32, [_p]
+    L.orc_hnsw_max_level.restype, L.orc_hnsw_max_level.argtypes = _i32, [_p]
+    L.orc_hnsw_levels.restype, L.orc_hnsw_levels.argtypes = None, [_p, _p]
+    L.orc_hnsw_export_level.restype, L.orc_hnsw_export_level.argtypes = _i64, [_p, _i32, _p, _p]
+    L.orc_hnsw_search.restype, L.orc_hnsw_search.argtypes = _i32, [_p, _p, _i32, _i32, _p, _p]
+    L.orc_hnsw_dist_evals.restype, L.orc_hnsw_dist_evals.argtypes = _i64, [_p]
+    L.orc_gather_score.restype = None
+    L.orc_gather_score.argtypes = [_p, _i64, _p, _p, _p, _i64, _int, _p]
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_p)
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _d64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ncores() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+# ---- pairwise ------------------------------------------------------------------------------
+def cosine_distance(a, b) -> float:
+    a, b = _d64(a), _d64(b)
+    return lib().orc_cosine_distance_ultra(_ptr(a), _ptr(b), a.size)
+
+
+def cosine_distance_direct(a, b) -> float:
+    a, b = _d64(a), _d64(b)
+    return lib().orc_cosine_distance_direct(_ptr(a), _ptr(b), a.size)
+
+
+def euclidean_distance(a, b) -> float:
+    a, b = _d64(a), _d64(b)
+    return lib().orc_euclidean_distance(_ptr(a), _ptr(b), a.size)
+
+
+def dot(a, b) -> float:
+    a, b = _d64(a), _d64(b)
+    return lib().orc_dot(_ptr(a), _ptr(b), a.size)
+
+
+def norm(a) -> float:
+    a = _d64(a)
+    return lib().orc_norm(_ptr(a), a.size)
+
+
+def row_norms(rows) -> np.ndarray:
+    rows = _f32(rows)
+    out = np.empty(rows.shape[0], dtype=np.float64)
+    lib().orc_row_norms_f32(_ptr(rows), rows.shape[0], rows.shape[1], _ptr(out))
+    return out
+
+
+# ---- java.util.Random ---------------------------------------------------------------------
+class JavaRandom:
+    def __init__(self, seed: int):
+        self._buf = C.create_string_buffer(int(lib().orc_rng_sizeof()))
+        lib().orc_rng_init(self._buf, seed)
+
+    def next_int(self, bound: int | None = None) -> int:
+        if bound is None:
+            return lib().orc_rng_next_int(self._buf)
+        return lib().orc_rng_next_int_bound(self._buf, bound)
+
+    def next_double(self) -> float:
+        return lib().orc_rng_next_double(self._buf)
+
+    def next_gaussian(self) -> float:
+        return lib().orc_rng_next_gaussian(self._buf)
+
+
+def gen_dataset(n, d, distribution=GAUSSIAN, num_clusters=10, noise=0.1, seed=42) -> np.ndarray:
+    """test/data_generator.clj:50-87; returns fp64 [n, d]."""
+    out = np.empty((n, d), dtype=np.float64)
+    lib().orc_gen_dataset(n, d, distribution, num_clusters, noise, seed, _ptr(out))
+    return out
+
+
+# ---- flat ----------------------------------------------------------------------------------
+def exact_knn(rows, queries, k, metric=COSINE, nthreads=None):
+    rows, queries = _f32(rows), _f32(queries)
+    nq = queries.shape[0]
+    n, d = rows.shape if rows.ndim == 2 else (0, queries.shape[1])
+    ids = np.empty((nq, k), dtype=np.int64)
+    dist = np.empty((nq, k), dtype=np.float64)
+    lib().orc_exact_knn_f32(_ptr(rows), n, d, _ptr(queries), nq, k, metric, _ptr(ids), _ptr(dist),
+                            nthreads or ncores())
+    return ids, dist
+
+
+def recall(approx_ids, exact_ids) -> float:
+    a = np.ascontiguousarray(approx_ids, dtype=np.int64)
+    e = np.ascontiguousarray(exact_ids, dtype=np.int64)
+    return lib().orc_recall(_ptr(a), _ptr(e), a.shape[0], a.shape[1])
+
+
+# ---- k-means / IVF ------------------------------------------------------------------------
+def kmeanspp_init(rows, nlist, metric=COSINE, seed=42, nthreads=None, literal=False) -> np.ndarray:
+    rows = _f32(rows)
+    out = np.empty(nlist, dtype=np.int64)
+    if literal:
+        lib().orc_kmeanspp_init_literal(_ptr(rows), rows.shape[0], rows.shape[1], nlist, metric, seed, _ptr(out))
+    else:
+        lib().orc_kmeanspp_init(_ptr(rows), rows.shape[0], rows.shape[1], nlist, metric, seed, _ptr(out),
+                                nthreads or ncores())
+    return out
+
+
+def assign(rows, centroids, metric=COSINE, nthreads=None) -> np.ndarray:
+    rows, centroids = _f32(rows), _d64(centroids)
+    out = np.empty(rows.shape[0], dtype=np.int32)
+    lib().orc_assign(_ptr(rows), rows.shape[0], rows.shape[1], _ptr(centroids), centroids.shape[0], metric,
+                     _ptr(out), nthreads or ncores())
+    return out
+
+
+def update_centroids(rows, assign_, centroids) -> np.ndarray:
+    rows = _f32(rows)
+    a = np.ascontiguousarray(assign_, dtype=np.int32)
+    c = _d64(centroids).copy()
+    lib().orc_update_centroids(_ptr(rows), rows.shape[0], rows.shape[1], _ptr(a), c.shape[0], _ptr(c))
+    return c
+
+
+def kmeans(rows, nlist, iters=10, metric=COSINE, seed=42, seed_rows=None, nthreads=None):
+    rows = _f32(rows)
+    n, d = rows.shape
+    cents = np.empty((nlist, d), dtype=np.float64)
+    asg = np.empty(n, dtype=np.int32)
+    sr = None if seed_rows is None else np.ascontiguousarray(seed_rows, dtype=np.int64)
+    lib().orc_kmeans(_ptr(rows), n, d, nlist, iters, metric, seed, None if sr is None else _ptr(sr),
+                     _ptr(cents), _ptr(asg), nthreads or ncores())
+    return cents, asg
+
+
+def build_lists(assign_, nlist):
+    a = np.ascontiguousarray(assign_, dtype=np.int32)
+    off = np.empty(nlist + 1, dtype=np.int64)
+    rows = np.empty(a.shape[0], dtype=np.int64)
+    lib().orc_build_lists(_ptr(a), a.shape[0], nlist, _ptr(off), _ptr(rows))
+    return off, rows
+
+
+def ivf_search(rows, centroids, assign_, queries, k, nprobe, coarse_metric=COSINE, nthreads=None,
+               return_probes=False):
+    rows, queries, centroids = _f32(rows), _f32(queries), _d64(centroids)
+    n, d = rows.shape
+    nlist = centroids.shape[0]
+    off, lrows = build_lists(assign_, nlist)
+    norms = row_norms(rows)
+    nq = queries.shape[0]
+    ids = np.empty((nq, k), dtype=np.int64)
+    dist = np.empty((nq, k), dtype=np.float64)
+    probes = np.empty((nq, nprobe), dtype=np.int32) if return_probes else None
+    lib().orc_ivf_search(_ptr(rows), n, d, _ptr(centroids), nlist, _ptr(off), _ptr(lrows), _ptr(norms),
+                         _ptr(queries), nq, k, nprobe, coarse_metric, _ptr(ids), _ptr(dist),
+                         None if probes is None else _ptr(probes), nthreads or ncores())
+    return (ids, dist, probes) if return_probes else (ids, dist)
+
+
+# ---- HNSW ---------------------------------------------------------------------------------
+class Hnsw:
+    """src/hnsw/ultra_fast.clj graph, seeded levels, insertion-ordered neighbour sets."""
+
+    def __init__(self, rows, metric=COSINE, M=16, ef_construction=200, level_seed=42):
+        self.rows = _f32(rows)
+        self.n, self.d = self.rows.shape
+        self._h = lib().orc_hnsw_create(_ptr(self.rows), self.n, self.d, metric, M, ef_construction, level_seed)
+        lib().orc_hnsw_build(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_hnsw_free(self._h)
+            self._h = None
+
+    @property
+    def entry(self) -> int:
+        return lib().orc_hnsw_entry(self._h)
+
+    @property
+    def max_level(self) -> int:
+        return lib().orc_hnsw_max_level(self._h)
+
+    def levels(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.int32)
+        lib().orc_hnsw_levels(self._h, _ptr(out))
+        return out
+
+    def export_level(self, level: int):
+        off = np.empty(self.n + 1, dtype=np.int64)
+        tot = lib().orc_hnsw_export_level(self._h, level, _ptr(off), None)
+        ids = np.empty(max(tot, 1), dtype=np.int32)
+        lib().orc_hnsw_export_level(self._h, level, _ptr(off), _ptr(ids))
+        return off, ids[:tot]
+
+    def search(self, queries, k, ef=0):
+        queries = _f32(queries)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), dtype=np.int64)
+        dist = np.empty((nq, k), dtype=np.float64)
+        for i in range(nq):
+            lib().orc_hnsw_search(self._h, _ptr(queries[i]), k, ef, _ptr(ids[i]), _ptr(dist[i]))
+        return ids, dist
+
+    def dist_evals(self) -> int:
+        return lib().orc_hnsw_dist_evals(self._h)
+
+
+def gather_score(rows, queries, pair_query, pair_row, metric=COSINE) -> np.ndarray:
+    rows, queries = _f32(rows), _f32(queries)
+    pq = np.ascontiguousarray(pair_query, dtype=np.int32)
+    pr = np.ascontiguousarray(pair_row, dtype=np.int32)
+    out = np.empty(pq.shape[0], dtype=np.float64)
+    lib().orc_gather_score(_ptr(rows), rows.shape[1], _ptr(queries), _ptr(pq), _ptr(pr), pq.shape[0], metric,
+                           _ptr(out))
+    return out

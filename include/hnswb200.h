@@ -1,0 +1,168 @@
+/*
+ * hnswb200.h — C ABI of libhnswb200.so: the B200 (sm_100a) distance core behind hnsw-clj's
+ * build-index / search-knn / search-batch* surface.
+ *
+ * The reference (pure Clojure) has no FFI of its own; its extension points are Clojure functions.
+ * Each entry point below names the reference interface it stands in for (file:line relative to the
+ * reference repo).  INTEGRATION.md shows the java.lang.foreign downcall stubs a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative hb_status otherwise; hb_last_error() gives the
+ *     calling thread's last message.  There is NO CPU fallback: without a usable sm_100 device every
+ *     compute call fails with HB_ERR_NO_DEVICE.
+ *   - `rows`, `queries` and output buffers may be HOST or DEVICE pointers (detected with
+ *     cudaPointerGetAttributes).  Host inputs are borrowed for the duration of the call only.
+ *   - ids are ROW INDICES (position in the `rows` passed at build); the host shim owns the String ids
+ *     (reference: ["vec_0" double[]] pairs, test/data_generator.clj:84-87).
+ *   - results are ascending by distance, ties in the reference's stable-sort order (row order; for IVF
+ *     probe rank first — src/hnsw/ann/partition/ivf_flat.clj:281-294).  Unused slots (k > candidates,
+ *     test/hnsw/core_test.clj:90-96) hold id -1 and distance +inf.
+ *   - values must be fp32-representable (HB_F32/HB_BF16 storage) unless HB_F64 is used: the reference
+ *     stores embeddings as double[] holding fp32 values.
+ */
+#ifndef HNSWB200_H
+#define HNSWB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_API __attribute__((visibility("default")))
+
+typedef struct hb_index hb_index;
+
+enum hb_status {
+    HB_OK = 0,
+    HB_ERR_INVALID = -1,   /* IllegalArgumentException in the reference (src/hnsw/api/simple.clj:13-14) */
+    HB_ERR_NO_DEVICE = -2, /* no CUDA device / not sm_100 */
+    HB_ERR_CUDA = -3,
+    HB_ERR_OOM = -4,
+    HB_ERR_UNSUPPORTED = -5
+};
+
+enum hb_dtype { HB_F32 = 0, HB_BF16 = 1, HB_F64 = 2 };
+
+/* :distance-fn of the reference mapped to an enum (src/hnsw/api.clj:16-19): cosine-distance-ultra,
+ * euclidean-distance-ultra; HB_IP ranks by descending dot-product (src/hnsw/simd_optimized.clj:283-293),
+ * an extension for BASELINE config 3. */
+enum hb_metric { HB_COSINE = 0, HB_L2 = 1, HB_IP = 2 };
+
+enum hb_index_type { HB_INDEX_FLAT = 0, HB_INDEX_IVF_FLAT = 1, HB_INDEX_HNSW = 2 };
+
+/* search arithmetic: HB_MODE_EXACT restates the reference's fp64 sequential sums on the device
+ * (bit-identical distances); HB_MODE_FAST selects candidates with tensor-core / fp32 arithmetic and
+ * re-scores them in fp64 in the reference's summation order (ids identical). */
+enum hb_mode { HB_MODE_EXACT = 0, HB_MODE_FAST = 1 };
+
+typedef struct hb_info {
+    int32_t type;   /* hb_index_type */
+    int32_t dtype;  /* storage dtype of the rows */
+    int32_t metric;
+    int32_t dim;
+    int64_t n;      /* rows */
+    int32_t nlist;  /* IVF: partitions; else 0   (index-info :partitions, ivf_flat.clj:319-327) */
+    int32_t max_level; /* HNSW: top level; else 0 */
+    int64_t device_bytes;
+} hb_info;
+
+/* ---- process ------------------------------------------------------------------------------ */
+HB_API int hb_init(int device);           /* select the device for this process (one process per GPU) */
+HB_API int hb_shutdown(void);
+HB_API const char *hb_last_error(void);
+HB_API int hb_version(void);
+HB_API int hb_set_stream(void *cuda_stream); /* launch on this stream (default: legacy stream 0) */
+HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches (default EXACT) */
+/* number of kernels this library launched since hb_init / the last reset (bench `gpu_launches`) */
+HB_API int64_t hb_launch_count(int reset);
+
+/* ---- distance core ------------------------------------------------------------------------ */
+/* sqrt(sum v^2) per row, sequential fp64.  Replaces the norm precompute at
+ * src/hnsw/ann/partition/ivf_flat.clj:161-179 and precompute-norms, src/hnsw/simd_optimized.clj:206-216. */
+HB_API int hb_row_norms(const void *rows, int64_t n, int32_t d, int dtype, double *out_norms);
+
+/* out[i*nb + j] = distance-fn(a_i, b_j): the batched form of the (fn [^doubles a ^doubles b]) :distance-fn
+ * extension point (src/hnsw/ultra_fast.clj:43-95; batch-distances-parallel, src/hnsw/simd_optimized.clj:164-179).
+ * HB_COSINE applies the zero-norm guard of cosine-distance-ultra (:92-95); HB_IP returns the dot product. */
+HB_API int hb_pairwise(const void *a, int64_t na, int adtype, const void *b, int64_t nb, int bdtype,
+                       int32_t d, int metric, double *out);
+
+/* ---- flat exact search ---------------------------------------------------------------------- */
+/* Device-resident copy of the rows (+ norms).  Replaces the data seq handed to compute-exact-knn
+ * (src/hnsw/bench.clj:72-84) / top-k-distances (src/hnsw/simd_optimized.clj:271-280). */
+HB_API int hb_flat_create(const void *rows, int64_t n, int32_t d, int dtype, int metric, hb_index **out);
+
+/* ---- IVF-FLAT -------------------------------------------------------------------------------- */
+/* build-ivf-flat-index (src/hnsw/ann/partition/ivf_flat.clj:137-211): norms, k-means++ with
+ * java.util.Random(seed) (:32-60), `iters` Lloyd rounds + final assignment (:92-131), list-major slabs.
+ * `metric` is the :distance-fn used for clustering and coarse routing; the list scan itself is always
+ * cosine, as in the reference (:217-234). */
+HB_API int hb_ivf_build(const void *rows, int64_t n, int32_t d, int dtype, int metric, int32_t nlist,
+                        int32_t iters, int64_t seed, hb_index **out);
+/* Same index from given centroids (fp64 [nlist x d]) and per-row assignments: parity mode for
+ * oracle-built partitions, and the load path for a persisted index. */
+HB_API int hb_ivf_import(const void *rows, int64_t n, int32_t d, int dtype, int metric,
+                         const double *centroids, int32_t nlist, const int32_t *assignments, hb_index **out);
+/* centroids fp64 [nlist x d] and assignments int32 [n] of a built index (either may be NULL) */
+HB_API int hb_ivf_export(const hb_index *index, double *out_centroids, int32_t *out_assignments);
+
+/* ---- search ---------------------------------------------------------------------------------- */
+/* search-knn / search-batch* for every index type (src/hnsw/ann/partition/ivf_flat.clj:305-317,
+ * src/hnsw/ultra_fast.clj:346-374, src/hnsw/api/protocol.clj:58-67; replaces the per-query fan-out of
+ * src/hnsw/helper/parallel_search.clj:15-49).  `queries` is [nq x d] in `qdtype` (HB_F32 or HB_F64).
+ * `param` is nprobe for IVF (:num-probes, ivf_flat.clj:243-251), ef for HNSW (0 = the reference's
+ * max(k,50), ultra_fast.clj:355), ignored for flat.  out_ids [nq x k] int64, out_dist [nq x k] fp64. */
+HB_API int hb_search(hb_index *index, const void *queries, int qdtype, int64_t nq, int32_t k, int32_t param,
+                     int64_t *out_ids, double *out_dist);
+/* IVF only: also return the probed list ids [nq x nprobe] in probe-rank order (-1 padded) */
+HB_API int hb_ivf_probes(hb_index *index, const void *queries, int qdtype, int64_t nq, int32_t nprobe,
+                         int32_t *out_probes);
+
+/* ---- k-means steps (IVF build) ------------------------------------------------------------- */
+/* kmeans-plus-plus-init (ivf_flat.clj:32-60): chosen data-row indices, int64 [nlist] */
+HB_API int hb_kmeanspp_init(const void *rows, int64_t n, int32_t d, int dtype, int metric, int32_t nlist,
+                            int64_t seed, int64_t *out_seed_rows);
+/* assign-to-nearest-centroid over all rows (ivf_flat.clj:79-90): strict <, lowest index wins */
+HB_API int hb_kmeans_assign(const void *rows, int64_t n, int32_t d, int dtype, int metric,
+                            const double *centroids, int32_t nlist, int32_t *out_assign);
+/* compute-centroid per cluster in row order, empty cluster keeps its centroid (ivf_flat.clj:66-77,112-116).
+ * `centroids` is updated in place.  If out_sums/out_counts are non-NULL the per-cluster fp64 sums
+ * [nlist x d] and counts [nlist] are returned instead of dividing (for the multi-GPU all-reduce). */
+HB_API int hb_kmeans_update(const void *rows, int64_t n, int32_t d, int dtype, const int32_t *assign,
+                            int32_t nlist, double *centroids, double *out_sums, int64_t *out_counts);
+/* partition-vectors-kmeans (ivf_flat.clj:92-131): seeds (k-means++ unless seed_rows given), iters Lloyd
+ * rounds, final assignment */
+HB_API int hb_kmeans(const void *rows, int64_t n, int32_t d, int dtype, int metric, int32_t nlist,
+                     int32_t iters, int64_t seed, const int64_t *seed_rows, double *out_centroids,
+                     int32_t *out_assign);
+
+/* ---- HNSW neighbour-candidate scoring ------------------------------------------------------ */
+/* Upload a graph built on the host (src/hnsw/ultra_fast.clj:216-344): per-node level, and per level a CSR
+ * adjacency over all n nodes (offsets int64 [n+1], neighbour ids int32) in the iteration order the search
+ * must follow.  level_offsets[l] / level_ids[l] for l = 0..max_level. */
+HB_API int hb_hnsw_create(const void *rows, int64_t n, int32_t d, int dtype, int metric, const int32_t *levels,
+                          int32_t max_level, int32_t entry_point, const int64_t *const *level_offsets,
+                          const int32_t *const *level_ids, hb_index **out);
+/* scores[p] = distance-fn(query[pair_query[p]], row[pair_row[p]]): the call at
+ * src/hnsw/ultra_fast.clj:192 batched over (query, neighbour-id) pairs (cf. batch-distance-calculation,
+ * src/hnsw/wip/parallel_build.clj:106-118).  Works on any index type (uses its rows). */
+HB_API int hb_gather_score(hb_index *index, const void *queries, int qdtype, int64_t nq,
+                           const int32_t *pair_query, const int32_t *pair_row, int64_t npairs,
+                           double *out_scores);
+
+/* ---- multi-GPU merge --------------------------------------------------------------------------- */
+/* Merge `nparts` per-shard top-k lists (dist [nparts x nq x k], ids likewise, already global row ids)
+ * into the global top-k: the sort-by :distance + take k at ivf_flat.clj:291-294 /
+ * partitioned_hnsw.clj:187-196, ties by (part, position). */
+HB_API int hb_topk_merge(const double *dist, const int64_t *ids, int32_t nparts, int64_t nq, int32_t k,
+                         int64_t *out_ids, double *out_dist);
+
+/* ---- bookkeeping -------------------------------------------------------------------------------- */
+HB_API int hb_index_info(const hb_index *index, hb_info *out);
+HB_API int hb_index_free(hb_index *index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNSWB200_H */

@@ -1,0 +1,147 @@
+"""Pins the CPU oracle against every known-answer the reference's own tests hold for the path
+(test/hnsw/core_test.clj:9-31) and against published java.util.Random(42) values, then checks the
+oracle's internal consistency (literal vs incremental k-means++, numpy twin of the arithmetic)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+
+# ---- reference KATs: test/hnsw/core_test.clj:9-20 (test-vector-distance) ---------------------
+def test_euclid_kats():
+    assert orc.euclidean_distance([1, 2, 3], [1, 2, 3]) == 0.0
+    assert orc.euclidean_distance([0, 0], [3, 4]) == 5.0
+    assert abs(orc.euclidean_distance([1, 2, 3], [4, 5, 6]) - 5.196152422706632) < 1e-5
+    assert orc.euclidean_distance([1, 2, 3], [4, 5, 6]) == 5.196152422706632
+
+
+# ---- reference KATs: test/hnsw/core_test.clj:22-31 (test-cosine-distance) --------------------
+def test_cosine_kats():
+    assert orc.cosine_distance([1, 2, 3], [1, 2, 3]) < 0.001
+    assert abs(orc.cosine_distance([1, 0], [-1, 0]) - 2.0) < 1e-3
+    assert abs(orc.cosine_distance([1, 2, 3], [4, 5, 6]) - 0.0253) < 0.01
+    # SURVEY Appendix C
+    assert orc.cosine_distance([1, 2, 3], [4, 5, 6]) == 0.025368153802923787
+    assert orc.cosine_distance([1, 0], [-1, 0]) == 2.0
+    # zero-norm guard, src/hnsw/ultra_fast.clj:92-95
+    assert orc.cosine_distance([0, 0, 0], [1, 2, 3]) == 1.0
+    assert orc.cosine_distance_direct([0, 0, 0], [1, 2, 3]) == 1.0
+
+
+def test_pairwise_matches_python_left_fold():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal(768).astype(np.float32).astype(np.float64)
+    b = rng.standard_normal(768).astype(np.float32).astype(np.float64)
+    dot = n1 = n2 = 0.0
+    for x, y in zip(a.tolist(), b.tolist()):  # python floats: IEEE fp64, no FMA
+        dot = dot + x * y
+        n1 = n1 + x * x
+        n2 = n2 + y * y
+    assert orc.cosine_distance(a, b) == 1.0 - dot / (math.sqrt(n1) * math.sqrt(n2))
+    assert orc.dot(a, b) == dot
+    assert orc.norm(a) == math.sqrt(n1)
+    s = 0.0
+    for x, y in zip(a.tolist(), b.tolist()):
+        s = s + (x - y) * (x - y)
+    assert orc.euclidean_distance(a, b) == math.sqrt(s)
+
+
+# ---- java.util.Random(42): published values ------------------------------
+def test_java_random_kats():
+    r = orc.JavaRandom(42)
+    assert [r.next_int() for _ in range(3)] == [-1170105035, 234785527, -1360544799]
+    r = orc.JavaRandom(42)
+    assert [r.next_int(10) for _ in range(5)] == [0, 3, 8, 4, 0]
+    r = orc.JavaRandom(42)
+    assert [r.next_int(100) for _ in range(5)] == [30, 63, 48, 84, 70]  # SURVEY Appendix C (restated twice, agree)
+    r = orc.JavaRandom(42)
+    assert r.next_double() == 0.7275636800328681
+    assert r.next_double() == 0.6832234717598454
+    assert orc.JavaRandom(42).next_int(31173) == 9197
+    assert orc.JavaRandom(42).next_int(1000000) == 431130
+    r = orc.JavaRandom(42)
+    g = r.next_gaussian()
+    assert abs(g - 1.1419053154730547) < 1e-15
+
+
+def test_exact_knn_matches_numpy_twin():
+    rng = np.random.default_rng(1)
+    rows = rng.standard_normal((300, 48)).astype(np.float32)
+    q = rng.standard_normal((7, 48)).astype(np.float32)
+    ids, dist = orc.exact_knn(rows, q, 10)
+    R, Q = rows.astype(np.float64), q.astype(np.float64)
+    for qi in range(7):
+        d = np.empty(300)
+        for i in range(300):
+            dot = nv = nq = 0.0
+            for x, y in zip(R[i].tolist(), Q[qi].tolist()):
+                dot = dot + x * y
+                nv = nv + x * x
+                nq = nq + y * y
+            d[i] = 1.0 - dot / (math.sqrt(nv) * math.sqrt(nq))
+        order = np.argsort(d, kind="stable")[:10]
+        assert ids[qi].tolist() == order.tolist()
+        assert dist[qi].tolist() == d[order].tolist()
+
+
+def test_exact_knn_edge_cases():
+    rows = np.eye(4, dtype=np.float32)
+    q = np.eye(4, dtype=np.float32)[:2]
+    ids, dist = orc.exact_knn(rows, q, 6)  # k > n: test/hnsw/core_test.clj:90-96
+    assert ids[0, 0] == 0 and (ids[:, 4:] == -1).all() and np.isinf(dist[:, 4:]).all()
+    # ties keep row order (stable sort): rows 1..3 are all at distance 1.0 from q0
+    assert ids[0].tolist()[:4] == [0, 1, 2, 3]
+    ids, dist = orc.exact_knn(np.zeros((0, 4), np.float32), q, 3)  # empty index -> nothing
+    assert (ids == -1).all()
+
+
+def test_kmeanspp_incremental_equals_literal():
+    rows = orc.gen_dataset(400, 16, orc.CLUSTERED, num_clusters=8, noise=0.1, seed=7).astype(np.float32)
+    a = orc.kmeanspp_init(rows, 12, seed=42)
+    b = orc.kmeanspp_init(rows, 12, seed=42, literal=True)
+    assert a.tolist() == b.tolist()
+    assert a[0] == orc.JavaRandom(42).next_int(400)
+    a2 = orc.kmeanspp_init(rows, 12, metric=orc.L2, seed=42)
+    b2 = orc.kmeanspp_init(rows, 12, metric=orc.L2, seed=42, literal=True)
+    assert a2.tolist() == b2.tolist()
+
+
+def test_kmeans_and_ivf_search_properties():
+    rows = orc.gen_dataset(1500, 24, orc.CLUSTERED, num_clusters=12, noise=0.15, seed=3).astype(np.float32)
+    q = orc.gen_dataset(20, 24, orc.CLUSTERED, num_clusters=12, noise=0.15, seed=4).astype(np.float32)
+    cents, asg = orc.kmeans(rows, 16, iters=5, seed=42)
+    assert asg.min() >= 0 and asg.max() < 16
+    # final assignment is consistent with the centroids
+    assert orc.assign(rows, cents).tolist() == asg.tolist()
+    # probing every list == exact search (ids and distance bits)
+    ids_all, d_all = orc.ivf_search(rows, cents, asg, q, 10, 16)
+    ids_ex, d_ex = orc.exact_knn(rows, q, 10)
+    assert ids_all.tolist() == ids_ex.tolist()
+    assert d_all.tolist() == d_ex.tolist()
+    ids4, d4, probes = orc.ivf_search(rows, cents, asg, q, 10, 4, return_probes=True)
+    assert probes.shape == (20, 4)
+    assert (np.diff(d4, axis=1) >= 0).all()  # ascending, test/hnsw/integration_test.clj:134-136
+    assert 0.5 < orc.recall(ids4, ids_ex) <= 1.0
+
+
+def test_hnsw_oracle_recall_and_shape():
+    rows = orc.gen_dataset(600, 16, orc.UNIT, seed=5).astype(np.float32)
+    g = orc.Hnsw(rows, M=8, ef_construction=60, level_seed=42)
+    q = rows[:25]
+    ids, dist = g.search(q, 10)
+    # self-query (test/hnsw/core_test.clj:46): the graph is approximate, most queries find themselves
+    assert (ids[:, 0] == np.arange(25)).mean() >= 0.8
+    assert (dist[:, 0] < 0.01).mean() >= 0.8
+    ex, _ = orc.exact_knn(rows, q, 10)
+    assert orc.recall(ids, ex) > 0.8
+    off, nb = g.export_level(0)
+    deg = np.diff(off)
+    assert deg.max() <= 16  # max-M = 2M at layer 0, src/hnsw/ultra_fast.clj:131,252
+    # gather_score of (query, neighbour) pairs equals the pairwise function
+    pq = np.array([0, 1, 2], np.int32)
+    pr = np.array([5, 6, 7], np.int32)
+    s = orc.gather_score(rows, q, pq, pr)
+    for t in range(3):
+        assert s[t] == orc.cosine_distance(q[pq[t]].astype(np.float64), rows[pr[t]].astype(np.float64))

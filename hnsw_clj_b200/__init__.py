@@ -1,0 +1,15 @@
+"""hnsw_clj_b200 — B200-native distance core behind hnsw-clj's build-index / search-knn / search-batch* surface.
+
+Python host side of the C ABI (libhnswb200.so); module names follow the reference's namespaces:
+  simd_optimized  <- hnsw.simd-optimized          (pairwise distances, norms, top-k)
+  flat            <- hnsw.bench/compute-exact-knn (exact flat search)
+  ivf_flat        <- hnsw.ann.partition.ivf-flat  (build-index / search-knn / index-info)
+  ultra_fast      <- hnsw.ultra-fast              (HNSW neighbour-candidate scoring on an uploaded graph)
+  api             <- hnsw.api + hnsw.api.protocol (index / search, ANNIndex + BatchSearchIndex)
+  parallel_search <- hnsw.helper.parallel-search  (batch fan-out, here one batched device call)
+  sharded         <- row-sharded multi-GPU search (torch.distributed all-gather + merge kernel)
+"""
+from . import _lib
+from ._lib import HbError, HbInvalid, launch_count  # noqa: F401
+
+__all__ = ["_lib", "HbError", "HbInvalid", "launch_count"]

@@ -1,0 +1,1007 @@
+// hb_api.cu — the C ABI of libhnswb200.so (include/hnswb200.h): handles, staging of host/device buffers and
+// the orchestration of the kernels behind hnsw-clj's build-index / search-knn / search-batch* surface.
+#include <float.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "hb_build.cuh"
+#include "hb_kernels.cuh"
+
+namespace hb {
+
+int64_t g_launches = 0;
+cudaStream_t g_stream = 0;
+int g_num_sms = 148;
+static int g_mode = HB_MODE_EXACT;
+static bool g_inited = false;
+static int g_device = -1;
+static std::mutex g_mu;
+static thread_local std::string t_err;
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+const void *stage_in(const void *p, size_t bytes, DevBuf &stage) {
+    if (bytes == 0) return p;
+    if (is_device_ptr(p)) return p;
+    void *d = stage.get(bytes);
+    HB_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, g_stream));
+    return d;
+}
+OutStage stage_out(void *user, size_t bytes, DevBuf &stage) {
+    OutStage o;
+    o.user = user;
+    o.bytes = bytes;
+    if (!user || bytes == 0) return o;
+    o.host = !is_device_ptr(user);
+    o.dev = o.host ? stage.get(bytes) : user;
+    return o;
+}
+void finish_out(const OutStage &o) {
+    if (o.user && o.host && o.bytes) HB_CUDA(cudaMemcpyAsync(o.user, o.dev, o.bytes, cudaMemcpyDeviceToHost, g_stream));
+}
+
+static size_t g_scratch_budget = 0;
+static size_t scratch_budget() {
+    if (!g_scratch_budget) {
+        const char *e = getenv("HB_SCRATCH_MB");
+        g_scratch_budget = (e && atoll(e) > 0) ? (size_t)atoll(e) << 20 : (size_t)8 << 30;
+    }
+    return g_scratch_budget;
+}
+
+static void ensure_init(int device = -1) {
+    if (g_inited && (device < 0 || device == g_device)) return;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw Error(HB_ERR_NO_DEVICE, "no CUDA device is visible (libhnswb200 has no CPU fallback)");
+    }
+    int dev = device;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    }
+    if (dev >= count) throw Error(HB_ERR_NO_DEVICE, "device index out of range");
+    cudaDeviceProp prop;
+    HB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        throw Error(HB_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100 (kernels are built for sm_100a only)");
+    HB_CUDA(cudaSetDevice(dev));
+    g_device = dev;
+    g_num_sms = prop.multiProcessorCount;
+    g_inited = true;
+}
+
+// all transient device buffers; grown on demand, released by hb_shutdown
+struct Workspace {
+    DevBuf in_a, in_b, in_c, in_d, out_a, out_b, out_c;
+    DevBuf qnorm, scratch, sel_val, sel_pos, cand_val, cand_id, plan, probes, pair_out, qsel, lq_off, tile_prefix, tmp,
+        misc, misc2, misc3, misc4;
+    void release() {
+        DevBuf *all[] = {&in_a, &in_b, &in_c, &in_d, &out_a, &out_b, &out_c, &qnorm, &scratch, &sel_val, &sel_pos, &cand_val,
+                         &cand_id, &plan, &probes, &pair_out, &qsel, &lq_off, &tile_prefix, &tmp, &misc, &misc2, &misc3, &misc4};
+        for (DevBuf *b : all) b->release();
+    }
+};
+static Workspace g_ws;
+
+template <typename F>
+static int guarded(F &&f) {
+    try {
+        std::lock_guard<std::mutex> lk(g_mu);
+        f();
+        return HB_OK;
+    } catch (const Error &e) {
+        t_err = e.what();
+        return e.status;
+    } catch (const std::exception &e) {
+        t_err = e.what();
+        return HB_ERR_CUDA;
+    }
+}
+
+static void sync_stream() { HB_CUDA(cudaStreamSynchronize(g_stream)); }
+
+// ---- java.util.Random (needed by kmeans-plus-plus-init, ivf_flat.clj:37: (Random. 42)) -------------
+// Implemented from the published LCG definition of java.util.Random (JDK javadoc).
+struct JavaRandom {
+    uint64_t s;
+    explicit JavaRandom(int64_t seed) : s(((uint64_t)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1)) {}
+    int32_t next(int bits) {
+        s = (s * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+        return (int32_t)(uint32_t)(s >> (48 - bits));
+    }
+    int32_t next_int(int32_t bound) {
+        int32_t r = next(31);
+        const int32_t m = bound - 1;
+        if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+        for (int32_t u = r;; u = next(31)) {
+            r = u % bound;
+            if ((int32_t)((uint32_t)u - (uint32_t)r + (uint32_t)m) >= 0) break;
+        }
+        return r;
+    }
+    double next_double() {
+        const int64_t hi = next(26), lo = next(27);
+        return (double)((hi << 27) + lo) * 0x1.0p-53;
+    }
+};
+
+static void metric_to_epi(int metric, bool guarded_cos, bool &l2, int &epi) {
+    l2 = metric == HB_L2;
+    if (metric == HB_COSINE) epi = guarded_cos ? EPI_COS_GUARD : EPI_COS;
+    else if (metric == HB_L2) epi = EPI_L2;
+    else if (metric == HB_IP) epi = EPI_NEGDOT;
+    else throw Error(HB_ERR_INVALID, "unknown metric");
+}
+static void check_dtype(int dtype) {
+    HB_REQUIRE(dtype == HB_F32 || dtype == HB_BF16 || dtype == HB_F64, "unknown dtype");
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+struct hb_index {
+    int type = HB_INDEX_FLAT, dtype = HB_F32, metric = HB_COSINE, d = 0;
+    int64_t n = 0;
+    // rows as given (flat / hnsw) or list-major slab (ivf)
+    DevBuf rows, norms;
+    // ivf
+    int nlist = 0;
+    int64_t max_list = 0;
+    DevBuf cents, cent_norm, list_off, list_rows, assign;
+    // hnsw
+    int max_level = 0, entry = -1;
+    DevBuf levels;
+    std::vector<DevBuf> adj_off, adj_ids;
+    int64_t device_bytes() const {
+        size_t b = rows.cap + norms.cap + cents.cap + cent_norm.cap + list_off.cap + list_rows.cap + assign.cap + levels.cap;
+        for (auto &x : adj_off) b += x.cap;
+        for (auto &x : adj_ids) b += x.cap;
+        return (int64_t)b;
+    }
+    void release() {
+        rows.release();
+        norms.release();
+        cents.release();
+        cent_norm.release();
+        list_off.release();
+        list_rows.release();
+        assign.release();
+        levels.release();
+        for (auto &x : adj_off) x.release();
+        for (auto &x : adj_ids) x.release();
+    }
+};
+
+namespace hb {
+
+static void fill_empty_results(int64_t *ids, double *dist, int64_t count) {
+    // small helper on the host side of the staging buffers: used only for degenerate calls (n == 0)
+    std::vector<int64_t> hi((size_t)count, -1);
+    std::vector<double> hd((size_t)count, INFINITY);
+    if (ids) HB_CUDA(cudaMemcpyAsync(ids, hi.data(), count * 8, cudaMemcpyHostToDevice, g_stream));
+    if (dist) HB_CUDA(cudaMemcpyAsync(dist, hd.data(), count * 8, cudaMemcpyHostToDevice, g_stream));
+    sync_stream();
+}
+
+// uploads the trivial one-list plan {list_off, lq_off, tile_prefix} for a dense rows x queries scan
+static void dense_plan(int64_t nrows, int64_t nq, int64_t *&list_off, int64_t *&lq_off, int64_t *&tile_prefix, DevBuf &buf) {
+    int64_t h[6] = {0, nrows, 0, nq, 0, ceil_div(nrows, kTileRows) * ceil_div(nq, kTileQ)};
+    int64_t *dptr = buf.as<int64_t>(6);
+    HB_CUDA(cudaMemcpyAsync(dptr, h, sizeof(h), cudaMemcpyHostToDevice, g_stream));
+    list_off = dptr;
+    lq_off = dptr + 2;
+    tile_prefix = dptr + 4;
+}
+
+// Exact flat search over rows [n x d] (device) — compute-exact-knn, src/hnsw/bench.clj:72-84, and
+// top-k-distances, src/hnsw/simd_optimized.clj:271-280.  ids/dist are device buffers [nq x k].
+static void flat_search_exact(const void *rows, int rdtype, const double *row_norm, int64_t n, int d, int metric,
+                              const void *queries, int qdtype, int64_t nq, int k, int64_t *ids, double *dist) {
+    if (nq == 0 || k == 0) return;
+    if (n == 0) {
+        fill_empty_results(ids, dist, nq * k);
+        return;
+    }
+    bool l2;
+    int epi;
+    metric_to_epi(metric, false, l2, epi);
+    const double *qn = nullptr;
+    if (metric == HB_COSINE) {
+        double *q = g_ws.qnorm.as<double>(nq);
+        launch_row_norms(queries, qdtype, nq, d, q);
+        qn = q;
+    }
+    // rows per pass so that the distance scratch [nq x rc] stays inside the budget
+    int64_t rc = (int64_t)(scratch_budget() / 8 / (size_t)nq);
+    rc = std::max<int64_t>(kTileRows, rc / kTileRows * kTileRows);
+    rc = std::min(rc, n);
+    const int64_t npass = ceil_div(n, rc);
+    // few queries + long rows: split each query's range so the select kernel fills the machine
+    int nsub = 1;
+    int64_t sub_len = rc;
+    if (nq < 2 * g_num_sms && rc > 32768) {
+        nsub = (int)std::min<int64_t>(ceil_div(2 * g_num_sms, nq), ceil_div(rc, 16384));
+        sub_len = ceil_div(rc, nsub);
+        nsub = (int)ceil_div(rc, sub_len);
+    }
+    const int64_t parts = npass * nsub;
+    double *scratch = g_ws.scratch.as<double>((size_t)nq * rc);
+    double *cval = parts > 1 ? g_ws.cand_val.as<double>((size_t)nq * parts * k) : dist;
+    int64_t *cid = parts > 1 ? g_ws.cand_id.as<int64_t>((size_t)nq * parts * k) : ids;
+    int64_t *plan = g_ws.plan.as<int64_t>((size_t)6 * npass);
+    const size_t esz = dtype_size(rdtype);
+    std::vector<int64_t> hplan((size_t)6 * npass);
+    for (int64_t pass = 0; pass < npass; ++pass) {
+        const int64_t len = std::min(rc, n - pass * rc);
+        int64_t *h = &hplan[(size_t)6 * pass];
+        h[0] = 0, h[1] = len, h[2] = 0, h[3] = nq, h[4] = 0, h[5] = ceil_div(len, kTileRows) * ceil_div(nq, kTileQ);
+    }
+    HB_CUDA(cudaMemcpyAsync(plan, hplan.data(), hplan.size() * 8, cudaMemcpyHostToDevice, g_stream));
+    for (int64_t pass = 0; pass < npass; ++pass) {
+        const int64_t r0 = pass * rc, len = std::min(rc, n - r0);
+        ScanParams S;
+        S.rows = (const char *)rows + (size_t)r0 * d * esz;
+        S.row_norm = row_norm ? row_norm + r0 : nullptr;
+        S.queries = queries;
+        S.q_norm = qn;
+        S.d = d;
+        S.nlist = 1;
+        S.list_off = plan + 6 * pass;
+        S.lq_off = plan + 6 * pass + 2;
+        S.tile_prefix = plan + 6 * pass + 4;
+        S.out_stride = len;
+        S.out = scratch;
+        S.epi = epi;
+        launch_pairscan(S, rdtype, qdtype, l2);
+        SelectParams L;
+        L.vals = scratch;
+        L.nseg = nq;
+        L.seg_stride = len;
+        L.seg_len_const = len;
+        L.nsub = nsub;
+        L.sub_len = sub_len;
+        L.out_seg_stride = parts;
+        L.out_slot_base = pass * nsub;
+        L.k = k;
+        L.out_val = cval;
+        L.out_pos = cid;
+        launch_select(L);
+        // positions within this pass -> global row ids
+        launch_offset_ids(cid + (size_t)pass * nsub * k, nq, (int64_t)nsub * k, parts * k, r0);
+    }
+    if (parts > 1) {
+        // candidates of a query are laid out [pass][sub][k]: ascending row blocks, each sorted by
+        // (distance, row) — so (distance, position) order here is (distance, row) order again
+        SelectParams L;
+        L.vals = cval;
+        L.nseg = nq;
+        L.seg_stride = parts * k;
+        L.seg_len_const = parts * k;
+        L.k = k;
+        L.out_val = dist;
+        int64_t *pos = g_ws.sel_pos.as<int64_t>((size_t)nq * k);
+        L.out_pos = pos;
+        launch_select(L);
+        launch_lookup_ids(pos, nq, k, cid, parts * k, ids);
+    }
+}
+
+// search-ivf-flat, src/hnsw/ann/partition/ivf_flat.clj:236-294, for a batch of queries.
+// probes_out (optional, device) [nq x nprobe] int32.
+static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int64_t nq, int k, int nprobe,
+                             int64_t *ids, double *dist, int32_t *probes_out) {
+    if (nq == 0) return;
+    const int d = ix->d, nlist = ix->nlist;
+    if (ix->n == 0 || nlist == 0) {
+        if (k > 0) fill_empty_results(ids, dist, nq * k);
+        if (probes_out) HB_CUDA(cudaMemsetAsync(probes_out, 0xFF, (size_t)nq * nprobe * 4, g_stream));
+        return;
+    }
+    const int np_eff = std::min(nprobe, nlist);
+    HB_REQUIRE(np_eff >= 1, "num-probes must be >= 1");
+    // queries in chunks so the candidate scratch stays inside the budget
+    int64_t qc = (int64_t)(scratch_budget() / 8 / ((size_t)np_eff * (size_t)std::max<int64_t>(ix->max_list, 1)));
+    qc = std::max<int64_t>(1, std::min(qc, nq));
+    qc = std::min<int64_t>(qc, ((1ll << 31) - 1) / np_eff);
+    const size_t qsz = dtype_size(qdtype);
+
+    double *qn = g_ws.qnorm.as<double>(nq);
+    launch_row_norms(queries, qdtype, nq, d, qn);  // :275-278
+    int64_t *plan = g_ws.plan.as<int64_t>(6);
+    double *coarse = g_ws.cand_val.as<double>((size_t)qc * nlist);
+    double *pval = g_ws.sel_val.as<double>((size_t)qc * np_eff);
+    int64_t *ppos = g_ws.sel_pos.as<int64_t>((size_t)qc * std::max(np_eff, k));
+    int32_t *probes = g_ws.probes.as<int32_t>((size_t)qc * np_eff);
+    int64_t *pair_out = g_ws.pair_out.as<int64_t>((size_t)qc * np_eff + 1);
+    int32_t *qsel = g_ws.qsel.as<int32_t>((size_t)qc * np_eff);
+    int64_t *lq_off = g_ws.lq_off.as<int64_t>(nlist + 1);
+    int64_t *tile_prefix = g_ws.tile_prefix.as<int64_t>(nlist + 1);
+    bool cl2;
+    int cepi;
+    metric_to_epi(ix->metric == HB_IP ? HB_COSINE : ix->metric, true, cl2, cepi);
+
+    for (int64_t q0 = 0; q0 < nq; q0 += qc) {
+        const int64_t nqc = std::min(qc, nq - q0);
+        const void *qptr = (const char *)queries + (size_t)q0 * d * qsz;
+        // coarse quantiser (:261-269): distance-fn(query, centroid) for all centroids, stable sort, take
+        {
+            int64_t h[6] = {0, nlist, 0, nqc, 0, ceil_div(nlist, kTileRows) * ceil_div(nqc, kTileQ)};
+            HB_CUDA(cudaMemcpyAsync(plan, h, sizeof(h), cudaMemcpyHostToDevice, g_stream));
+            ScanParams S;
+            S.rows = ix->cents.p;
+            S.row_norm = (const double *)ix->cent_norm.p;
+            S.queries = qptr;
+            S.q_norm = qn + q0;
+            S.d = d;
+            S.nlist = 1;
+            S.list_off = plan;
+            S.lq_off = plan + 2;
+            S.tile_prefix = plan + 4;
+            S.out_stride = nlist;
+            S.out = coarse;
+            S.epi = cepi;
+            launch_pairscan(S, HB_F64, qdtype, cl2);
+            SelectParams L;
+            L.vals = coarse;
+            L.nseg = nqc;
+            L.seg_stride = nlist;
+            L.seg_len_const = nlist;
+            L.k = np_eff;
+            L.out_val = pval;
+            L.out_pos = ppos;
+            launch_select(L);
+        }
+        const int64_t np = nqc * np_eff;
+        ivf_plan(ppos, np, nlist, (const int64_t *)ix->list_off.p, probes, pair_out, qsel, lq_off, tile_prefix,
+                 kTileRows, kTileQ, g_ws.tmp);
+        if (probes_out) {
+            if (np_eff == nprobe) {
+                HB_CUDA(cudaMemcpyAsync(probes_out + (size_t)q0 * nprobe, probes, (size_t)np * 4, cudaMemcpyDeviceToDevice, g_stream));
+            } else {
+                HB_CUDA(cudaMemsetAsync(probes_out + (size_t)q0 * nprobe, 0xFF, (size_t)nqc * nprobe * 4, g_stream));
+                HB_CUDA(cudaMemcpy2DAsync(probes_out + (size_t)q0 * nprobe, (size_t)nprobe * 4, probes, (size_t)np_eff * 4,
+                                          (size_t)np_eff * 4, (size_t)nqc, cudaMemcpyDeviceToDevice, g_stream));
+            }
+        }
+        if (k == 0) continue;
+        int64_t total = 0;
+        HB_CUDA(cudaMemcpyAsync(&total, pair_out + np, 8, cudaMemcpyDeviceToHost, g_stream));
+        sync_stream();
+        double *scratch = g_ws.scratch.as<double>((size_t)std::max<int64_t>(total, 1));
+        // list scan (:217-234): always cosine via precomputed norms, no zero guard; lists in probe order (:281-288)
+        ScanParams S;
+        S.rows = ix->rows.p;
+        S.row_norm = (const double *)ix->norms.p;
+        S.queries = qptr;
+        S.q_norm = qn + q0;
+        S.d = d;
+        S.nlist = nlist;
+        S.list_off = (const int64_t *)ix->list_off.p;
+        S.lq_off = lq_off;
+        S.qsel = qsel;
+        S.pair_div = np_eff;
+        S.pair_out = pair_out;
+        S.tile_prefix = tile_prefix;
+        S.out = scratch;
+        S.epi = EPI_COS;
+        launch_pairscan(S, ix->dtype, qdtype, false);
+        // merge (:291-294): stable sort of the concatenation in probe order, take k
+        SelectParams L;
+        L.vals = scratch;
+        L.nseg = nqc;
+        L.seg_off = pair_out;
+        L.seg_off_stride = np_eff;
+        L.k = k;
+        L.out_val = dist + (size_t)q0 * k;
+        L.out_pos = ppos;
+        launch_select(L);
+        launch_ivf_resolve(ppos, nqc, k, np_eff, probes, pair_out, (const int64_t *)ix->list_off.p,
+                           (const int64_t *)ix->list_rows.p, ids + (size_t)q0 * k);
+    }
+}
+
+// partition-vectors-kmeans, src/hnsw/ann/partition/ivf_flat.clj:92-131, on device rows.
+// cents [nlist x d] fp64 (device), assign [n] int32 (device); seeds (device int64[nlist]) are filled by
+// k-means++ unless given.
+static void kmeans_exact(const void *rows, int dtype, int64_t n, int d, int metric, int nlist, int iters, int64_t seed,
+                         const int64_t *seed_rows_dev, double *cents, int32_t *assign, int64_t *seeds_out_dev) {
+    HB_REQUIRE(n >= 1 && nlist >= 1, "k-means needs at least one row and one partition");
+    HB_REQUIRE(n < (1ll << 31), "n must be < 2^31");
+    HB_REQUIRE(metric == HB_COSINE || metric == HB_L2, "k-means distance-fn must be cosine or euclidean");
+    const bool l2 = metric == HB_L2;
+    double *norm = g_ws.misc.as<double>(n);
+    launch_row_norms(rows, dtype, n, d, norm);
+    int64_t *seeds = seeds_out_dev ? seeds_out_dev : g_ws.misc2.as<int64_t>(nlist);
+    if (seed_rows_dev) {
+        if (seeds != seed_rows_dev) HB_CUDA(cudaMemcpyAsync(seeds, seed_rows_dev, (size_t)nlist * 8, cudaMemcpyDeviceToDevice, g_stream));
+    } else {
+        // kmeans-plus-plus-init (:32-60)
+        JavaRandom rng(seed);
+        std::vector<double> u((size_t)nlist);
+        const int64_t first = rng.next_int((int32_t)n);
+        for (int t = 1; t < nlist; ++t) u[t] = rng.next_double();
+        double *ud = g_ws.misc3.as<double>((size_t)nlist + 2 + 2 * (size_t)n);
+        double *total = ud + nlist;
+        double *mind = ud + nlist + 2;
+        double *cum = mind + n;
+        int64_t *pick = g_ws.misc4.as<int64_t>(1);
+        HB_CUDA(cudaMemcpyAsync(ud, u.data(), (size_t)nlist * 8, cudaMemcpyHostToDevice, g_stream));
+        HB_CUDA(cudaMemcpyAsync(pick, &first, 8, cudaMemcpyHostToDevice, g_stream));
+        HB_CUDA(cudaMemcpyAsync(seeds, &first, 8, cudaMemcpyHostToDevice, g_stream));
+        launch_fill_f64(mind, n, DBL_MAX);
+        KppParams K;
+        K.rows = rows;
+        K.dtype = dtype;
+        K.n = n;
+        K.d = d;
+        K.row_norm = norm;
+        K.l2 = l2;
+        K.mind = mind;
+        K.cum = cum;
+        K.total = total;
+        K.pick = pick;
+        for (int t = 1; t < nlist; ++t) {
+            K.u = ud + t;
+            K.out_seed = seeds + t;
+            launch_kpp_step(K);
+        }
+        sync_stream();  // u (host vector) must outlive the copy; also bounds queue depth
+    }
+    launch_init_centroids(rows, dtype, d, seeds, nlist, cents);
+    double *cnorm = g_ws.misc3.as<double>((size_t)nlist + 2 + 2 * (size_t)n);  // reuse: [nlist] norms
+    int64_t *list_off = g_ws.lq_off.as<int64_t>(nlist + 1);
+    int64_t *list_rows = g_ws.cand_id.as<int64_t>(n);
+    AssignParams A;
+    A.rows = rows;
+    A.row_norm = norm;
+    A.n = n;
+    A.d = d;
+    A.cents = cents;
+    A.cent_norm = cnorm;
+    A.nlist = nlist;
+    A.epi = l2 ? EPI_L2 : EPI_COS_GUARD;
+    A.out_assign = assign;
+    for (int it = 0; it <= iters; ++it) {
+        launch_row_norms(cents, HB_F64, nlist, d, cnorm);
+        launch_assign(A, dtype, l2);
+        if (it == iters) break;  // final assignment pass (:119-131)
+        build_lists(assign, n, nlist, list_off, list_rows, g_ws.tmp);
+        launch_update_centroids(rows, dtype, d, list_off, list_rows, nlist, cents, nullptr, nullptr);
+    }
+}
+
+// Turns (rows, centroids, assignments) on the device into the list-major index layout.
+static void ivf_finalize(hb_index *ix, const void *rows_dev, const double *row_norm_dev) {
+    const int64_t n = ix->n;
+    const int d = ix->d, nlist = ix->nlist;
+    int64_t *list_off = ix->list_off.as<int64_t>(nlist + 1);
+    int64_t *list_rows = ix->list_rows.as<int64_t>(std::max<int64_t>(n, 1));
+    build_lists((const int32_t *)ix->assign.p, n, nlist, list_off, list_rows, g_ws.tmp);
+    void *slab = ix->rows.get(std::max<size_t>((size_t)n * d * dtype_size(ix->dtype), 16));
+    double *snorm = ix->norms.as<double>(std::max<int64_t>(n, 1));
+    launch_gather_rows(rows_dev, ix->dtype, d, list_rows, n, slab, row_norm_dev, snorm);
+    double *cn = ix->cent_norm.as<double>(nlist);
+    launch_row_norms(ix->cents.p, HB_F64, nlist, d, cn);
+    std::vector<int64_t> off((size_t)nlist + 1);
+    HB_CUDA(cudaMemcpyAsync(off.data(), list_off, off.size() * 8, cudaMemcpyDeviceToHost, g_stream));
+    sync_stream();
+    ix->max_list = 0;
+    for (int l = 0; l < nlist; ++l) ix->max_list = std::max(ix->max_list, off[l + 1] - off[l]);
+}
+
+}  // namespace hb
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+HB_API int hb_init(int device) {
+    return guarded([&] { ensure_init(device < 0 ? 0 : device); });
+}
+HB_API int hb_shutdown(void) {
+    return guarded([&] {
+        if (g_inited) cudaStreamSynchronize(g_stream);
+        g_ws.release();
+    });
+}
+HB_API const char *hb_last_error(void) { return t_err.c_str(); }
+HB_API int hb_version(void) { return 100; }
+HB_API int hb_set_stream(void *cuda_stream) {
+    return guarded([&] { g_stream = (cudaStream_t)cuda_stream; });
+}
+HB_API int hb_set_mode(int mode) {
+    return guarded([&] {
+        HB_REQUIRE(mode == HB_MODE_EXACT || mode == HB_MODE_FAST, "unknown mode");
+        g_mode = mode;
+    });
+}
+HB_API int hb_set_option(const char *name, int64_t value) {
+    return guarded([&] {
+        HB_REQUIRE(name, "null option name");
+        if (!strcmp(name, "scratch_mb")) {
+            HB_REQUIRE(value >= 1, "scratch_mb must be >= 1");
+            g_scratch_budget = (size_t)value << 20;
+        } else {
+            throw Error(HB_ERR_INVALID, std::string("unknown option ") + name);
+        }
+    });
+}
+HB_API int64_t hb_launch_count(int reset) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+HB_API int hb_row_norms(const void *rows, int64_t n, int32_t d, int dtype, double *out_norms) {
+    return guarded([&] {
+        ensure_init();
+        check_dtype(dtype);
+        HB_REQUIRE(n >= 0 && d >= 1 && (n == 0 || (rows && out_norms)), "bad arguments");
+        if (n == 0) return;
+        const void *r = stage_in(rows, (size_t)n * d * dtype_size(dtype), g_ws.in_a);
+        OutStage o = stage_out(out_norms, (size_t)n * 8, g_ws.out_a);
+        launch_row_norms(r, dtype, n, d, (double *)o.dev);
+        finish_out(o);
+        sync_stream();
+    });
+}
+
+HB_API int hb_pairwise(const void *a, int64_t na, int adtype, const void *b, int64_t nb, int bdtype, int32_t d,
+                       int metric, double *out) {
+    return guarded([&] {
+        ensure_init();
+        check_dtype(adtype);
+        check_dtype(bdtype);
+        HB_REQUIRE(adtype != HB_BF16, "`a` must be fp32 or fp64");
+        HB_REQUIRE(na >= 0 && nb >= 0 && d >= 1, "bad arguments");
+        if (na == 0 || nb == 0) return;
+        HB_REQUIRE(a && b && out, "null buffer");
+        const void *qa = stage_in(a, (size_t)na * d * dtype_size(adtype), g_ws.in_a);
+        const void *rb = stage_in(b, (size_t)nb * d * dtype_size(bdtype), g_ws.in_b);
+        OutStage o = stage_out(out, (size_t)na * nb * 8, g_ws.out_a);
+        bool l2;
+        int epi;
+        metric_to_epi(metric, true, l2, epi);
+        if (metric == HB_IP) epi = EPI_DOT;
+        const double *qn = nullptr, *rn = nullptr;
+        if (metric == HB_COSINE) {
+            double *x = g_ws.qnorm.as<double>(na);
+            double *y = g_ws.misc.as<double>(nb);
+            launch_row_norms(qa, adtype, na, d, x);
+            launch_row_norms(rb, bdtype, nb, d, y);
+            qn = x;
+            rn = y;
+        }
+        int64_t *lo, *lq, *tp;
+        dense_plan(nb, na, lo, lq, tp, g_ws.plan);
+        ScanParams S;
+        S.rows = rb;
+        S.row_norm = rn;
+        S.queries = qa;
+        S.q_norm = qn;
+        S.d = d;
+        S.nlist = 1;
+        S.list_off = lo;
+        S.lq_off = lq;
+        S.tile_prefix = tp;
+        S.out_stride = nb;
+        S.out = (double *)o.dev;
+        S.epi = epi;
+        launch_pairscan(S, bdtype, adtype, l2);
+        finish_out(o);
+        sync_stream();
+    });
+}
+
+HB_API int hb_flat_create(const void *rows, int64_t n, int32_t d, int dtype, int metric, hb_index **out) {
+    return guarded([&] {
+        ensure_init();
+        check_dtype(dtype);
+        HB_REQUIRE(out, "null out");
+        HB_REQUIRE(n >= 0 && d >= 1 && (n == 0 || rows), "bad arguments");
+        HB_REQUIRE(metric == HB_COSINE || metric == HB_L2 || metric == HB_IP, "unknown metric");
+        hb_index *ix = new hb_index();
+        try {
+            ix->type = HB_INDEX_FLAT;
+            ix->dtype = dtype;
+            ix->metric = metric;
+            ix->d = d;
+            ix->n = n;
+            const size_t bytes = (size_t)n * d * dtype_size(dtype);
+            void *r = ix->rows.get(std::max<size_t>(bytes, 16));
+            if (bytes)
+                HB_CUDA(cudaMemcpyAsync(r, rows, bytes, is_device_ptr(rows) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, g_stream));
+            double *nm = ix->norms.as<double>(std::max<int64_t>(n, 1));
+            launch_row_norms(r, dtype, n, d, nm);
+            sync_stream();
+        } catch (...) {
+            ix->release();
+            delete ix;
+            throw;
+        }
+        *out = ix;
+    });
+}
+
+static void ivf_common_checks(const void *rows, int64_t n, int32_t d, int dtype, int metric, int32_t nlist) {
+    check_dtype(dtype);
+    HB_REQUIRE(n >= 1 && d >= 1 && rows, "build needs at least one row");
+    HB_REQUIRE(nlist >= 1, "num-partitions must be >= 1");
+    HB_REQUIRE(metric == HB_COSINE || metric == HB_L2, "IVF distance-fn must be cosine or euclidean");
+}
+
+HB_API int hb_ivf_build(const void *rows, int64_t n, int32_t d, int dtype, int metric, int32_t nlist, int32_t iters,
+                        int64_t seed, hb_index **out) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(out, "null out");
+        ivf_common_checks(rows, n, d, dtype, metric, nlist);
+        HB_REQUIRE(iters >= 0, "max-iterations must be >= 0");
+        hb_index *ix = new hb_index();
+        try {
+            ix->type = HB_INDEX_IVF_FLAT;
+            ix->dtype = dtype;
+            ix->metric = metric;
+            ix->d = d;
+            ix->n = n;
+            ix->nlist = nlist;
+            const void *r = stage_in(rows, (size_t)n * d * dtype_size(dtype), g_ws.in_a);
+            double *cents = ix->cents.as<double>((size_t)nlist * d);
+            int32_t *assign = ix->assign.as<int32_t>(n);
+            kmeans_exact(r, dtype, n, d, metric, nlist, iters, seed, nullptr, cents, assign, nullptr);
+            ivf_finalize(ix, r, (const double *)g_ws.misc.p);
+        } catch (...) {
+            ix->release();
+            delete ix;
+            throw;
+        }
+        *out = ix;
+    });
+}
+
+HB_API int hb_ivf_import(const void *rows, int64_t n, int32_t d, int dtype, int metric, const double *centroids,
+                         int32_t nlist, const int32_t *assignments, hb_index **out) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(out && centroids && assignments, "null buffer");
+        ivf_common_checks(rows, n, d, dtype, metric, nlist);
+        hb_index *ix = new hb_index();
+        try {
+            ix->type = HB_INDEX_IVF_FLAT;
+            ix->dtype = dtype;
+            ix->metric = metric;
+            ix->d = d;
+            ix->n = n;
+            ix->nlist = nlist;
+            const void *r = stage_in(rows, (size_t)n * d * dtype_size(dtype), g_ws.in_a);
+            double *cents = ix->cents.as<double>((size_t)nlist * d);
+            int32_t *assign = ix->assign.as<int32_t>(n);
+            HB_CUDA(cudaMemcpyAsync(cents, centroids, (size_t)nlist * d * 8, cudaMemcpyDefault, g_stream));
+            HB_CUDA(cudaMemcpyAsync(assign, assignments, (size_t)n * 4, cudaMemcpyDefault, g_stream));
+            double *norm = g_ws.misc.as<double>(n);
+            launch_row_norms(r, dtype, n, d, norm);
+            ivf_finalize(ix, r, norm);
+        } catch (...) {
+            ix->release();
+            delete ix;
+            throw;
+        }
+        *out = ix;
+    });
+}
+
+HB_API int hb_ivf_export(const hb_index *index, double *out_centroids, int32_t *out_assignments) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(index && index->type == HB_INDEX_IVF_FLAT, "not an IVF-FLAT index");
+        if (out_centroids)
+            HB_CUDA(cudaMemcpyAsync(out_centroids, index->cents.p, (size_t)index->nlist * index->d * 8, cudaMemcpyDefault, g_stream));
+        if (out_assignments)
+            HB_CUDA(cudaMemcpyAsync(out_assignments, index->assign.p, (size_t)index->n * 4, cudaMemcpyDefault, g_stream));
+        sync_stream();
+    });
+}
+
+HB_API int hb_search(hb_index *index, const void *queries, int qdtype, int64_t nq, int32_t k, int32_t param,
+                     int64_t *out_ids, double *out_dist) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(index, "null index");
+        HB_REQUIRE(qdtype == HB_F32 || qdtype == HB_F64, "queries must be fp32 or fp64");
+        HB_REQUIRE(nq >= 0 && k >= 0, "bad arguments");
+        if (nq == 0 || k == 0) return;
+        HB_REQUIRE(queries && out_ids && out_dist, "null buffer");
+        HB_REQUIRE(k <= 1024, "k > 1024 is not supported");
+        HB_REQUIRE(g_mode == HB_MODE_EXACT, "HB_MODE_FAST is not available in this build");
+        const void *q = stage_in(queries, (size_t)nq * index->d * dtype_size(qdtype), g_ws.in_b);
+        OutStage oi = stage_out(out_ids, (size_t)nq * k * 8, g_ws.out_a);
+        OutStage od = stage_out(out_dist, (size_t)nq * k * 8, g_ws.out_b);
+        if (index->type == HB_INDEX_FLAT) {
+            flat_search_exact(index->rows.p, index->dtype, (const double *)index->norms.p, index->n, index->d, index->metric, q,
+                              qdtype, nq, k, (int64_t *)oi.dev, (double *)od.dev);
+        } else if (index->type == HB_INDEX_IVF_FLAT) {
+            HB_REQUIRE(param >= 1, "num-probes must be >= 1");
+            ivf_search_exact(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev, nullptr);
+        } else {
+            throw Error(HB_ERR_UNSUPPORTED, "search on this index type is not implemented");
+        }
+        finish_out(oi);
+        finish_out(od);
+        sync_stream();
+    });
+}
+
+HB_API int hb_ivf_probes(hb_index *index, const void *queries, int qdtype, int64_t nq, int32_t nprobe,
+                         int32_t *out_probes) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(index && index->type == HB_INDEX_IVF_FLAT, "not an IVF-FLAT index");
+        HB_REQUIRE(qdtype == HB_F32 || qdtype == HB_F64, "queries must be fp32 or fp64");
+        HB_REQUIRE(nq >= 0 && nprobe >= 1, "bad arguments");
+        if (nq == 0) return;
+        HB_REQUIRE(queries && out_probes, "null buffer");
+        const void *q = stage_in(queries, (size_t)nq * index->d * dtype_size(qdtype), g_ws.in_b);
+        OutStage op = stage_out(out_probes, (size_t)nq * nprobe * 4, g_ws.out_c);
+        ivf_search_exact(index, q, qdtype, nq, 0, nprobe, nullptr, nullptr, (int32_t *)op.dev);
+        finish_out(op);
+        sync_stream();
+    });
+}
+
+HB_API int hb_kmeanspp_init(const void *rows, int64_t n, int32_t d, int dtype, int metric, int32_t nlist, int64_t seed,
+                            int64_t *out_seed_rows) {
+    return guarded([&] {
+        ensure_init();
+        ivf_common_checks(rows, n, d, dtype, metric, nlist);
+        HB_REQUIRE(out_seed_rows, "null buffer");
+        const void *r = stage_in(rows, (size_t)n * d * dtype_size(dtype), g_ws.in_a);
+        OutStage o = stage_out(out_seed_rows, (size_t)nlist * 8, g_ws.out_a);
+        double *cents = g_ws.cand_val.as<double>((size_t)nlist * d);
+        int32_t *assign = g_ws.probes.as<int32_t>(n);
+        // iters = -1: seeds only (kmeans_exact's loop body runs `it <= iters`)
+        kmeans_exact(r, dtype, n, d, metric, nlist, -1, seed, nullptr, cents, assign, (int64_t *)o.dev);
+        finish_out(o);
+        sync_stream();
+    });
+}
+
+HB_API int hb_kmeans_assign(const void *rows, int64_t n, int32_t d, int dtype, int metric, const double *centroids,
+                            int32_t nlist, int32_t *out_assign) {
+    return guarded([&] {
+        ensure_init();
+        ivf_common_checks(rows, n, d, dtype, metric, nlist);
+        HB_REQUIRE(centroids && out_assign, "null buffer");
+        const void *r = stage_in(rows, (size_t)n * d * dtype_size(dtype), g_ws.in_a);
+        const double *c = (const double *)stage_in(centroids, (size_t)nlist * d * 8, g_ws.in_c);
+        OutStage o = stage_out(out_assign, (size_t)n * 4, g_ws.out_a);
+        double *norm = g_ws.misc.as<double>(n);
+        double *cnorm = g_ws.qnorm.as<double>(nlist);
+        launch_row_norms(r, dtype, n, d, norm);
+        launch_row_norms(c, HB_F64, nlist, d, cnorm);
+        AssignParams A;
+        A.rows = r;
+        A.row_norm = norm;
+        A.n = n;
+        A.d = d;
+        A.cents = c;
+        A.cent_norm = cnorm;
+        A.nlist = nlist;
+        A.epi = metric == HB_L2 ? EPI_L2 : EPI_COS_GUARD;
+        A.out_assign = (int32_t *)o.dev;
+        launch_assign(A, dtype, metric == HB_L2);
+        finish_out(o);
+        sync_stream();
+    });
+}
+
+HB_API int hb_kmeans_update(const void *rows, int64_t n, int32_t d, int dtype, const int32_t *assign, int32_t nlist,
+                            double *centroids, double *out_sums, int64_t *out_counts) {
+    return guarded([&] {
+        ensure_init();
+        ivf_common_checks(rows, n, d, dtype, HB_COSINE, nlist);
+        HB_REQUIRE(assign && (centroids || out_sums), "null buffer");
+        const void *r = stage_in(rows, (size_t)n * d * dtype_size(dtype), g_ws.in_a);
+        const int32_t *a = (const int32_t *)stage_in(assign, (size_t)n * 4, g_ws.in_c);
+        int64_t *list_off = g_ws.lq_off.as<int64_t>(nlist + 1);
+        int64_t *list_rows = g_ws.cand_id.as<int64_t>(n);
+        build_lists(a, n, nlist, list_off, list_rows, g_ws.tmp);
+        if (out_sums) {
+            OutStage os = stage_out(out_sums, (size_t)nlist * d * 8, g_ws.out_a);
+            OutStage oc = stage_out(out_counts, (size_t)nlist * 8, g_ws.out_b);
+            launch_update_centroids(r, dtype, d, list_off, list_rows, nlist, nullptr, (double *)os.dev, (int64_t *)oc.dev);
+            finish_out(os);
+            finish_out(oc);
+        } else {
+            const bool host = !is_device_ptr(centroids);
+            double *c = centroids;
+            if (host) {
+                c = g_ws.out_a.as<double>((size_t)nlist * d);
+                HB_CUDA(cudaMemcpyAsync(c, centroids, (size_t)nlist * d * 8, cudaMemcpyHostToDevice, g_stream));
+            }
+            launch_update_centroids(r, dtype, d, list_off, list_rows, nlist, c, nullptr, nullptr);
+            if (host) HB_CUDA(cudaMemcpyAsync(centroids, c, (size_t)nlist * d * 8, cudaMemcpyDeviceToHost, g_stream));
+        }
+        sync_stream();
+    });
+}
+
+HB_API int hb_kmeans(const void *rows, int64_t n, int32_t d, int dtype, int metric, int32_t nlist, int32_t iters,
+                     int64_t seed, const int64_t *seed_rows, double *out_centroids, int32_t *out_assign) {
+    return guarded([&] {
+        ensure_init();
+        ivf_common_checks(rows, n, d, dtype, metric, nlist);
+        HB_REQUIRE(iters >= 0, "max-iterations must be >= 0");
+        HB_REQUIRE(out_centroids && out_assign, "null buffer");
+        const void *r = stage_in(rows, (size_t)n * d * dtype_size(dtype), g_ws.in_a);
+        const int64_t *sr = seed_rows ? (const int64_t *)stage_in(seed_rows, (size_t)nlist * 8, g_ws.in_c) : nullptr;
+        OutStage oc = stage_out(out_centroids, (size_t)nlist * d * 8, g_ws.out_a);
+        OutStage oa = stage_out(out_assign, (size_t)n * 4, g_ws.out_b);
+        kmeans_exact(r, dtype, n, d, metric, nlist, iters, seed, sr, (double *)oc.dev, (int32_t *)oa.dev, nullptr);
+        finish_out(oc);
+        finish_out(oa);
+        sync_stream();
+    });
+}
+
+HB_API int hb_hnsw_create(const void *rows, int64_t n, int32_t d, int dtype, int metric, const int32_t *levels,
+                          int32_t max_level, int32_t entry_point, const int64_t *const *level_offsets,
+                          const int32_t *const *level_ids, hb_index **out) {
+    return guarded([&] {
+        ensure_init();
+        check_dtype(dtype);
+        HB_REQUIRE(out, "null out");
+        HB_REQUIRE(n >= 0 && d >= 1 && (n == 0 || (rows && levels)), "bad arguments");
+        HB_REQUIRE(metric == HB_COSINE || metric == HB_L2, "HNSW distance-fn must be cosine or euclidean");
+        HB_REQUIRE(n == 0 || (max_level >= 0 && entry_point >= 0 && entry_point < n && level_offsets && level_ids), "bad graph");
+        hb_index *ix = new hb_index();
+        try {
+            ix->type = HB_INDEX_HNSW;
+            ix->dtype = dtype;
+            ix->metric = metric;
+            ix->d = d;
+            ix->n = n;
+            ix->max_level = n ? max_level : 0;
+            ix->entry = n ? entry_point : -1;
+            const size_t bytes = (size_t)n * d * dtype_size(dtype);
+            void *r = ix->rows.get(std::max<size_t>(bytes, 16));
+            if (bytes) HB_CUDA(cudaMemcpyAsync(r, rows, bytes, cudaMemcpyDefault, g_stream));
+            double *nm = ix->norms.as<double>(std::max<int64_t>(n, 1));
+            launch_row_norms(r, dtype, n, d, nm);
+            if (n) {
+                int32_t *lv = ix->levels.as<int32_t>(n);
+                HB_CUDA(cudaMemcpyAsync(lv, levels, (size_t)n * 4, cudaMemcpyDefault, g_stream));
+                ix->adj_off.resize((size_t)max_level + 1);
+                ix->adj_ids.resize((size_t)max_level + 1);
+                for (int l = 0; l <= max_level; ++l) {
+                    HB_REQUIRE(level_offsets[l] && level_ids[l], "null adjacency level");
+                    int64_t *o = ix->adj_off[l].as<int64_t>(n + 1);
+                    HB_CUDA(cudaMemcpyAsync(o, level_offsets[l], (size_t)(n + 1) * 8, cudaMemcpyDefault, g_stream));
+                    int64_t tot = 0;
+                    if (is_device_ptr(level_offsets[l])) {
+                        HB_CUDA(cudaMemcpyAsync(&tot, level_offsets[l] + n, 8, cudaMemcpyDeviceToHost, g_stream));
+                        sync_stream();
+                    } else {
+                        tot = level_offsets[l][n];
+                    }
+                    int32_t *a = ix->adj_ids[l].as<int32_t>(std::max<int64_t>(tot, 1));
+                    if (tot) HB_CUDA(cudaMemcpyAsync(a, level_ids[l], (size_t)tot * 4, cudaMemcpyDefault, g_stream));
+                }
+            }
+            sync_stream();
+        } catch (...) {
+            ix->release();
+            delete ix;
+            throw;
+        }
+        *out = ix;
+    });
+}
+
+HB_API int hb_gather_score(hb_index *index, const void *queries, int qdtype, int64_t nq, const int32_t *pair_query,
+                           const int32_t *pair_row, int64_t npairs, double *out_scores) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(index, "null index");
+        HB_REQUIRE(qdtype == HB_F32 || qdtype == HB_F64, "queries must be fp32 or fp64");
+        HB_REQUIRE(nq >= 0 && npairs >= 0, "bad arguments");
+        if (npairs == 0) return;
+        HB_REQUIRE(queries && pair_query && pair_row && out_scores, "null buffer");
+        HB_REQUIRE(index->type != HB_INDEX_IVF_FLAT, "gather-score needs rows in original order (flat or HNSW index)");
+        const int d = index->d;
+        const void *q = stage_in(queries, (size_t)nq * d * dtype_size(qdtype), g_ws.in_b);
+        const int32_t *pq = (const int32_t *)stage_in(pair_query, (size_t)npairs * 4, g_ws.in_c);
+        const int32_t *pr = (const int32_t *)stage_in(pair_row, (size_t)npairs * 4, g_ws.in_d);
+        OutStage o = stage_out(out_scores, (size_t)npairs * 8, g_ws.out_a);
+        bool l2;
+        int epi;
+        metric_to_epi(index->metric, true, l2, epi);
+        if (index->metric == HB_IP) epi = EPI_DOT;
+        const double *qn = nullptr;
+        if (index->metric == HB_COSINE) {
+            double *x = g_ws.qnorm.as<double>(nq);
+            launch_row_norms(q, qdtype, nq, d, x);
+            qn = x;
+        }
+        launch_gather_score(index->rows.p, index->dtype, (const double *)index->norms.p, q, qdtype, qn, d, pq, pr, npairs, l2, epi,
+                            (double *)o.dev);
+        finish_out(o);
+        sync_stream();
+    });
+}
+
+HB_API int hb_topk_merge(const double *dist, const int64_t *ids, int32_t nparts, int64_t nq, int32_t k, int64_t *out_ids,
+                         double *out_dist) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(nparts >= 1 && nq >= 0 && k >= 0, "bad arguments");
+        if (nq == 0 || k == 0) return;
+        HB_REQUIRE(dist && ids && out_ids && out_dist, "null buffer");
+        HB_REQUIRE(k <= 1024, "k > 1024 is not supported");
+        const size_t cnt = (size_t)nparts * nq * k;
+        const double *dd = (const double *)stage_in(dist, cnt * 8, g_ws.in_a);
+        const int64_t *di = (const int64_t *)stage_in(ids, cnt * 8, g_ws.in_b);
+        OutStage oi = stage_out(out_ids, (size_t)nq * k * 8, g_ws.out_a);
+        OutStage od = stage_out(out_dist, (size_t)nq * k * 8, g_ws.out_b);
+        double *cval = g_ws.cand_val.as<double>(cnt);
+        int64_t *cid = g_ws.cand_id.as<int64_t>(cnt);
+        launch_parts_to_query_major(dd, di, nparts, nq, k, cval, cid);
+        // unused slots of a part carry id -1 / +inf: they sort last among equal distances only if real +inf
+        // distances are absent, which holds for every finite input
+        SelectParams L;
+        L.vals = cval;
+        L.nseg = nq;
+        L.seg_stride = (int64_t)nparts * k;
+        L.seg_len_const = (int64_t)nparts * k;
+        L.k = k;
+        L.out_val = (double *)od.dev;
+        int64_t *pos = g_ws.sel_pos.as<int64_t>((size_t)nq * k);
+        L.out_pos = pos;
+        launch_select(L);
+        launch_lookup_ids(pos, nq, k, cid, (int64_t)nparts * k, (int64_t *)oi.dev);
+        finish_out(oi);
+        finish_out(od);
+        sync_stream();
+    });
+}
+
+HB_API int hb_index_info(const hb_index *index, hb_info *out) {
+    return guarded([&] {
+        HB_REQUIRE(index && out, "null argument");
+        out->type = index->type;
+        out->dtype = index->dtype;
+        out->metric = index->metric;
+        out->dim = index->d;
+        out->n = index->n;
+        out->nlist = index->nlist;
+        out->max_level = index->max_level;
+        out->device_bytes = index->device_bytes();
+    });
+}
+
+HB_API int hb_index_free(hb_index *index) {
+    return guarded([&] {
+        if (!index) return;
+        if (g_inited) cudaStreamSynchronize(g_stream);
+        index->release();
+        delete index;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// hb_kernels.cuh — launcher declarations for the sm_100a kernels of libhnswb200.
+#pragma once
+#include "hb_common.cuh"
+
+namespace hb {
+
+// -------------------------------------------------------------------------------------------
+// Exact pair scan (hb_pairscan.cu): a tiled fp64 "GEMM" whose every (row, query) accumulator is
+// the reference's sequential index-order sum.  Work is a set of lists; list l pairs the slab rows
+// [list_off[l], list_off[l+1]) with the query selections qsel[lq_off[l] .. lq_off[l+1]).
+// -------------------------------------------------------------------------------------------
+constexpr int kTileRows = 128;  // TR
+constexpr int kTileQ = 64;      // TQ
+
+struct ScanParams {
+    const void *rows = nullptr;        // slab [*, d], row dtype
+    const double *row_norm = nullptr;  // sqrt(sum v^2) per slab row (cosine epilogues)
+    const void *queries = nullptr;     // [*, d], query dtype
+    const double *q_norm = nullptr;    // per query
+    int d = 0;
+    int nlist = 0;
+    const int64_t *list_off = nullptr;     // [nlist+1] slab rows of each list
+    const int64_t *lq_off = nullptr;       // [nlist+1] selections of each list
+    const int32_t *qsel = nullptr;         // selection -> pair id        (NULL: identity)
+    const int32_t *pair_query = nullptr;   // pair id -> query index      (NULL: identity)
+    int32_t pair_div = 0;                  // if > 0 and pair_query NULL: query = pair / pair_div
+    const int64_t *pair_out = nullptr;     // pair id -> base offset in out (NULL: pair * out_stride)
+    int64_t out_stride = 0;
+    const int64_t *tile_prefix = nullptr;  // [nlist+1] exclusive prefix of tiles per list
+    double *out = nullptr;                 // distances
+    int epi = EPI_COS;
+};
+void launch_pairscan(const ScanParams &P, int rdtype, int qdtype, bool l2);
+
+// k-means assignment (hb_pairscan.cu): argmin over centroids of the same exact distances, strict <,
+// lowest index wins (ivf_flat.clj:79-90).
+struct AssignParams {
+    const void *rows = nullptr;  // points [n, d]
+    const double *row_norm = nullptr;
+    int64_t n = 0;
+    int d = 0;
+    const double *cents = nullptr;  // [nlist, d] fp64
+    const double *cent_norm = nullptr;
+    int nlist = 0;
+    int epi = EPI_COS_GUARD;
+    int32_t *out_assign = nullptr;
+    double *out_best = nullptr;  // optional: the winning distance
+};
+void launch_assign(const AssignParams &P, int rdtype, bool l2);
+
+// sqrt(sum v^2) per row, sequential fp64 (ivf_flat.clj:171-177)
+void launch_row_norms(const void *rows, int dtype, int64_t n, int d, double *out);
+
+// out[p] = epi(sum over the row pair_row[p] and query pair_query[p]) — one thread per pair,
+// sequential (ultra_fast.clj:192).
+void launch_gather_score(const void *rows, int rdtype, const double *row_norm, const void *queries, int qdtype,
+                         const double *q_norm, int d, const int32_t *pair_query, const int32_t *pair_row,
+                         int64_t npairs, bool l2, int epi, double *out);
+
+// -------------------------------------------------------------------------------------------
+// Segmented top-k selection (hb_select.cu).  Segment s covers vals[seg_begin(s) .. +seg_len(s));
+// ordering is (value by Double/compare, position) — position order is the reference's stable-sort
+// order for every caller.  Writes k (key, position-in-segment) pairs per segment; unused slots
+// have pos -1 / +inf.
+// -------------------------------------------------------------------------------------------
+struct SelectParams {
+    const double *vals = nullptr;
+    int64_t nseg = 0;                  // segments (one per query)
+    const int64_t *seg_off = nullptr;  // segment s spans [seg_off[s*seg_off_stride], seg_off[(s+1)*seg_off_stride])
+    int64_t seg_off_stride = 1;
+    int64_t seg_stride = 0;            // if seg_off == NULL: segment s spans [s*seg_stride, +seg_len_const)
+    int64_t seg_len_const = 0;
+    // optional split of every segment into nsub sub-ranges of sub_len candidates, one CTA each (few queries,
+    // long segments); sub-range j of segment s writes slot s*out_seg_stride + out_slot_base + j
+    int nsub = 1;
+    int64_t sub_len = 0;
+    int64_t out_seg_stride = 1;
+    int64_t out_slot_base = 0;
+    int k = 0;
+    double *out_val = nullptr;   // [slots, k]
+    int64_t *out_pos = nullptr;  // [slots, k] position within the segment (-1: unused)
+};
+void launch_select(const SelectParams &P);
+
+
+}  // namespace hb

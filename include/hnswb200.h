@@ -74,6 +74,8 @@ HB_API const char *hb_last_error(void);
 HB_API int hb_version(void);
 HB_API int hb_set_stream(void *cuda_stream); /* launch on this stream (default: legacy stream 0) */
 HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches (default EXACT) */
+/* tuning knobs: "scratch_mb" = budget for the transient distance scratch (default 8192) */
+HB_API int hb_set_option(const char *name, int64_t value);
 /* number of kernels this library launched since hb_init / the last reset (bench `gpu_launches`) */
 HB_API int64_t hb_launch_count(int reset);
 

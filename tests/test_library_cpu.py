@@ -1,0 +1,72 @@
+"""CPU-side checks of the boundary: the C-ABI library builds/loads, exports every symbol include/hnswb200.h
+declares, refuses to compute without a device (no CPU fallback), and the host mirror's pure logic."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from hnsw_clj_b200.build import build_library
+
+    build_library()
+    from hnsw_clj_b200 import _lib
+
+    return _lib
+
+
+def test_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "hnswb200.h")).read()
+    declared = set(re.findall(r"HB_API\s+[\w\s\*]+?\b(hb_\w+)\s*\(", header))
+    assert len(declared) >= 24
+    L = lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    assert L.hb_version() >= 100
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    from hnsw_clj_b200 import simd_optimized as so
+    from hnsw_clj_b200.flat import FlatIndex
+
+    with pytest.raises(lib.HbError) as e:
+        so.cosine_distance([1, 2, 3], [4, 5, 6])
+    assert e.value.status == lib.ERR_NO_DEVICE
+    with pytest.raises(lib.HbError):
+        FlatIndex(np.eye(4, dtype=np.float32))
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "hnsw_clj_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle-built", "").replace("oracle's", ""), f
+
+
+def test_host_helpers(lib):
+    from hnsw_clj_b200 import flat, index, ivf_flat
+
+    assert index.metric_code("cosine") == lib.COSINE and index.metric_code(":euclidean") == lib.L2
+    with pytest.raises(ValueError):
+        index.metric_code("manhattan")
+    ids, rows = index.split_data([("a", [1.0, 2.0]), ("b", [3.0, 4.0])])
+    assert ids == ["a", "b"] and rows.shape == (2, 2) and rows.dtype == np.float64
+    ids, rows = index.split_data(np.ones((3, 2), np.float32))
+    assert ids is None and rows.dtype == np.float32
+    maps = index.results_to_maps(np.array([[1, 0, -1]]), np.array([[0.1, 0.2, np.inf]]), ["x", "y"])
+    assert maps == [[{"id": "y", "distance": 0.1}, {"id": "x", "distance": 0.2}]]
+    assert ivf_flat._num_probes("balanced", None) == 4 and ivf_flat._num_probes(":precise", None) == 12
+    assert ivf_flat._num_probes("custom", 32) == 32 and ivf_flat._num_probes("custom", None) == 4
+    assert flat.calc_recall([{"id": 1}, {"id": 2}], [{"id": 2}, {"id": 3}]) == 0.5
+    assert flat.recall_at_k(np.array([[1, 2, -1]]), np.array([[2, 3, -1]])) == 0.5

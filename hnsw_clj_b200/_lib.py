@@ -46,6 +46,7 @@ SIGNATURES = {
     "hb_set_stream": (_int, [_p]),
     "hb_set_mode": (_int, [_int]),
     "hb_set_option": (_int, [C.c_char_p, _i64]),
+    "hb_get_stat": (_int, [C.c_char_p, C.POINTER(C.c_double)]),
     "hb_launch_count": (_i64, [_int]),
     "hb_row_norms": (_int, [_p, _i64, _i32, _int, _p]),
     "hb_pairwise": (_int, [_p, _i64, _int, _p, _i64, _int, _i32, _int, _p]),
@@ -132,6 +133,12 @@ def ptr(x) -> int | None:
 
 def set_option(name: str, value: int) -> None:
     check(lib().hb_set_option(name.encode(), int(value)))
+
+
+def get_stat(name: str) -> float:
+    v = C.c_double()
+    check(lib().hb_get_stat(name.encode(), C.byref(v)))
+    return v.value
 
 
 def launch_count(reset: bool = False) -> int:

@@ -114,6 +114,46 @@ static int guarded(F &&f) {
 
 static void sync_stream() { HB_CUDA(cudaStreamSynchronize(g_stream)); }
 
+// ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ------
+enum ProfTag { PROF_SCAN = 0, PROF_COARSE = 1, PROF_SELECT = 2, PROF_PLAN = 3, PROF_ASSIGN = 4, PROF_NTAGS = 5 };
+static bool g_profile = false;
+struct ProfSpan {
+    cudaEvent_t a, b;
+    int tag;
+};
+static std::vector<ProfSpan> g_spans;
+static double g_prof_ms[PROF_NTAGS] = {0};
+static int64_t g_prof_n[PROF_NTAGS] = {0};
+struct Prof {
+    bool on;
+    ProfSpan sp;
+    explicit Prof(int tag) : on(g_profile) {
+        if (!on) return;
+        sp.tag = tag;
+        cudaEventCreate(&sp.a);
+        cudaEventCreate(&sp.b);
+        cudaEventRecord(sp.a, g_stream);
+    }
+    ~Prof() {
+        if (!on) return;
+        cudaEventRecord(sp.b, g_stream);
+        g_spans.push_back(sp);
+    }
+};
+static void prof_collect() {
+    for (auto &sp : g_spans) {
+        cudaEventSynchronize(sp.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, sp.a, sp.b);
+        g_prof_ms[sp.tag] += ms;
+        g_prof_n[sp.tag] += 1;
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    g_spans.clear();
+}
+double fp64_peak_tflops();  // hb_microbench.cu
+
 // ---- java.util.Random (needed by kmeans-plus-plus-init, ivf_flat.clj:37: (Random. 42)) -------------
 // Implemented from the published LCG definition of java.util.Random (JDK javadoc).
 struct JavaRandom {
@@ -267,7 +307,11 @@ static void flat_search_exact(const void *rows, int rdtype, const double *row_no
         S.out_stride = len;
         S.out = scratch;
         S.epi = epi;
-        launch_pairscan(S, rdtype, qdtype, l2);
+        {
+            Prof pr(PROF_SCAN);
+            launch_pairscan(S, rdtype, qdtype, l2);
+        }
+        Prof pr2(PROF_SELECT);
         SelectParams L;
         L.vals = scratch;
         L.nseg = nq;
@@ -355,6 +399,7 @@ static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int6
             S.out_stride = nlist;
             S.out = coarse;
             S.epi = cepi;
+            Prof pr(PROF_COARSE);
             launch_pairscan(S, HB_F64, qdtype, cl2);
             SelectParams L;
             L.vals = coarse;
@@ -367,8 +412,11 @@ static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int6
             launch_select(L);
         }
         const int64_t np = nqc * np_eff;
-        ivf_plan(ppos, np, nlist, (const int64_t *)ix->list_off.p, probes, pair_out, qsel, lq_off, tile_prefix,
-                 kTileRows, kTileQ, g_ws.tmp);
+        {
+            Prof prp(PROF_PLAN);
+            ivf_plan(ppos, np, nlist, (const int64_t *)ix->list_off.p, probes, pair_out, qsel, lq_off, tile_prefix,
+                     kTileRows, kTileQ, g_ws.tmp);
+        }
         if (probes_out) {
             if (np_eff == nprobe) {
                 HB_CUDA(cudaMemcpyAsync(probes_out + (size_t)q0 * nprobe, probes, (size_t)np * 4, cudaMemcpyDeviceToDevice, g_stream));
@@ -399,7 +447,11 @@ static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int6
         S.tile_prefix = tile_prefix;
         S.out = scratch;
         S.epi = EPI_COS;
-        launch_pairscan(S, ix->dtype, qdtype, false);
+        {
+            Prof pr(PROF_SCAN);
+            launch_pairscan(S, ix->dtype, qdtype, false);
+        }
+        Prof prs(PROF_SELECT);
         // merge (:291-294): stable sort of the concatenation in probe order, take k
         SelectParams L;
         L.vals = scratch;
@@ -478,7 +530,10 @@ static void kmeans_exact(const void *rows, int dtype, int64_t n, int d, int metr
     A.out_assign = assign;
     for (int it = 0; it <= iters; ++it) {
         launch_row_norms(cents, HB_F64, nlist, d, cnorm);
-        launch_assign(A, dtype, l2);
+        {
+            Prof pr(PROF_ASSIGN);
+            launch_assign(A, dtype, l2);
+        }
         if (it == iters) break;  // final assignment pass (:119-131)
         build_lists(assign, n, nlist, list_off, list_rows, g_ws.tmp);
         launch_update_centroids(rows, dtype, d, list_off, list_rows, nlist, cents, nullptr, nullptr);
@@ -537,9 +592,31 @@ HB_API int hb_set_option(const char *name, int64_t value) {
         if (!strcmp(name, "scratch_mb")) {
             HB_REQUIRE(value >= 1, "scratch_mb must be >= 1");
             g_scratch_budget = (size_t)value << 20;
+        } else if (!strcmp(name, "profile")) {
+            prof_collect();
+            g_profile = value != 0;
+            for (int i = 0; i < PROF_NTAGS; ++i) g_prof_ms[i] = 0, g_prof_n[i] = 0;
         } else {
             throw Error(HB_ERR_INVALID, std::string("unknown option ") + name);
         }
+    });
+}
+HB_API int hb_get_stat(const char *name, double *out) {
+    return guarded([&] {
+        HB_REQUIRE(name && out, "null argument");
+        static const char *ms_names[PROF_NTAGS] = {"scan_ms", "coarse_ms", "select_ms", "plan_ms", "assign_ms"};
+        static const char *n_names[PROF_NTAGS] = {"scan_count", "coarse_count", "select_count", "plan_count", "assign_count"};
+        prof_collect();
+        for (int i = 0; i < PROF_NTAGS; ++i) {
+            if (!strcmp(name, ms_names[i])) { *out = g_prof_ms[i]; return; }
+            if (!strcmp(name, n_names[i])) { *out = (double)g_prof_n[i]; return; }
+        }
+        if (!strcmp(name, "fp64_peak_tflops")) {
+            ensure_init();
+            *out = fp64_peak_tflops();
+            return;
+        }
+        throw Error(HB_ERR_INVALID, std::string("unknown stat ") + name);
     });
 }
 HB_API int64_t hb_launch_count(int reset) {

@@ -74,8 +74,13 @@ HB_API const char *hb_last_error(void);
 HB_API int hb_version(void);
 HB_API int hb_set_stream(void *cuda_stream); /* launch on this stream (default: legacy stream 0) */
 HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches (default EXACT) */
-/* tuning knobs: "scratch_mb" = budget for the transient distance scratch (default 8192) */
+/* knobs: "scratch_mb" = budget for the transient distance scratch (default 8192); "profile" = 1 records
+ * CUDA events around the main kernels (and resets the counters) */
 HB_API int hb_set_option(const char *name, int64_t value);
+/* measurements: "scan_ms"/"scan_count" (list/flat scan kernel), "coarse_ms", "select_ms", "plan_ms", "assign_ms"
+ * (device time between the events, accumulated since "profile" was set), "fp64_peak_tflops" (runs a DFMA
+ * microbenchmark: the measured peak of the pipe the exact kernels are bound by) */
+HB_API int hb_get_stat(const char *name, double *out);
 /* number of kernels this library launched since hb_init / the last reset (bench `gpu_launches`) */
 HB_API int64_t hb_launch_count(int reset);
 

@@ -16,8 +16,13 @@ namespace hb {
 
 namespace {
 
-constexpr int TR = kTileRows, TQ = kTileQ, KC = 32, NT = 256, RT = 8, QT = 4;
-constexpr int kSmemBytes = 2 * KC * (TR + TQ) * (int)sizeof(double);  // 98,304 B
+constexpr int TR = kTileRows, TQ = kTileQ, KC = 16, NT = 128, RT = 8, QT = 8;
+constexpr int kSmemBytes = 2 * KC * (TR + TQ) * (int)sizeof(double);  // 49,152 B
+// Thread (tx = tid & 7, ty = tid >> 3) owns rows  {2*ty + 32*i + {0,1}}, i < 4  and queries {2*tx + 16*j + {0,1}}, j < 4:
+// every LDS.128 of a warp then reads one contiguous run of 16-byte chunks (no bank conflicts; identical
+// quarter-warps are served by one wavefront), 8 LDS.128 feed 64 DFMA.
+__device__ __forceinline__ int row_of(int ty, int i) { return 2 * ty + 32 * (i >> 1) + (i & 1); }
+__device__ __forceinline__ int qry_of(int tx, int j) { return 2 * tx + 16 * (j >> 1) + (j & 1); }
 
 template <typename T>
 __device__ __forceinline__ T zero_of() { return T(0); }
@@ -55,22 +60,20 @@ __device__ __forceinline__ void load_run(const T *__restrict__ p, int k0, int d,
 template <int ARITH>
 __device__ __forceinline__ void tile_mac(const double *__restrict__ rsb, const double *__restrict__ qsb, int kmax,
                                          double (&acc)[RT][QT], int tx, int ty) {
-    const double *rp0 = rsb + ty * RT;
-    const double *qp0 = qsb + tx * QT;
-#pragma unroll 4
+    const double *rp0 = rsb + 2 * ty;
+    const double *qp0 = qsb + 2 * tx;
+#pragma unroll 2
     for (int k = 0; k < kmax; ++k) {
-        const double2 *rp = reinterpret_cast<const double2 *>(rp0 + k * TR);
-        const double2 *qp = reinterpret_cast<const double2 *>(qp0 + k * TQ);
         double r[RT], q[QT];
 #pragma unroll
         for (int i = 0; i < RT / 2; ++i) {
-            double2 t = rp[i];
+            const double2 t = *reinterpret_cast<const double2 *>(rp0 + k * TR + 32 * i);
             r[2 * i] = t.x;
             r[2 * i + 1] = t.y;
         }
 #pragma unroll
         for (int j = 0; j < QT / 2; ++j) {
-            double2 t = qp[j];
+            const double2 t = *reinterpret_cast<const double2 *>(qp0 + k * TQ + 16 * j);
             q[2 * j] = t.x;
             q[2 * j + 1] = t.y;
         }
@@ -86,9 +89,9 @@ __device__ __forceinline__ void tile_mac(const double *__restrict__ rsb, const d
 template <typename TRow, typename TQry, int ARITH, bool VEC>
 __device__ __forceinline__ void run_tile(const TRow *__restrict__ rowp, bool row_valid, const TQry *__restrict__ qp,
                                          bool q_valid, int d, double *smem, double (&acc)[RT][QT]) {
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int lrow = tid & (TR - 1), rk = (tid >> 7) * 16;  // loader: row, k offset (16 elements)
-    const int lq = tid & (TQ - 1), qk = (tid >> 6) * 8;     // loader: query, k offset (8 elements)
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+    const int lrow = tid;                                  // loader: one row, the whole 16-element run
+    const int lq = tid & (TQ - 1), qk = (tid >> 6) * 8;    // loader: query, k offset (8 elements)
     double *rs = smem;                 // [2][KC][TR]
     double *qs = smem + 2 * KC * TR;   // [2][KC][TQ]
 #pragma unroll
@@ -99,32 +102,31 @@ __device__ __forceinline__ void run_tile(const TRow *__restrict__ rowp, bool row
     Run<TRow, 16> rv;
     Run<TQry, 8> qv;
     const int nchunks = (d + KC - 1) / KC;
-    load_run<TRow, 16, VEC>(rowp, rk, d, row_valid, rv);
+    load_run<TRow, 16, VEC>(rowp, 0, d, row_valid, rv);
     load_run<TQry, 8, VEC>(qp, qk, d, q_valid, qv);
     for (int c = 0; c < nchunks; ++c) {
         double *rsb = rs + (c & 1) * KC * TR;
         double *qsb = qs + (c & 1) * KC * TQ;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) rsb[(rk + i) * TR + lrow] = to_f64(rv[i]);
+        for (int i = 0; i < 16; ++i) rsb[i * TR + lrow] = to_f64(rv[i]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) qsb[(qk + i) * TQ + lq] = to_f64(qv[i]);
         __syncthreads();
         if (c + 1 < nchunks) {
-            load_run<TRow, 16, VEC>(rowp, (c + 1) * KC + rk, d, row_valid, rv);
+            load_run<TRow, 16, VEC>(rowp, (c + 1) * KC, d, row_valid, rv);
             load_run<TQry, 8, VEC>(qp, (c + 1) * KC + qk, d, q_valid, qv);
         }
         const int kmax = min(KC, d - c * KC);
         if (kmax == KC) tile_mac<ARITH>(rsb, qsb, KC, acc, tx, ty);
         else tile_mac<ARITH>(rsb, qsb, kmax, acc, tx, ty);
-        // the buffer written next iteration is the other one; the barrier at its top of loop orders
-        // this iteration's reads of (c&1) against the writes two iterations later
+        // the next iteration writes the other buffer; its barrier orders this iteration's reads of (c&1)
+        // against the writes two iterations later
     }
     __syncthreads();
 }
 
 template <typename TRow, typename TQry, int ARITH, bool VEC>
-__global__ void __launch_bounds__(NT, (sizeof(TRow) == 8 || sizeof(TQry) == 8) ? 1 : 2)
-pairscan_kernel(const ScanParams P) {
+__global__ void __launch_bounds__(NT, 2) pairscan_kernel(const ScanParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *smem = reinterpret_cast<double *>(smem_raw);
     __shared__ int s_tile[4];
@@ -134,7 +136,7 @@ pairscan_kernel(const ScanParams P) {
     __shared__ double s_qn[TQ];
     __shared__ double s_rn[TR];
 
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
     const int64_t total = P.tile_prefix[P.nlist];
     const TRow *rows = static_cast<const TRow *>(P.rows);
     const TQry *queries = static_cast<const TQry *>(P.queries);
@@ -177,13 +179,11 @@ pairscan_kernel(const ScanParams P) {
             s_qidx[tid] = qi;
             s_qout[tid] = ob;
             s_qn[tid] = qn;
-        } else if (tid >= 128) {
-            const int r = tid - 128;
-            s_rn[r] = (P.row_norm && r < nrows) ? P.row_norm[row0 + r] : 0.0;
         }
+        s_rn[tid] = (P.row_norm && tid < nrows) ? P.row_norm[row0 + tid] : 0.0;
         __syncthreads();
 
-        const int lrow = tid & (TR - 1), lq = tid & (TQ - 1);
+        const int lrow = tid, lq = tid & (TQ - 1);
         const bool row_valid = lrow < nrows;
         const int my_q = s_qidx[lq];
         const TRow *rowp = rows + (row0 + (row_valid ? lrow : 0)) * (int64_t)P.d;
@@ -193,14 +193,14 @@ pairscan_kernel(const ScanParams P) {
 
 #pragma unroll
         for (int j = 0; j < QT; ++j) {
-            const int q = tx * QT + j;
+            const int q = qry_of(tx, j);
             if (q < nqt) {
                 const double qn = s_qn[q];
-                double *o = P.out + s_qout[q] + (int64_t)rt * TR + ty * RT;
+                double *o = P.out + s_qout[q] + (int64_t)rt * TR;
 #pragma unroll
                 for (int i = 0; i < RT; ++i) {
-                    const int r = ty * RT + i;
-                    if (r < nrows) o[i] = apply_epi(P.epi, acc[i][j], qn, s_rn[r]);
+                    const int r = row_of(ty, i);
+                    if (r < nrows) o[r] = apply_epi(P.epi, acc[i][j], qn, s_rn[r]);
                 }
             }
         }
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(NT, 1) assign_kernel(const AssignParams P) {
     double *smem = reinterpret_cast<double *>(smem_raw);
     __shared__ double s_rn[TR];
     __shared__ double s_cn[TQ];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
     const TRow *rows = static_cast<const TRow *>(P.rows);
     const int64_t ntiles = (P.n + TR - 1) / TR;
     const int nct = (P.nlist + TQ - 1) / TQ;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NT, 1) assign_kernel(const AssignParams P) {
         const int64_t row0 = t * TR;
         const int nrows = (int)min((int64_t)TR, P.n - row0);
         __syncthreads();
-        if (tid < TR) s_rn[tid] = (P.row_norm && tid < nrows) ? P.row_norm[row0 + tid] : 0.0;
+        s_rn[tid] = (P.row_norm && tid < nrows) ? P.row_norm[row0 + tid] : 0.0;
         double best[RT];
         int bidx[RT];
 #pragma unroll
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(NT, 1) assign_kernel(const AssignParams P) {
             best[i] = DBL_MAX;
             bidx[i] = INT_MAX;
         }
-        const int lrow = tid & (TR - 1), lq = tid & (TQ - 1);
+        const int lrow = tid, lq = tid & (TQ - 1);
         const bool row_valid = lrow < nrows;
         const TRow *rowp = rows + (row0 + (row_valid ? lrow : 0)) * (int64_t)P.d;
         for (int ct = 0; ct < nct; ++ct) {
@@ -245,16 +245,17 @@ __global__ void __launch_bounds__(NT, 1) assign_kernel(const AssignParams P) {
             const double *qp = P.cents + (int64_t)(c0 + (q_valid ? lq : 0)) * P.d;
             double acc[RT][QT];
             run_tile<TRow, double, ARITH, VEC>(rowp, row_valid, qp, q_valid, P.d, smem, acc);
+            // a thread's queries are not in index order (qry_of); keep "lowest index wins" explicit
 #pragma unroll
             for (int j = 0; j < QT; ++j) {
-                const int q = tx * QT + j;
+                const int q = qry_of(tx, j);
                 if (q < ncq) {
                     const double cn = s_cn[q];
 #pragma unroll
                     for (int i = 0; i < RT; ++i) {
                         // distance-fn(vector, centroid): n1 = row, n2 = centroid; products commute
-                        const double dist = apply_epi(P.epi, acc[i][j], s_rn[ty * RT + i], cn);
-                        if (dist < best[i]) {
+                        const double dist = apply_epi(P.epi, acc[i][j], s_rn[row_of(ty, i)], cn);
+                        if (dist < best[i] || (dist == best[i] && c0 + q < bidx[i])) {
                             best[i] = dist;
                             bidx[i] = c0 + q;
                         }
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(NT, 1) assign_kernel(const AssignParams P) {
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
 #pragma unroll
-            for (int m = 8; m >= 1; m >>= 1) {
+            for (int m = 4; m >= 1; m >>= 1) {
                 const double od = __shfl_xor_sync(0xffffffffu, best[i], m);
                 const int oi = __shfl_xor_sync(0xffffffffu, bidx[i], m);
                 if (od < best[i] || (od == best[i] && oi < bidx[i])) {
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(NT, 1) assign_kernel(const AssignParams P) {
         if (tx == 0) {
 #pragma unroll
             for (int i = 0; i < RT; ++i) {
-                const int r = ty * RT + i;
+                const int r = row_of(ty, i);
                 if (r < nrows) {
                     P.out_assign[row0 + r] = bidx[i] == INT_MAX ? 0 : bidx[i];
                     if (P.out_best) P.out_best[row0 + r] = best[i];

@@ -4,7 +4,7 @@ and a small all-gather plus the merge kernel (hb_topk_merge) gives the global to
 
 This is the reference's own scale-out model — independent sub-indexes searched in parallel and merged by
 (sort-by :distance) + (take k) (src/hnsw/ann/partition/partitioned_hnsw.clj:149-196) — applied to the lists
-of ONE global IVF-FLAT index, so results are identical to the single-GPU (and oracle) results.
+of ONE global IVF-FLAT index, so results are identical to the single-GPU results.
 torch.distributed is plumbing only: the collective carries G*nq*k (distance, id) pairs.
 """
 from __future__ import annotations
@@ -88,10 +88,11 @@ def all_gather_merge(ids, dist, world: int, group=None):
     if was_numpy:
         ids, dist = torch.from_numpy(np.ascontiguousarray(ids)), torch.from_numpy(np.ascontiguousarray(dist))
     nq, k = ids.shape
-    all_ids = torch.empty((world, nq, k), dtype=torch.int64, device=ids.device)
-    all_dist = torch.empty((world, nq, k), dtype=torch.float64, device=ids.device)
+    all_ids = torch.empty((world * nq, k), dtype=torch.int64, device=ids.device)
+    all_dist = torch.empty((world * nq, k), dtype=torch.float64, device=ids.device)
     dist_.all_gather_into_tensor(all_ids, ids.contiguous(), group=group)
     dist_.all_gather_into_tensor(all_dist, dist.contiguous(), group=group)
+    all_ids, all_dist = all_ids.view(world, nq, k), all_dist.view(world, nq, k)
     out_ids = torch.empty_like(ids)
     out_dist = torch.empty_like(dist)
     if ids.is_cuda:

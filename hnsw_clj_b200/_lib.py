@@ -62,6 +62,7 @@ SIGNATURES = {
     "hb_kmeans": (_int, [_p, _i64, _i32, _int, _int, _i32, _i32, _i64, _p, _p, _p]),
     "hb_hnsw_create": (_int, [_p, _i64, _i32, _int, _int, _p, _i32, _i32, _pp, _pp, _pp]),
     "hb_gather_score": (_int, [_p, _p, _int, _i64, _p, _p, _i64, _p]),
+    "hb_fast_scores": (_int, [_p, _p, _int, _i64, _p, _p, _p]),
     "hb_topk_merge": (_int, [_p, _p, _i32, _i64, _i32, _p, _p]),
     "hb_index_info": (_int, [_p, C.POINTER(HbInfo)]),
     "hb_index_free": (_int, [_p]),
@@ -139,6 +140,11 @@ def get_stat(name: str) -> float:
     v = C.c_double()
     check(lib().hb_get_stat(name.encode(), C.byref(v)))
     return v.value
+
+
+def set_mode(mode: int) -> None:
+    """MODE_EXACT (default) or MODE_FAST (tensor-core candidate pass + fp64 re-score + proof; same results)."""
+    check(lib().hb_set_mode(int(mode)))
 
 
 def launch_count(reset: bool = False) -> int:

@@ -1,6 +1,7 @@
 // hb_api.cu — the C ABI of libhnswb200.so (include/hnswb200.h): handles, staging of host/device buffers and
 // the orchestration of the kernels behind hnsw-clj's build-index / search-knn / search-batch* surface.
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -9,6 +10,7 @@
 #include <vector>
 
 #include "hb_build.cuh"
+#include "hb_fast.cuh"
 #include "hb_kernels.cuh"
 
 namespace hb {
@@ -115,7 +117,7 @@ static int guarded(F &&f) {
 static void sync_stream() { HB_CUDA(cudaStreamSynchronize(g_stream)); }
 
 // ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ------
-enum ProfTag { PROF_SCAN = 0, PROF_COARSE = 1, PROF_SELECT = 2, PROF_PLAN = 3, PROF_ASSIGN = 4, PROF_NTAGS = 5 };
+enum ProfTag { PROF_SCAN = 0, PROF_COARSE = 1, PROF_SELECT = 2, PROF_PLAN = 3, PROF_ASSIGN = 4, PROF_TC = 5, PROF_PACK = 6, PROF_RESCORE = 7, PROF_NTAGS = 8 };
 static bool g_profile = false;
 struct ProfSpan {
     cudaEvent_t a, b;
@@ -190,6 +192,29 @@ static void check_dtype(int dtype) {
     HB_REQUIRE(dtype == HB_F32 || dtype == HB_BF16 || dtype == HB_F64, "unknown dtype");
 }
 
+// digit images of one set of vectors (hb_fast.cuh)
+struct FastSideBufs {
+    DevBuf img, rs, ro, tile_off, stats, list_off;
+    int ns = 0, kbn = 0;
+    int64_t ntiles = 0;
+    bool built = false, usable = false;
+    size_t bytes() const { return img.cap + rs.cap + ro.cap + tile_off.cap + stats.cap + list_off.cap; }
+    void release() {
+        img.release();
+        rs.release();
+        ro.release();
+        tile_off.release();
+        stats.release();
+        list_off.release();
+        built = false;
+    }
+};
+
+static bool g_fast_debug = false;
+static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
+static int64_t g_fast_queries = 0;   // queries answered in FAST mode ...
+static int64_t g_fast_fallbacks = 0; // ... of which recomputed by the exact path (proof failed)
+
 }  // namespace hb
 
 using namespace hb;
@@ -207,10 +232,13 @@ struct hb_index {
     int max_level = 0, entry = -1;
     DevBuf levels;
     std::vector<DevBuf> adj_off, adj_ids;
+    // HB_MODE_FAST: digit images of the rows (all index types) and of the centroids (IVF), built on first use
+    hb::FastSideBufs fast_rows, fast_cents;
     int64_t device_bytes() const {
         size_t b = rows.cap + norms.cap + cents.cap + cent_norm.cap + list_off.cap + list_rows.cap + assign.cap + levels.cap;
         for (auto &x : adj_off) b += x.cap;
         for (auto &x : adj_ids) b += x.cap;
+        b += fast_rows.bytes() + fast_cents.bytes();
         return (int64_t)b;
     }
     void release() {
@@ -224,6 +252,8 @@ struct hb_index {
         levels.release();
         for (auto &x : adj_off) x.release();
         for (auto &x : adj_ids) x.release();
+        fast_rows.release();
+        fast_cents.release();
     }
 };
 
@@ -559,6 +589,549 @@ static void ivf_finalize(hb_index *ix, const void *rows_dev, const double *row_n
     for (int l = 0; l < nlist; ++l) ix->max_list = std::max(ix->max_list, off[l + 1] - off[l]);
 }
 
+
+// =================================================================================================
+// HB_MODE_FAST orchestration (scheme: hb_fast.cuh)
+// =================================================================================================
+struct FastWs {
+    DevBuf dig, qu, ql1, qscale, qeps, thr, cnt, cnegv, crel, cpos, selval, selpos, pq, pr, exact;
+    DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_slotq, u_slotrel;
+    DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_slotq, t_slotrel;
+    DevBuf ppos, ppos0, ok_a, ok_b, relk, probes0, pair_out0, qsel0, lq_off0, uprefix0, uprefix, flat_plan, idx, gq, gids, gdist,
+        tmp2;
+    void release() {
+        DevBuf *all[] = {&dig, &qu, &ql1, &qscale, &qeps, &thr, &cnt, &cnegv, &crel, &cpos, &selval, &selpos, &pq, &pr, &exact,
+                         &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_slotq, &u_slotrel,
+                         &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_slotq, &t_slotrel,
+                         &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
+                         &idx, &gq, &gids, &gdist, &tmp2};
+        for (DevBuf *b : all) b->release();
+    }
+};
+static FastWs g_fw;
+
+constexpr int kFastKK = 64;     // candidates re-scored per query (= THRESH buckets)
+constexpr int kFastMaxK = 48;   // largest k served by the candidate pass
+constexpr int kFastCap = 2048;  // candidate slots per query
+
+static void build_fast_side(FastSideBufs &S, const void *rows, int dtype, int d, int nlist, const int64_t *list_off_dev,
+                            const double *norm_dev, int ns) {
+    S.kbn = (int)ceil_div(d, kFastKB);
+    S.ns = ns;
+    int64_t *toff = S.tile_off.as<int64_t>((size_t)nlist + 1);
+    launch_tile_offsets(list_off_dev, nlist, toff);
+    int64_t nt = 0;
+    HB_CUDA(cudaMemcpyAsync(&nt, toff + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
+    sync_stream();
+    S.ntiles = nt;
+    const size_t img_bytes = (size_t)nt * S.kbn * ns * kFastImg;
+    void *img = S.img.get(std::max<size_t>(img_bytes, 16));
+    HB_CUDA(cudaMemsetAsync(img, 0, std::max<size_t>(img_bytes, 16), g_stream));
+    float *rs = S.rs.as<float>((size_t)std::max<int64_t>(nt * kFastTile, 1));
+    float *ro = S.ro.as<float>((size_t)std::max<int64_t>(nt * kFastTile, 1));
+    HB_CUDA(cudaMemsetAsync(rs, 0, (size_t)std::max<int64_t>(nt * kFastTile, 1) * 4, g_stream));
+    launch_fill_f32(ro, nt * kFastTile, -INFINITY);
+    float *stats = S.stats.as<float>(4);
+    HB_CUDA(cudaMemsetAsync(stats, 0, 16, g_stream));
+    launch_quant_rows(rows, dtype, d, S.kbn, ns, nlist, list_off_dev, toff, norm_dev, (int8_t *)img, rs, ro, stats);
+    float hs[4] = {0, 0, 0, 0};
+    HB_CUDA(cudaMemcpyAsync(hs, stats, 16, cudaMemcpyDeviceToHost, g_stream));
+    sync_stream();
+    S.usable = hs[2] == 0.0f && std::isfinite(hs[0]) && std::isfinite(hs[1]);
+    S.built = true;
+}
+
+// rows side of any index (IVF: slab lists; flat/HNSW: one list of all rows)
+static FastSideBufs &fast_rows_side(hb_index *ix, bool cosine) {
+    FastSideBufs &S = ix->fast_rows;
+    if (S.built && S.ns == g_fast_ns) return S;
+    S.release();
+    if (ix->type == HB_INDEX_IVF_FLAT) {
+        build_fast_side(S, ix->rows.p, ix->dtype, ix->d, ix->nlist, (const int64_t *)ix->list_off.p, (const double *)ix->norms.p,
+                        g_fast_ns);
+    } else {
+        int64_t h[2] = {0, ix->n};
+        int64_t *lo = S.list_off.as<int64_t>(2);
+        HB_CUDA(cudaMemcpyAsync(lo, h, 16, cudaMemcpyHostToDevice, g_stream));
+        sync_stream();
+        build_fast_side(S, ix->rows.p, ix->dtype, ix->d, 1, lo, cosine ? (const double *)ix->norms.p : nullptr, g_fast_ns);
+    }
+    return S;
+}
+static FastSideBufs &fast_cents_side(hb_index *ix) {
+    FastSideBufs &S = ix->fast_cents;
+    if (S.built && S.ns == g_fast_ns) return S;
+    S.release();
+    int64_t h[2] = {0, ix->nlist};
+    int64_t *lo = S.list_off.as<int64_t>(2);
+    HB_CUDA(cudaMemcpyAsync(lo, h, 16, cudaMemcpyHostToDevice, g_stream));
+    sync_stream();
+    build_fast_side(S, ix->cents.p, HB_F64, ix->d, 1, lo, (const double *)ix->cent_norm.p, g_fast_ns);
+    return S;
+}
+
+struct FastPlan {  // which (query, list) pairs a pass covers
+    int nlist = 0;
+    const int64_t *lq_off = nullptr;       // [nlist+1] selections per list
+    const int64_t *unit_prefix = nullptr;  // [nlist+1] exclusive prefix of ceil(selections / 128)
+    const int32_t *qsel = nullptr;         // selection -> pair (NULL: identity)
+    const int64_t *pair_out = nullptr;     // pair -> offset of its segment (NULL: flat)
+    int pair_div = 0;                      // query = pair / pair_div (0: pair == query)
+    int nunits = 0;
+    int tile_limit = 0, tile_div = 0;
+};
+struct FastJob {
+    FastSideBufs *side = nullptr;
+    const int64_t *list_off = nullptr;  // slab rows per list (B side)
+    const void *rows_exact = nullptr;   // for the fp64 re-score
+    int rdtype = HB_F32;
+    const double *row_norm = nullptr;
+    const void *queries = nullptr;
+    int qdtype = HB_F32;
+    int64_t nq = 0;
+    const double *qn = nullptr;
+    int d = 0;
+    int metric = HB_COSINE;  // HB_COSINE or HB_IP: how scores relate to the exact distance
+    int epi = EPI_COS;
+    int k = 0;
+    FastPlan emit, thresh;
+    bool shared_units = false;  // thresh covers the same units as emit (fewer tiles)
+    int64_t *out_rel = nullptr;
+    double *out_dist = nullptr;
+    int32_t *out_ok = nullptr;
+};
+
+static UnitPlan make_units(const FastPlan &F, DevBuf &b_list, DevBuf &b_sel0, DevBuf &b_nsel, DevBuf &b_ntile, DevBuf &b_item0,
+                           DevBuf &b_slotq, DevBuf &b_slotrel, const int64_t *tile_off) {
+    UnitPlan U;
+    const size_t nu = (size_t)std::max(F.nunits, 1);
+    U.unit_list = b_list.as<int32_t>(nu);
+    U.unit_sel0 = b_sel0.as<int32_t>(nu);
+    U.unit_nsel = b_nsel.as<int32_t>(nu);
+    U.unit_ntile = b_ntile.as<int32_t>(nu + 1);
+    U.unit_item0 = b_item0.as<int32_t>(nu + 1);
+    U.slot_query = b_slotq.as<int32_t>(nu * kFastTile);
+    U.slot_rel0 = b_slotrel.as<int32_t>(nu * kFastTile);
+    launch_unit_plan(F.nlist, F.lq_off, F.unit_prefix, tile_off, F.nunits, F.tile_limit, F.tile_div, F.qsel, F.pair_out, F.pair_div,
+                     nullptr, U);
+    return U;
+}
+
+// queries must already be quantised into g_fw.dig / qu / ql1 (fast_quant_queries)
+static void fast_quant_queries(const void *queries, int qdtype, int64_t nq, int d) {
+    const int kbn = (int)ceil_div(d, kFastKB);
+    int8_t *dig = g_fw.dig.as<int8_t>((size_t)nq * g_fast_ns * kbn * kFastKB);
+    launch_quant_queries(queries, qdtype, nq, d, kbn, g_fast_ns, dig, g_fw.qu.as<double>(nq), g_fw.ql1.as<double>(nq));
+}
+
+static void fast_topk(const FastJob &J) {
+    FastWs &W = g_fw;
+    const FastSideBufs &S = *J.side;
+    const int ns = S.ns, kbn = S.kbn, kk = kFastKK, cap = kFastCap;
+    const int64_t nq = J.nq;
+    double *qscale = W.qscale.as<double>(nq), *qeps = W.qeps.as<double>(nq);
+    launch_query_bounds((const double *)W.qu.p, (const double *)W.ql1.p, J.qn, nq, ns, J.d, J.metric, (const float *)S.stats.p, qscale,
+                        qeps);
+    float *thr = W.thr.as<float>(nq);
+    int32_t *cnt = W.cnt.as<int32_t>(nq);
+    double *cnegv = W.cnegv.as<double>((size_t)nq * cap);
+    int32_t *crel = W.crel.as<int32_t>((size_t)nq * cap);
+    int32_t *cpos = W.cpos.as<int32_t>((size_t)nq * cap);
+    launch_fill_f32(thr, nq, -INFINITY);
+    HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
+    launch_fill_f64(cnegv, nq * cap, INFINITY);
+
+    UnitPlan U, T;
+    int8_t *aimg = nullptr, *aimg0 = nullptr;
+    {
+        Prof pr(PROF_PACK);
+        U = make_units(J.emit, W.u_list, W.u_sel0, W.u_nsel, W.u_ntile, W.u_item0, W.u_slotq, W.u_slotrel, (const int64_t *)S.tile_off.p);
+        aimg = W.aimg.as<int8_t>((size_t)std::max(J.emit.nunits, 1) * kbn * ns * kFastImg);
+        launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.emit.nunits, U.slot_query, aimg);
+        if (J.shared_units) {
+            T = U;
+            T.unit_ntile = W.t_ntile.as<int32_t>((size_t)J.emit.nunits + 1);
+            T.unit_item0 = W.t_item0.as<int32_t>((size_t)J.emit.nunits + 1);
+            launch_unit_plan(J.thresh.nlist, J.thresh.lq_off, J.thresh.unit_prefix, (const int64_t *)S.tile_off.p, J.thresh.nunits,
+                             J.thresh.tile_limit, J.thresh.tile_div, J.thresh.qsel, J.thresh.pair_out, J.thresh.pair_div, nullptr, T);
+            aimg0 = aimg;
+        } else {
+            T = make_units(J.thresh, W.t_list, W.t_sel0, W.t_nsel, W.t_ntile, W.t_item0, W.t_slotq, W.t_slotrel,
+                           (const int64_t *)S.tile_off.p);
+            aimg0 = W.aimg0.as<int8_t>((size_t)std::max(J.thresh.nunits, 1) * kbn * ns * kFastImg);
+            launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.thresh.nunits, T.slot_query, aimg0);
+        }
+    }
+    TcParams P;
+    P.bimg = (const int8_t *)S.img.p;
+    P.kbn = kbn;
+    P.tile_off = (const int64_t *)S.tile_off.p;
+    P.list_off = J.list_off;
+    P.rs = (const float *)S.rs.p;
+    P.ro = (const float *)S.ro.p;
+    P.thr = thr;
+    P.cap = cap;
+    P.cnt = cnt;
+    P.cand_negv = cnegv;
+    P.cand_rel = crel;
+    P.cand_pos = cpos;
+    double *selval = W.selval.as<double>((size_t)nq * kk);
+    int64_t *selpos = W.selpos.as<int64_t>((size_t)nq * kk);
+    auto select_candidates = [&] {
+        Prof pr(PROF_SELECT);
+        SelectParams L;
+        L.vals = cnegv;
+        L.nseg = nq;
+        L.seg_stride = cap;
+        L.seg_len_const = cap;
+        L.k = kk;
+        L.out_val = selval;
+        L.out_pos = selpos;
+        launch_select(L);
+    };
+    {
+        // sample pass: candidates of a subset of the rows (nearest list / every 8th tile) -> their kk-th best
+        // score seeds the thresholds of the full pass
+        Prof pr(PROF_TC);
+        P.aimg = aimg0;
+        P.nunits = J.thresh.nunits;
+        P.unit_list = T.unit_list;
+        P.unit_item0 = T.unit_item0;
+        P.slot_query = T.slot_query;
+        P.slot_rel0 = T.slot_rel0;
+        P.tile_stride = J.thresh.tile_div > 1 ? J.thresh.tile_div : 1;
+        launch_tc_pass(P, ns, FAST_EMIT);
+    }
+    select_candidates();
+    launch_thr_from_sample(selval, cnt, nq, kk, cap, thr);
+    HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
+    launch_fill_f64(cnegv, nq * cap, INFINITY);
+    {
+        Prof pr(PROF_TC);
+        P.tile_stride = 1;
+        P.aimg = aimg;
+        P.nunits = J.emit.nunits;
+        P.unit_list = U.unit_list;
+        P.unit_item0 = U.unit_item0;
+        P.slot_query = U.slot_query;
+        P.slot_rel0 = U.slot_rel0;
+        launch_tc_pass(P, ns, FAST_EMIT);
+    }
+    select_candidates();
+    double *exact = W.exact.as<double>((size_t)nq * kk);
+    {
+        Prof pr(PROF_RESCORE);
+        int32_t *pq = W.pq.as<int32_t>((size_t)nq * kk), *prow = W.pr.as<int32_t>((size_t)nq * kk);
+        launch_rescore_pairs(selpos, selval, cpos, nq, kk, cap, pq, prow);
+        launch_gather_score(J.rows_exact, J.rdtype, J.row_norm, J.queries, J.qdtype, J.qn, J.d, pq, prow, nq * kk, false, J.epi, exact);
+        FinalParams F;
+        F.nq = nq;
+        F.k = J.k;
+        F.kk = kk;
+        F.cap = cap;
+        F.sel_pos = selpos;
+        F.sel_negv = selval;
+        F.exact = exact;
+        F.cand_rel = crel;
+        F.cnt = cnt;
+        F.thr = thr;
+        F.q_scale = qscale;
+        F.q_eps = qeps;
+        F.metric = J.metric;
+        F.out_rel = J.out_rel;
+        F.out_dist = J.out_dist;
+        F.out_ok = J.out_ok;
+        launch_fast_final(F);
+    }
+    if (g_fast_debug) {
+        std::vector<int32_t> hc((size_t)nq), hok((size_t)nq);
+        std::vector<float> ht((size_t)nq);
+        std::vector<double> he((size_t)nq), hs((size_t)nq), hsel((size_t)nq * kk), hex((size_t)nq * kk);
+        HB_CUDA(cudaMemcpyAsync(hc.data(), cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, g_stream));
+        HB_CUDA(cudaMemcpyAsync(hok.data(), J.out_ok, (size_t)nq * 4, cudaMemcpyDeviceToHost, g_stream));
+        HB_CUDA(cudaMemcpyAsync(ht.data(), thr, (size_t)nq * 4, cudaMemcpyDeviceToHost, g_stream));
+        HB_CUDA(cudaMemcpyAsync(he.data(), qeps, (size_t)nq * 8, cudaMemcpyDeviceToHost, g_stream));
+        HB_CUDA(cudaMemcpyAsync(hs.data(), qscale, (size_t)nq * 8, cudaMemcpyDeviceToHost, g_stream));
+        HB_CUDA(cudaMemcpyAsync(hsel.data(), selval, (size_t)nq * kk * 8, cudaMemcpyDeviceToHost, g_stream));
+        HB_CUDA(cudaMemcpyAsync(hex.data(), exact, (size_t)nq * kk * 8, cudaMemcpyDeviceToHost, g_stream));
+        sync_stream();
+        int64_t nok = 0, over = 0, cmin = 1 << 30, cmax = 0, csum = 0;
+        for (int64_t q = 0; q < nq; ++q) {
+            nok += hok[q];
+            over += hc[q] > cap;
+            cmin = std::min<int64_t>(cmin, hc[q]);
+            cmax = std::max<int64_t>(cmax, hc[q]);
+            csum += hc[q];
+        }
+        fprintf(stderr, "[hb fast] nq=%lld k=%d units=%d/%d ok=%lld overflow=%lld cand min/mean/max=%lld/%.1f/%lld\n", (long long)nq,
+                J.k, J.thresh.nunits, J.emit.nunits, (long long)nok, (long long)over, (long long)cmin, (double)csum / nq, (long long)cmax);
+        for (int64_t q = 0; q < std::min<int64_t>(nq, 3); ++q) {
+            double kth = 0;
+            std::vector<double> ex(hex.begin() + q * kk, hex.begin() + (q + 1) * kk);
+            std::sort(ex.begin(), ex.end());
+            kth = ex[std::min(J.k, kk) - 1];
+            fprintf(stderr, "  q%lld cnt=%d thr=%g scale=%g eps=%g sel[kk-1]=%g -> t_sim=%g exact kth dist=%g ok=%d\n", (long long)q, hc[q],
+                    ht[q], hs[q], he[q], hsel[q * kk + kk - 1], -hsel[q * kk + kk - 1] * hs[q], kth, hok[q]);
+        }
+    }
+}
+
+// single-list plan {lq_off = [0, nq], unit_prefix = [0, ceil(nq/128)]} on the device
+static void flat_fast_plan(int64_t nq, FastPlan &E, FastPlan &T, DevBuf &buf) {
+    int64_t h[4] = {0, nq, 0, ceil_div(nq, kFastTile)};
+    int64_t *dptr = buf.as<int64_t>(4);
+    HB_CUDA(cudaMemcpyAsync(dptr, h, sizeof(h), cudaMemcpyHostToDevice, g_stream));
+    sync_stream();  // h is a stack array
+    E.nlist = 1;
+    E.lq_off = dptr;
+    E.unit_prefix = dptr + 2;
+    E.nunits = (int)h[3];
+    T = E;
+    T.tile_div = 8;
+}
+
+// Re-runs `exact_fn(sub_queries, nsub, sub_ids, sub_dist)` for the queries whose proof failed and scatters the results.
+template <typename F>
+static void fast_fallback(const int32_t *ok_dev, const void *queries, int qdtype, int64_t nq, int d, int k, int64_t *ids,
+                          double *dist, F &&exact_fn) {
+    std::vector<int32_t> ok((size_t)nq);
+    HB_CUDA(cudaMemcpyAsync(ok.data(), ok_dev, (size_t)nq * 4, cudaMemcpyDeviceToHost, g_stream));
+    sync_stream();
+    std::vector<int32_t> bad;
+    for (int64_t q = 0; q < nq; ++q)
+        if (!ok[(size_t)q]) bad.push_back((int32_t)q);
+    g_fast_queries += nq;
+    g_fast_fallbacks += (int64_t)bad.size();
+    if (bad.empty()) return;
+    const int64_t nb = (int64_t)bad.size();
+    const size_t qsz = dtype_size(qdtype);
+    int32_t *idx = g_fw.idx.as<int32_t>(nb);
+    HB_CUDA(cudaMemcpyAsync(idx, bad.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, g_stream));
+    void *gq = g_fw.gq.get((size_t)nb * d * qsz);
+    launch_gather_bytes(queries, idx, nb, (int64_t)d * qsz, gq);
+    int64_t *gids = g_fw.gids.as<int64_t>((size_t)nb * k);
+    double *gdist = g_fw.gdist.as<double>((size_t)nb * k);
+    exact_fn(gq, nb, gids, gdist);
+    launch_scatter_rows64(gids, idx, nb, k, ids);
+    launch_scatter_rows64(gdist, idx, nb, k, dist);
+    sync_stream();  // `bad` (host) was the source of an async copy
+}
+
+static bool fast_metric_ok(int metric) { return metric == HB_COSINE || metric == HB_IP; }
+
+// compute-exact-knn / top-k-distances in FAST mode
+static void flat_search_fast(hb_index *ix, const void *queries, int qdtype, int64_t nq, int k, int64_t *ids, double *dist) {
+    const bool cosine = ix->metric == HB_COSINE;
+    if (nq == 0 || k == 0) return;
+    if (ix->n == 0 || k > kFastMaxK || !fast_metric_ok(ix->metric) || ix->n >= (1ll << 31)) {
+        flat_search_exact(ix->rows.p, ix->dtype, (const double *)ix->norms.p, ix->n, ix->d, ix->metric, queries, qdtype, nq, k, ids, dist);
+        return;
+    }
+    FastSideBufs &S = fast_rows_side(ix, cosine);
+    if (!S.usable) {
+        flat_search_exact(ix->rows.p, ix->dtype, (const double *)ix->norms.p, ix->n, ix->d, ix->metric, queries, qdtype, nq, k, ids, dist);
+        return;
+    }
+    const int d = ix->d;
+    const size_t qsz = dtype_size(qdtype);
+    const int64_t qc = 16384;
+    for (int64_t q0 = 0; q0 < nq; q0 += qc) {
+        const int64_t nqc = std::min(qc, nq - q0);
+        const void *qptr = (const char *)queries + (size_t)q0 * d * qsz;
+        double *qn = g_ws.qnorm.as<double>(nqc);
+        launch_row_norms(qptr, qdtype, nqc, d, qn);
+        fast_quant_queries(qptr, qdtype, nqc, d);
+        FastJob J;
+        J.side = &S;
+        J.list_off = (const int64_t *)S.list_off.p;
+        J.rows_exact = ix->rows.p;
+        J.rdtype = ix->dtype;
+        J.row_norm = cosine ? (const double *)ix->norms.p : nullptr;
+        J.queries = qptr;
+        J.qdtype = qdtype;
+        J.nq = nqc;
+        J.qn = qn;
+        J.d = d;
+        J.metric = ix->metric;
+        J.epi = cosine ? EPI_COS : EPI_NEGDOT;
+        J.k = k;
+        flat_fast_plan(nqc, J.emit, J.thresh, g_fw.flat_plan);
+        J.shared_units = true;
+        J.out_rel = ids + (size_t)q0 * k;
+        J.out_dist = dist + (size_t)q0 * k;
+        J.out_ok = g_fw.ok_a.as<int32_t>(nq) + q0;
+        fast_topk(J);
+    }
+    fast_fallback((const int32_t *)g_fw.ok_a.p, queries, qdtype, nq, d, k, ids, dist,
+                  [&](const void *gq, int64_t nb, int64_t *gids, double *gdist) {
+                      flat_search_exact(ix->rows.p, ix->dtype, (const double *)ix->norms.p, ix->n, ix->d, ix->metric, gq, qdtype, nb,
+                                        k, gids, gdist);
+                  });
+}
+
+// search-ivf-flat in FAST mode: coarse routing and the probed-list scan both run the candidate pass
+static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64_t nq, int k, int nprobe, int64_t *ids,
+                            double *dist) {
+    if (nq == 0 || k == 0) return;
+    const int d = ix->d, nlist = ix->nlist;
+    const int np_eff = std::min(nprobe, nlist);
+    if (ix->n == 0 || nlist == 0 || k > kFastMaxK || ix->n >= (1ll << 31) || np_eff < 1) {
+        ivf_search_exact(ix, queries, qdtype, nq, k, nprobe, ids, dist, nullptr);
+        return;
+    }
+    FastSideBufs &S = fast_rows_side(ix, true);
+    if (!S.usable) {
+        ivf_search_exact(ix, queries, qdtype, nq, k, nprobe, ids, dist, nullptr);
+        return;
+    }
+    const bool fast_coarse = ix->metric == HB_COSINE && np_eff <= kFastMaxK && nlist >= 2 * kFastTile;
+    FastSideBufs *C = fast_coarse ? &fast_cents_side(ix) : nullptr;
+    const bool coarse_tc = C && C->usable;
+    const size_t qsz = dtype_size(qdtype);
+    int64_t qc = std::max<int64_t>(kFastTile, (1ll << 20) / np_eff);
+    qc = std::min(qc, nq);
+    FastWs &W = g_fw;
+    int32_t *ok_all = W.ok_a.as<int32_t>(nq);
+    for (int64_t q0 = 0; q0 < nq; q0 += qc) {
+        const int64_t nqc = std::min(qc, nq - q0);
+        const void *qptr = (const char *)queries + (size_t)q0 * d * qsz;
+        double *qn = g_ws.qnorm.as<double>(nqc);
+        launch_row_norms(qptr, qdtype, nqc, d, qn);
+        fast_quant_queries(qptr, qdtype, nqc, d);
+        int64_t *ppos = W.ppos.as<int64_t>((size_t)nqc * np_eff);
+        int32_t *ok_c = W.ok_b.as<int32_t>(nqc);
+        if (coarse_tc) {
+            Prof pr(PROF_COARSE);
+            FastJob J;
+            J.side = C;
+            J.list_off = (const int64_t *)C->list_off.p;
+            J.rows_exact = ix->cents.p;
+            J.rdtype = HB_F64;
+            J.row_norm = (const double *)ix->cent_norm.p;
+            J.queries = qptr;
+            J.qdtype = qdtype;
+            J.nq = nqc;
+            J.qn = qn;
+            J.d = d;
+            J.metric = HB_COSINE;
+            J.epi = EPI_COS_GUARD;
+            J.k = np_eff;
+            flat_fast_plan(nqc, J.emit, J.thresh, W.flat_plan);
+            J.shared_units = true;
+            J.out_rel = ppos;
+            J.out_dist = W.tmp2.as<double>((size_t)nqc * np_eff);
+            J.out_ok = ok_c;
+            fast_topk(J);
+        } else {
+            Prof pr(PROF_COARSE);
+            bool cl2;
+            int cepi;
+            metric_to_epi(ix->metric == HB_IP ? HB_COSINE : ix->metric, true, cl2, cepi);
+            int64_t *plan = g_ws.plan.as<int64_t>(6);
+            double *coarse = g_ws.cand_val.as<double>((size_t)nqc * nlist);
+            double *pval = g_ws.sel_val.as<double>((size_t)nqc * np_eff);
+            int64_t h[6] = {0, nlist, 0, nqc, 0, ceil_div(nlist, kTileRows) * ceil_div(nqc, kTileQ)};
+            HB_CUDA(cudaMemcpyAsync(plan, h, sizeof(h), cudaMemcpyHostToDevice, g_stream));
+            sync_stream();
+            ScanParams Sc;
+            Sc.rows = ix->cents.p;
+            Sc.row_norm = (const double *)ix->cent_norm.p;
+            Sc.queries = qptr;
+            Sc.q_norm = qn;
+            Sc.d = d;
+            Sc.nlist = 1;
+            Sc.list_off = plan;
+            Sc.lq_off = plan + 2;
+            Sc.tile_prefix = plan + 4;
+            Sc.out_stride = nlist;
+            Sc.out = coarse;
+            Sc.epi = cepi;
+            launch_pairscan(Sc, HB_F64, qdtype, cl2);
+            SelectParams L;
+            L.vals = coarse;
+            L.nseg = nqc;
+            L.seg_stride = nlist;
+            L.seg_len_const = nlist;
+            L.k = np_eff;
+            L.out_val = pval;
+            L.out_pos = ppos;
+            launch_select(L);
+            {
+                float one_bits;
+                const int32_t one = 1;
+                memcpy(&one_bits, &one, 4);
+                launch_fill_f32((float *)ok_c, nqc, one_bits);  // int32 1 in every slot
+            }
+        }
+        // plans: all (query, probe) pairs for EMIT, the nearest list of every query for THRESH
+        const int64_t np = nqc * np_eff;
+        int32_t *probes = g_ws.probes.as<int32_t>((size_t)np);
+        int64_t *pair_out = g_ws.pair_out.as<int64_t>((size_t)np + 1);
+        int32_t *qsel = g_ws.qsel.as<int32_t>((size_t)np);
+        int64_t *lq_off = g_ws.lq_off.as<int64_t>(nlist + 1);
+        int64_t *uprefix = W.uprefix.as<int64_t>(nlist + 1);
+        int64_t *ppos0 = W.ppos0.as<int64_t>(nqc);
+        int32_t *probes0 = W.probes0.as<int32_t>(nqc);
+        int64_t *pair_out0 = W.pair_out0.as<int64_t>(nqc + 1);
+        int32_t *qsel0 = W.qsel0.as<int32_t>(nqc);
+        int64_t *lq_off0 = W.lq_off0.as<int64_t>(nlist + 1);
+        int64_t *uprefix0 = W.uprefix0.as<int64_t>(nlist + 1);
+        {
+            Prof prp(PROF_PLAN);
+            ivf_plan(ppos, np, nlist, (const int64_t *)ix->list_off.p, probes, pair_out, qsel, lq_off, uprefix, 1 << 30, kFastTile,
+                     g_ws.tmp);
+            launch_first_column(ppos, nqc, np_eff, ppos0);
+            ivf_plan(ppos0, nqc, nlist, (const int64_t *)ix->list_off.p, probes0, pair_out0, qsel0, lq_off0, uprefix0, 1 << 30,
+                     kFastTile, g_ws.tmp);
+        }
+        int64_t nu = 0, nu0 = 0;
+        HB_CUDA(cudaMemcpyAsync(&nu, uprefix + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
+        HB_CUDA(cudaMemcpyAsync(&nu0, uprefix0 + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
+        sync_stream();
+        int64_t *relk = W.relk.as<int64_t>((size_t)nqc * k);
+        FastJob J;
+        J.side = &S;
+        J.list_off = (const int64_t *)ix->list_off.p;
+        J.rows_exact = ix->rows.p;
+        J.rdtype = ix->dtype;
+        J.row_norm = (const double *)ix->norms.p;
+        J.queries = qptr;
+        J.qdtype = qdtype;
+        J.nq = nqc;
+        J.qn = qn;
+        J.d = d;
+        J.metric = HB_COSINE;  // the list scan is always cosine (ivf_flat.clj:217-234)
+        J.epi = EPI_COS;
+        J.k = k;
+        J.emit.nlist = nlist;
+        J.emit.lq_off = lq_off;
+        J.emit.unit_prefix = uprefix;
+        J.emit.qsel = qsel;
+        J.emit.pair_out = pair_out;
+        J.emit.pair_div = np_eff;
+        J.emit.nunits = (int)nu;
+        J.thresh.nlist = nlist;
+        J.thresh.lq_off = lq_off0;
+        J.thresh.unit_prefix = uprefix0;
+        J.thresh.qsel = qsel0;
+        J.thresh.pair_out = nullptr;
+        J.thresh.pair_div = 1;
+        J.thresh.nunits = (int)nu0;
+        J.thresh.tile_limit = 4;
+        J.shared_units = false;
+        J.out_rel = relk;
+        J.out_dist = dist + (size_t)q0 * k;
+        J.out_ok = ok_all + q0;
+        fast_topk(J);
+        launch_ivf_resolve(relk, nqc, k, np_eff, probes, pair_out, (const int64_t *)ix->list_off.p, (const int64_t *)ix->list_rows.p,
+                           ids + (size_t)q0 * k);
+        launch_and_flags(ok_all + q0, ok_c, nqc);
+    }
+    fast_fallback(ok_all, queries, qdtype, nq, d, k, ids, dist, [&](const void *gq, int64_t nb, int64_t *gids, double *gdist) {
+        ivf_search_exact(ix, gq, qdtype, nb, k, nprobe, gids, gdist, nullptr);
+    });
+}
+
 }  // namespace hb
 
 // =================================================================================================
@@ -573,6 +1146,7 @@ HB_API int hb_shutdown(void) {
     return guarded([&] {
         if (g_inited) cudaStreamSynchronize(g_stream);
         g_ws.release();
+        g_fw.release();
     });
 }
 HB_API const char *hb_last_error(void) { return t_err.c_str(); }
@@ -592,10 +1166,16 @@ HB_API int hb_set_option(const char *name, int64_t value) {
         if (!strcmp(name, "scratch_mb")) {
             HB_REQUIRE(value >= 1, "scratch_mb must be >= 1");
             g_scratch_budget = (size_t)value << 20;
+        } else if (!strcmp(name, "fast_debug")) {
+            g_fast_debug = value != 0;
+        } else if (!strcmp(name, "fast_digits")) {
+            HB_REQUIRE(value == 2 || value == 3, "fast_digits must be 2 or 3");
+            g_fast_ns = (int)value;
         } else if (!strcmp(name, "profile")) {
             prof_collect();
             g_profile = value != 0;
             for (int i = 0; i < PROF_NTAGS; ++i) g_prof_ms[i] = 0, g_prof_n[i] = 0;
+            g_fast_queries = g_fast_fallbacks = 0;
         } else {
             throw Error(HB_ERR_INVALID, std::string("unknown option ") + name);
         }
@@ -604,13 +1184,15 @@ HB_API int hb_set_option(const char *name, int64_t value) {
 HB_API int hb_get_stat(const char *name, double *out) {
     return guarded([&] {
         HB_REQUIRE(name && out, "null argument");
-        static const char *ms_names[PROF_NTAGS] = {"scan_ms", "coarse_ms", "select_ms", "plan_ms", "assign_ms"};
-        static const char *n_names[PROF_NTAGS] = {"scan_count", "coarse_count", "select_count", "plan_count", "assign_count"};
+        static const char *ms_names[PROF_NTAGS] = {"scan_ms", "coarse_ms", "select_ms", "plan_ms", "assign_ms", "tc_ms", "pack_ms", "rescore_ms"};
+        static const char *n_names[PROF_NTAGS] = {"scan_count", "coarse_count", "select_count", "plan_count", "assign_count", "tc_count", "pack_count", "rescore_count"};
         prof_collect();
         for (int i = 0; i < PROF_NTAGS; ++i) {
             if (!strcmp(name, ms_names[i])) { *out = g_prof_ms[i]; return; }
             if (!strcmp(name, n_names[i])) { *out = (double)g_prof_n[i]; return; }
         }
+        if (!strcmp(name, "fast_queries")) { *out = (double)g_fast_queries; return; }
+        if (!strcmp(name, "fast_fallbacks")) { *out = (double)g_fast_fallbacks; return; }
         if (!strcmp(name, "fp64_peak_tflops")) {
             ensure_init();
             *out = fp64_peak_tflops();
@@ -806,16 +1388,18 @@ HB_API int hb_search(hb_index *index, const void *queries, int qdtype, int64_t n
         if (nq == 0 || k == 0) return;
         HB_REQUIRE(queries && out_ids && out_dist, "null buffer");
         HB_REQUIRE(k <= 1024, "k > 1024 is not supported");
-        HB_REQUIRE(g_mode == HB_MODE_EXACT, "HB_MODE_FAST is not available in this build");
         const void *q = stage_in(queries, (size_t)nq * index->d * dtype_size(qdtype), g_ws.in_b);
         OutStage oi = stage_out(out_ids, (size_t)nq * k * 8, g_ws.out_a);
         OutStage od = stage_out(out_dist, (size_t)nq * k * 8, g_ws.out_b);
         if (index->type == HB_INDEX_FLAT) {
-            flat_search_exact(index->rows.p, index->dtype, (const double *)index->norms.p, index->n, index->d, index->metric, q,
-                              qdtype, nq, k, (int64_t *)oi.dev, (double *)od.dev);
+            if (g_mode == HB_MODE_FAST) flat_search_fast(index, q, qdtype, nq, k, (int64_t *)oi.dev, (double *)od.dev);
+            else
+                flat_search_exact(index->rows.p, index->dtype, (const double *)index->norms.p, index->n, index->d, index->metric, q,
+                                  qdtype, nq, k, (int64_t *)oi.dev, (double *)od.dev);
         } else if (index->type == HB_INDEX_IVF_FLAT) {
             HB_REQUIRE(param >= 1, "num-probes must be >= 1");
-            ivf_search_exact(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev, nullptr);
+            if (g_mode == HB_MODE_FAST) ivf_search_fast(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev);
+            else ivf_search_exact(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev, nullptr);
         } else {
             throw Error(HB_ERR_UNSUPPORTED, "search on this index type is not implemented");
         }
@@ -1054,6 +1638,58 @@ HB_API int hb_topk_merge(const double *dist, const int64_t *ids, int32_t nparts,
         launch_lookup_ids(pos, nq, k, cid, (int64_t)nparts * k, (int64_t *)oi.dev);
         finish_out(oi);
         finish_out(od);
+        sync_stream();
+    });
+}
+
+HB_API int hb_fast_scores(hb_index *index, const void *queries, int qdtype, int64_t nq, float *out_scores, double *out_scale,
+                          double *out_eps) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(index && index->type == HB_INDEX_FLAT, "hb_fast_scores needs a flat index");
+        HB_REQUIRE(qdtype == HB_F32 || qdtype == HB_F64, "queries must be fp32 or fp64");
+        HB_REQUIRE(fast_metric_ok(index->metric), "FAST mode serves cosine and inner-product");
+        HB_REQUIRE(nq >= 1 && index->n >= 1 && queries && out_scores, "bad arguments");
+        const int d = index->d;
+        const bool cosine = index->metric == HB_COSINE;
+        const void *q = stage_in(queries, (size_t)nq * d * dtype_size(qdtype), g_ws.in_b);
+        FastSideBufs &S = fast_rows_side(index, cosine);
+        double *qn = g_ws.qnorm.as<double>(nq);
+        launch_row_norms(q, qdtype, nq, d, qn);
+        fast_quant_queries(q, qdtype, nq, d);
+        FastPlan E, T;
+        flat_fast_plan(nq, E, T, g_fw.flat_plan);
+        UnitPlan U = make_units(E, g_fw.u_list, g_fw.u_sel0, g_fw.u_nsel, g_fw.u_ntile, g_fw.u_item0, g_fw.u_slotq, g_fw.u_slotrel,
+                                (const int64_t *)S.tile_off.p);
+        int8_t *aimg = g_fw.aimg.as<int8_t>((size_t)E.nunits * S.kbn * S.ns * kFastImg);
+        launch_pack_units((const int8_t *)g_fw.dig.p, S.kbn, S.ns, E.nunits, U.slot_query, aimg);
+        const size_t cnt = (size_t)E.nunits * S.ntiles * kFastTile * kFastTile;
+        OutStage os = stage_out(out_scores, cnt * 4, g_ws.out_a);
+        OutStage oc = stage_out(out_scale, (size_t)nq * 8, g_ws.out_b);
+        OutStage oe = stage_out(out_eps, (size_t)nq * 8, g_ws.out_c);
+        double *qscale = g_fw.qscale.as<double>(nq), *qeps = g_fw.qeps.as<double>(nq);
+        launch_query_bounds((const double *)g_fw.qu.p, (const double *)g_fw.ql1.p, qn, nq, S.ns, d, index->metric,
+                            (const float *)S.stats.p, qscale, qeps);
+        TcParams P;
+        P.aimg = aimg;
+        P.bimg = (const int8_t *)S.img.p;
+        P.kbn = S.kbn;
+        P.nunits = E.nunits;
+        P.unit_list = U.unit_list;
+        P.unit_item0 = U.unit_item0;
+        P.tile_off = (const int64_t *)S.tile_off.p;
+        P.list_off = (const int64_t *)S.list_off.p;
+        P.slot_query = U.slot_query;
+        P.slot_rel0 = U.slot_rel0;
+        P.rs = (const float *)S.rs.p;
+        P.ro = (const float *)S.ro.p;
+        P.dump = (float *)os.dev;
+        launch_tc_pass(P, S.ns, FAST_DUMP);
+        if (oc.dev) HB_CUDA(cudaMemcpyAsync(oc.dev, qscale, (size_t)nq * 8, cudaMemcpyDeviceToDevice, g_stream));
+        if (oe.dev) HB_CUDA(cudaMemcpyAsync(oe.dev, qeps, (size_t)nq * 8, cudaMemcpyDeviceToDevice, g_stream));
+        finish_out(os);
+        finish_out(oc);
+        finish_out(oe);
         sync_stream();
     });
 }

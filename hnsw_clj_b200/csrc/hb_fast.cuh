@@ -1,0 +1,140 @@
+// hb_fast.cuh — HB_MODE_FAST: tensor-core candidate pass with a proof of exactness.
+//
+// The reference ranks by fp64 distances.  FAST mode reproduces those results bit for
+// bit in three steps:
+//   1. candidate pass (hb_tc.cu): every (query, row) score of the probed lists is computed on the 5th-gen
+//      tensor cores as an EXACT integer dot product of block-fixed-point digits (tcgen05.mma kind::i8,
+//      int32 accumulators in TMEM).  Rows and queries are quantised to NS signed 8-bit digits per element
+//      with one scale per vector, so the only error is the quantisation itself, which is bounded a priori
+//      per query (eps_q, below) — no assumption about the tensor core's floating-point accumulation.
+//   2. the kk best candidates per query are re-scored with the reference's sequential fp64 arithmetic
+//      (gather_score_kernel) and ordered by the reference's (distance, position) rule;
+//   3. a query is accepted only if its exact k-th best similarity beats every rejected row's upper bound
+//      (approximate score + eps_q); otherwise it is recomputed by the exact fp64 path.  Accepted results are
+//      therefore identical (ids and distance bits) to the exact path and to the oracle.
+//
+// Layout of the digit images (what the kernel's bulk copies land in shared memory, already in the canonical
+// K-major SWIZZLE_128B form of the UMMA shared-memory descriptor):
+//   image[tile][kb][slice] = 128 vectors x 128 bytes; byte (r, c) at (r/8)*1024 + (r%8)*128 + (((c/16) ^ (r%8))*16) + c%16
+// tile = 128 consecutive slab rows of one list (B side) or the 128 query slots of one unit (A side);
+// kb = block of 128 dimensions; slice 0 is the most significant digit.
+#pragma once
+#include "hb_common.cuh"
+
+namespace hb {
+
+constexpr int kFastTile = 128;          // rows per B tile = query slots per unit = UMMA M = UMMA N
+constexpr int kFastKB = 128;            // dimensions per k-block (one 128-byte swizzle row of int8)
+constexpr int kFastImg = kFastTile * kFastKB;  // bytes of one (tile, kb, slice) image
+
+// quantisation range: |m| <= qmax so that every digit fits int8 after the balanced split
+__host__ __device__ constexpr double fast_qmax(int ns) { return ns == 2 ? 32000.0 : 8000000.0; }
+// |x/u - m| <= kFastRound (division by reciprocal in fp64 + round to nearest)
+constexpr double kFastRound = 0.5000001;
+
+struct FastSide {           // quantised vectors of one side, device pointers
+    int8_t *img = nullptr;  // B side: [ntiles][kbn][ns][kFastImg]
+    float *rs = nullptr;    // per slab position (padded to tiles): score = S * rs + ro
+    float *ro = nullptr;    // 0 for a real row, -inf for padding
+};
+
+// ---- preparation kernels (hb_fastprep.cu) ---------------------------------------------------------------
+// B side: quantise the rows of every list into tile images.  tile_off[l] = first tile of list l.
+// norm: fp64 norms per slab row (cosine) or NULL (inner product: rs = scale only).
+// stats[0] = max over rows of u_r*w_r, stats[1] = max of ||r||_1*w_r  (w_r = 1/norm or 1): for eps_q;
+// stats[2] > 0 if some row has a zero / non-finite norm (the index is then not eligible for FAST mode).
+// The caller zeroes img / rs / stats and fills ro with -inf (padding) beforehand.
+void launch_fill_f32(float *p, int64_t n, float v);
+void launch_quant_rows(const void *rows, int dtype, int d, int kbn, int ns, int nlist, const int64_t *list_off,
+                       const int64_t *tile_off, const double *norm, int8_t *img, float *rs, float *ro, float *stats);
+// tile_off[l] = exclusive prefix of ceil(len_l / 128)   (device, [nlist+1]); single block
+void launch_tile_offsets(const int64_t *list_off, int nlist, int64_t *tile_off);
+
+// A side: digits of every query [nq][ns][kbn*128] + per-query scale u_q, L1 norm
+void launch_quant_queries(const void *queries, int qdtype, int64_t nq, int d, int kbn, int ns, int8_t *dig, double *qu,
+                          double *ql1);
+
+// Units: unit = (list, block of <= 128 selections of that list).  From lq_off/unit_prefix (= exclusive prefix of
+// ceil(lq_len/128) per list) derive per unit: list id, first selection, and the exclusive prefix of row tiles
+// (items) with at most `tile_limit` leading tiles per unit (tile_limit <= 0: all).
+struct UnitPlan {
+    int32_t *unit_list = nullptr;   // [nunits]
+    int32_t *unit_sel0 = nullptr;   // [nunits] first selection
+    int32_t *unit_nsel = nullptr;   // [nunits] selections (<= 128)
+    int32_t *unit_ntile = nullptr;  // [nunits+1] scratch: row tiles per unit
+    int32_t *unit_item0 = nullptr;  // [nunits+1]
+    int32_t *slot_query = nullptr;  // [nunits*128] query index or -1
+    int32_t *slot_rel0 = nullptr;   // [nunits*128] position of the (query, list) segment inside the query's concatenation
+};
+void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_prefix, const int64_t *tile_off, int nunits,
+                      int tile_limit, int tile_div, const int32_t *qsel, const int64_t *pair_out, int pair_div,
+                      const int32_t *pair_query, UnitPlan U);
+// gathers the digits of each unit's queries into A images [nunits][kbn][ns][kFastImg]
+void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int32_t *slot_query, int8_t *aimg);
+
+// ---- the tensor-core pass (hb_tc.cu) -------------------------------------------------------------------
+enum FastMode { FAST_EMIT = 1, FAST_DUMP = 2 };
+struct TcParams {
+    const int8_t *aimg = nullptr;
+    const int8_t *bimg = nullptr;
+    int kbn = 0;
+    int nunits = 0;
+    const int32_t *unit_list = nullptr;
+    const int32_t *unit_item0 = nullptr;
+    const int64_t *tile_off = nullptr;  // first B tile of each list
+    const int64_t *list_off = nullptr;  // first slab row of each list
+    const int32_t *slot_query = nullptr;
+    const int32_t *slot_rel0 = nullptr;
+    const float *rs = nullptr;
+    const float *ro = nullptr;
+    float *thr = nullptr;  // per query lower bound of its 64th best score: raised by THRESH and by EMIT (atomic max)
+    int tile_stride = 1;   // item j of a unit is row tile j*tile_stride of its list (THRESH samples every 8th tile of a flat list)
+    // EMIT
+    int cap = 0;
+    int32_t *cnt = nullptr;      // per query
+    double *cand_negv = nullptr; // [nq][cap]  -score (ascending = best first)
+    int32_t *cand_rel = nullptr; // [nq][cap]  position in the query's concatenated probed lists
+    int32_t *cand_pos = nullptr; // [nq][cap]  slab row
+    // DUMP
+    float *dump = nullptr;       // [items][128 slots][128 rows]
+};
+void launch_tc_pass(const TcParams &P, int ns, int mode);
+
+// ---- final ordering + proof (hb_fastprep.cu) ------------------------------------------------------------
+// Per query: the kk selected candidates (sel_pos = index into the query's cand arrays, -1 unused) with their
+// exact fp64 distances -> top-k by (distance, rel) + the acceptance test.  One CTA per query.
+struct FinalParams {
+    int64_t nq = 0;
+    int k = 0, kk = 0, cap = 0;
+    const int64_t *sel_pos = nullptr;   // [nq][kk]
+    const double *sel_negv = nullptr;   // [nq][kk] approximate -score of the selected
+    const double *exact = nullptr;      // [nq][kk] exact distances
+    const int32_t *cand_rel = nullptr;
+    const int32_t *cnt = nullptr;
+    const float *thr = nullptr;
+    const double *q_scale = nullptr;    // per query: similarity = score * q_scale
+    const double *q_eps = nullptr;      // per query bound on |similarity - approximate similarity|
+    int metric = HB_COSINE;
+    int64_t *out_rel = nullptr;         // [nq][k] rel of the winners (-1 unused)
+    double *out_dist = nullptr;         // [nq][k]
+    int32_t *out_ok = nullptr;          // [nq] 1 = proven exact
+};
+void launch_fast_final(const FinalParams &P);
+
+// per query: q_scale = u_q / ||q|| (cosine) or u_q (ip); q_eps from the index stats
+void launch_query_bounds(const double *qu, const double *ql1, const double *qnorm, int64_t nq, int ns, int d, int metric,
+                         const float *stats, double *q_scale, double *q_eps);
+// pairs for the exact re-score: pair_query[q*kk+j] = q, pair_row = cand_pos[q][sel_pos] (or 0 with valid=0)
+void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const int32_t *cand_pos, int64_t nq, int kk, int cap,
+                          int32_t *pair_query, int32_t *pair_row);
+// fallback plumbing: dst[i] = src[idx[i]] (rows of row_bytes, multiple of 4) and dst[idx[i]] = src[i] (rows of k 8-byte words)
+void launch_gather_bytes(const void *src, const int32_t *idx, int64_t n, int64_t row_bytes, void *dst);
+void launch_scatter_rows64(const void *src, const int32_t *idx, int64_t n, int k, void *dst);
+// first[q] = pos[q*stride]  (probe rank 0 of every query)
+void launch_first_column(const int64_t *pos, int64_t nq, int stride, int64_t *first);
+// thr[q] = max(thr[q], kk-th best sample candidate) where the sample pass collected kk..cap candidates
+void launch_thr_from_sample(const double *sel_negv, const int32_t *cnt, int64_t nq, int kk, int cap, float *thr);
+// ok[q] &= other[q]
+void launch_and_flags(int32_t *ok, const int32_t *other, int64_t nq);
+
+}  // namespace hb

@@ -1,0 +1,509 @@
+// hb_fastprep.cu — preparation and finishing kernels of HB_MODE_FAST (see hb_fast.cuh for the scheme).
+//
+// Quantisation (both sides): u = max|x| / qmax, m_i = rint(x_i / u) computed in fp64, so |x_i - u*m_i| <= kFastRound*u.
+// m is split into NS balanced signed 8-bit digits, most significant first.  For a pair (q, r):
+//      | q.r - u_q*u_r*sum(mq_i*mr_i) |  <=  kFastRound * (u_q*||r||_1 + u_r*||q||_1) + kFastRound^2 * d * u_q*u_r
+// which, divided by the norms (cosine), is the eps_q of launch_query_bounds once the per-row factors are
+// replaced by their maxima over the index (stats[0], stats[1]).
+#include <float.h>
+#include <math.h>
+
+#include "hb_fast.cuh"
+
+namespace hb {
+namespace {
+
+inline int blocks_for(int64_t n, int bs) { return (int)ceil_div(n > 0 ? n : 1, bs); }
+
+__device__ __forceinline__ int64_t img_offset(int r, int c) {  // byte (r, c) of a 128 x 128 B swizzled image
+    return (int64_t)(r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 4) ^ (r & 7)) << 4) | (c & 15));
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+// digits of m (|m| <= qmax), most significant first
+template <int NS>
+__device__ __forceinline__ void split_digits(int m, int8_t (&dg)[NS]) {
+    if (NS == 2) {
+        const int lo = (int)(int8_t)(m & 255);
+        dg[1] = (int8_t)lo;
+        dg[0] = (int8_t)((m - lo) >> 8);
+    } else {
+        const int l0 = (int)(int8_t)(m & 255);
+        const int m1 = (m - l0) >> 8;
+        const int l1 = (int)(int8_t)(m1 & 255);
+        dg[NS - 1] = (int8_t)l0;
+        dg[NS == 2 ? 0 : 1] = (int8_t)l1;
+        dg[0] = (int8_t)((m1 - l1) >> 8);
+    }
+}
+
+__global__ void tile_offsets_kernel(const int64_t *__restrict__ list_off, int nlist, int64_t *__restrict__ tile_off) {
+    // single thread block; nlist <= a few 100k: a serial walk by one thread is microseconds and runs once per index
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int64_t run = 0;
+        for (int l = 0; l < nlist; ++l) {
+            tile_off[l] = run;
+            run += (list_off[l + 1] - list_off[l] + kFastTile - 1) / kFastTile;
+        }
+        tile_off[nlist] = run;
+    }
+}
+
+__global__ void fill_f32_kernel(float *p, int64_t n, float v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// one warp per slab row
+template <typename T, int NS>
+__global__ void __launch_bounds__(256) quant_rows_kernel(const T *__restrict__ rows, int64_t n, int d, int kbn, int nlist,
+                                                         const int64_t *__restrict__ list_off,
+                                                         const int64_t *__restrict__ tile_off,
+                                                         const double *__restrict__ norm, int8_t *__restrict__ img,
+                                                         float *__restrict__ rs, float *__restrict__ ro,
+                                                         float *__restrict__ stats) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    int lo = 0, hi = nlist;  // last l with list_off[l] <= r
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (list_off[mid] <= r) lo = mid;
+        else hi = mid;
+    }
+    const int64_t in_list = r - list_off[lo];
+    const int64_t tile = tile_off[lo] + in_list / kFastTile;
+    const int tr = (int)(in_list % kFastTile);
+    const T *x = rows + r * (int64_t)d;
+    double amax = 0.0, l1 = 0.0;
+    for (int i = lane; i < d; i += 32) {
+        const double v = fabs(to_f64(x[i]));
+        amax = fmax(amax, v);
+        l1 += v;
+    }
+    amax = warp_max(amax);
+    l1 = warp_sum(l1);
+    const double u = amax > 0.0 ? amax / fast_qmax(NS) : 1.0;
+    const double inv = 1.0 / u;
+    int8_t *base = img + tile * kbn * NS * (int64_t)kFastImg;
+    const int dpad = kbn * kFastKB;
+    for (int i0 = lane * 4; i0 < dpad; i0 += 128) {  // 4 consecutive dims per lane: one 32-bit store per digit
+        uint32_t w[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) w[s] = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = i0 + e;
+            int m = 0;
+            if (i < d) m = (int)rint(to_f64(x[i]) * inv);
+            int8_t dg[NS];
+            split_digits<NS>(m, dg);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) w[s] |= (uint32_t)(uint8_t)dg[s] << (8 * e);
+        }
+        const int kb = i0 / kFastKB, c = i0 % kFastKB;
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            *reinterpret_cast<uint32_t *>(base + ((int64_t)kb * NS + s) * kFastImg + img_offset(tr, c)) = w[s];
+    }
+    if (lane == 0) {
+        const double nr = norm ? norm[r] : 1.0;
+        const bool usable = nr > 0.0 && isfinite(nr);
+        const double w = usable ? 1.0 / nr : 0.0;
+        const double f = NS == 2 ? 1.0 : 65536.0;
+        rs[tile * kFastTile + tr] = (float)(u * w * f);
+        ro[tile * kFastTile + tr] = usable ? 0.0f : -INFINITY;
+        atomicMax(reinterpret_cast<int *>(&stats[0]), __float_as_int(__double2float_ru(u * w)));
+        atomicMax(reinterpret_cast<int *>(&stats[1]), __float_as_int(__double2float_ru(l1 * w * (1.0 + 1e-9))));
+        if (!usable) atomicMax(reinterpret_cast<int *>(&stats[2]), __float_as_int(1.0f));
+    }
+}
+
+// one warp per query: plain digit rows [q][s][dpad]
+template <typename T, int NS>
+__global__ void __launch_bounds__(256) quant_queries_kernel(const T *__restrict__ queries, int64_t nq, int d, int kbn,
+                                                            int8_t *__restrict__ dig, double *__restrict__ qu,
+                                                            double *__restrict__ ql1) {
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const T *x = queries + q * (int64_t)d;
+    double amax = 0.0, l1 = 0.0;
+    for (int i = lane; i < d; i += 32) {
+        const double v = fabs(to_f64(x[i]));
+        amax = fmax(amax, v);
+        l1 += v;
+    }
+    amax = warp_max(amax);
+    l1 = warp_sum(l1);
+    const double u = amax > 0.0 ? amax / fast_qmax(NS) : 1.0;
+    const double inv = 1.0 / u;
+    const int dpad = kbn * kFastKB;
+    int8_t *base = dig + q * (int64_t)NS * dpad;
+    for (int i0 = lane * 4; i0 < dpad; i0 += 128) {
+        uint32_t w[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) w[s] = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = i0 + e;
+            int m = 0;
+            if (i < d) m = (int)rint(to_f64(x[i]) * inv);
+            int8_t dg[NS];
+            split_digits<NS>(m, dg);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) w[s] |= (uint32_t)(uint8_t)dg[s] << (8 * e);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) *reinterpret_cast<uint32_t *>(base + (int64_t)s * dpad + i0) = w[s];
+    }
+    if (lane == 0) {
+        qu[q] = u;
+        ql1[q] = l1 * (1.0 + 1e-9);
+    }
+}
+
+__global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, const int64_t *__restrict__ unit_prefix,
+                                 const int64_t *__restrict__ tile_off, int nunits, int tile_limit, int tile_div, UnitPlan U) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u > nunits) return;
+    if (u == nunits) {
+        U.unit_ntile[u] = 0;
+        return;
+    }
+    int lo = 0, hi = nlist;  // last l with unit_prefix[l] <= u (lists without selections share a prefix value:
+    while (hi - lo > 1) {    //  take the LAST such list, the one that actually owns unit u)
+        const int mid = (lo + hi) >> 1;
+        if (unit_prefix[mid] <= u) lo = mid;
+        else hi = mid;
+    }
+    const int l = lo;
+    const int j = u - (int)unit_prefix[l];
+    const int64_t sel0 = lq_off[l] + (int64_t)j * kFastTile;
+    const int nsel = (int)min((int64_t)kFastTile, lq_off[l + 1] - sel0);
+    int nt = (int)(tile_off[l + 1] - tile_off[l]);
+    if (tile_div > 1) nt = (nt + tile_div - 1) / tile_div;  // tiles 0, tile_div, 2*tile_div, ...
+    if (tile_limit > 0) nt = min(nt, tile_limit);
+    U.unit_list[u] = l;
+    U.unit_sel0[u] = (int32_t)sel0;
+    U.unit_nsel[u] = nsel;
+    U.unit_ntile[u] = nt;
+}
+
+// exclusive prefix of ntile -> item0 (single block)
+__global__ void __launch_bounds__(1024) unit_scan_kernel(const int32_t *__restrict__ ntile, int count, int32_t *__restrict__ item0) {
+    __shared__ int s_part[1024];
+    __shared__ int s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < count; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < count ? ntile[i] : 0;
+        s_part[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            const int t = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0;
+            __syncthreads();
+            s_part[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < count) item0[i] = s_run + s_part[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_run += s_part[1023];
+        __syncthreads();
+    }
+}
+
+__global__ void unit_slots_kernel(int nunits, const int32_t *__restrict__ unit_sel0, const int32_t *__restrict__ unit_nsel,
+                                  const int32_t *__restrict__ qsel, const int64_t *__restrict__ pair_out, int pair_div,
+                                  const int32_t *__restrict__ pair_query, int32_t *__restrict__ slot_query,
+                                  int32_t *__restrict__ slot_rel0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)nunits * kFastTile) return;
+    const int u = (int)(i / kFastTile), s = (int)(i % kFastTile);
+    int q = -1, rel0 = 0;
+    if (s < unit_nsel[u]) {
+        const int64_t sel = (int64_t)unit_sel0[u] + s;
+        const int64_t p = qsel ? (int64_t)qsel[sel] : sel;
+        q = pair_query ? pair_query[p] : (pair_div > 0 ? (int)(p / pair_div) : (int)p);
+        if (pair_out) rel0 = (int32_t)(pair_out[p] - pair_out[(int64_t)q * (pair_div > 0 ? pair_div : 1)]);
+    }
+    slot_query[i] = q;
+    slot_rel0[i] = rel0;
+}
+
+// grid (nunits, kbn): copies the 16-byte chunks of the unit's query digits into swizzled images
+template <int NS>
+__global__ void __launch_bounds__(256) pack_units_kernel(const int8_t *__restrict__ dig, int kbn,
+                                                         const int32_t *__restrict__ slot_query, int8_t *__restrict__ aimg) {
+    const int u = blockIdx.x, kb = blockIdx.y;
+    const int dpad = kbn * kFastKB;
+    int8_t *dst = aimg + ((int64_t)u * kbn + kb) * NS * kFastImg;
+    for (int i = threadIdx.x; i < NS * kFastTile * 8; i += blockDim.x) {
+        const int ch = i & 7, slot = (i >> 3) % kFastTile, s = i / (8 * kFastTile);
+        const int q = slot_query[(int64_t)u * kFastTile + slot];
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q >= 0) v = *reinterpret_cast<const uint4 *>(dig + ((int64_t)q * NS + s) * dpad + kb * kFastKB + ch * 16);
+        *reinterpret_cast<uint4 *>(dst + (int64_t)s * kFastImg + img_offset(slot, ch * 16)) = v;
+    }
+}
+
+__global__ void query_bounds_kernel(const double *__restrict__ qu, const double *__restrict__ ql1,
+                                    const double *__restrict__ qnorm, int64_t nq, int ns, int d, int metric,
+                                    const float *__restrict__ stats, double *__restrict__ q_scale,
+                                    double *__restrict__ q_eps) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const double w = metric == HB_COSINE ? 1.0 / qnorm[q] : 1.0;
+    const double umax_r = (double)stats[0], l1max_r = (double)stats[1];
+    const double us = qu[q] * w;
+    double eps = kFastRound * (us * l1max_r + umax_r * ql1[q] * w) + kFastRound * kFastRound * d * us * umax_r;
+    if (ns == 3) eps += us * umax_r * (double)d * 16384.0 * 513.0;  // dropped digit products (1,2), (2,1), (2,2)
+    eps *= 1.0 + 1e-6;
+    const bool bad = !(w > 0.0) || !isfinite(w) || stats[2] > 0.0f;
+    q_scale[q] = bad ? 0.0 : us;
+    q_eps[q] = bad ? INFINITY : eps;
+}
+
+// unused candidate slots hold +inf (-score): the selection may return them when a query has fewer than kk candidates
+__global__ void rescore_pairs_kernel(const int64_t *__restrict__ sel_pos, const double *__restrict__ sel_negv,
+                                     const int32_t *__restrict__ cand_pos, int64_t nq, int kk, int cap,
+                                     int32_t *__restrict__ pair_query, int32_t *__restrict__ pair_row) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * kk) return;
+    const int64_t q = i / kk;
+    const int64_t p = sel_pos[i];
+    pair_query[i] = (int32_t)q;
+    pair_row[i] = (p >= 0 && sel_negv[i] < INFINITY) ? cand_pos[q * cap + p] : 0;
+}
+
+// One CTA (128 threads) per query.  Entry j < kk: exact distance + rel; rank by (distance key, rel).
+__global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
+    __shared__ uint64_t s_key[128];
+    __shared__ int32_t s_rel[128];
+    __shared__ double s_kth;
+    const int64_t q = blockIdx.x;
+    const int j = threadIdx.x;
+    const int kk = P.kk, k = P.k;
+    const int cnt = P.cnt[q];
+    uint64_t key = kKeyEmpty;
+    int32_t rel = INT_MAX;
+    double dist = INFINITY;
+    if (j < kk) {
+        const int64_t p = P.sel_pos[q * kk + j];
+        if (p >= 0 && P.sel_negv[q * kk + j] < INFINITY) {
+            dist = P.exact[q * kk + j];
+            key = dist_key(dist);
+            rel = P.cand_rel[q * P.cap + p];
+        }
+    }
+    s_key[j] = key;
+    s_rel[j] = rel;
+    if (j == 0) s_kth = INFINITY;
+    __syncthreads();
+    int rank = 0, nvalid = 0;
+    for (int i = 0; i < kk; ++i) {
+        const uint64_t ki = s_key[i];
+        const int32_t ri = s_rel[i];
+        nvalid += ki != kKeyEmpty;
+        if (i != j && (ki < key || (ki == key && (ri < rel || (ri == rel && i < j))))) ++rank;
+    }
+    if (j < kk && key != kKeyEmpty && rank < k) {
+        P.out_rel[q * k + rank] = rel;
+        P.out_dist[q * k + rank] = dist;
+        if (rank == min(k, nvalid) - 1) s_kth = dist;
+    }
+    for (int r = nvalid + j; r < k; r += blockDim.x) {
+        P.out_rel[q * k + r] = -1;
+        P.out_dist[q * k + r] = INFINITY;
+    }
+    __syncthreads();
+    if (j == 0) {
+        // rejected rows: emitted but not selected (score <= worst selected) or never emitted (score < thr)
+        bool ok = cnt <= P.cap;
+        const float thr = P.thr[q];
+        const bool none_rejected = cnt <= kk && thr == -INFINITY;
+        if (ok && !none_rejected) {
+            if (nvalid < k) ok = false;  // rejected rows would be needed to fill k
+            else {
+                const double t_v = cnt > kk ? -P.sel_negv[q * kk + kk - 1] : (double)thr;
+                const double t_sim = t_v * P.q_scale[q];
+                const double t_up = t_sim + P.q_eps[q] + 1e-6 * fabs(t_sim);
+                const double kth = s_kth;  // exact k-th best distance among the selected
+                const double sim_k = P.metric == HB_COSINE ? 1.0 - kth : -kth;
+                ok = (sim_k - t_up) > 1e-12 && isfinite(t_up);
+            }
+        }
+        P.out_ok[q] = ok ? 1 : 0;
+    }
+}
+
+__global__ void gather_bytes_kernel(const uint32_t *__restrict__ src, const int32_t *__restrict__ idx, int64_t n, int64_t row_words,
+                                    uint32_t *__restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * row_words) return;
+    const int64_t r = i / row_words, w = i % row_words;
+    dst[i] = src[(int64_t)idx[r] * row_words + w];
+}
+__global__ void scatter_rows64_kernel(const uint64_t *__restrict__ src, const int32_t *__restrict__ idx, int64_t n, int k,
+                                      uint64_t *__restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * k) return;
+    const int64_t r = i / k, w = i % k;
+    dst[(int64_t)idx[r] * k + w] = src[i];
+}
+__global__ void first_column_kernel(const int64_t *__restrict__ pos, int64_t nq, int stride, int64_t *__restrict__ first) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) first[q] = pos[q * stride];
+}
+// seed thresholds from the sample pass: the kk-th best candidate of the sample is a row, so >= kk rows score at least that
+__global__ void thr_from_sample_kernel(const double *__restrict__ sel_negv, const int32_t *__restrict__ cnt, int64_t nq, int kk,
+                                       int cap, float *__restrict__ thr) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int c = cnt[q];
+    if (c >= kk && c <= cap) {
+        // -sel_negv is a float score widened to double: the conversion back is exact
+        const float t = (float)(-sel_negv[q * kk + kk - 1]);
+        if (t > thr[q]) thr[q] = t;
+    }
+}
+__global__ void and_flags_kernel(int32_t *__restrict__ ok, const int32_t *__restrict__ other, int64_t nq) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) ok[q] = ok[q] & other[q];
+}
+
+}  // namespace
+
+void launch_gather_bytes(const void *src, const int32_t *idx, int64_t n, int64_t row_bytes, void *dst) {
+    if (n == 0) return;
+    HB_REQUIRE(row_bytes % 4 == 0, "gather rows must be whole 32-bit words");
+    gather_bytes_kernel<<<blocks_for(n * (row_bytes / 4), 256), 256, 0, g_stream>>>((const uint32_t *)src, idx, n, row_bytes / 4,
+                                                                                     (uint32_t *)dst);
+    HB_LAUNCH_CHECK();
+}
+void launch_scatter_rows64(const void *src, const int32_t *idx, int64_t n, int k, void *dst) {
+    if (n * k == 0) return;
+    scatter_rows64_kernel<<<blocks_for(n * k, 256), 256, 0, g_stream>>>((const uint64_t *)src, idx, n, k, (uint64_t *)dst);
+    HB_LAUNCH_CHECK();
+}
+void launch_first_column(const int64_t *pos, int64_t nq, int stride, int64_t *first) {
+    if (nq == 0) return;
+    first_column_kernel<<<blocks_for(nq, 256), 256, 0, g_stream>>>(pos, nq, stride, first);
+    HB_LAUNCH_CHECK();
+}
+void launch_thr_from_sample(const double *sel_negv, const int32_t *cnt, int64_t nq, int kk, int cap, float *thr) {
+    if (nq == 0) return;
+    thr_from_sample_kernel<<<blocks_for(nq, 256), 256, 0, g_stream>>>(sel_negv, cnt, nq, kk, cap, thr);
+    HB_LAUNCH_CHECK();
+}
+void launch_and_flags(int32_t *ok, const int32_t *other, int64_t nq) {
+    if (nq == 0) return;
+    and_flags_kernel<<<blocks_for(nq, 256), 256, 0, g_stream>>>(ok, other, nq);
+    HB_LAUNCH_CHECK();
+}
+
+void launch_tile_offsets(const int64_t *list_off, int nlist, int64_t *tile_off) {
+    tile_offsets_kernel<<<1, 32, 0, g_stream>>>(list_off, nlist, tile_off);
+    HB_LAUNCH_CHECK();
+}
+
+void launch_quant_rows(const void *rows, int dtype, int d, int kbn, int ns, int nlist, const int64_t *list_off,
+                       const int64_t *tile_off, const double *norm, int8_t *img, float *rs, float *ro, float *stats) {
+    // caller has zeroed img/rs/stats and filled ro with -inf for the padded tile positions
+    int64_t n = 0;
+    HB_CUDA(cudaMemcpyAsync(&n, list_off + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
+    HB_CUDA(cudaStreamSynchronize(g_stream));
+    if (n == 0) return;
+    const int grid = blocks_for(n * 32, 256);
+#define HB_QR(T, NS_) quant_rows_kernel<T, NS_><<<grid, 256, 0, g_stream>>>((const T *)rows, n, d, kbn, nlist, list_off, tile_off, norm, img, rs, ro, stats)
+    if (ns == 2) {
+        if (dtype == HB_F32) HB_QR(float, 2);
+        else if (dtype == HB_BF16) HB_QR(__nv_bfloat16, 2);
+        else HB_QR(double, 2);
+    } else {
+        if (dtype == HB_F32) HB_QR(float, 3);
+        else if (dtype == HB_BF16) HB_QR(__nv_bfloat16, 3);
+        else HB_QR(double, 3);
+    }
+#undef HB_QR
+    HB_LAUNCH_CHECK();
+}
+
+void launch_fill_f32(float *p, int64_t n, float v) {
+    if (n == 0) return;
+    fill_f32_kernel<<<blocks_for(n, 256), 256, 0, g_stream>>>(p, n, v);
+    HB_LAUNCH_CHECK();
+}
+
+void launch_quant_queries(const void *queries, int qdtype, int64_t nq, int d, int kbn, int ns, int8_t *dig, double *qu,
+                          double *ql1) {
+    if (nq == 0) return;
+    const int grid = blocks_for(nq * 32, 256);
+#define HB_QQ(T, NS_) quant_queries_kernel<T, NS_><<<grid, 256, 0, g_stream>>>((const T *)queries, nq, d, kbn, dig, qu, ql1)
+    if (ns == 2) {
+        if (qdtype == HB_F32) HB_QQ(float, 2);
+        else HB_QQ(double, 2);
+    } else {
+        if (qdtype == HB_F32) HB_QQ(float, 3);
+        else HB_QQ(double, 3);
+    }
+#undef HB_QQ
+    HB_LAUNCH_CHECK();
+}
+
+void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_prefix, const int64_t *tile_off, int nunits,
+                      int tile_limit, int tile_div, const int32_t *qsel, const int64_t *pair_out, int pair_div,
+                      const int32_t *pair_query, UnitPlan U) {
+    if (nunits == 0) return;
+    unit_plan_kernel<<<blocks_for(nunits + 1, 256), 256, 0, g_stream>>>(nlist, lq_off, unit_prefix, tile_off, nunits, tile_limit,
+                                                                        tile_div, U);
+    HB_LAUNCH_CHECK();
+    unit_scan_kernel<<<1, 1024, 0, g_stream>>>(U.unit_ntile, nunits + 1, U.unit_item0);
+    HB_LAUNCH_CHECK();
+    unit_slots_kernel<<<blocks_for((int64_t)nunits * kFastTile, 256), 256, 0, g_stream>>>(
+        nunits, U.unit_sel0, U.unit_nsel, qsel, pair_out, pair_div, pair_query, U.slot_query, U.slot_rel0);
+    HB_LAUNCH_CHECK();
+}
+
+void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int32_t *slot_query, int8_t *aimg) {
+    if (nunits == 0) return;
+    dim3 grid((unsigned)nunits, (unsigned)kbn);
+    if (ns == 2) pack_units_kernel<2><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg);
+    else pack_units_kernel<3><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg);
+    HB_LAUNCH_CHECK();
+}
+
+void launch_query_bounds(const double *qu, const double *ql1, const double *qnorm, int64_t nq, int ns, int d, int metric,
+                         const float *stats, double *q_scale, double *q_eps) {
+    if (nq == 0) return;
+    query_bounds_kernel<<<blocks_for(nq, 256), 256, 0, g_stream>>>(qu, ql1, qnorm, nq, ns, d, metric, stats, q_scale, q_eps);
+    HB_LAUNCH_CHECK();
+}
+
+void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const int32_t *cand_pos, int64_t nq, int kk, int cap,
+                          int32_t *pair_query, int32_t *pair_row) {
+    if (nq * kk == 0) return;
+    rescore_pairs_kernel<<<blocks_for(nq * kk, 256), 256, 0, g_stream>>>(sel_pos, sel_negv, cand_pos, nq, kk, cap, pair_query,
+                                                                         pair_row);
+    HB_LAUNCH_CHECK();
+}
+
+void launch_fast_final(const FinalParams &P) {
+    if (P.nq == 0) return;
+    HB_REQUIRE(P.kk <= 128 && P.k <= P.kk, "fast final: k <= kk <= 128");
+    fast_final_kernel<<<(unsigned)P.nq, 128, 0, g_stream>>>(P);
+    HB_LAUNCH_CHECK();
+}
+
+}  // namespace hb

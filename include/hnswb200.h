@@ -51,9 +51,11 @@ enum hb_metric { HB_COSINE = 0, HB_L2 = 1, HB_IP = 2 };
 
 enum hb_index_type { HB_INDEX_FLAT = 0, HB_INDEX_IVF_FLAT = 1, HB_INDEX_HNSW = 2 };
 
-/* search arithmetic: HB_MODE_EXACT restates the reference's fp64 sequential sums on the device
- * (bit-identical distances); HB_MODE_FAST selects candidates with tensor-core / fp32 arithmetic and
- * re-scores them in fp64 in the reference's summation order (ids identical). */
+/* search arithmetic: HB_MODE_EXACT restates the reference's fp64 sequential sums on the device for every
+ * pair; HB_MODE_FAST selects candidates on the tensor cores (exact int8-digit dot products, tcgen05), re-scores
+ * them in fp64 in the reference's summation order and accepts a query only when an a-priori error bound proves
+ * the top-k complete — otherwise the query is recomputed by the exact path.  Both modes return identical ids
+ * and distance bits. */
 enum hb_mode { HB_MODE_EXACT = 0, HB_MODE_FAST = 1 };
 
 typedef struct hb_info {
@@ -75,10 +77,13 @@ HB_API int hb_version(void);
 HB_API int hb_set_stream(void *cuda_stream); /* launch on this stream (default: legacy stream 0) */
 HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches (default EXACT) */
 /* knobs: "scratch_mb" = budget for the transient distance scratch (default 8192); "profile" = 1 records
- * CUDA events around the main kernels (and resets the counters) */
+ * CUDA events around the main kernels (and resets the counters); "fast_digits" = 2 | 3 signed 8-bit digits per
+ * element in the HB_MODE_FAST candidate pass (16- or 24-bit block-fixed-point mantissas) */
 HB_API int hb_set_option(const char *name, int64_t value);
-/* measurements: "scan_ms"/"scan_count" (list/flat scan kernel), "coarse_ms", "select_ms", "plan_ms", "assign_ms"
- * (device time between the events, accumulated since "profile" was set), "fp64_peak_tflops" (runs a DFMA
+/* measurements: "scan_ms"/"scan_count" (list/flat scan kernel), "coarse_ms", "select_ms", "plan_ms", "assign_ms",
+ * "tc_ms" (tensor-core candidate passes), "pack_ms", "rescore_ms"
+ * (device time between the events, accumulated since "profile" was set), "fast_queries" / "fast_fallbacks"
+ * (queries served in FAST mode / of those recomputed by the exact path), "fp64_peak_tflops" (runs a DFMA
  * microbenchmark: the measured peak of the pipe the exact kernels are bound by) */
 HB_API int hb_get_stat(const char *name, double *out);
 /* number of kernels this library launched since hb_init / the last reset (bench `gpu_launches`) */
@@ -157,6 +162,16 @@ HB_API int hb_hnsw_create(const void *rows, int64_t n, int32_t d, int dtype, int
 HB_API int hb_gather_score(hb_index *index, const void *queries, int qdtype, int64_t nq,
                            const int32_t *pair_query, const int32_t *pair_row, int64_t npairs,
                            double *out_scores);
+
+/* ---- FAST-mode diagnostics ----------------------------------------------------------------------- */
+/* The candidate pass of HB_MODE_FAST on a flat index, unfiltered: for every (query, row) the tensor-core score
+ * (exact integer dot product of the quantised digits times the row scale).  Batched form of
+ * batch-distances-parallel (src/hnsw/simd_optimized.clj:164-179) at candidate precision; used by the parity
+ * tests to pin the tcgen05 path.  out_scores is [ceil(nq/128)][ceil(n/128)][128 query slots][128 rows] fp32;
+ * similarity (cosine) or dot (HB_IP) of query q and row r = out_scores[q/128][r/128][q%128][r%128] * out_scale[q],
+ * and |that - exact| <= out_eps[q].  out_scale / out_eps may be NULL. */
+HB_API int hb_fast_scores(hb_index *index, const void *queries, int qdtype, int64_t nq, float *out_scores,
+                          double *out_scale, double *out_eps);
 
 /* ---- multi-GPU merge --------------------------------------------------------------------------- */
 /* Merge `nparts` per-shard top-k lists (dist [nparts x nq x k], ids likewise, already global row ids)

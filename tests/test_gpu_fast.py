@@ -1,0 +1,197 @@
+"""GPU parity of HB_MODE_FAST (tcgen05 int8-digit candidate pass + fp64 re-score + proof, hb_fast.cuh).
+
+1. the tensor-core scores are pinned BIT-EXACTLY against a numpy restatement of the quantisation and the
+   integer digit products (any descriptor / swizzle / pipeline mistake shows up here);
+2. FAST searches return the same ids and the same fp64 distance bits as the exact device path and the CPU
+   oracle, whatever fraction of queries the proof accepts (the rest take the exact path)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hnsw_clj_b200 as pkg
+    from hnsw_clj_b200 import _lib
+
+    _lib.check(_lib.lib().hb_init(0))
+    yield pkg
+    _lib.set_mode(_lib.MODE_EXACT)
+    _lib.set_option("fast_digits", 2)
+
+
+def same_bits(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and bool((a.view(np.int64) == b.view(np.int64)).all())
+
+
+def clustered(n, d, seed, centres=16, noise=0.1):
+    r = np.random.default_rng(seed)
+    c = r.standard_normal((centres, d))
+    return (c[r.integers(0, centres, n)] + noise * r.standard_normal((n, d))).astype(np.float32)
+
+
+# ---- numpy restatement of hb_fastprep.cu's quantisation and hb_tc.cu's digit products ---------------------
+def quantise(x, ns):
+    x = x.astype(np.float64)
+    amax = np.abs(x).max(axis=1)
+    qmax = 32000.0 if ns == 2 else 8000000.0
+    u = np.where(amax > 0, amax / qmax, 1.0)
+    m = np.rint(x * (1.0 / u)[:, None]).astype(np.int64)
+    digs = []
+    rest = m
+    for _ in range(ns - 1):
+        lo = ((rest & 255) ^ 128) - 128  # signed low byte
+        digs.append(lo)
+        rest = (rest - lo) >> 8
+    digs.append(rest)
+    return u, digs[::-1]  # most significant first
+
+
+def emulate_scores(rows, queries, ns, cosine):
+    ur, dr = quantise(rows, ns)
+    uq, dq = quantise(queries, ns)
+    c = [np.zeros((len(queries), len(rows)), dtype=np.int64) for _ in range(3)]
+    for a in range(ns):
+        for b in range(ns):
+            if a + b <= 2:
+                c[a + b] += dq[a] @ dr[b].T
+    # fmaf(f(c0), 65536, fmaf(f(c1), 256, f(c2))): products by powers of two are exact, one rounding per fma
+    inner = (c[1].astype(np.float32).astype(np.float64) * 256.0 + c[2].astype(np.float32).astype(np.float64)).astype(np.float32)
+    s = (c[0].astype(np.float32).astype(np.float64) * 65536.0 + inner.astype(np.float64)).astype(np.float32)
+    rn = orc.row_norms(rows) if cosine else np.ones(len(rows))
+    rs = (ur * (1.0 / rn) * (1.0 if ns == 2 else 65536.0)).astype(np.float32)
+    v = (s.astype(np.float64) * rs.astype(np.float64)[None, :]).astype(np.float32)
+    qn = orc.row_norms(queries) if cosine else np.ones(len(queries))
+    return v, uq * (1.0 / qn)
+
+
+def fast_scores(hb, ix, queries, n):
+    from hnsw_clj_b200 import _lib
+
+    nq = len(queries)
+    nu, nt = -(-nq // 128), -(-n // 128)
+    out = np.empty((nu, nt, 128, 128), dtype=np.float32)
+    scale = np.empty(nq, dtype=np.float64)
+    eps = np.empty(nq, dtype=np.float64)
+    _lib.check(_lib.lib().hb_fast_scores(ix._h, _lib.ptr(queries), _lib.dtype_code(queries), nq, _lib.ptr(out), _lib.ptr(scale),
+                                         _lib.ptr(eps)))
+    dense = out.transpose(0, 2, 1, 3).reshape(nu * 128, nt * 128)[:nq, :n]
+    return dense, scale, eps
+
+
+@pytest.mark.parametrize("ns", [2, 3])
+@pytest.mark.parametrize("n,d,nq,metric", [(300, 768, 130, "cosine"), (128, 128, 1, "cosine"), (1000, 100, 257, "ip"),
+                                           (129, 40, 5, "cosine"), (2048, 768, 128, "ip")])
+def test_tensor_core_scores_bit_exact(hb, ns, n, d, nq, metric):
+    from hnsw_clj_b200 import _lib
+    from hnsw_clj_b200.flat import FlatIndex
+
+    _lib.set_option("fast_digits", ns)
+    rows = clustered(n, d, 11 * n + d)
+    queries = clustered(nq, d, 7 * n + d + 1)
+    with FlatIndex(rows, metric) as ix:
+        got, scale, eps = fast_scores(hb, ix, queries, n)
+    want, want_scale = emulate_scores(rows, queries, ns, metric == "cosine")
+    assert (got.view(np.int32) == want.view(np.int32)).all(), f"{(got != want).sum()} of {got.size} scores differ"
+    assert np.allclose(scale, want_scale, rtol=1e-15)
+    # the a-priori bound really bounds the error of the candidate scores
+    exact = queries.astype(np.float64) @ rows.astype(np.float64).T
+    if metric == "cosine":
+        exact = exact / orc.row_norms(queries)[:, None] / orc.row_norms(rows)[None, :]
+    err = np.abs(got.astype(np.float64) * scale[:, None] - exact)
+    assert (err <= eps[:, None]).all()
+    if metric == "cosine":
+        assert eps.max() < (2e-3 if ns == 2 else 1e-4)
+
+
+@pytest.mark.parametrize("ns", [2, 3])
+@pytest.mark.parametrize("n,d,nq,k,metric", [(3000, 96, 70, 10, "cosine"), (2000, 768, 200, 10, "cosine"), (129, 5, 3, 1, "cosine"),
+                                             (5000, 128, 300, 48, "ip"), (40, 16, 9, 10, "cosine"), (700, 64, 130, 10, "ip")])
+def test_flat_fast_equals_exact(hb, ns, n, d, nq, k, metric):
+    from hnsw_clj_b200 import _lib
+    from hnsw_clj_b200.flat import FlatIndex
+
+    rows = clustered(n, d, n + d, centres=8)
+    queries = clustered(nq, d, n + d + 1, centres=8)
+    with FlatIndex(rows, metric) as ix:
+        _lib.set_mode(_lib.MODE_EXACT)
+        eids, edist = ix.search_raw(queries, k)
+        _lib.set_option("fast_digits", ns)
+        _lib.set_option("profile", 1)
+        _lib.set_mode(_lib.MODE_FAST)
+        try:
+            fids, fdist = ix.search_raw(queries, k)
+        finally:
+            _lib.set_mode(_lib.MODE_EXACT)
+        served, fell = _lib.get_stat("fast_queries"), _lib.get_stat("fast_fallbacks")
+        _lib.set_option("profile", 0)
+    assert fids.tolist() == eids.tolist()
+    assert same_bits(fdist, edist)
+    assert served == nq
+    if metric == "cosine" and n >= 1000:
+        assert fell <= 0.5 * nq, f"{fell} of {nq} queries fell back to the exact path"
+    if metric == "cosine":
+        oids, odist = orc.exact_knn(rows, queries, k)
+        assert fids.tolist() == oids.tolist() and same_bits(fdist, odist)
+
+
+@pytest.mark.parametrize("ns", [2, 3])
+@pytest.mark.parametrize("n,d,nlist,nprobe,nq,k", [(6000, 64, 32, 8, 300, 10), (20000, 768, 512, 16, 700, 10),
+                                                   (3000, 32, 24, 4, 50, 10), (4000, 128, 300, 40, 129, 5)])
+def test_ivf_fast_equals_exact_and_oracle(hb, ns, n, d, nlist, nprobe, nq, k):
+    from hnsw_clj_b200 import _lib, ivf_flat
+
+    rows = clustered(n, d, n + nlist, centres=max(8, nlist // 2))
+    queries = clustered(nq, d, n + nlist + 1, centres=max(8, nlist // 2))
+    ix = ivf_flat.build_index(rows, num_partitions=nlist, max_iterations=2)
+    try:
+        _lib.set_mode(_lib.MODE_EXACT)
+        eids, edist = ix.search_raw(queries, k, nprobe)
+        _lib.set_option("fast_digits", ns)
+        _lib.set_option("profile", 1)
+        _lib.set_mode(_lib.MODE_FAST)
+        try:
+            fids, fdist = ix.search_raw(queries, k, nprobe)
+        finally:
+            _lib.set_mode(_lib.MODE_EXACT)
+        served, fell = _lib.get_stat("fast_queries"), _lib.get_stat("fast_fallbacks")
+        _lib.set_option("profile", 0)
+        cents, asg = ix.export()
+    finally:
+        ix.close()
+    assert fids.tolist() == eids.tolist()
+    assert same_bits(fdist, edist)
+    assert served == nq
+    print(f"ivf fast ns={ns} n={n} nlist={nlist}: {int(fell)} of {nq} queries fell back")
+    oids, odist = orc.ivf_search(rows, cents, asg, queries[:64], k, nprobe)
+    assert fids[:64].tolist() == oids.tolist() and same_bits(fdist[:64], odist)
+
+
+def test_fast_duplicates_fall_back_and_stay_exact(hb):
+    """Exact duplicates make the k-th / (k+1)-th gap zero: the proof must refuse and the exact path answer."""
+    from hnsw_clj_b200 import _lib
+    from hnsw_clj_b200.flat import FlatIndex
+
+    base = clustered(30, 64, 5)
+    rows = np.concatenate([base] * 100)  # every row 100 times: the tie spans the candidate cut, order is by row index
+    queries = base[:20] + np.float32(0.01)
+    with FlatIndex(rows, "cosine") as ix:
+        eids, edist = ix.search_raw(queries, 10)
+        _lib.set_option("profile", 1)
+        _lib.set_mode(_lib.MODE_FAST)
+        try:
+            fids, fdist = ix.search_raw(queries, 10)
+        finally:
+            _lib.set_mode(_lib.MODE_EXACT)
+        fell = _lib.get_stat("fast_fallbacks")
+        _lib.set_option("profile", 0)
+    assert fids.tolist() == eids.tolist() and same_bits(fdist, edist)
+    assert fell == 20
+    oids, _ = orc.exact_knn(rows, queries, 10)
+    assert fids.tolist() == oids.tolist()

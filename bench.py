@@ -239,6 +239,8 @@ def run_ours(args, w, key):
     except Exception:
         pass
 
+    fast = args.mode == "fast"
+    hb.set_option("fast_digits", args.digits)
     k, nprobe, nq = w["k"], w["nprobe"], w["nq"]
     rows, queries = gen_gpu(w, device)
     torch.cuda.synchronize()
@@ -272,6 +274,7 @@ def run_ours(args, w, key):
         torch.cuda.synchronize()
 
     # ---- timed region: device-resident inputs -------------------------------------------------------------
+    hb.set_mode(hb.MODE_FAST if fast else hb.MODE_EXACT)
     for _ in range(args.warmup):
         search(queries)
     barrier()
@@ -292,7 +295,10 @@ def run_ours(args, w, key):
     clk = clocks.stop() if rank == 0 else {}
     scan_ms = hb.get_stat("scan_ms")
     scan_n = max(hb.get_stat("scan_count"), 1.0)
-    stats = {n: hb.get_stat(n) / args.steps for n in ("scan_ms", "coarse_ms", "select_ms", "plan_ms")}
+    stats = {n: hb.get_stat(n) / args.steps for n in ("scan_ms", "coarse_ms", "select_ms", "plan_ms", "tc_ms", "tc_sample_ms",
+                                                         "pack_ms", "rescore_ms")}
+    tc_ms, tc_n = hb.get_stat("tc_ms"), max(hb.get_stat("tc_count"), 1.0)
+    fast_served, fast_fell = hb.get_stat("fast_queries"), hb.get_stat("fast_fallbacks")
     hb.set_option("profile", 0)
     if world > 1:
         t = torch.tensor([ms], device=device)
@@ -341,44 +347,80 @@ def run_ours(args, w, key):
         return
 
     # ---- recall@10 against the exact flat search of the same rows (device, exact path) ----------------
+    hb.set_mode(hb.MODE_EXACT)
     ids_np = ids.cpu().numpy() if hb._is_torch(ids) else ids
+    dists_np = dists.cpu().numpy() if hb._is_torch(dists) else dists
     e2e_same = bool((h_ids.numpy() == ids_np).all())
     with FlatIndex(rows) as fx:
         exact_ids, _ = fx.search_raw(queries, k)
     recall = recall_at_k(ids_np, exact_ids)
+    fast_vs_exact = None
+    if fast and world == 1:
+        # the same search in EXACT mode (fp64 for every pair): FAST must return the same ids and distance bits
+        x_ids = torch.empty((nq, k), dtype=torch.int64, device=device)
+        x_dist = torch.empty((nq, k), dtype=torch.float64, device=device)
+        gix.search_raw(queries, k, nprobe, out_ids=x_ids, out_dist=x_dist)
+        fast_vs_exact = {"queries": nq, "ids_equal": bool((x_ids.cpu().numpy() == ids_np).all()),
+                         "dist_bits_equal": bool((x_dist.cpu().numpy().view(np.int64) == dists_np.view(np.int64)).all()),
+                         "served_by_candidate_pass": int(fast_served - fast_fell), "exact_fallbacks": int(fast_fell),
+                         "per_steps": args.steps}
 
     # ---- roofline of the dominant kernel (the list scan) ---------------------------------------------------
     rows_np = rows.cpu().numpy()
     q_np = queries.cpu().numpy()
+    items = None
     if world == 1:
         probes = gix.probes(queries, nprobe)
         lens = np.bincount(asg, minlength=w["nlist"])
         pairs = float(lens[probes.reshape(-1)].sum())
+        per_list_q = np.bincount(probes.reshape(-1)[probes.reshape(-1) >= 0], minlength=w["nlist"])
+        items = float((np.ceil(per_list_q / 128.0) * np.ceil(lens / 128.0)).sum())
     else:
         pairs = float("nan")
     flops = 2.0 * pairs * w["d"]
-    unique_bytes = float(w["n"]) * w["d"] * 4 + nq * w["d"] * 4 + pairs * 8  # slab once + queries + distance scratch out
-    t_scan = (scan_ms / scan_n) * 1e-3
     bf16_peak = peaks.get("bf16_tflops", 1590.0)
-    try:
-        fp64_peak = hb.get_stat("fp64_peak_tflops")
-    except Exception:
-        fp64_peak = None
-    roofline = {
-        "kernel": "pairscan_kernel<float,float,FMA> (IVF list-major scan, exact fp64)",
-        "bound": "tensor", "achieved": flops / t_scan / 1e12 if world == 1 else None, "peak": bf16_peak, "unit": "TFLOP/s",
-        "frac": (flops / t_scan / 1e12 / bf16_peak) if world == 1 else None,
-        "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s",
-        "traffic": None,
-        "launch_ms": t_scan * 1e3, "launches_per_step": scan_n / args.steps,
-        "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": unique_bytes,
-        "hbm_gbs_at_unique_bytes": unique_bytes / t_scan / 1e9 if world == 1 else None,
-        "fp64_pipe": {"achieved_tflops": flops / t_scan / 1e12 if world == 1 else None, "peak_tflops_measured": fp64_peak,
-                      "frac": (flops / t_scan / 1e12 / fp64_peak) if (world == 1 and fp64_peak) else None,
-                      "note": "this round's scan is the EXACT path: one sequential fp64 FMA chain per (query,row) pair, "
-                              "bound by the fp64 pipe; the tensor-core candidate pass + fp64 re-rank is the next step"},
-        "step_breakdown_ms": stats,
-    }
+    peak_src = "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s"
+    if fast:
+        # tc_pass_kernel: the candidate pass over every probed (query, list) pair.  Algorithmic work = one 768-dim dot
+        # per pair; the kernel executes it as digits^2 int8 GEMM products on zero-padded 128 x 128 tiles.
+        t_tc = (tc_ms / tc_n) * 1e-3
+        nprod = 4 if args.digits == 2 else 6
+        dpad = -(-w["d"] // 128) * 128
+        int8_ops = 2.0 * items * 128 * 128 * dpad * nprod if items else None
+        img_bytes = float(w["n"]) * dpad * args.digits + nq * nprobe * dpad * args.digits  # digit images read once
+        roofline = {
+            "kernel": f"tc_pass_kernel<{args.digits},EMIT> (tcgen05.mma kind::i8, IVF list scan candidate pass)",
+            "bound": "tensor", "achieved": flops / t_tc / 1e12 if world == 1 else None, "peak": bf16_peak, "unit": "TFLOP/s",
+            "frac": (flops / t_tc / 1e12 / bf16_peak) if world == 1 else None, "peak_source": peak_src, "traffic": None,
+            "launch_ms": t_tc * 1e3, "launches_per_step": tc_n / args.steps,
+            "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": img_bytes,
+            "hbm_gbs_at_unique_bytes": img_bytes / t_tc / 1e9 if world == 1 else None,
+            "int8_pipe": {"executed_tops": int8_ops / t_tc / 1e12 if int8_ops else None,
+                          "nominal_peak_tops": 2.0 * bf16_peak, "frac": (int8_ops / t_tc / 1e12 / (2.0 * bf16_peak)) if int8_ops else None,
+                          "note": "executed = digit products on padded tiles; peak = 2 x measured bf16 (int8 runs at twice the "
+                                  "bf16 rate on tcgen05)"},
+            "step_breakdown_ms": stats,
+        }
+    else:
+        unique_bytes = float(w["n"]) * w["d"] * 4 + nq * w["d"] * 4 + pairs * 8  # slab once + queries + distance scratch out
+        t_scan = (scan_ms / scan_n) * 1e-3
+        try:
+            fp64_peak = hb.get_stat("fp64_peak_tflops")
+        except Exception:
+            fp64_peak = None
+        roofline = {
+            "kernel": "pairscan_kernel<float,float,FMA> (IVF list-major scan, exact fp64)",
+            "bound": "tensor", "achieved": flops / t_scan / 1e12 if world == 1 else None, "peak": bf16_peak, "unit": "TFLOP/s",
+            "frac": (flops / t_scan / 1e12 / bf16_peak) if world == 1 else None, "peak_source": peak_src,
+            "traffic": None,
+            "launch_ms": t_scan * 1e3, "launches_per_step": scan_n / args.steps,
+            "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": unique_bytes,
+            "hbm_gbs_at_unique_bytes": unique_bytes / t_scan / 1e9 if world == 1 else None,
+            "fp64_pipe": {"achieved_tflops": flops / t_scan / 1e12 if world == 1 else None, "peak_tflops_measured": fp64_peak,
+                          "frac": (flops / t_scan / 1e12 / fp64_peak) if (world == 1 and fp64_peak) else None,
+                          "note": "EXACT mode: one sequential fp64 FMA chain per (query,row) pair, bound by the fp64 pipe"},
+            "step_breakdown_ms": stats,
+        }
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample + parity on that sample ---------
     cpu = None
@@ -389,17 +431,20 @@ def run_ours(args, w, key):
                "sample": f"first {r['sample']} of {nq} queries, one pass, {r['cores']} threads (one query per task)"}
         s = r["sample"]
         parity = {"sample_queries": s, "ids_equal": bool((ids_np[:s] == r["ids"]).all()),
-                  "dist_bits_equal": bool((dists.cpu().numpy()[:s].view(np.int64) == r["dist"].view(np.int64)).all())}
+                  "dist_bits_equal": bool((dists_np[:s].view(np.int64) == r["dist"].view(np.int64)).all())}
 
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(w, key), "recall_at_10": recall, "mode": "exact (fp64, bit-identical to the oracle)",
+        "config": {"workload": workload_name(w, key), "recall_at_10": recall,
+                   "mode": (f"fast: tcgen05 int8 x{args.digits}-digit candidate pass + fp64 re-score + proof, exact fallback "
+                            "(ids and distance bits identical to exact mode)") if fast else "exact (fp64 for every pair)",
                    "l2": "inputs_larger_than_l2 (index slab 3.07 GB vs 126 MB L2)",
                    "sharding": "lists of one global index, l mod N; all-gather + merge" if world > 1 else "single GPU",
                    "build_s": build_s, "e2e_results_equal_device_results": e2e_same},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "fast_vs_exact": fast_vs_exact,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -415,6 +460,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
+                    help="fast: tensor-core candidate pass + fp64 re-score + proof (same results); exact: fp64 for every pair")
+    ap.add_argument("--digits", type=int, default=2, choices=[2, 3], help="int8 digits per element in fast mode")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]

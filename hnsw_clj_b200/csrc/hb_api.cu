@@ -117,7 +117,7 @@ static int guarded(F &&f) {
 static void sync_stream() { HB_CUDA(cudaStreamSynchronize(g_stream)); }
 
 // ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ------
-enum ProfTag { PROF_SCAN = 0, PROF_COARSE = 1, PROF_SELECT = 2, PROF_PLAN = 3, PROF_ASSIGN = 4, PROF_TC = 5, PROF_PACK = 6, PROF_RESCORE = 7, PROF_NTAGS = 8 };
+enum ProfTag { PROF_SCAN = 0, PROF_COARSE = 1, PROF_SELECT = 2, PROF_PLAN = 3, PROF_ASSIGN = 4, PROF_TC = 5, PROF_PACK = 6, PROF_RESCORE = 7, PROF_TC_SAMPLE = 8, PROF_NTAGS = 9 };
 static bool g_profile = false;
 struct ProfSpan {
     cudaEvent_t a, b;
@@ -129,7 +129,7 @@ static int64_t g_prof_n[PROF_NTAGS] = {0};
 struct Prof {
     bool on;
     ProfSpan sp;
-    explicit Prof(int tag) : on(g_profile) {
+    explicit Prof(int tag) : on(g_profile && tag >= 0) {
         if (!on) return;
         sp.tag = tag;
         cudaEventCreate(&sp.a);
@@ -696,6 +696,7 @@ struct FastJob {
     int k = 0;
     FastPlan emit, thresh;
     bool shared_units = false;  // thresh covers the same units as emit (fewer tiles)
+    bool profile = true;        // record the per-stage events (the coarse job is timed as a whole by its caller)
     int64_t *out_rel = nullptr;
     double *out_dist = nullptr;
     int32_t *out_ok = nullptr;
@@ -744,7 +745,7 @@ static void fast_topk(const FastJob &J) {
     UnitPlan U, T;
     int8_t *aimg = nullptr, *aimg0 = nullptr;
     {
-        Prof pr(PROF_PACK);
+        Prof pr(J.profile ? PROF_PACK : -1);
         U = make_units(J.emit, W.u_list, W.u_sel0, W.u_nsel, W.u_ntile, W.u_item0, W.u_slotq, W.u_slotrel, (const int64_t *)S.tile_off.p);
         aimg = W.aimg.as<int8_t>((size_t)std::max(J.emit.nunits, 1) * kbn * ns * kFastImg);
         launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.emit.nunits, U.slot_query, aimg);
@@ -778,7 +779,7 @@ static void fast_topk(const FastJob &J) {
     double *selval = W.selval.as<double>((size_t)nq * kk);
     int64_t *selpos = W.selpos.as<int64_t>((size_t)nq * kk);
     auto select_candidates = [&] {
-        Prof pr(PROF_SELECT);
+        Prof pr(J.profile ? PROF_SELECT : -1);
         SelectParams L;
         L.vals = cnegv;
         L.nseg = nq;
@@ -792,7 +793,7 @@ static void fast_topk(const FastJob &J) {
     {
         // sample pass: candidates of a subset of the rows (nearest list / every 8th tile) -> their kk-th best
         // score seeds the thresholds of the full pass
-        Prof pr(PROF_TC);
+        Prof pr(J.profile ? PROF_TC_SAMPLE : -1);
         P.aimg = aimg0;
         P.nunits = J.thresh.nunits;
         P.unit_list = T.unit_list;
@@ -807,7 +808,7 @@ static void fast_topk(const FastJob &J) {
     HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
     launch_fill_f64(cnegv, nq * cap, INFINITY);
     {
-        Prof pr(PROF_TC);
+        Prof pr(J.profile ? PROF_TC : -1);
         P.tile_stride = 1;
         P.aimg = aimg;
         P.nunits = J.emit.nunits;
@@ -820,7 +821,7 @@ static void fast_topk(const FastJob &J) {
     select_candidates();
     double *exact = W.exact.as<double>((size_t)nq * kk);
     {
-        Prof pr(PROF_RESCORE);
+        Prof pr(J.profile ? PROF_RESCORE : -1);
         int32_t *pq = W.pq.as<int32_t>((size_t)nq * kk), *prow = W.pr.as<int32_t>((size_t)nq * kk);
         launch_rescore_pairs(selpos, selval, cpos, nq, kk, cap, pq, prow);
         launch_gather_score(J.rows_exact, J.rdtype, J.row_norm, J.queries, J.qdtype, J.qn, J.d, pq, prow, nq * kk, false, J.epi, exact);
@@ -1015,6 +1016,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
             J.d = d;
             J.metric = HB_COSINE;
             J.epi = EPI_COS_GUARD;
+            J.profile = false;
             J.k = np_eff;
             flat_fast_plan(nqc, J.emit, J.thresh, W.flat_plan);
             J.shared_units = true;
@@ -1184,8 +1186,8 @@ HB_API int hb_set_option(const char *name, int64_t value) {
 HB_API int hb_get_stat(const char *name, double *out) {
     return guarded([&] {
         HB_REQUIRE(name && out, "null argument");
-        static const char *ms_names[PROF_NTAGS] = {"scan_ms", "coarse_ms", "select_ms", "plan_ms", "assign_ms", "tc_ms", "pack_ms", "rescore_ms"};
-        static const char *n_names[PROF_NTAGS] = {"scan_count", "coarse_count", "select_count", "plan_count", "assign_count", "tc_count", "pack_count", "rescore_count"};
+        static const char *ms_names[PROF_NTAGS] = {"scan_ms", "coarse_ms", "select_ms", "plan_ms", "assign_ms", "tc_ms", "pack_ms", "rescore_ms", "tc_sample_ms"};
+        static const char *n_names[PROF_NTAGS] = {"scan_count", "coarse_count", "select_count", "plan_count", "assign_count", "tc_count", "pack_count", "rescore_count", "tc_sample_count"};
         prof_collect();
         for (int i = 0; i < PROF_NTAGS; ++i) {
             if (!strcmp(name, ms_names[i])) { *out = g_prof_ms[i]; return; }

@@ -81,7 +81,8 @@ HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches 
  * element in the HB_MODE_FAST candidate pass (16- or 24-bit block-fixed-point mantissas) */
 HB_API int hb_set_option(const char *name, int64_t value);
 /* measurements: "scan_ms"/"scan_count" (list/flat scan kernel), "coarse_ms", "select_ms", "plan_ms", "assign_ms",
- * "tc_ms" (tensor-core candidate passes), "pack_ms", "rescore_ms"
+ * "tc_ms" (tensor-core candidate pass over all probed lists), "tc_sample_ms" (its threshold-seeding pass), "pack_ms",
+ * "rescore_ms"
  * (device time between the events, accumulated since "profile" was set), "fast_queries" / "fast_fallbacks"
  * (queries served in FAST mode / of those recomputed by the exact path), "fp64_peak_tflops" (runs a DFMA
  * microbenchmark: the measured peak of the pipe the exact kernels are bound by) */

@@ -740,7 +740,6 @@ static void fast_topk(const FastJob &J) {
     int32_t *cpos = W.cpos.as<int32_t>((size_t)nq * cap);
     launch_fill_f32(thr, nq, -INFINITY);
     HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
-    launch_fill_f64(cnegv, nq * cap, INFINITY);
 
     UnitPlan U, T;
     int8_t *aimg = nullptr, *aimg0 = nullptr;
@@ -780,15 +779,7 @@ static void fast_topk(const FastJob &J) {
     int64_t *selpos = W.selpos.as<int64_t>((size_t)nq * kk);
     auto select_candidates = [&] {
         Prof pr(J.profile ? PROF_SELECT : -1);
-        SelectParams L;
-        L.vals = cnegv;
-        L.nseg = nq;
-        L.seg_stride = cap;
-        L.seg_len_const = cap;
-        L.k = kk;
-        L.out_val = selval;
-        L.out_pos = selpos;
-        launch_select(L);
+        launch_cand_select(cnegv, cnt, nq, kk, cap, selval, selpos);
     };
     {
         // sample pass: candidates of a subset of the rows (nearest list / every 8th tile) -> their kk-th best
@@ -806,7 +797,6 @@ static void fast_topk(const FastJob &J) {
     select_candidates();
     launch_thr_from_sample(selval, cnt, nq, kk, cap, thr);
     HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
-    launch_fill_f64(cnegv, nq * cap, INFINITY);
     {
         Prof pr(J.profile ? PROF_TC : -1);
         P.tile_stride = 1;
@@ -824,7 +814,7 @@ static void fast_topk(const FastJob &J) {
         Prof pr(J.profile ? PROF_RESCORE : -1);
         int32_t *pq = W.pq.as<int32_t>((size_t)nq * kk), *prow = W.pr.as<int32_t>((size_t)nq * kk);
         launch_rescore_pairs(selpos, selval, cpos, nq, kk, cap, pq, prow);
-        launch_gather_score(J.rows_exact, J.rdtype, J.row_norm, J.queries, J.qdtype, J.qn, J.d, pq, prow, nq * kk, false, J.epi, exact);
+        launch_rescore(J.rows_exact, J.rdtype, J.row_norm, J.queries, J.qdtype, J.qn, J.d, pq, prow, nq * kk, J.epi, exact);
         FinalParams F;
         F.nq = nq;
         F.k = J.k;

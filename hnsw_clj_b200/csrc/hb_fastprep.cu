@@ -348,6 +348,107 @@ __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
     }
 }
 
+
+// ---- candidate selection: the kk best (lowest -score) of the cnt[q] candidates a query collected -------------------
+// One CTA per query; only the min(cnt, cap) live entries are read.  Keys = (order-preserving bits of the fp32 score,
+// slot) packed in 64 bits, bitonic-sorted in shared memory at the next power of two >= count.
+__device__ __forceinline__ uint32_t f32_desc_key(float v) {  // larger score -> smaller key
+    uint32_t b = __float_as_uint(v);
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // ascending order-preserving
+    return ~b;
+}
+__global__ void __launch_bounds__(256) cand_select_kernel(const double *__restrict__ cand_negv, const int32_t *__restrict__ cnt,
+                                                          int kk, int cap, double *__restrict__ sel_negv,
+                                                          int64_t *__restrict__ sel_pos) {
+    extern __shared__ uint64_t s_keys[];
+    const int64_t q = blockIdx.x;
+    const int n = min(cnt[q], cap);
+    int m = 64;
+    while (m < n) m <<= 1;
+    const double *v = cand_negv + q * cap;
+    for (int i = threadIdx.x; i < m; i += blockDim.x)
+        s_keys[i] = i < n ? ((uint64_t)f32_desc_key((float)(-v[i])) << 32) | (uint32_t)i : ~0ull;
+    for (int size = 2; size <= m; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < m / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const uint64_t a = s_keys[lo], b = s_keys[hi];
+                if ((a > b) == asc) {
+                    s_keys[lo] = b;
+                    s_keys[hi] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < kk; j += blockDim.x) {
+        const bool ok = j < n;
+        const int slot = ok ? (int)(uint32_t)s_keys[j] : -1;
+        sel_pos[q * kk + j] = slot;
+        sel_negv[q * kk + j] = ok ? v[slot] : INFINITY;
+    }
+}
+
+// ---- exact re-score of (query, row) pairs: one thread per pair walks the reference's sequential fp64 sum
+// (src/hnsw/ultra_fast.clj:53-95, ivf_flat.clj:224-226); a warp stages its 32 rows chunk by chunk through shared
+// memory with full-line loads (the rows are scattered, 3-6 KB each), queries are read directly (one query per
+// group of kk pairs: broadcast).
+template <typename TRow, typename TQry, int ARITH>
+__global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ rows, const double *__restrict__ row_norm,
+                                                      const TQry *__restrict__ queries, const double *__restrict__ q_norm, int d,
+                                                      const int32_t *__restrict__ pair_query, const int32_t *__restrict__ pair_row,
+                                                      int64_t npairs, int epi, double *__restrict__ out) {
+    constexpr int CH = 128 / (int)sizeof(TRow);  // elements per 128-byte chunk
+    constexpr int LPR = 8;                        // lanes per row chunk (16 B each)
+    __shared__ __align__(16) unsigned char s_raw[4][32][128 + 16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < npairs;
+    const int qi = live ? pair_query[p] : 0, ri = live ? pair_row[p] : 0;
+    const TQry *qp = queries + (int64_t)qi * d;
+    double s = 0.0;
+    const int nch = (d + CH - 1) / CH;
+    const bool vec = (((size_t)d * sizeof(TRow)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0);
+    for (int c = 0; c < nch; ++c) {
+        // cooperative load: row j of the warp's 32 pairs, its 128-byte chunk c, by lanes (j%4)*8 .. +7 over 8 rounds
+        __syncwarp();
+#pragma unroll
+        for (int round = 0; round < 32 / (32 / LPR); ++round) {
+            const int j = round * (32 / LPR) + lane / LPR;
+            const int part = lane % LPR;
+            const int rj = __shfl_sync(0xffffffffu, ri, j);
+            const int e0 = c * CH + part * (16 / (int)sizeof(TRow));
+            uint4 val = make_uint4(0, 0, 0, 0);
+            const TRow *src = rows + (int64_t)rj * d + e0;
+            if (vec && e0 + 16 / (int)sizeof(TRow) <= d) val = __ldg(reinterpret_cast<const uint4 *>(src));
+            else {
+                alignas(16) TRow tmp[16 / sizeof(TRow)];
+#pragma unroll
+                for (int e = 0; e < 16 / (int)sizeof(TRow); ++e) tmp[e] = (e0 + e < d) ? src[e] : TRow(0.0f);
+                val = *reinterpret_cast<uint4 *>(tmp);
+            }
+            *reinterpret_cast<uint4 *>(&s_raw[warp][j][part * 16]) = val;
+        }
+        __syncwarp();
+        // own row chunk back as 128-bit reads (row stride 144 B: conflict-free per quarter warp)
+        const uint4 *mine = reinterpret_cast<const uint4 *>(&s_raw[warp][lane][0]);
+        constexpr int PER = 16 / (int)sizeof(TRow);
+        const int kmax = min(CH, d - c * CH);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint4 bits = mine[w];
+            const TRow *el = reinterpret_cast<const TRow *>(&bits);
+#pragma unroll
+            for (int e = 0; e < PER; ++e)
+                if (w * PER + e < kmax) s = mac_seq<ARITH>(to_f64(qp[c * CH + w * PER + e]), to_f64(el[e]), s);
+        }
+    }
+    if (live) out[p] = apply_epi(epi, s, q_norm ? q_norm[qi] : 0.0, row_norm ? row_norm[ri] : 0.0);
+}
+
 __global__ void gather_bytes_kernel(const uint32_t *__restrict__ src, const int32_t *__restrict__ idx, int64_t n, int64_t row_words,
                                     uint32_t *__restrict__ dst) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -384,6 +485,44 @@ __global__ void and_flags_kernel(int32_t *__restrict__ ok, const int32_t *__rest
 }
 
 }  // namespace
+
+void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq, int kk, int cap, double *sel_negv,
+                        int64_t *sel_pos) {
+    if (nq == 0) return;
+    HB_REQUIRE(cap <= 4096 && kk <= 64, "candidate select: cap <= 4096, kk <= 64");
+    cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos);
+    HB_LAUNCH_CHECK();
+}
+
+namespace {
+template <typename TRow, typename TQry>
+void rescore_arith(const void *rows, const double *row_norm, const void *queries, const double *q_norm, int d, const int32_t *pq,
+                   const int32_t *pr, int64_t npairs, int epi, double *out) {
+    const int grid = blocks_for(npairs, 128);
+    constexpr bool exact = is_f32_repr<TRow>::value && is_f32_repr<TQry>::value;
+    if (exact)
+        rescore_kernel<TRow, TQry, ARITH_FMA><<<grid, 128, 0, g_stream>>>((const TRow *)rows, row_norm, (const TQry *)queries, q_norm,
+                                                                           d, pq, pr, npairs, epi, out);
+    else
+        rescore_kernel<TRow, TQry, ARITH_MULADD><<<grid, 128, 0, g_stream>>>((const TRow *)rows, row_norm, (const TQry *)queries,
+                                                                              q_norm, d, pq, pr, npairs, epi, out);
+    HB_LAUNCH_CHECK();
+}
+}  // namespace
+
+void launch_rescore(const void *rows, int rdtype, const double *row_norm, const void *queries, int qdtype, const double *q_norm,
+                    int d, const int32_t *pair_query, const int32_t *pair_row, int64_t npairs, int epi, double *out) {
+    if (npairs == 0) return;
+#define HB_RS(TR_, TQ_) rescore_arith<TR_, TQ_>(rows, row_norm, queries, q_norm, d, pair_query, pair_row, npairs, epi, out)
+    if (rdtype == HB_F32 && qdtype == HB_F32) HB_RS(float, float);
+    else if (rdtype == HB_F32 && qdtype == HB_F64) HB_RS(float, double);
+    else if (rdtype == HB_BF16 && qdtype == HB_F32) HB_RS(__nv_bfloat16, float);
+    else if (rdtype == HB_BF16 && qdtype == HB_F64) HB_RS(__nv_bfloat16, double);
+    else if (rdtype == HB_F64 && qdtype == HB_F32) HB_RS(double, float);
+    else if (rdtype == HB_F64 && qdtype == HB_F64) HB_RS(double, double);
+    else throw Error(HB_ERR_INVALID, "unsupported dtype for the exact re-score");
+#undef HB_RS
+}
 
 void launch_gather_bytes(const void *src, const int32_t *idx, int64_t n, int64_t row_bytes, void *dst) {
     if (n == 0) return;

@@ -241,6 +241,9 @@ def run_ours(args, w, key):
 
     fast = args.mode == "fast"
     hb.set_option("fast_digits", args.digits)
+    for kv in args.opt:
+        name, _, val = kv.partition("=")
+        hb.set_option(name, int(val))
     k, nprobe, nq = w["k"], w["nprobe"], w["nq"]
     rows, queries = gen_gpu(w, device)
     torch.cuda.synchronize()
@@ -462,6 +465,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
                     help="fast: tensor-core candidate pass + fp64 re-score + proof (same results); exact: fp64 for every pair")
+    ap.add_argument("--opt", action="append", default=[], help="library knob name=value (hb_set_option), repeatable")
     ap.add_argument("--digits", type=int, default=2, choices=[2, 3], help="int8 digits per element in fast mode")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -155,6 +155,7 @@ static void prof_collect() {
     g_spans.clear();
 }
 double fp64_peak_tflops();  // hb_microbench.cu
+double mma_clocks_per_instr(int kind);
 
 // ---- java.util.Random (needed by kmeans-plus-plus-init, ivf_flat.clj:37: (Random. 42)) -------------
 // Implemented from the published LCG definition of java.util.Random (JDK javadoc).
@@ -211,6 +212,7 @@ struct FastSideBufs {
 };
 
 static bool g_fast_debug = false;
+static bool g_tc_interleave = true;
 static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
 static int64_t g_fast_queries = 0;   // queries answered in FAST mode ...
 static int64_t g_fast_fallbacks = 0; // ... of which recomputed by the exact path (proof failed)
@@ -677,9 +679,17 @@ struct FastPlan {  // which (query, list) pairs a pass covers
     const int32_t *qsel = nullptr;         // selection -> pair (NULL: identity)
     const int64_t *pair_out = nullptr;     // pair -> offset of its segment (NULL: flat)
     int pair_div = 0;                      // query = pair / pair_div (0: pair == query)
-    int nunits = 0;
+    int nunits = 0;       // unit slots (interleaved layouts pad the real count up to a multiple of the SM count)
+    int nunits_real = 0;
+    int interleave = 0;
     int tile_limit = 0, tile_div = 0;
 };
+// pads the unit count so that the slots can be interleaved across the persistent CTAs (unit_plan_kernel)
+static void set_units(FastPlan &F, int64_t real, bool interleave) {
+    F.nunits_real = (int)real;
+    F.interleave = (interleave && real > 2 * g_num_sms) ? g_num_sms : 0;
+    F.nunits = F.interleave ? (int)(ceil_div(real, F.interleave) * F.interleave) : (int)real;
+}
 struct FastJob {
     FastSideBufs *side = nullptr;
     const int64_t *list_off = nullptr;  // slab rows per list (B side)
@@ -713,8 +723,8 @@ static UnitPlan make_units(const FastPlan &F, DevBuf &b_list, DevBuf &b_sel0, De
     U.unit_item0 = b_item0.as<int32_t>(nu + 1);
     U.slot_query = b_slotq.as<int32_t>(nu * kFastTile);
     U.slot_rel0 = b_slotrel.as<int32_t>(nu * kFastTile);
-    launch_unit_plan(F.nlist, F.lq_off, F.unit_prefix, tile_off, F.nunits, F.tile_limit, F.tile_div, F.qsel, F.pair_out, F.pair_div,
-                     nullptr, U);
+    launch_unit_plan(F.nlist, F.lq_off, F.unit_prefix, tile_off, F.nunits, F.nunits_real, F.interleave, F.tile_limit, F.tile_div, F.qsel,
+                     F.pair_out, F.pair_div, nullptr, U);
     return U;
 }
 
@@ -753,7 +763,8 @@ static void fast_topk(const FastJob &J) {
             T.unit_ntile = W.t_ntile.as<int32_t>((size_t)J.emit.nunits + 1);
             T.unit_item0 = W.t_item0.as<int32_t>((size_t)J.emit.nunits + 1);
             launch_unit_plan(J.thresh.nlist, J.thresh.lq_off, J.thresh.unit_prefix, (const int64_t *)S.tile_off.p, J.thresh.nunits,
-                             J.thresh.tile_limit, J.thresh.tile_div, J.thresh.qsel, J.thresh.pair_out, J.thresh.pair_div, nullptr, T);
+                             J.thresh.nunits_real, J.thresh.interleave, J.thresh.tile_limit, J.thresh.tile_div, J.thresh.qsel,
+                             J.thresh.pair_out, J.thresh.pair_div, nullptr, T);
             aimg0 = aimg;
         } else {
             T = make_units(J.thresh, W.t_list, W.t_sel0, W.t_nsel, W.t_ntile, W.t_item0, W.t_slotq, W.t_slotrel,
@@ -876,7 +887,7 @@ static void flat_fast_plan(int64_t nq, FastPlan &E, FastPlan &T, DevBuf &buf) {
     E.nlist = 1;
     E.lq_off = dptr;
     E.unit_prefix = dptr + 2;
-    E.nunits = (int)h[3];
+    set_units(E, h[3], false);
     T = E;
     T.tile_div = 8;
 }
@@ -1101,14 +1112,14 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         J.emit.qsel = qsel;
         J.emit.pair_out = pair_out;
         J.emit.pair_div = np_eff;
-        J.emit.nunits = (int)nu;
+        set_units(J.emit, nu, g_tc_interleave);
         J.thresh.nlist = nlist;
         J.thresh.lq_off = lq_off0;
         J.thresh.unit_prefix = uprefix0;
         J.thresh.qsel = qsel0;
         J.thresh.pair_out = nullptr;
         J.thresh.pair_div = 1;
-        J.thresh.nunits = (int)nu0;
+        set_units(J.thresh, nu0, false);
         J.thresh.tile_limit = 4;
         J.shared_units = false;
         J.out_rel = relk;
@@ -1158,6 +1169,8 @@ HB_API int hb_set_option(const char *name, int64_t value) {
         if (!strcmp(name, "scratch_mb")) {
             HB_REQUIRE(value >= 1, "scratch_mb must be >= 1");
             g_scratch_budget = (size_t)value << 20;
+        } else if (!strcmp(name, "tc_interleave")) {
+            g_tc_interleave = value != 0;
         } else if (!strcmp(name, "fast_debug")) {
             g_fast_debug = value != 0;
         } else if (!strcmp(name, "fast_digits")) {
@@ -1185,6 +1198,14 @@ HB_API int hb_get_stat(const char *name, double *out) {
         }
         if (!strcmp(name, "fast_queries")) { *out = (double)g_fast_queries; return; }
         if (!strcmp(name, "fast_fallbacks")) { *out = (double)g_fast_fallbacks; return; }
+        if (!strncmp(name, "mma_clocks_", 11)) {
+            ensure_init();
+            const char *k = name + 11;
+            const int kind = !strcmp(k, "i8") ? 0 : !strcmp(k, "bf16") ? 1 : !strcmp(k, "e4m3") ? 2 : !strcmp(k, "tf32") ? 3 : -1;
+            HB_REQUIRE(kind >= 0, "mma_clocks_{i8,bf16,e4m3,tf32}");
+            *out = mma_clocks_per_instr(kind);
+            return;
+        }
         if (!strcmp(name, "fp64_peak_tflops")) {
             ensure_init();
             *out = fp64_peak_tflops();

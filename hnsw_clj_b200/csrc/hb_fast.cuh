@@ -66,9 +66,10 @@ struct UnitPlan {
     int32_t *slot_query = nullptr;  // [nunits*128] query index or -1
     int32_t *slot_rel0 = nullptr;   // [nunits*128] position of the (query, list) segment inside the query's concatenation
 };
+// nunits = unit slots (>= nunits_real; a multiple of `interleave` when interleave > 0, see unit_plan_kernel)
 void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_prefix, const int64_t *tile_off, int nunits,
-                      int tile_limit, int tile_div, const int32_t *qsel, const int64_t *pair_out, int pair_div,
-                      const int32_t *pair_query, UnitPlan U);
+                      int nunits_real, int interleave, int tile_limit, int tile_div, const int32_t *qsel, const int64_t *pair_out,
+                      int pair_div, const int32_t *pair_query, UnitPlan U);
 // gathers the digits of each unit's queries into A images [nunits][kbn][ns][kFastImg]
 void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int32_t *slot_query, int8_t *aimg);
 

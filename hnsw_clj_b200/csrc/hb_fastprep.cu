@@ -174,11 +174,27 @@ __global__ void __launch_bounds__(256) quant_queries_kernel(const T *__restrict_
 }
 
 __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, const int64_t *__restrict__ unit_prefix,
-                                 const int64_t *__restrict__ tile_off, int nunits, int tile_limit, int tile_div, UnitPlan U) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u > nunits) return;
-    if (u == nunits) {
-        U.unit_ntile[u] = 0;
+                                 const int64_t *__restrict__ tile_off, int nunits, int nunits_real, int interleave,
+                                 int tile_limit, int tile_div, UnitPlan U) {
+    const int slot_u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot_u > nunits) return;
+    if (slot_u == nunits) {
+        U.unit_ntile[slot_u] = 0;
+        return;
+    }
+    // interleave > 0: unit slots are laid out so that the contiguous item ranges the CTAs take visit the real units
+    // round-robin (slot c*rows + r <- real unit r*interleave + c): the units of one list then run on neighbouring
+    // CTAs at the same time and share their row tiles through L2.
+    int u = slot_u;
+    if (interleave > 0) {
+        const int rows = nunits / interleave;
+        u = (slot_u % rows) * interleave + slot_u / rows;
+    }
+    if (u >= nunits_real) {
+        U.unit_list[slot_u] = 0;
+        U.unit_sel0[slot_u] = 0;
+        U.unit_nsel[slot_u] = 0;
+        U.unit_ntile[slot_u] = 0;
         return;
     }
     int lo = 0, hi = nlist;  // last l with unit_prefix[l] <= u (lists without selections share a prefix value:
@@ -194,10 +210,10 @@ __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, 
     int nt = (int)(tile_off[l + 1] - tile_off[l]);
     if (tile_div > 1) nt = (nt + tile_div - 1) / tile_div;  // tiles 0, tile_div, 2*tile_div, ...
     if (tile_limit > 0) nt = min(nt, tile_limit);
-    U.unit_list[u] = l;
-    U.unit_sel0[u] = (int32_t)sel0;
-    U.unit_nsel[u] = nsel;
-    U.unit_ntile[u] = nt;
+    U.unit_list[slot_u] = l;
+    U.unit_sel0[slot_u] = (int32_t)sel0;
+    U.unit_nsel[slot_u] = nsel;
+    U.unit_ntile[slot_u] = nt;
 }
 
 // exclusive prefix of ntile -> item0 (single block)
@@ -602,11 +618,11 @@ void launch_quant_queries(const void *queries, int qdtype, int64_t nq, int d, in
 }
 
 void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_prefix, const int64_t *tile_off, int nunits,
-                      int tile_limit, int tile_div, const int32_t *qsel, const int64_t *pair_out, int pair_div,
-                      const int32_t *pair_query, UnitPlan U) {
+                      int nunits_real, int interleave, int tile_limit, int tile_div, const int32_t *qsel, const int64_t *pair_out,
+                      int pair_div, const int32_t *pair_query, UnitPlan U) {
     if (nunits == 0) return;
-    unit_plan_kernel<<<blocks_for(nunits + 1, 256), 256, 0, g_stream>>>(nlist, lq_off, unit_prefix, tile_off, nunits, tile_limit,
-                                                                        tile_div, U);
+    unit_plan_kernel<<<blocks_for(nunits + 1, 256), 256, 0, g_stream>>>(nlist, lq_off, unit_prefix, tile_off, nunits, nunits_real,
+                                                                        interleave, tile_limit, tile_div, U);
     HB_LAUNCH_CHECK();
     unit_scan_kernel<<<1, 1024, 0, g_stream>>>(U.unit_ntile, nunits + 1, U.unit_item0);
     HB_LAUNCH_CHECK();

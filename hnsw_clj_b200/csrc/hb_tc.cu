@@ -275,52 +275,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
             tc_fence_after();
             tphase ^= 1u;
             const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+            // 4 x 32 columns; NOT fully unrolled: the body must stay inside the instruction cache (one warp per
+            // scheduler cannot hide instruction-fetch misses).  Within a 32-column step the bucket of column
+            // (h*16 + j) is a compile-time register.
+#pragma unroll 1
+            for (int c32 = 0; c32 < kFastTile / 32; ++c32) {
 #pragma unroll
-            for (int cc = 0; cc < kFastTile / 16; ++cc) {
-                uint32_t c0[16], c1[16], c2[16];
-                tmem_ld16(tlane + cc * 16, c0);
-                tmem_ld16(tlane + kFastTile + cc * 16, c1);
-                tmem_ld16(tlane + 2 * kFastTile + cc * 16, c2);
-                tmem_ld_wait();
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float s = fmaf((float)(int)c0[j], 65536.0f, fmaf((float)(int)c1[j], 256.0f, (float)(int)c2[j]));
-                    v[j] = fmaf(s, s_rs[par][cc * 16 + j], s_ro[par][cc * 16 + j]);
-                }
-                if (MODE != FAST_DUMP) {
+                for (int h = 0; h < 2; ++h) {
+                    const int col0 = c32 * 32 + h * 16;
+                    uint32_t c0[16], c1[16], c2[16];
+                    tmem_ld16(tlane + col0, c0);
+                    tmem_ld16(tlane + kFastTile + col0, c1);
+                    tmem_ld16(tlane + 2 * kFastTile + col0, c2);
+                    tmem_ld_wait();
+                    float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int b = (cc * 16 + j) % NB;
-                        const float lo = fminf(b1[b], v[j]);
-                        b1[b] = fmaxf(b1[b], v[j]);
-                        b2[b] = fmaxf(b2[b], lo);
+                        const float s = fmaf((float)(int)c0[j], 65536.0f, fmaf((float)(int)c1[j], 256.0f, (float)(int)c2[j]));
+                        v[j] = fmaf(s, s_rs[par][col0 + j], s_ro[par][col0 + j]);
                     }
-                }
-                if (MODE == FAST_EMIT) {
-                    uint32_t mask = 0;
-                    const float cut = fmaxf(thr, -FLT_MAX);  // padding rows score -inf: never candidates
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) mask |= (v[j] >= cut ? 1u : 0u) << j;
-                    if (mask) {
-                        int base = atomicAdd(&P.cnt[qi], __popc(mask));
+                    if (MODE != FAST_DUMP) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            if ((mask >> j) & 1u) {
-                                if (base < P.cap) {
-                                    const int64_t o = (int64_t)qi * P.cap + base;
-                                    P.cand_negv[o] = -(double)v[j];
-                                    P.cand_rel[o] = rel0 + t * kFastTile + cc * 16 + j;
-                                    P.cand_pos[o] = (int32_t)(row0 + cc * 16 + j);
-                                }
-                                ++base;
-                            }
+                            const int b = h * 16 + j;
+                            const float lo = fminf(b1[b], v[j]);
+                            b1[b] = fmaxf(b1[b], v[j]);
+                            b2[b] = fmaxf(b2[b], lo);
                         }
                     }
-                } else if (MODE == FAST_DUMP) {
-                    float *o = P.dump + ((int64_t)item * kFastTile + slot) * kFastTile + cc * 16;
+                    if (MODE == FAST_EMIT) {
+                        uint32_t mask = 0;
+                        const float cut = fmaxf(thr, -FLT_MAX);  // padding rows score -inf: never candidates
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = v[j];
+                        for (int j = 0; j < 16; ++j) mask |= (v[j] >= cut ? 1u : 0u) << j;
+                        if (mask) {
+                            int base = atomicAdd(&P.cnt[qi], __popc(mask));
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if ((mask >> j) & 1u) {
+                                    if (base < P.cap) {
+                                        const int64_t o = (int64_t)qi * P.cap + base;
+                                        P.cand_negv[o] = -(double)v[j];
+                                        P.cand_rel[o] = rel0 + t * kFastTile + col0 + j;
+                                        P.cand_pos[o] = (int32_t)(row0 + col0 + j);
+                                    }
+                                    ++base;
+                                }
+                            }
+                        }
+                    } else if (MODE == FAST_DUMP) {
+                        float *o = P.dump + ((int64_t)item * kFastTile + slot) * kFastTile + col0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = v[j];
+                    }
                 }
             }
             tc_fence_before();

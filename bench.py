@@ -288,11 +288,15 @@ def run_ours(args, w, key):
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.ncu_region:
+        hb.set_option("cuda_profiler", 1)
     e0.record()
     for _ in range(args.steps):
         ids, dists = search(queries)
     e1.record()
     barrier()
+    if args.ncu_region:
+        hb.set_option("cuda_profiler", 0)
     ms = e0.elapsed_time(e1) / args.steps
     launches = hb.launch_count()
     clk = clocks.stop() if rank == 0 else {}
@@ -466,6 +470,8 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
                     help="fast: tensor-core candidate pass + fp64 re-score + proof (same results); exact: fp64 for every pair")
     ap.add_argument("--opt", action="append", default=[], help="library knob name=value (hb_set_option), repeatable")
+    ap.add_argument("--ncu-region", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (for `ncu --profile-from-start off`)")
     ap.add_argument("--digits", type=int, default=2, choices=[2, 3], help="int8 digits per element in fast mode")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -5,6 +5,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda_profiler_api.h>
+
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -1176,6 +1178,11 @@ HB_API int hb_set_option(const char *name, int64_t value) {
         } else if (!strcmp(name, "fast_digits")) {
             HB_REQUIRE(value == 2 || value == 3, "fast_digits must be 2 or 3");
             g_fast_ns = (int)value;
+        } else if (!strcmp(name, "cuda_profiler")) {
+            // brackets the region `ncu --profile-from-start off` captures (bench.py: the timed steps only)
+            ensure_init();
+            HB_CUDA(cudaDeviceSynchronize());
+            if (value) HB_CUDA(cudaProfilerStart()); else HB_CUDA(cudaProfilerStop());
         } else if (!strcmp(name, "profile")) {
             prof_collect();
             g_profile = value != 0;

@@ -13,6 +13,7 @@
 
 #include "hb_build.cuh"
 #include "hb_fast.cuh"
+#include "hb_hnsw.cuh"
 #include "hb_kernels.cuh"
 
 namespace hb {
@@ -119,7 +120,7 @@ static int guarded(F &&f) {
 static void sync_stream() { HB_CUDA(cudaStreamSynchronize(g_stream)); }
 
 // ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ------
-enum ProfTag { PROF_SCAN = 0, PROF_COARSE = 1, PROF_SELECT = 2, PROF_PLAN = 3, PROF_ASSIGN = 4, PROF_TC = 5, PROF_PACK = 6, PROF_RESCORE = 7, PROF_TC_SAMPLE = 8, PROF_NTAGS = 9 };
+enum ProfTag { PROF_SCAN = 0, PROF_COARSE = 1, PROF_SELECT = 2, PROF_PLAN = 3, PROF_ASSIGN = 4, PROF_TC = 5, PROF_PACK = 6, PROF_RESCORE = 7, PROF_TC_SAMPLE = 8, PROF_HNSW = 9, PROF_NTAGS = 10 };
 static bool g_profile = false;
 struct ProfSpan {
     cudaEvent_t a, b;
@@ -218,6 +219,9 @@ static bool g_tc_interleave = true;
 static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
 static int64_t g_fast_queries = 0;   // queries answered in FAST mode ...
 static int64_t g_fast_fallbacks = 0; // ... of which recomputed by the exact path (proof failed)
+static int64_t g_hnsw_scored = 0;    // (query, row) pairs scored by the HNSW search since "profile" was set
+static int64_t g_hnsw_overflows = 0; // queries re-run with their candidate queue in global memory
+static int g_hnsw_cand_cap = 0;      // shared-memory candidate queue slots (0: 4 * ef, at least 256)
 
 }  // namespace hb
 
@@ -236,12 +240,17 @@ struct hb_index {
     int max_level = 0, entry = -1;
     DevBuf levels;
     std::vector<DevBuf> adj_off, adj_ids;
+    DevBuf adj_off_ptrs, adj_ids_ptrs;                                   // device arrays of the per-level pointers
+    DevBuf hn_visited, hn_vlist, hn_ctrl, hn_over, hn_gcand_d, hn_gcand_i;  // search state (hb_hnsw.cu), grown on demand
+    int64_t hn_slots = 0;
     // HB_MODE_FAST: digit images of the rows (all index types) and of the centroids (IVF), built on first use
     hb::FastSideBufs fast_rows, fast_cents;
     int64_t device_bytes() const {
         size_t b = rows.cap + norms.cap + cents.cap + cent_norm.cap + list_off.cap + list_rows.cap + assign.cap + levels.cap;
         for (auto &x : adj_off) b += x.cap;
         for (auto &x : adj_ids) b += x.cap;
+        b += adj_off_ptrs.cap + adj_ids_ptrs.cap + hn_visited.cap + hn_vlist.cap + hn_ctrl.cap + hn_over.cap + hn_gcand_d.cap +
+             hn_gcand_i.cap;
         b += fast_rows.bytes() + fast_cents.bytes();
         return (int64_t)b;
     }
@@ -256,6 +265,8 @@ struct hb_index {
         levels.release();
         for (auto &x : adj_off) x.release();
         for (auto &x : adj_ids) x.release();
+        for (DevBuf *x : {&adj_off_ptrs, &adj_ids_ptrs, &hn_visited, &hn_vlist, &hn_ctrl, &hn_over, &hn_gcand_d, &hn_gcand_i}) x->release();
+        hn_slots = 0;
         fast_rows.release();
         fast_cents.release();
     }
@@ -1142,6 +1153,103 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
 // =================================================================================================
 // C ABI
 // =================================================================================================
+
+// search-knn over an uploaded HNSW graph (src/hnsw/ultra_fast.clj:346-374), batched: one warp per query
+static void hnsw_search(hb_index *ix, const void *queries, int qdtype, int64_t nq, int k, int ef_param, int64_t *ids, double *dist) {
+    if (nq == 0 || k == 0) return;
+    if (ix->n == 0 || ix->entry < 0) {
+        fill_empty_results(ids, dist, nq * k);
+        return;
+    }
+    HB_REQUIRE(nq < (1ll << 31) && ix->n < (1ll << 31), "too many queries / rows for the HNSW search");
+    const int ef = ef_param > 0 ? ef_param : std::max(k, 50);  // :355
+    HB_REQUIRE(ef <= 4096, "ef > 4096 is not supported");
+    const int d = ix->d;
+    bool l2;
+    int epi;
+    metric_to_epi(ix->metric, true, l2, epi);
+    const double *qn = nullptr;
+    if (ix->metric == HB_COSINE) {
+        double *x = g_ws.qnorm.as<double>(nq);
+        launch_row_norms(queries, qdtype, nq, d, x);
+        qn = x;
+    }
+    HnswSearchParams P;
+    P.rows = ix->rows.p;
+    P.row_norm = ix->metric == HB_COSINE ? (const double *)ix->norms.p : nullptr;
+    P.d = d;
+    P.max_level = ix->max_level;
+    P.entry = ix->entry;
+    P.adj_off = (const int64_t *const *)ix->adj_off_ptrs.p;
+    P.adj_ids = (const int32_t *const *)ix->adj_ids_ptrs.p;
+    P.queries = queries;
+    P.q_norm = qn;
+    P.ef = ef;
+    P.k = k;
+    P.epi = epi;
+    P.ef_cap = ((ef + 1 + 3) / 4) * 4;
+    int cc = g_hnsw_cand_cap > 0 ? g_hnsw_cand_cap : std::max(256, 4 * ef);
+    const int W = hnsw_warps_per_cta();
+    const size_t smem_max = 200 * 1024;
+    while (cc > 16 && (size_t)W * hnsw_warp_smem(P.ef_cap, cc) > smem_max) cc /= 2;
+    P.cand_cap_smem = cc;
+    P.warp_smem = hnsw_warp_smem(P.ef_cap, cc);
+    HB_REQUIRE((size_t)W * P.warp_smem <= 227 * 1024, "ef too large for the shared-memory queues");
+    const int ctas_per_sm = std::max<int>(1, std::min<size_t>(4, (220 * 1024) / ((size_t)W * P.warp_smem + 1024)));
+    const int grid = (int)std::min<int64_t>((int64_t)g_num_sms * ctas_per_sm, ceil_div(nq, W));
+    const int64_t slots = (int64_t)g_num_sms * 4 * W;  // upper bound of grid * W, so the buffers are allocated once
+    P.vwords = ceil_div(ix->n, 32);
+    P.vcap = 8192;
+    if (ix->hn_slots != slots) {
+        uint32_t *v = ix->hn_visited.as<uint32_t>((size_t)slots * P.vwords);
+        HB_CUDA(cudaMemsetAsync(v, 0, (size_t)slots * P.vwords * 4, g_stream));  // the kernel leaves it all zero
+        ix->hn_vlist.as<int32_t>((size_t)slots * P.vcap);
+        ix->hn_slots = slots;
+    }
+    P.visited = (uint32_t *)ix->hn_visited.p;
+    P.vlist = (int32_t *)ix->hn_vlist.p;
+    // ctrl: [0] work counter, [1] overflow count, [2..3] scored pairs (u64)
+    int32_t *ctrl = ix->hn_ctrl.as<int32_t>(4);
+    HB_CUDA(cudaMemsetAsync(ctrl, 0, 16, g_stream));
+    int32_t *over = ix->hn_over.as<int32_t>(nq);
+    P.next_work = ctrl;
+    P.n_overflow = ctrl + 1;
+    P.n_scored = (unsigned long long *)(ctrl + 2);
+    P.overflow_list = over;
+    P.nwork = (int)nq;
+    P.out_ids = ids;
+    P.out_dist = dist;
+    {
+        Prof pr(PROF_HNSW);
+        launch_hnsw_search(P, ix->dtype, qdtype, l2, grid);
+    }
+    int32_t h[4];
+    HB_CUDA(cudaMemcpyAsync(h, ctrl, 16, cudaMemcpyDeviceToHost, g_stream));
+    sync_stream();
+    if (h[1] > 0) {
+        // the rare query whose candidate queue outgrew shared memory: same kernel, queue in global memory (a node is
+        // offered at most once per layer, so n slots always suffice)
+        const int nover = h[1];
+        g_hnsw_overflows += nover;
+        const int grid2 = (int)std::min<int64_t>(grid, ceil_div(nover, W));
+        P.g_cand_cap = (int)std::min<int64_t>(ix->n + 1, INT32_MAX);
+        P.g_cand_d = ix->hn_gcand_d.as<double>((size_t)grid2 * W * P.g_cand_cap);
+        P.g_cand_i = ix->hn_gcand_i.as<int32_t>((size_t)grid2 * W * P.g_cand_cap);
+        P.work_list = over;
+        P.nwork = nover;
+        HB_CUDA(cudaMemsetAsync(ctrl, 0, 8, g_stream));
+        P.overflow_list = (int32_t *)g_ws.misc.as<int32_t>(nover);
+        Prof pr(PROF_HNSW);
+        launch_hnsw_search(P, ix->dtype, qdtype, l2, grid2);
+        HB_CUDA(cudaMemcpyAsync(h, ctrl, 16, cudaMemcpyDeviceToHost, g_stream));
+        sync_stream();
+        if (h[1] > 0) throw Error(HB_ERR_CUDA, "HNSW candidate queue overflowed its global-memory capacity");
+    }
+    unsigned long long sc;
+    memcpy(&sc, &h[2], 8);
+    g_hnsw_scored += (int64_t)sc;
+}
+
 extern "C" {
 
 HB_API int hb_init(int device) {
@@ -1188,6 +1296,10 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             g_profile = value != 0;
             for (int i = 0; i < PROF_NTAGS; ++i) g_prof_ms[i] = 0, g_prof_n[i] = 0;
             g_fast_queries = g_fast_fallbacks = 0;
+            g_hnsw_scored = g_hnsw_overflows = 0;
+        } else if (!strcmp(name, "hnsw_cand_cap")) {
+            HB_REQUIRE(value >= 0 && value <= 8192, "hnsw_cand_cap must be 0..8192");
+            g_hnsw_cand_cap = (int)value;
         } else {
             throw Error(HB_ERR_INVALID, std::string("unknown option ") + name);
         }
@@ -1196,8 +1308,8 @@ HB_API int hb_set_option(const char *name, int64_t value) {
 HB_API int hb_get_stat(const char *name, double *out) {
     return guarded([&] {
         HB_REQUIRE(name && out, "null argument");
-        static const char *ms_names[PROF_NTAGS] = {"scan_ms", "coarse_ms", "select_ms", "plan_ms", "assign_ms", "tc_ms", "pack_ms", "rescore_ms", "tc_sample_ms"};
-        static const char *n_names[PROF_NTAGS] = {"scan_count", "coarse_count", "select_count", "plan_count", "assign_count", "tc_count", "pack_count", "rescore_count", "tc_sample_count"};
+        static const char *ms_names[PROF_NTAGS] = {"scan_ms", "coarse_ms", "select_ms", "plan_ms", "assign_ms", "tc_ms", "pack_ms", "rescore_ms", "tc_sample_ms", "hnsw_ms"};
+        static const char *n_names[PROF_NTAGS] = {"scan_count", "coarse_count", "select_count", "plan_count", "assign_count", "tc_count", "pack_count", "rescore_count", "tc_sample_count", "hnsw_count"};
         prof_collect();
         for (int i = 0; i < PROF_NTAGS; ++i) {
             if (!strcmp(name, ms_names[i])) { *out = g_prof_ms[i]; return; }
@@ -1205,6 +1317,8 @@ HB_API int hb_get_stat(const char *name, double *out) {
         }
         if (!strcmp(name, "fast_queries")) { *out = (double)g_fast_queries; return; }
         if (!strcmp(name, "fast_fallbacks")) { *out = (double)g_fast_fallbacks; return; }
+        if (!strcmp(name, "hnsw_scored")) { *out = (double)g_hnsw_scored; return; }
+        if (!strcmp(name, "hnsw_overflows")) { *out = (double)g_hnsw_overflows; return; }
         if (!strncmp(name, "mma_clocks_", 11)) {
             ensure_init();
             const char *k = name + 11;
@@ -1420,6 +1534,9 @@ HB_API int hb_search(hb_index *index, const void *queries, int qdtype, int64_t n
             HB_REQUIRE(param >= 1, "num-probes must be >= 1");
             if (g_mode == HB_MODE_FAST) ivf_search_fast(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev);
             else ivf_search_exact(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev, nullptr);
+        } else if (index->type == HB_INDEX_HNSW) {
+            HB_REQUIRE(param >= 0, "ef must be >= 0");
+            hnsw_search(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev);
         } else {
             throw Error(HB_ERR_UNSUPPORTED, "search on this index type is not implemented");
         }
@@ -1584,6 +1701,13 @@ HB_API int hb_hnsw_create(const void *rows, int64_t n, int32_t d, int dtype, int
                     int32_t *a = ix->adj_ids[l].as<int32_t>(std::max<int64_t>(tot, 1));
                     if (tot) HB_CUDA(cudaMemcpyAsync(a, level_ids[l], (size_t)tot * 4, cudaMemcpyDefault, g_stream));
                 }
+                std::vector<const void *> po((size_t)max_level + 1), pi((size_t)max_level + 1);
+                for (int l = 0; l <= max_level; ++l) po[l] = ix->adj_off[l].p, pi[l] = ix->adj_ids[l].p;
+                HB_CUDA(cudaMemcpyAsync(ix->adj_off_ptrs.as<const void *>(po.size()), po.data(), po.size() * sizeof(void *),
+                                        cudaMemcpyHostToDevice, g_stream));
+                HB_CUDA(cudaMemcpyAsync(ix->adj_ids_ptrs.as<const void *>(pi.size()), pi.data(), pi.size() * sizeof(void *),
+                                        cudaMemcpyHostToDevice, g_stream));
+                sync_stream();  // po / pi are locals
             }
             sync_stream();
         } catch (...) {

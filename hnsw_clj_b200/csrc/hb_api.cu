@@ -609,13 +609,13 @@ static void ivf_finalize(hb_index *ix, const void *rows_dev, const double *row_n
 // HB_MODE_FAST orchestration (scheme: hb_fast.cuh)
 // =================================================================================================
 struct FastWs {
-    DevBuf dig, qu, ql1, qscale, qeps, thr, cnt, cnegv, crel, cpos, selval, selpos, pq, pr, exact;
+    DevBuf dig, qu, ql1, qscale, qeps, qmargin, thr, cnt, cnegv, crel, cpos, selval, selpos, pq, pr, exact;
     DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_slotq, u_slotrel;
     DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_slotq, t_slotrel;
     DevBuf ppos, ppos0, ok_a, ok_b, relk, probes0, pair_out0, qsel0, lq_off0, uprefix0, uprefix, flat_plan, idx, gq, gids, gdist,
         tmp2;
     void release() {
-        DevBuf *all[] = {&dig, &qu, &ql1, &qscale, &qeps, &thr, &cnt, &cnegv, &crel, &cpos, &selval, &selpos, &pq, &pr, &exact,
+        DevBuf *all[] = {&dig, &qu, &ql1, &qscale, &qeps, &qmargin, &thr, &cnt, &cnegv, &crel, &cpos, &selval, &selpos, &pq, &pr, &exact,
                          &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_slotq, &u_slotrel,
                          &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_slotq, &t_slotrel,
                          &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
@@ -754,8 +754,9 @@ static void fast_topk(const FastJob &J) {
     const int ns = S.ns, kbn = S.kbn, kk = kFastKK, cap = kFastCap;
     const int64_t nq = J.nq;
     double *qscale = W.qscale.as<double>(nq), *qeps = W.qeps.as<double>(nq);
+    float *qmargin = W.qmargin.as<float>(nq);
     launch_query_bounds((const double *)W.qu.p, (const double *)W.ql1.p, J.qn, nq, ns, J.d, J.metric, (const float *)S.stats.p, qscale,
-                        qeps);
+                        qeps, qmargin);
     float *thr = W.thr.as<float>(nq);
     int32_t *cnt = W.cnt.as<int32_t>(nq);
     double *cnegv = W.cnegv.as<double>((size_t)nq * cap);
@@ -794,6 +795,8 @@ static void fast_topk(const FastJob &J) {
     P.rs = (const float *)S.rs.p;
     P.ro = (const float *)S.ro.p;
     P.thr = thr;
+    P.margin = qmargin;
+    P.k = J.k;
     P.cap = cap;
     P.cnt = cnt;
     P.cand_negv = cnegv;
@@ -819,7 +822,7 @@ static void fast_topk(const FastJob &J) {
         launch_tc_pass(P, ns, FAST_EMIT);
     }
     select_candidates();
-    launch_thr_from_sample(selval, cnt, nq, kk, cap, thr);
+    launch_thr_from_sample(selval, cnt, nq, kk, cap, J.k, qmargin, thr);
     HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
     {
         Prof pr(J.profile ? PROF_TC : -1);
@@ -837,7 +840,7 @@ static void fast_topk(const FastJob &J) {
     {
         Prof pr(J.profile ? PROF_RESCORE : -1);
         int32_t *pq = W.pq.as<int32_t>((size_t)nq * kk), *prow = W.pr.as<int32_t>((size_t)nq * kk);
-        launch_rescore_pairs(selpos, selval, cpos, nq, kk, cap, pq, prow);
+        launch_rescore_pairs(selpos, selval, cpos, nq, kk, cap, J.k, qmargin, pq, prow);
         launch_rescore(J.rows_exact, J.rdtype, J.row_norm, J.queries, J.qdtype, J.qn, J.d, pq, prow, nq * kk, J.epi, exact);
         FinalParams F;
         F.nq = nq;
@@ -847,6 +850,7 @@ static void fast_topk(const FastJob &J) {
         F.sel_pos = selpos;
         F.sel_negv = selval;
         F.exact = exact;
+        F.pair_row = prow;
         F.cand_rel = crel;
         F.cnt = cnt;
         F.thr = thr;
@@ -1813,7 +1817,7 @@ HB_API int hb_fast_scores(hb_index *index, const void *queries, int qdtype, int6
         OutStage oe = stage_out(out_eps, (size_t)nq * 8, g_ws.out_c);
         double *qscale = g_fw.qscale.as<double>(nq), *qeps = g_fw.qeps.as<double>(nq);
         launch_query_bounds((const double *)g_fw.qu.p, (const double *)g_fw.ql1.p, qn, nq, S.ns, d, index->metric,
-                            (const float *)S.stats.p, qscale, qeps);
+                            (const float *)S.stats.p, qscale, qeps, g_fw.qmargin.as<float>(nq));
         TcParams P;
         P.aimg = aimg;
         P.bimg = (const int8_t *)S.img.p;

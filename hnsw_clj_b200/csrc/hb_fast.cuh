@@ -88,7 +88,9 @@ struct TcParams {
     const int32_t *slot_rel0 = nullptr;
     const float *rs = nullptr;
     const float *ro = nullptr;
-    float *thr = nullptr;  // per query lower bound of its 64th best score: raised by THRESH and by EMIT (atomic max)
+    float *thr = nullptr;  // per query: rows scoring below it cannot matter (see the epilogue); raised with atomic max
+    const float *margin = nullptr;  // per query, in score units: > 2 eps_q (query_bounds_kernel)
+    int k = 0;                      // results wanted per query
     int tile_stride = 1;   // item j of a unit is row tile j*tile_stride of its list (THRESH samples every 8th tile of a flat list)
     // EMIT
     int cap = 0;
@@ -110,6 +112,7 @@ struct FinalParams {
     const int64_t *sel_pos = nullptr;   // [nq][kk]
     const double *sel_negv = nullptr;   // [nq][kk] approximate -score of the selected
     const double *exact = nullptr;      // [nq][kk] exact distances
+    const int32_t *pair_row = nullptr;  // [nq][kk] row that was re-scored, -1: not re-scored
     const int32_t *cand_rel = nullptr;
     const int32_t *cnt = nullptr;
     const float *thr = nullptr;
@@ -124,10 +127,10 @@ void launch_fast_final(const FinalParams &P);
 
 // per query: q_scale = u_q / ||q|| (cosine) or u_q (ip); q_eps from the index stats
 void launch_query_bounds(const double *qu, const double *ql1, const double *qnorm, int64_t nq, int ns, int d, int metric,
-                         const float *stats, double *q_scale, double *q_eps);
+                         const float *stats, double *q_scale, double *q_eps, float *q_margin);
 // pairs for the exact re-score: pair_query[q*kk+j] = q, pair_row = cand_pos[q][sel_pos] (or 0 with valid=0)
 void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const int32_t *cand_pos, int64_t nq, int kk, int cap,
-                          int32_t *pair_query, int32_t *pair_row);
+                          int k, const float *margin, int32_t *pair_query, int32_t *pair_row);
 // kk best of the min(cnt, cap) candidates of every query (ascending -score); unused slots: pos -1, +inf
 void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq, int kk, int cap, double *sel_negv,
                         int64_t *sel_pos);
@@ -140,7 +143,8 @@ void launch_scatter_rows64(const void *src, const int32_t *idx, int64_t n, int k
 // first[q] = pos[q*stride]  (probe rank 0 of every query)
 void launch_first_column(const int64_t *pos, int64_t nq, int stride, int64_t *first);
 // thr[q] = max(thr[q], kk-th best sample candidate) where the sample pass collected kk..cap candidates
-void launch_thr_from_sample(const double *sel_negv, const int32_t *cnt, int64_t nq, int kk, int cap, float *thr);
+void launch_thr_from_sample(const double *sel_negv, const int32_t *cnt, int64_t nq, int kk, int cap, int k, const float *margin,
+                            float *thr);
 // ok[q] &= other[q]
 void launch_and_flags(int32_t *ok, const int32_t *other, int64_t nq);
 

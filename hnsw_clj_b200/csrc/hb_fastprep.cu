@@ -277,30 +277,48 @@ __global__ void __launch_bounds__(256) pack_units_kernel(const int8_t *__restric
 __global__ void query_bounds_kernel(const double *__restrict__ qu, const double *__restrict__ ql1,
                                     const double *__restrict__ qnorm, int64_t nq, int ns, int d, int metric,
                                     const float *__restrict__ stats, double *__restrict__ q_scale,
-                                    double *__restrict__ q_eps) {
+                                    double *__restrict__ q_eps, float *__restrict__ q_margin) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const double w = metric == HB_COSINE ? 1.0 / qnorm[q] : 1.0;
     const double umax_r = (double)stats[0], l1max_r = (double)stats[1];
     const double us = qu[q] * w;
     double eps = kFastRound * (us * l1max_r + umax_r * ql1[q] * w) + kFastRound * kFastRound * d * us * umax_r;
+    // the epilogue drops the low 8 bits of the lowest-weight accumulator and rounds one int32 -> fp32 conversion:
+    // < 2 * 256 units of the integer score (in units of the accumulator weight 2^0 (ns = 2) or 2^16 (ns = 3))
+    eps += 1024.0 * (ns == 3 ? 65536.0 : 1.0) * us * umax_r;
     if (ns == 3) eps += us * umax_r * (double)d * 16384.0 * 513.0;  // dropped digit products (1,2), (2,1), (2,2)
     eps *= 1.0 + 1e-6;
     const bool bad = !(w > 0.0) || !isfinite(w) || stats[2] > 0.0f;
     q_scale[q] = bad ? 0.0 : us;
     q_eps[q] = bad ? INFINITY : eps;
+    // in score units (similarity = score * q_scale): two candidate scores further apart than this are ordered like their
+    // exact similarities, with room for the final test's own slack
+    q_margin[q] = (bad || !(us > 0.0)) ? INFINITY : __double2float_ru(2.2 * eps / us);
 }
 
 // unused candidate slots hold +inf (-score): the selection may return them when a query has fewer than kk candidates
+// Only the candidates that can still reach the exact top-k are re-scored: the k best by approximate score and every
+// further one within `margin` (> 2 eps_q) of the k-th.  The others get pair_row = -1 and count as rejected rows in
+// fast_final_kernel's proof.
 __global__ void rescore_pairs_kernel(const int64_t *__restrict__ sel_pos, const double *__restrict__ sel_negv,
-                                     const int32_t *__restrict__ cand_pos, int64_t nq, int kk, int cap,
-                                     int32_t *__restrict__ pair_query, int32_t *__restrict__ pair_row) {
+                                     const int32_t *__restrict__ cand_pos, int64_t nq, int kk, int cap, int k,
+                                     const float *__restrict__ margin, int32_t *__restrict__ pair_query,
+                                     int32_t *__restrict__ pair_row) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq * kk) return;
     const int64_t q = i / kk;
+    const int j = (int)(i - q * kk);
     const int64_t p = sel_pos[i];
+    const double nv = sel_negv[i];
+    bool want = p >= 0 && nv < INFINITY;
+    if (want && j >= k) {
+        const double nk = sel_negv[q * kk + k - 1];  // the list is ascending in -score
+        const double m = (double)margin[q] + 4e-6 * fabs(nk);
+        want = !(nk < INFINITY) || nv <= nk + m;
+    }
     pair_query[i] = (int32_t)q;
-    pair_row[i] = (p >= 0 && sel_negv[i] < INFINITY) ? cand_pos[q * cap + p] : 0;
+    pair_row[i] = want ? cand_pos[q * cap + p] : -1;
 }
 
 // One CTA (128 threads) per query.  Entry j < kk: exact distance + rel; rank by (distance key, rel).
@@ -308,6 +326,7 @@ __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
     __shared__ uint64_t s_key[128];
     __shared__ int32_t s_rel[128];
     __shared__ double s_kth;
+    __shared__ int s_skipped;
     const int64_t q = blockIdx.x;
     const int j = threadIdx.x;
     const int kk = P.kk, k = P.k;
@@ -315,17 +334,25 @@ __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
     uint64_t key = kKeyEmpty;
     int32_t rel = INT_MAX;
     double dist = INFINITY;
+    if (j == 0) {
+        s_kth = INFINITY;
+        s_skipped = INT_MAX;
+    }
+    __syncthreads();
     if (j < kk) {
         const int64_t p = P.sel_pos[q * kk + j];
         if (p >= 0 && P.sel_negv[q * kk + j] < INFINITY) {
-            dist = P.exact[q * kk + j];
-            key = dist_key(dist);
-            rel = P.cand_rel[q * P.cap + p];
+            if (P.pair_row[q * kk + j] >= 0) {
+                dist = P.exact[q * kk + j];
+                key = dist_key(dist);
+                rel = P.cand_rel[q * P.cap + p];
+            } else {
+                atomicMin(&s_skipped, j);  // selected but not re-scored: the best of them bounds the others
+            }
         }
     }
     s_key[j] = key;
     s_rel[j] = rel;
-    if (j == 0) s_kth = INFINITY;
     __syncthreads();
     int rank = 0, nvalid = 0;
     for (int i = 0; i < kk; ++i) {
@@ -345,14 +372,18 @@ __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
     }
     __syncthreads();
     if (j == 0) {
-        // rejected rows: emitted but not selected (score <= worst selected) or never emitted (score < thr)
+        // rejected rows: selected but not re-scored (score <= the best of them), emitted but not selected (score <= worst
+        // selected) or never emitted (score < thr)
         bool ok = cnt <= P.cap;
         const float thr = P.thr[q];
-        const bool none_rejected = cnt <= kk && thr == -INFINITY;
+        const int skipped = s_skipped;
+        const bool none_rejected = cnt <= kk && thr == -INFINITY && skipped == INT_MAX;
         if (ok && !none_rejected) {
             if (nvalid < k) ok = false;  // rejected rows would be needed to fill k
             else {
-                const double t_v = cnt > kk ? -P.sel_negv[q * kk + kk - 1] : (double)thr;
+                double t_v = (double)thr;
+                if (cnt > kk) t_v = fmax(t_v, -P.sel_negv[q * kk + kk - 1]);
+                if (skipped != INT_MAX) t_v = fmax(t_v, -P.sel_negv[q * kk + skipped]);
                 const double t_sim = t_v * P.q_scale[q];
                 const double t_up = t_sim + P.q_eps[q] + 1e-6 * fabs(t_sim);
                 const double kth = s_kth;  // exact k-th best distance among the selected
@@ -422,8 +453,9 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
     __shared__ __align__(16) unsigned char s_raw[4][32][128 + 16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = p < npairs;
-    const int qi = live ? pair_query[p] : 0, ri = live ? pair_row[p] : 0;
+    const int qi = p < npairs ? pair_query[p] : 0, ri = p < npairs ? pair_row[p] : -1;
+    const bool live = ri >= 0;  // pairs the caller does not need carry row -1
+    if (__all_sync(0xffffffffu, !live)) return;
     const TQry *qp = queries + (int64_t)qi * d;
     double s = 0.0;
     const int nch = (d + CH - 1) / CH;
@@ -439,7 +471,8 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
             const int e0 = c * CH + part * (16 / (int)sizeof(TRow));
             uint4 val = make_uint4(0, 0, 0, 0);
             const TRow *src = rows + (int64_t)rj * d + e0;
-            if (vec && e0 + 16 / (int)sizeof(TRow) <= d) val = __ldg(reinterpret_cast<const uint4 *>(src));
+            if (rj < 0) {
+            } else if (vec && e0 + 16 / (int)sizeof(TRow) <= d) val = __ldg(reinterpret_cast<const uint4 *>(src));
             else {
                 alignas(16) TRow tmp[16 / sizeof(TRow)];
 #pragma unroll
@@ -463,6 +496,7 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
         }
     }
     if (live) out[p] = apply_epi(epi, s, q_norm ? q_norm[qi] : 0.0, row_norm ? row_norm[ri] : 0.0);
+    else if (p < npairs) out[p] = INFINITY;
 }
 
 __global__ void gather_bytes_kernel(const uint32_t *__restrict__ src, const int32_t *__restrict__ idx, int64_t n, int64_t row_words,
@@ -484,16 +518,21 @@ __global__ void first_column_kernel(const int64_t *__restrict__ pos, int64_t nq,
     if (q < nq) first[q] = pos[q * stride];
 }
 // seed thresholds from the sample pass: the kk-th best candidate of the sample is a row, so >= kk rows score at least that
+// ... and its k-th best candidate is a row too: a row more than `margin` below it can never enter the exact top-k
 __global__ void thr_from_sample_kernel(const double *__restrict__ sel_negv, const int32_t *__restrict__ cnt, int64_t nq, int kk,
-                                       int cap, float *__restrict__ thr) {
+                                       int cap, int k, const float *__restrict__ margin, float *__restrict__ thr) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const int c = cnt[q];
-    if (c >= kk && c <= cap) {
-        // -sel_negv is a float score widened to double: the conversion back is exact
-        const float t = (float)(-sel_negv[q * kk + kk - 1]);
-        if (t > thr[q]) thr[q] = t;
+    if (c > cap) return;
+    float t = thr[q];
+    // -sel_negv is a float score widened to double: the conversion back is exact
+    if (c >= kk) t = fmaxf(t, (float)(-sel_negv[q * kk + kk - 1]));
+    if (k <= kk && c >= k) {
+        const float sk = (float)(-sel_negv[q * kk + k - 1]);
+        t = fmaxf(t, sk - margin[q] - 4e-6f * fabsf(sk));
     }
+    thr[q] = t;
 }
 __global__ void and_flags_kernel(int32_t *__restrict__ ok, const int32_t *__restrict__ other, int64_t nq) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -557,9 +596,10 @@ void launch_first_column(const int64_t *pos, int64_t nq, int stride, int64_t *fi
     first_column_kernel<<<blocks_for(nq, 256), 256, 0, g_stream>>>(pos, nq, stride, first);
     HB_LAUNCH_CHECK();
 }
-void launch_thr_from_sample(const double *sel_negv, const int32_t *cnt, int64_t nq, int kk, int cap, float *thr) {
+void launch_thr_from_sample(const double *sel_negv, const int32_t *cnt, int64_t nq, int kk, int cap, int k, const float *margin,
+                            float *thr) {
     if (nq == 0) return;
-    thr_from_sample_kernel<<<blocks_for(nq, 256), 256, 0, g_stream>>>(sel_negv, cnt, nq, kk, cap, thr);
+    thr_from_sample_kernel<<<blocks_for(nq, 256), 256, 0, g_stream>>>(sel_negv, cnt, nq, kk, cap, k, margin, thr);
     HB_LAUNCH_CHECK();
 }
 void launch_and_flags(int32_t *ok, const int32_t *other, int64_t nq) {
@@ -640,17 +680,18 @@ void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int
 }
 
 void launch_query_bounds(const double *qu, const double *ql1, const double *qnorm, int64_t nq, int ns, int d, int metric,
-                         const float *stats, double *q_scale, double *q_eps) {
+                         const float *stats, double *q_scale, double *q_eps, float *q_margin) {
     if (nq == 0) return;
-    query_bounds_kernel<<<blocks_for(nq, 256), 256, 0, g_stream>>>(qu, ql1, qnorm, nq, ns, d, metric, stats, q_scale, q_eps);
+    query_bounds_kernel<<<blocks_for(nq, 256), 256, 0, g_stream>>>(qu, ql1, qnorm, nq, ns, d, metric, stats, q_scale, q_eps,
+                                                                   q_margin);
     HB_LAUNCH_CHECK();
 }
 
 void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const int32_t *cand_pos, int64_t nq, int kk, int cap,
-                          int32_t *pair_query, int32_t *pair_row) {
+                          int k, const float *margin, int32_t *pair_query, int32_t *pair_row) {
     if (nq * kk == 0) return;
-    rescore_pairs_kernel<<<blocks_for(nq * kk, 256), 256, 0, g_stream>>>(sel_pos, sel_negv, cand_pos, nq, kk, cap, pair_query,
-                                                                         pair_row);
+    rescore_pairs_kernel<<<blocks_for(nq * kk, 256), 256, 0, g_stream>>>(sel_pos, sel_negv, cand_pos, nq, kk, cap, k, margin,
+                                                                         pair_query, pair_row);
     HB_LAUNCH_CHECK();
 }
 

@@ -13,10 +13,11 @@
 //   warp 1      MMA issuer: one lane issues tcgen05.mma.kind::i8 (M = N = 128, K = 32) from shared-memory
 //               descriptors (K-major, SWIZZLE_128B), commits to the stage's "empty" barrier and, after the
 //               last k-block, to the "accumulators full" barrier; also owns the TMEM allocation;
-//   warps 2..5  epilogue: thread = query slot = TMEM lane; tcgen05.ld 16 columns (rows) at a time, combine
-//               the three digit-weight accumulators, apply the per-row scale (1/norm folded in) and append
-//               rows at or above the query's running threshold to its candidate list, while 32 two-deep
-//               buckets keep raising that threshold (it always has >= 64 emitted rows at or above it).
+//   warps 2..9  epilogue: thread = (query slot = TMEM lane, half of the tile's columns); tcgen05.ld 16 columns
+//               (rows) at a time, combine the three digit-weight accumulators, apply the per-row scale (1/norm
+//               folded in) and stash rows at or above the query's running threshold in shared memory (appended
+//               to the query's candidate list with one atomic per batch), while 2 x 16 two-deep buckets per
+//               slot keep raising that threshold (it always has >= 64 emitted rows at or above it).
 //               The score matrix never goes to HBM.
 // Work = items (unit, row tile); item ranges are split evenly across CTAs, consecutive items share the unit so
 // the A images stay hot in L2.
@@ -28,9 +29,12 @@
 namespace hb {
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 512;
-constexpr int NB = 32;  // threshold buckets (two best scores each: >= 64 rows at or above the bucket minimum)
+constexpr int NB = 16;     // threshold buckets per thread (two best scores each; two threads per query slot: >= 64 rows)
+constexpr int STASH = 8;   // candidates a thread keeps in shared memory before it appends them to the query's list
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -137,6 +141,29 @@ __device__ __forceinline__ int find_unit(const int32_t *__restrict__ item0, int 
     return lo;
 }
 
+// Appends a thread's stashed candidates (score, position inside the list) to its query's candidate list, at
+// `base_in` if the slots were reserved beforehand, else behind one atomic reservation.
+// Kept out of line: the epilogue must stay small.
+struct CandOut {
+    int32_t *cnt;
+    double *negv;
+    int32_t *rel, *pos;
+    int cap;
+};
+__device__ __noinline__ void flush_stash(const CandOut C, int qi, int rel0, int64_t list_row0, int n, int base_in,
+                                         const uint2 *stash) {
+    int base = base_in >= 0 ? base_in : atomicAdd(&C.cnt[qi], n);
+    for (int i = 0; i < n; ++i, ++base) {
+        if (base < C.cap) {
+            const uint2 e = stash[i * EPI_THREADS];
+            const int64_t o = (int64_t)qi * C.cap + base;
+            C.negv[o] = -(double)__uint_as_float(e.x);
+            C.rel[o] = rel0 + (int)e.y;
+            C.pos[o] = (int32_t)(list_row0 + (int)e.y);
+        }
+    }
+}
+
 template <int NS, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P) {
     using Cfg = TcCfg<NS>;
@@ -148,6 +175,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_rs[2][kFastTile];
     __shared__ float s_ro[2][kFastTile];
+    __shared__ float s_m[2][2][2][kFastTile];              // [item parity][second / first best][column half][slot]: bucket minima
+    __shared__ __align__(8) uint2 s_stash[STASH][EPI_THREADS];  // per-thread pending candidates (score bits, list position)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t stage0 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -163,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
             mbar_init(smem_u32(&s_empty[s]), 1);
         }
         mbar_init(smem_u32(&s_tmem_full), 1);
-        mbar_init(smem_u32(&s_tmem_empty), 4);
+        mbar_init(smem_u32(&s_tmem_empty), EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -238,112 +267,184 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
             }
         }
     } else {
-        // ===== epilogue: thread = query slot = TMEM lane =====
-        const int quarter = warp & 3;  // TMEM lanes this warp may touch: 32*quarter ..
+        // ===== epilogue: 8 warps; thread = (query slot = TMEM lane, half of the tile's 128 columns) =====
+        const int quarter = warp & 3;              // TMEM lanes this warp may touch: 32*quarter ..
+        const int half = (warp - 2) >> 2;          // columns 64*half ..
         const int slot = quarter * 32 + lane;
-        const int et = (warp - 2) * 32 + lane;  // 0..127, for cooperative loads
+        const int et = (warp - 2) * 32 + lane;     // 0..255
+        const uint2 *my_stash = &s_stash[0][et];
+        const CandOut C{P.cnt, P.cand_negv, P.cand_rel, P.cand_pos, P.cap};
+        const int kq = P.k;
         uint32_t tphase = 0;
         int u = item_begin < item_end ? find_unit(P.unit_item0, P.nunits, item_begin) : 0;
-        int qi = -1, rel0 = 0;
-        float thr = INFINITY;
-        // Running lower bound of the query's 64th best score: bucket b holds the two best scores among the rows
-        // with (row % NB == b) seen in this unit, so min_b(b2) has at least 2*NB = 64 rows at or above it.
+        int qi = -1, rel0 = 0, nst = 0, list_len = 0, resv = 0, resv_base = 0;
+        int64_t list_row0 = 0;
+        float thr = INFINITY, margin = INFINITY, pend_m1 = -INFINITY, pend_m2 = -INFINITY;
+        bool have_pend = false;
+        // Running lower bounds on the query's best scores.  Bucket b of this thread holds the two best scores among the
+        // rows with (column % NB == b) of its column half seen in this unit:
+        //   min_b(b2) has >= 2*NB = 32 rows at or above it, the minimum over the two threads of a slot 64 (all emitted:
+        //   the 64 re-scored candidates can be taken from them);
+        //   min_b(b1) has >= NB = 16 rows at or above it (32 over both threads): for k <= 16 (32) the k-th best score is at
+        //   least that, and a row more than `margin` (> 2 eps_q) below it can never enter the exact top-k.
         float b1[NB], b2[NB];
         int it = 0;
         for (int item = item_begin; item < item_end; ++item, ++it) {
             while (item >= P.unit_item0[u + 1]) ++u;
             const int t = (item - P.unit_item0[u]) * P.tile_stride;
-            const int ntu = P.unit_item0[u + 1] - P.unit_item0[u];
-            const bool last_of_unit = (item - P.unit_item0[u]) == ntu - 1 || item == item_end - 1;
-            if (item == item_begin || item == P.unit_item0[u]) {
-                qi = P.slot_query[(int64_t)u * kFastTile + slot];
-                rel0 = P.slot_rel0[(int64_t)u * kFastTile + slot];
-                if (MODE == FAST_EMIT) thr = qi >= 0 ? P.thr[qi] : INFINITY;
-                if (MODE != FAST_DUMP) {
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) b1[b] = b2[b] = -INFINITY;
-                }
-            }
+            const bool new_unit = item == item_begin || item == P.unit_item0[u];
             const int l = P.unit_list[u];
             const int64_t btile = P.tile_off[l] + t;
-            const int64_t row0 = P.list_off[l] + (int64_t)t * kFastTile;
             const int par = it & 1;
-            s_rs[par][et] = P.rs[btile * kFastTile + et];
-            s_ro[par][et] = P.ro[btile * kFastTile + et];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et < kFastTile) s_rs[par][et] = P.rs[btile * kFastTile + et] * 256.0f;
+            else s_ro[par][et - kFastTile] = P.ro[btile * kFastTile + et - kFastTile];
+            float thr_g = -INFINITY;
+            if (MODE == FAST_EMIT && !new_unit && qi >= 0) thr_g = P.thr[qi];  // raised meanwhile by other CTAs
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            bool flood = false;
+            if (MODE == FAST_EMIT) {
+                if (have_pend && qi >= 0) {
+                    // every row counted in the buckets was emitted under a threshold <= the new one, so raising thr keeps
+                    // "at least 64 candidates at or above thr" true
+                    float c = fminf(pend_m2, s_m[par ^ 1][0][half ^ 1][slot]);
+                    if (kq <= 2 * NB) {
+                        const float c1 = fminf(pend_m1, s_m[par ^ 1][1][half ^ 1][slot]);
+                        c = fmaxf(c, c1 - margin - 4e-6f * fabsf(c1));
+                    }
+                    if (c > thr) {
+                        thr = c;
+                        atomic_max_float(&P.thr[qi], thr);
+                    }
+                }
+                if (new_unit) {
+                    if (nst > 0) flush_stash(C, qi, rel0, list_row0, nst, -1, my_stash);
+                    nst = 0;
+                    qi = P.slot_query[(int64_t)u * kFastTile + slot];
+                    rel0 = P.slot_rel0[(int64_t)u * kFastTile + slot];
+                    list_row0 = P.list_off[l];
+                    list_len = (int)(P.list_off[l + 1] - list_row0);
+                    thr = qi >= 0 ? P.thr[qi] : INFINITY;
+                    margin = qi >= 0 ? P.margin[qi] : INFINITY;
+                    have_pend = false;
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) b1[b] = b2[b] = -INFINITY;
+                } else {
+                    thr = fmaxf(thr, thr_g);
+                }
+                // no bound yet: every real row of this tile will be a candidate -- reserve their slots now, so that the
+                // round trip of the atomic overlaps the wait for the accumulators
+                flood = qi >= 0 && thr == -INFINITY;
+                if (flood) {
+                    if (nst > 0) flush_stash(C, qi, rel0, list_row0, nst, -1, my_stash);
+                    nst = 0;
+                    resv = min(max(list_len - t * kFastTile - half * 64, 0), 64);
+                    resv_base = resv > 0 ? atomicAdd(&P.cnt[qi], resv) : 0;
+                }
+            }
             mbar_wait(smem_u32(&s_tmem_full), tphase);
             tc_fence_after();
             tphase ^= 1u;
-            const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-            // 4 x 32 columns; NOT fully unrolled: the body must stay inside the instruction cache (one warp per
-            // scheduler cannot hide instruction-fetch misses).  Within a 32-column step the bucket of column
-            // (h*16 + j) is a compile-time register.
-#pragma unroll 1
-            for (int c32 = 0; c32 < kFastTile / 32; ++c32) {
+            const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
+            // phase A: accumulators -> one fp32 score per column, in registers; then the accumulators are free again
+            float v[64];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int col0 = c32 * 32 + h * 16;
-                    uint32_t c0[16], c1[16], c2[16];
-                    tmem_ld16(tlane + col0, c0);
-                    tmem_ld16(tlane + kFastTile + col0, c1);
-                    tmem_ld16(tlane + 2 * kFastTile + col0, c2);
-                    tmem_ld_wait();
-                    float v[16];
+            for (int c16 = 0; c16 < 4; ++c16) {
+                uint32_t c0[16], c1[16], c2[16];
+                tmem_ld16(tlane + c16 * 16, c0);
+                tmem_ld16(tlane + kFastTile + c16 * 16, c1);
+                tmem_ld16(tlane + 2 * kFastTile + c16 * 16, c2);
+                tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float s = fmaf((float)(int)c0[j], 65536.0f, fmaf((float)(int)c1[j], 256.0f, (float)(int)c2[j]));
-                        v[j] = fmaf(s, s_rs[par][col0 + j], s_ro[par][col0 + j]);
-                    }
-                    if (MODE != FAST_DUMP) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int b = h * 16 + j;
-                            const float lo = fminf(b1[b], v[j]);
-                            b1[b] = fmaxf(b1[b], v[j]);
-                            b2[b] = fmaxf(b2[b], lo);
-                        }
-                    }
-                    if (MODE == FAST_EMIT) {
-                        uint32_t mask = 0;
-                        const float cut = fmaxf(thr, -FLT_MAX);  // padding rows score -inf: never candidates
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) mask |= (v[j] >= cut ? 1u : 0u) << j;
-                        if (mask) {
-                            int base = atomicAdd(&P.cnt[qi], __popc(mask));
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                if ((mask >> j) & 1u) {
-                                    if (base < P.cap) {
-                                        const int64_t o = (int64_t)qi * P.cap + base;
-                                        P.cand_negv[o] = -(double)v[j];
-                                        P.cand_rel[o] = rel0 + t * kFastTile + col0 + j;
-                                        P.cand_pos[o] = (int32_t)(row0 + col0 + j);
-                                    }
-                                    ++base;
-                                }
-                            }
-                        }
-                    } else if (MODE == FAST_DUMP) {
-                        float *o = P.dump + ((int64_t)item * kFastTile + slot) * kFastTile + col0;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = v[j];
-                    }
+                for (int j = 0; j < 16; ++j) {
+                    // S / 256 = c0 * 256 + c1 + c2 / 256; the dropped fraction is bounded in eps_q (query_bounds_kernel)
+                    const int lo = (int)c1[j] + ((int)c2[j] >> 8);
+                    const float s = fmaf((float)(int)c0[j], 256.0f, (float)lo);
+                    const int col = half * 64 + c16 * 16 + j;
+                    v[c16 * 16 + j] = fmaf(s, s_rs[par][col], s_ro[par][col]);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_tmem_empty));
-            if (MODE != FAST_DUMP && qi >= 0) {
-                // every row counted in the buckets was emitted (EMIT) under a threshold <= the new one, so raising
-                // thr keeps "at least 64 candidates at or above thr" true
-                float m = b2[0];
+            // phase B: thresholds and candidates
+            if (MODE == FAST_EMIT) {
+                const float cut = fmaxf(thr, -FLT_MAX);  // padding rows score -inf: never candidates
 #pragma unroll
-                for (int b = 1; b < NB; ++b) m = fminf(m, b2[b]);
-                thr = fmaxf(thr, m);
-                if (last_of_unit) {
-                    if (thr > -INFINITY) atomic_max_float(&P.thr[qi], thr);
+                for (int g = 0; g < 8; ++g) {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int j = g * 8 + jj, b = j % NB;
+                        const float lo = fminf(b1[b], v[j]);
+                        b1[b] = fmaxf(b1[b], v[j]);
+                        b2[b] = fmaxf(b2[b], lo);
+                        mask |= (v[j] >= cut ? 1u : 0u) << jj;
+                    }
+                    // the whole warp empties its stashes together: one round trip of the atomics instead of one per lane
+                    if (__any_sync(0xffffffffu, nst + __popc(mask) > STASH)) {
+                        if (nst > 0) {
+                            flush_stash(C, qi, rel0, list_row0, nst, flood ? resv_base : -1, my_stash);
+                            if (flood) {
+                                resv_base += nst;
+                                resv -= nst;
+                            }
+                            nst = 0;
+                        }
+                    }
+                    if (mask) {
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            if ((mask >> jj) & 1u) {
+                                s_stash[nst][et] =
+                                    make_uint2(__float_as_uint(v[g * 8 + jj]), (uint32_t)(t * kFastTile + half * 64 + g * 8 + jj));
+                                ++nst;
+                            }
+                        }
+                    }
                 }
+                if (flood) {
+                    if (nst > 0) flush_stash(C, qi, rel0, list_row0, nst, resv_base, my_stash);
+                    // the reservation assumed that exactly the real rows pass; anything else sends the query to the exact path
+                    if (resv != nst) atomicAdd(&P.cnt[qi], P.cap + 1);
+                    nst = 0;
+                    resv = 0;
+                }
+                float m1 = b1[0], m2 = b2[0];
+#pragma unroll
+                for (int b = 1; b < NB; ++b) {
+                    m1 = fminf(m1, b1[b]);
+                    m2 = fminf(m2, b2[b]);
+                }
+                s_m[par][0][half][slot] = m2;
+                s_m[par][1][half][slot] = m1;
+                pend_m1 = m1;
+                pend_m2 = m2;
+                have_pend = true;
+                if (kq <= NB && qi >= 0) {
+                    const float c = m1 - margin - 4e-6f * fabsf(m1);
+                    if (c > thr) {
+                        thr = c;
+                        atomic_max_float(&P.thr[qi], thr);
+                    }
+                }
+            } else {
+                float *o = P.dump + ((int64_t)item * kFastTile + slot) * kFastTile + half * 64;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) o[j] = v[j];
             }
+        }
+        if (MODE == FAST_EMIT) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (have_pend && qi >= 0) {
+                const int pp = (it - 1) & 1;
+                float c = fminf(pend_m2, s_m[pp][0][half ^ 1][slot]);
+                if (kq <= 2 * NB) {
+                    const float c1 = fminf(pend_m1, s_m[pp][1][half ^ 1][slot]);
+                    c = fmaxf(c, c1 - margin - 4e-6f * fabsf(c1));
+                }
+                if (c > thr) atomic_max_float(&P.thr[qi], c);
+            }
+            if (nst > 0) flush_stash(C, qi, rel0, list_row0, nst, -1, my_stash);
         }
     }
 

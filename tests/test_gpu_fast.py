@@ -61,12 +61,12 @@ def emulate_scores(rows, queries, ns, cosine):
         for b in range(ns):
             if a + b <= 2:
                 c[a + b] += dq[a] @ dr[b].T
-    # fmaf(f(c0), 65536, fmaf(f(c1), 256, f(c2))): products by powers of two are exact, one rounding per fma
-    inner = (c[1].astype(np.float32).astype(np.float64) * 256.0 + c[2].astype(np.float32).astype(np.float64)).astype(np.float32)
-    s = (c[0].astype(np.float32).astype(np.float64) * 65536.0 + inner.astype(np.float64)).astype(np.float32)
+    # epilogue of hb_tc.cu: lo = c1 + (c2 >> 8) in int32; s = fmaf(f(c0), 256, f(lo)); v = s * (rs * 256)
+    lo = (c[1] + (c[2] >> 8)).astype(np.int32)
+    s = (c[0].astype(np.float32).astype(np.float64) * 256.0 + lo.astype(np.float32).astype(np.float64)).astype(np.float32)
     rn = orc.row_norms(rows) if cosine else np.ones(len(rows))
     rs = (ur * (1.0 / rn) * (1.0 if ns == 2 else 65536.0)).astype(np.float32)
-    v = (s.astype(np.float64) * rs.astype(np.float64)[None, :]).astype(np.float32)
+    v = (s.astype(np.float64) * (rs.astype(np.float64) * 256.0)[None, :]).astype(np.float32)
     qn = orc.row_norms(queries) if cosine else np.ones(len(queries))
     return v, uq * (1.0 / qn)
 

@@ -217,6 +217,7 @@ struct FastSideBufs {
 static bool g_fast_debug = false;
 static bool g_tc_interleave = true;
 static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
+static int g_fast_sample_tiles = 2;  // IVF: row tiles of the nearest list scored by the threshold-seeding pass
 static int64_t g_fast_queries = 0;   // queries answered in FAST mode ...
 static int64_t g_fast_fallbacks = 0; // ... of which recomputed by the exact path (proof failed)
 static int64_t g_hnsw_scored = 0;    // (query, row) pairs scored by the HNSW search since "profile" was set
@@ -609,13 +610,13 @@ static void ivf_finalize(hb_index *ix, const void *rows_dev, const double *row_n
 // HB_MODE_FAST orchestration (scheme: hb_fast.cuh)
 // =================================================================================================
 struct FastWs {
-    DevBuf dig, qu, ql1, qscale, qeps, qmargin, thr, cnt, cnegv, crel, cpos, selval, selpos, pq, pr, exact;
+    DevBuf dig, q64, pslot, srow, ptotal, qu, ql1, qscale, qeps, qmargin, thr, cnt, cnegv, crel, cpos, selval, selpos, pq, pr, exact;
     DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_slotq, u_slotrel;
     DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_slotq, t_slotrel;
     DevBuf ppos, ppos0, ok_a, ok_b, relk, probes0, pair_out0, qsel0, lq_off0, uprefix0, uprefix, flat_plan, idx, gq, gids, gdist,
         tmp2;
     void release() {
-        DevBuf *all[] = {&dig, &qu, &ql1, &qscale, &qeps, &qmargin, &thr, &cnt, &cnegv, &crel, &cpos, &selval, &selpos, &pq, &pr, &exact,
+        DevBuf *all[] = {&dig, &q64, &pslot, &srow, &ptotal, &qu, &ql1, &qscale, &qeps, &qmargin, &thr, &cnt, &cnegv, &crel, &cpos, &selval, &selpos, &pq, &pr, &exact,
                          &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_slotq, &u_slotrel,
                          &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_slotq, &t_slotrel,
                          &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
@@ -711,6 +712,7 @@ struct FastJob {
     const double *row_norm = nullptr;
     const void *queries = nullptr;
     int qdtype = HB_F32;
+    const double *q64 = nullptr;  // the queries widened to fp64 (launch_widen_queries)
     int64_t nq = 0;
     const double *qn = nullptr;
     int d = 0;
@@ -840,8 +842,11 @@ static void fast_topk(const FastJob &J) {
     {
         Prof pr(J.profile ? PROF_RESCORE : -1);
         int32_t *pq = W.pq.as<int32_t>((size_t)nq * kk), *prow = W.pr.as<int32_t>((size_t)nq * kk);
-        launch_rescore_pairs(selpos, selval, cpos, nq, kk, cap, J.k, qmargin, pq, prow);
-        launch_rescore(J.rows_exact, J.rdtype, J.row_norm, J.queries, J.qdtype, J.qn, J.d, pq, prow, nq * kk, J.epi, exact);
+        int32_t *pslot = W.pslot.as<int32_t>((size_t)nq * kk), *srow = W.srow.as<int32_t>((size_t)nq * kk);
+        int32_t *ptotal = W.ptotal.as<int32_t>(1);
+        launch_rescore_pairs(selpos, selval, cpos, nq, kk, cap, J.k, qmargin, srow, exact, ptotal, pq, prow, pslot);
+        launch_rescore(J.rows_exact, J.rdtype, J.row_norm, J.q64, J.qdtype == HB_F32, J.qn, J.d, pq, prow, pslot, ptotal, nq * kk, J.epi,
+                       exact);
         FinalParams F;
         F.nq = nq;
         F.k = J.k;
@@ -850,7 +855,7 @@ static void fast_topk(const FastJob &J) {
         F.sel_pos = selpos;
         F.sel_negv = selval;
         F.exact = exact;
-        F.pair_row = prow;
+        F.pair_row = srow;
         F.cand_rel = crel;
         F.cnt = cnt;
         F.thr = thr;
@@ -874,6 +879,11 @@ static void fast_topk(const FastJob &J) {
         HB_CUDA(cudaMemcpyAsync(hsel.data(), selval, (size_t)nq * kk * 8, cudaMemcpyDeviceToHost, g_stream));
         HB_CUDA(cudaMemcpyAsync(hex.data(), exact, (size_t)nq * kk * 8, cudaMemcpyDeviceToHost, g_stream));
         sync_stream();
+        std::vector<int32_t> hpr((size_t)nq * kk);
+        HB_CUDA(cudaMemcpy(hpr.data(), W.srow.p, (size_t)nq * kk * 4, cudaMemcpyDeviceToHost));
+        int64_t nres = 0;
+        for (int32_t r : hpr) nres += r >= 0;
+        fprintf(stderr, "[hb fast] re-scored %.1f of %d selected candidates per query\n", (double)nres / nq, kk);
         int64_t nok = 0, over = 0, cmin = 1 << 30, cmax = 0, csum = 0;
         for (int64_t q = 0; q < nq; ++q) {
             nok += hok[q];
@@ -960,6 +970,7 @@ static void flat_search_fast(hb_index *ix, const void *queries, int qdtype, int6
         double *qn = g_ws.qnorm.as<double>(nqc);
         launch_row_norms(qptr, qdtype, nqc, d, qn);
         fast_quant_queries(qptr, qdtype, nqc, d);
+        const double *q64 = launch_widen_queries(qptr, qdtype, nqc * d, g_fw.q64.as<double>((size_t)nqc * d));
         FastJob J;
         J.side = &S;
         J.list_off = (const int64_t *)S.list_off.p;
@@ -968,6 +979,7 @@ static void flat_search_fast(hb_index *ix, const void *queries, int qdtype, int6
         J.row_norm = cosine ? (const double *)ix->norms.p : nullptr;
         J.queries = qptr;
         J.qdtype = qdtype;
+        J.q64 = q64;
         J.nq = nqc;
         J.qn = qn;
         J.d = d;
@@ -1017,6 +1029,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         double *qn = g_ws.qnorm.as<double>(nqc);
         launch_row_norms(qptr, qdtype, nqc, d, qn);
         fast_quant_queries(qptr, qdtype, nqc, d);
+        const double *q64 = launch_widen_queries(qptr, qdtype, nqc * d, g_fw.q64.as<double>((size_t)nqc * d));
         int64_t *ppos = W.ppos.as<int64_t>((size_t)nqc * np_eff);
         int32_t *ok_c = W.ok_b.as<int32_t>(nqc);
         if (coarse_tc) {
@@ -1029,6 +1042,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
             J.row_norm = (const double *)ix->cent_norm.p;
             J.queries = qptr;
             J.qdtype = qdtype;
+            J.q64 = q64;
             J.nq = nqc;
             J.qn = qn;
             J.d = d;
@@ -1117,6 +1131,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         J.row_norm = (const double *)ix->norms.p;
         J.queries = qptr;
         J.qdtype = qdtype;
+        J.q64 = q64;
         J.nq = nqc;
         J.qn = qn;
         J.d = d;
@@ -1137,7 +1152,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         J.thresh.pair_out = nullptr;
         J.thresh.pair_div = 1;
         set_units(J.thresh, nu0, false);
-        J.thresh.tile_limit = 4;
+        J.thresh.tile_limit = g_fast_sample_tiles;
         J.shared_units = false;
         J.out_rel = relk;
         J.out_dist = dist + (size_t)q0 * k;
@@ -1290,6 +1305,9 @@ HB_API int hb_set_option(const char *name, int64_t value) {
         } else if (!strcmp(name, "fast_digits")) {
             HB_REQUIRE(value == 2 || value == 3, "fast_digits must be 2 or 3");
             g_fast_ns = (int)value;
+        } else if (!strcmp(name, "fast_sample_tiles")) {
+            HB_REQUIRE(value >= 1 && value <= 64, "fast_sample_tiles must be 1..64");
+            g_fast_sample_tiles = (int)value;
         } else if (!strcmp(name, "cuda_profiler")) {
             // brackets the region `ncu --profile-from-start off` captures (bench.py: the timed steps only)
             ensure_init();

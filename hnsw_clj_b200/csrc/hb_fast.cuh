@@ -128,15 +128,20 @@ void launch_fast_final(const FinalParams &P);
 // per query: q_scale = u_q / ||q|| (cosine) or u_q (ip); q_eps from the index stats
 void launch_query_bounds(const double *qu, const double *ql1, const double *qnorm, int64_t nq, int ns, int d, int metric,
                          const float *stats, double *q_scale, double *q_eps, float *q_margin);
-// pairs for the exact re-score: pair_query[q*kk+j] = q, pair_row = cand_pos[q][sel_pos] (or 0 with valid=0)
+// pairs for the exact re-score: per selected slot the row or -1 (slot_row), exact = +inf where not re-scored, and the
+// dense list of wanted (query, row, slot) triples with its length in *total
 void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const int32_t *cand_pos, int64_t nq, int kk, int cap,
-                          int k, const float *margin, int32_t *pair_query, int32_t *pair_row);
+                          int k, const float *margin, int32_t *slot_row, double *exact, int32_t *total, int32_t *pair_query,
+                          int32_t *pair_row, int32_t *pair_slot);
 // kk best of the min(cnt, cap) candidates of every query (ascending -score); unused slots: pos -1, +inf
 void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq, int kk, int cap, double *sel_negv,
                         int64_t *sel_pos);
 // exact fp64 distance of (query, row) pairs in the reference's summation order (cosine / -dot epilogues, no L2)
-void launch_rescore(const void *rows, int rdtype, const double *row_norm, const void *queries, int qdtype, const double *q_norm,
-                    int d, const int32_t *pair_query, const int32_t *pair_row, int64_t npairs, int epi, double *out);
+void launch_rescore(const void *rows, int rdtype, const double *row_norm, const double *queries64, bool q_f32_repr,
+                    const double *q_norm, int d, const int32_t *pair_query, const int32_t *pair_row, const int32_t *pair_slot,
+                    const int32_t *total, int64_t max_pairs, int epi, double *out);
+// fp64 copy of the queries for the re-score (returns `queries` itself when they already are fp64)
+const double *launch_widen_queries(const void *queries, int qdtype, int64_t count, double *buf);
 // fallback plumbing: dst[i] = src[idx[i]] (rows of row_bytes, multiple of 4) and dst[idx[i]] = src[i] (rows of k 8-byte words)
 void launch_gather_bytes(const void *src, const int32_t *idx, int64_t n, int64_t row_bytes, void *dst);
 void launch_scatter_rows64(const void *src, const int32_t *idx, int64_t n, int k, void *dst);

@@ -299,26 +299,50 @@ __global__ void query_bounds_kernel(const double *__restrict__ qu, const double 
 
 // unused candidate slots hold +inf (-score): the selection may return them when a query has fewer than kk candidates
 // Only the candidates that can still reach the exact top-k are re-scored: the k best by approximate score and every
-// further one within `margin` (> 2 eps_q) of the k-th.  The others get pair_row = -1 and count as rejected rows in
-// fast_final_kernel's proof.
-__global__ void rescore_pairs_kernel(const int64_t *__restrict__ sel_pos, const double *__restrict__ sel_negv,
-                                     const int32_t *__restrict__ cand_pos, int64_t nq, int kk, int cap, int k,
-                                     const float *__restrict__ margin, int32_t *__restrict__ pair_query,
-                                     int32_t *__restrict__ pair_row) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq * kk) return;
-    const int64_t q = i / kk;
-    const int j = (int)(i - q * kk);
-    const int64_t p = sel_pos[i];
-    const double nv = sel_negv[i];
-    bool want = p >= 0 && nv < INFINITY;
-    if (want && j >= k) {
-        const double nk = sel_negv[q * kk + k - 1];  // the list is ascending in -score
-        const double m = (double)margin[q] + 4e-6 * fabs(nk);
-        want = !(nk < INFINITY) || nv <= nk + m;
+// further one within `margin` (> 2 eps_q) of the k-th.  One warp per query writes, per selected slot, the row (or -1:
+// not re-scored, counted as a rejected row in fast_final_kernel's proof; its exact distance reads +inf) and appends the
+// wanted (query, row, slot) triples to a dense pair list, so that the re-score kernel runs full warps.
+__global__ void __launch_bounds__(256) rescore_pairs_kernel(const int64_t *__restrict__ sel_pos, const double *__restrict__ sel_negv,
+                                                            const int32_t *__restrict__ cand_pos, int64_t nq, int kk, int cap, int k,
+                                                            const float *__restrict__ margin, int32_t *__restrict__ slot_row,
+                                                            double *__restrict__ exact, int32_t *__restrict__ total,
+                                                            int32_t *__restrict__ pair_query, int32_t *__restrict__ pair_row,
+                                                            int32_t *__restrict__ pair_slot) {
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const double nk = k <= kk ? sel_negv[q * kk + k - 1] : INFINITY;  // the list is ascending in -score
+    const double lim = nk + (double)margin[q] + 4e-6 * fabs(nk);
+    int row[2] = {-1, -1};
+    int nwant = 0;
+    unsigned bal[2] = {0u, 0u};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = h * 32 + lane;
+        bool want = false;
+        if (j < kk) {
+            const int64_t p = sel_pos[q * kk + j];
+            const double nv = sel_negv[q * kk + j];
+            want = p >= 0 && nv < INFINITY && (j < k || !(nk < INFINITY) || nv <= lim);
+            if (want) row[h] = cand_pos[q * cap + p];
+            slot_row[q * kk + j] = row[h];
+            if (!want) exact[q * kk + j] = INFINITY;
+        }
+        bal[h] = __ballot_sync(0xffffffffu, want);
+        nwant += __popc(bal[h]);
     }
-    pair_query[i] = (int32_t)q;
-    pair_row[i] = want ? cand_pos[q * cap + p] : -1;
+    int base = 0;
+    if (lane == 0 && nwant > 0) base = atomicAdd(total, nwant);
+    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (row[h] >= 0) {
+            const int o = base + (h ? __popc(bal[0]) : 0) + __popc(bal[h] & ((1u << lane) - 1u));
+            pair_query[o] = (int32_t)q;
+            pair_row[o] = row[h];
+            pair_slot[o] = (int32_t)(q * kk + h * 32 + lane);
+        }
+    }
 }
 
 // One CTA (128 threads) per query.  Entry j < kk: exact distance + rel; rank by (distance key, rel).
@@ -441,62 +465,120 @@ __global__ void __launch_bounds__(256) cand_select_kernel(const double *__restri
 
 // ---- exact re-score of (query, row) pairs: one thread per pair walks the reference's sequential fp64 sum
 // (src/hnsw/ultra_fast.clj:53-95, ivf_flat.clj:224-226); a warp stages its 32 rows chunk by chunk through shared
-// memory with full-line loads (the rows are scattered, 3-6 KB each), queries are read directly (one query per
-// group of kk pairs: broadcast).
-template <typename TRow, typename TQry, int ARITH>
+// memory with full-line loads (the rows are scattered, 3-6 KB each); the queries were widened to fp64 once per call
+// (one query per group of kk pairs: broadcast loads).
+template <typename T>
+struct Widen;
+template <>
+struct Widen<float> {
+    static constexpr int PER = 4;  // elements per 16 bytes
+    __device__ static __forceinline__ double at(const uint4 &v, int e) {
+        return (double)__uint_as_float(e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w);
+    }
+};
+template <>
+struct Widen<__nv_bfloat16> {
+    static constexpr int PER = 8;
+    __device__ static __forceinline__ double at(const uint4 &v, int e) {
+        const uint32_t w = (e >> 1) == 0 ? v.x : (e >> 1) == 1 ? v.y : (e >> 1) == 2 ? v.z : v.w;
+        return (double)__uint_as_float((e & 1) ? (w & 0xFFFF0000u) : (w << 16));
+    }
+};
+template <>
+struct Widen<double> {
+    static constexpr int PER = 2;
+    __device__ static __forceinline__ double at(const uint4 &v, int e) {
+        return e == 0 ? __hiloint2double((int)v.y, (int)v.x) : __hiloint2double((int)v.w, (int)v.z);
+    }
+};
+
+template <typename TRow, int ARITH>
 __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ rows, const double *__restrict__ row_norm,
-                                                      const TQry *__restrict__ queries, const double *__restrict__ q_norm, int d,
+                                                      const double *__restrict__ queries, const double *__restrict__ q_norm, int d,
                                                       const int32_t *__restrict__ pair_query, const int32_t *__restrict__ pair_row,
-                                                      int64_t npairs, int epi, double *__restrict__ out) {
+                                                      const int32_t *__restrict__ pair_slot, const int32_t *__restrict__ total,
+                                                      int epi, double *__restrict__ out) {
     constexpr int CH = 128 / (int)sizeof(TRow);  // elements per 128-byte chunk
-    constexpr int LPR = 8;                        // lanes per row chunk (16 B each)
+    constexpr int EPL = 16 / (int)sizeof(TRow);  // elements per lane and round (16 B)
+    constexpr int PER = Widen<TRow>::PER;
     __shared__ __align__(16) unsigned char s_raw[4][32][128 + 16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int qi = p < npairs ? pair_query[p] : 0, ri = p < npairs ? pair_row[p] : -1;
-    const bool live = ri >= 0;  // pairs the caller does not need carry row -1
-    if (__all_sync(0xffffffffu, !live)) return;
-    const TQry *qp = queries + (int64_t)qi * d;
-    double s = 0.0;
+    const int npairs = *total;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p - lane >= npairs) return;  // whole warp past the end of the pair list
+    const bool live = p < npairs;
+    const int qi = live ? pair_query[p] : 0, ri = live ? pair_row[p] : -1;
+    const double *qp = queries + (int64_t)qi * d;
     const int nch = (d + CH - 1) / CH;
     const bool vec = (((size_t)d * sizeof(TRow)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0);
-    for (int c = 0; c < nch; ++c) {
-        // cooperative load: row j of the warp's 32 pairs, its 128-byte chunk c, by lanes (j%4)*8 .. +7 over 8 rounds
-        __syncwarp();
+    const bool qvec = (d % 2 == 0) && ((reinterpret_cast<uintptr_t>(queries) & 15) == 0);
+    // cooperative loads: in round r, lanes 8*(j%4) .. +7 fetch the 128-byte chunk of the warp's row j = 4*r + lane/8
+    const int part = lane & 7;
+    const TRow *src[8];
 #pragma unroll
-        for (int round = 0; round < 32 / (32 / LPR); ++round) {
-            const int j = round * (32 / LPR) + lane / LPR;
-            const int part = lane % LPR;
-            const int rj = __shfl_sync(0xffffffffu, ri, j);
-            const int e0 = c * CH + part * (16 / (int)sizeof(TRow));
+    for (int r = 0; r < 8; ++r) {
+        const int rj = __shfl_sync(0xffffffffu, ri, r * 4 + (lane >> 3));
+        src[r] = rj >= 0 ? rows + (int64_t)rj * d : nullptr;
+    }
+    uint4 pre[8];
+    auto fetch = [&](int c) {
+        const int e0 = c * CH + part * EPL;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
             uint4 val = make_uint4(0, 0, 0, 0);
-            const TRow *src = rows + (int64_t)rj * d + e0;
-            if (rj < 0) {
-            } else if (vec && e0 + 16 / (int)sizeof(TRow) <= d) val = __ldg(reinterpret_cast<const uint4 *>(src));
+            if (src[r] == nullptr) {
+            } else if (vec && e0 + EPL <= d) val = __ldg(reinterpret_cast<const uint4 *>(src[r] + e0));
             else {
-                alignas(16) TRow tmp[16 / sizeof(TRow)];
+                alignas(16) TRow tmp[EPL];
 #pragma unroll
-                for (int e = 0; e < 16 / (int)sizeof(TRow); ++e) tmp[e] = (e0 + e < d) ? src[e] : TRow(0.0f);
+                for (int e = 0; e < EPL; ++e) tmp[e] = (e0 + e < d) ? src[r][e0 + e] : TRow(0.0f);
                 val = *reinterpret_cast<uint4 *>(tmp);
             }
-            *reinterpret_cast<uint4 *>(&s_raw[warp][j][part * 16]) = val;
+            pre[r] = val;
         }
+    };
+    fetch(0);
+    double s = 0.0;
+    for (int c = 0; c < nch; ++c) {
         __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) *reinterpret_cast<uint4 *>(&s_raw[warp][r * 4 + (lane >> 3)][part * 16]) = pre[r];
+        __syncwarp();
+        if (c + 1 < nch) fetch(c + 1);  // in flight while this chunk is accumulated
         // own row chunk back as 128-bit reads (row stride 144 B: conflict-free per quarter warp)
         const uint4 *mine = reinterpret_cast<const uint4 *>(&s_raw[warp][lane][0]);
-        constexpr int PER = 16 / (int)sizeof(TRow);
         const int kmax = min(CH, d - c * CH);
+        if (live) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const uint4 bits = mine[w];
-            const TRow *el = reinterpret_cast<const TRow *>(&bits);
+            for (int w = 0; w < 8; ++w) {
+                const uint4 bits = mine[w];
 #pragma unroll
-            for (int e = 0; e < PER; ++e)
-                if (w * PER + e < kmax) s = mac_seq<ARITH>(to_f64(qp[c * CH + w * PER + e]), to_f64(el[e]), s);
+                for (int e = 0; e < PER; e += 2) {
+                    const int i0 = w * PER + e;
+                    if (i0 < kmax) {
+                        double q0, q1 = 0.0;
+                        if (qvec && i0 + 1 < kmax) {
+                            const double2 qq = __ldg(reinterpret_cast<const double2 *>(qp + c * CH + i0));
+                            q0 = qq.x;
+                            q1 = qq.y;
+                        } else {
+                            q0 = qp[c * CH + i0];
+                            if (i0 + 1 < kmax) q1 = qp[c * CH + i0 + 1];
+                        }
+                        s = mac_seq<ARITH>(q0, Widen<TRow>::at(bits, e), s);
+                        if (i0 + 1 < kmax) s = mac_seq<ARITH>(q1, Widen<TRow>::at(bits, e + 1), s);
+                    }
+                }
+            }
         }
     }
-    if (live) out[p] = apply_epi(epi, s, q_norm ? q_norm[qi] : 0.0, row_norm ? row_norm[ri] : 0.0);
-    else if (p < npairs) out[p] = INFINITY;
+    if (live) out[pair_slot[p]] = apply_epi(epi, s, q_norm ? q_norm[qi] : 0.0, row_norm ? row_norm[ri] : 0.0);
+}
+
+template <typename T>
+__global__ void widen_queries_kernel(const T *__restrict__ in, int64_t count, double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = to_f64(in[i]);
 }
 
 __global__ void gather_bytes_kernel(const uint32_t *__restrict__ src, const int32_t *__restrict__ idx, int64_t n, int64_t row_words,
@@ -550,33 +632,45 @@ void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq,
 }
 
 namespace {
-template <typename TRow, typename TQry>
-void rescore_arith(const void *rows, const double *row_norm, const void *queries, const double *q_norm, int d, const int32_t *pq,
-                   const int32_t *pr, int64_t npairs, int epi, double *out) {
-    const int grid = blocks_for(npairs, 128);
-    constexpr bool exact = is_f32_repr<TRow>::value && is_f32_repr<TQry>::value;
-    if (exact)
-        rescore_kernel<TRow, TQry, ARITH_FMA><<<grid, 128, 0, g_stream>>>((const TRow *)rows, row_norm, (const TQry *)queries, q_norm,
-                                                                           d, pq, pr, npairs, epi, out);
+template <typename TRow>
+void rescore_arith(const void *rows, const double *row_norm, const double *queries, bool q_f32_repr, const double *q_norm, int d,
+                   const int32_t *pq, const int32_t *pr, const int32_t *ps, const int32_t *total, int64_t max_pairs, int epi,
+                   double *out) {
+    const int grid = blocks_for(max_pairs, 128);
+    // both factors fp32-representable: the fp64 product is exact, DFMA rounds like multiply-then-add
+    if (is_f32_repr<TRow>::value && q_f32_repr)
+        rescore_kernel<TRow, ARITH_FMA><<<grid, 128, 0, g_stream>>>((const TRow *)rows, row_norm, queries, q_norm, d, pq, pr, ps, total,
+                                                                     epi, out);
     else
-        rescore_kernel<TRow, TQry, ARITH_MULADD><<<grid, 128, 0, g_stream>>>((const TRow *)rows, row_norm, (const TQry *)queries,
-                                                                              q_norm, d, pq, pr, npairs, epi, out);
+        rescore_kernel<TRow, ARITH_MULADD><<<grid, 128, 0, g_stream>>>((const TRow *)rows, row_norm, queries, q_norm, d, pq, pr, ps,
+                                                                        total, epi, out);
     HB_LAUNCH_CHECK();
 }
 }  // namespace
 
-void launch_rescore(const void *rows, int rdtype, const double *row_norm, const void *queries, int qdtype, const double *q_norm,
-                    int d, const int32_t *pair_query, const int32_t *pair_row, int64_t npairs, int epi, double *out) {
-    if (npairs == 0) return;
-#define HB_RS(TR_, TQ_) rescore_arith<TR_, TQ_>(rows, row_norm, queries, q_norm, d, pair_query, pair_row, npairs, epi, out)
-    if (rdtype == HB_F32 && qdtype == HB_F32) HB_RS(float, float);
-    else if (rdtype == HB_F32 && qdtype == HB_F64) HB_RS(float, double);
-    else if (rdtype == HB_BF16 && qdtype == HB_F32) HB_RS(__nv_bfloat16, float);
-    else if (rdtype == HB_BF16 && qdtype == HB_F64) HB_RS(__nv_bfloat16, double);
-    else if (rdtype == HB_F64 && qdtype == HB_F32) HB_RS(double, float);
-    else if (rdtype == HB_F64 && qdtype == HB_F64) HB_RS(double, double);
+// queries64: the queries widened to fp64 (launch_widen_queries); q_f32_repr: they hold fp32-representable values.
+// The dense pair list (pair_query / pair_row / pair_slot, *total entries, at most max_pairs) comes from
+// launch_rescore_pairs; out[pair_slot] receives the distance.
+void launch_rescore(const void *rows, int rdtype, const double *row_norm, const double *queries64, bool q_f32_repr,
+                    const double *q_norm, int d, const int32_t *pair_query, const int32_t *pair_row, const int32_t *pair_slot,
+                    const int32_t *total, int64_t max_pairs, int epi, double *out) {
+    if (max_pairs == 0) return;
+#define HB_RS(T_) rescore_arith<T_>(rows, row_norm, queries64, q_f32_repr, q_norm, d, pair_query, pair_row, pair_slot, total, max_pairs, epi, out)
+    if (rdtype == HB_F32) HB_RS(float);
+    else if (rdtype == HB_BF16) HB_RS(__nv_bfloat16);
+    else if (rdtype == HB_F64) HB_RS(double);
     else throw Error(HB_ERR_INVALID, "unsupported dtype for the exact re-score");
 #undef HB_RS
+}
+
+// fp64 copy of the queries for the re-score (returns `queries` itself when they already are fp64)
+const double *launch_widen_queries(const void *queries, int qdtype, int64_t count, double *buf) {
+    if (qdtype == HB_F64) return (const double *)queries;
+    if (count == 0) return buf;
+    if (qdtype == HB_F32) widen_queries_kernel<float><<<blocks_for(count, 256), 256, 0, g_stream>>>((const float *)queries, count, buf);
+    else throw Error(HB_ERR_INVALID, "queries must be fp32 or fp64");
+    HB_LAUNCH_CHECK();
+    return buf;
 }
 
 void launch_gather_bytes(const void *src, const int32_t *idx, int64_t n, int64_t row_bytes, void *dst) {
@@ -688,10 +782,13 @@ void launch_query_bounds(const double *qu, const double *ql1, const double *qnor
 }
 
 void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const int32_t *cand_pos, int64_t nq, int kk, int cap,
-                          int k, const float *margin, int32_t *pair_query, int32_t *pair_row) {
+                          int k, const float *margin, int32_t *slot_row, double *exact, int32_t *total, int32_t *pair_query,
+                          int32_t *pair_row, int32_t *pair_slot) {
     if (nq * kk == 0) return;
-    rescore_pairs_kernel<<<blocks_for(nq * kk, 256), 256, 0, g_stream>>>(sel_pos, sel_negv, cand_pos, nq, kk, cap, k, margin,
-                                                                         pair_query, pair_row);
+    HB_REQUIRE(kk <= 64, "re-score pairs: kk <= 64");
+    HB_CUDA(cudaMemsetAsync(total, 0, 4, g_stream));
+    rescore_pairs_kernel<<<blocks_for(nq * 32, 256), 256, 0, g_stream>>>(sel_pos, sel_negv, cand_pos, nq, kk, cap, k, margin, slot_row,
+                                                                         exact, total, pair_query, pair_row, pair_slot);
     HB_LAUNCH_CHECK();
 }
 

@@ -100,7 +100,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # synthetic data (clustered, cf. test/data_generator.clj:74-79)
 # ---------------------------------------------------------------------------------------------------------
-def gen_gpu(w, device):
+def gen_gpu(w, device, query_seed=43):
     import torch
 
     g = torch.Generator(device=device)
@@ -112,7 +112,7 @@ def gen_gpu(w, device):
         m = min(step, w["n"] - i)
         idx = torch.randint(0, w["centres"], (m,), generator=g, device=device)
         rows[i:i + m] = centres[idx] + w["noise"] * torch.randn((m, w["d"]), generator=g, device=device)
-    g.manual_seed(43)
+    g.manual_seed(query_seed)
     idx = torch.randint(0, w["centres"], (w["nq"],), generator=g, device=device)
     queries = centres[idx] + w["noise"] * torch.randn((w["nq"], w["d"]), generator=g, device=device)
     return rows, queries.contiguous()
@@ -245,7 +245,11 @@ def run_ours(args, w, key):
         name, _, val = kv.partition("=")
         hb.set_option(name, int(val))
     k, nprobe, nq = w["k"], w["nprobe"], w["nq"]
-    rows, queries = gen_gpu(w, device)
+    # N > 1: "replicas" = every GPU holds the whole index (3 GB of 180 GB) and answers its OWN batch of nq queries: no
+    # data-path collective, weak scaling, value = N * nq / t.  "lists" = ONE batch against the lists of the index
+    # sharded l mod N, all-gather + merge kernel: strong scaling (the layout for an index larger than one GPU).
+    replicas = world > 1 and args.shard == "replicas"
+    rows, queries = gen_gpu(w, device, query_seed=43 + (rank if replicas else 0))
     torch.cuda.synchronize()
 
     # ---- build (untimed setup; reported) -------------------------------------------------------------
@@ -262,11 +266,14 @@ def run_ours(args, w, key):
         dist.broadcast(tc, 0)
         dist.broadcast(ta, 0)
         cents, asg = tc.cpu().numpy(), ta.cpu().numpy()
+    if world > 1 and not replicas:
         if rank == 0:
             gix.close()
         shard = ShardedIVFFlat(rows, cents, asg, rank, world)
         search = lambda q: shard.search(q, k, nprobe)  # noqa: E731
     else:
+        if rank != 0:
+            gix = ivf_flat.import_index(rows, cents, asg)  # the same index as rank 0's, without re-clustering
         out_ids = torch.empty((nq, k), dtype=torch.int64, device=device)
         out_dist = torch.empty((nq, k), dtype=torch.float64, device=device)
         search = lambda q: gix.search_raw(q, k, nprobe, out_ids=out_ids, out_dist=out_dist)  # noqa: E731
@@ -311,7 +318,8 @@ def run_ours(args, w, key):
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = nq / (ms * 1e-3)
+    jobs = world if replicas else 1  # query batches answered per step over all ranks
+    value = jobs * nq / (ms * 1e-3)
 
     # ---- e2e: host (pinned) queries in, host results out, through the C ABI -----------------------------
     hq = torch.empty((nq, w["d"]), dtype=torch.float32, pin_memory=True)
@@ -321,7 +329,7 @@ def run_ours(args, w, key):
     dq = torch.empty_like(queries)
 
     def e2e_step():
-        if world > 1:
+        if world > 1 and not replicas:
             dq.copy_(hq, non_blocking=True)  # every rank needs the whole batch
             i, d_ = search(dq)
             if rank == 0:
@@ -343,9 +351,9 @@ def run_ours(args, w, key):
         t = torch.tensor([e2e_ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e = {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+    e2e = {"value": jobs * nq / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(hq.numel() * 4) * (world if world > 1 else 1),
-           "d2h_bytes_per_step": int(h_ids.numel() * 8 + h_dist.numel() * 8)}
+           "d2h_bytes_per_step": int(h_ids.numel() * 8 + h_dist.numel() * 8) * jobs}
 
     if rank != 0:
         if world > 1:
@@ -362,7 +370,8 @@ def run_ours(args, w, key):
         exact_ids, _ = fx.search_raw(queries, k)
     recall = recall_at_k(ids_np, exact_ids)
     fast_vs_exact = None
-    if fast and world == 1:
+    single = world == 1 or replicas  # this rank ran the whole single-GPU path
+    if fast and single:
         # the same search in EXACT mode (fp64 for every pair): FAST must return the same ids and distance bits
         x_ids = torch.empty((nq, k), dtype=torch.int64, device=device)
         x_dist = torch.empty((nq, k), dtype=torch.float64, device=device)
@@ -376,7 +385,7 @@ def run_ours(args, w, key):
     rows_np = rows.cpu().numpy()
     q_np = queries.cpu().numpy()
     items = None
-    if world == 1:
+    if single:
         probes = gix.probes(queries, nprobe)
         lens = np.bincount(asg, minlength=w["nlist"])
         pairs = float(lens[probes.reshape(-1)].sum())
@@ -397,11 +406,11 @@ def run_ours(args, w, key):
         img_bytes = float(w["n"]) * dpad * args.digits + nq * nprobe * dpad * args.digits  # digit images read once
         roofline = {
             "kernel": f"tc_pass_kernel<{args.digits},EMIT> (tcgen05.mma kind::i8, IVF list scan candidate pass)",
-            "bound": "tensor", "achieved": flops / t_tc / 1e12 if world == 1 else None, "peak": bf16_peak, "unit": "TFLOP/s",
-            "frac": (flops / t_tc / 1e12 / bf16_peak) if world == 1 else None, "peak_source": peak_src, "traffic": None,
+            "bound": "tensor", "achieved": flops / t_tc / 1e12 if single else None, "peak": bf16_peak, "unit": "TFLOP/s",
+            "frac": (flops / t_tc / 1e12 / bf16_peak) if single else None, "peak_source": peak_src, "traffic": None,
             "launch_ms": t_tc * 1e3, "launches_per_step": tc_n / args.steps,
             "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": img_bytes,
-            "hbm_gbs_at_unique_bytes": img_bytes / t_tc / 1e9 if world == 1 else None,
+            "hbm_gbs_at_unique_bytes": img_bytes / t_tc / 1e9 if single else None,
             "int8_pipe": {"executed_tops": int8_ops / t_tc / 1e12 if int8_ops else None,
                           "nominal_peak_tops": 2.0 * bf16_peak, "frac": (int8_ops / t_tc / 1e12 / (2.0 * bf16_peak)) if int8_ops else None,
                           "note": "executed = digit products on padded tiles; peak = 2 x measured bf16 (int8 runs at twice the "
@@ -417,14 +426,14 @@ def run_ours(args, w, key):
             fp64_peak = None
         roofline = {
             "kernel": "pairscan_kernel<float,float,FMA> (IVF list-major scan, exact fp64)",
-            "bound": "tensor", "achieved": flops / t_scan / 1e12 if world == 1 else None, "peak": bf16_peak, "unit": "TFLOP/s",
-            "frac": (flops / t_scan / 1e12 / bf16_peak) if world == 1 else None, "peak_source": peak_src,
+            "bound": "tensor", "achieved": flops / t_scan / 1e12 if single else None, "peak": bf16_peak, "unit": "TFLOP/s",
+            "frac": (flops / t_scan / 1e12 / bf16_peak) if single else None, "peak_source": peak_src,
             "traffic": None,
             "launch_ms": t_scan * 1e3, "launches_per_step": scan_n / args.steps,
             "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": unique_bytes,
-            "hbm_gbs_at_unique_bytes": unique_bytes / t_scan / 1e9 if world == 1 else None,
-            "fp64_pipe": {"achieved_tflops": flops / t_scan / 1e12 if world == 1 else None, "peak_tflops_measured": fp64_peak,
-                          "frac": (flops / t_scan / 1e12 / fp64_peak) if (world == 1 and fp64_peak) else None,
+            "hbm_gbs_at_unique_bytes": unique_bytes / t_scan / 1e9 if single else None,
+            "fp64_pipe": {"achieved_tflops": flops / t_scan / 1e12 if single else None, "peak_tflops_measured": fp64_peak,
+                          "frac": (flops / t_scan / 1e12 / fp64_peak) if (single and fp64_peak) else None,
                           "note": "EXACT mode: one sequential fp64 FMA chain per (query,row) pair, bound by the fp64 pipe"},
             "step_breakdown_ms": stats,
         }
@@ -442,13 +451,15 @@ def run_ours(args, w, key):
 
     line = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if (world > 1 and not replicas) else "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(w, key), "recall_at_10": recall,
                    "mode": (f"fast: tcgen05 int8 x{args.digits}-digit candidate pass + fp64 re-score + proof, exact fallback "
                             "(ids and distance bits identical to exact mode)") if fast else "exact (fp64 for every pair)",
                    "l2": "inputs_larger_than_l2 (index slab 3.07 GB vs 126 MB L2)",
-                   "sharding": "lists of one global index, l mod N; all-gather + merge" if world > 1 else "single GPU",
+                   "sharding": ("single GPU" if world == 1 else
+                                f"replicas: the whole index on each of {world} GPUs, one {nq}-query batch per GPU per step, no collective"
+                                if replicas else "lists of one global index, l mod N; one batch; all-gather + merge"),
                    "build_s": build_s, "e2e_results_equal_device_results": e2e_same},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         "fast_vs_exact": fast_vs_exact,
@@ -467,6 +478,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shard", default="replicas", choices=["replicas", "lists"],
+                    help="N > 1: replicas (whole index per GPU, one batch per GPU, weak scaling) or lists (one batch, lists "
+                         "sharded l mod N, all-gather + merge, strong scaling)")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
                     help="fast: tensor-core candidate pass + fp64 re-score + proof (same results); exact: fp64 for every pair")
     ap.add_argument("--opt", action="append", default=[], help="library knob name=value (hb_set_option), repeatable")

@@ -626,9 +626,10 @@ struct FastWs {
 };
 static FastWs g_fw;
 
-constexpr int kFastKK = 64;     // candidates re-scored per query (= THRESH buckets)
-constexpr int kFastMaxK = 48;   // largest k served by the candidate pass
-constexpr int kFastCap = 2048;  // candidate slots per query
+constexpr int kFastMaxK = 112;  // largest k served by the candidate pass
+// candidates selected (and at most re-scored) per query / candidate slots per query
+static int fast_kk(int k) { return k <= 48 ? 64 : 128; }
+static int fast_cap(int k) { return k <= 48 ? 2048 : 4096; }
 
 static void build_fast_side(FastSideBufs &S, const void *rows, int dtype, int d, int nlist, const int64_t *list_off_dev,
                             const double *norm_dev, int ns) {
@@ -753,7 +754,7 @@ static void fast_quant_queries(const void *queries, int qdtype, int64_t nq, int 
 static void fast_topk(const FastJob &J) {
     FastWs &W = g_fw;
     const FastSideBufs &S = *J.side;
-    const int ns = S.ns, kbn = S.kbn, kk = kFastKK, cap = kFastCap;
+    const int ns = S.ns, kbn = S.kbn, kk = fast_kk(J.k), cap = fast_cap(J.k);
     const int64_t nq = J.nq;
     double *qscale = W.qscale.as<double>(nq), *qeps = W.qeps.as<double>(nq);
     float *qmargin = W.qmargin.as<float>(nq);
@@ -799,6 +800,7 @@ static void fast_topk(const FastJob &J) {
     P.thr = thr;
     P.margin = qmargin;
     P.k = J.k;
+    P.kk = kk;
     P.cap = cap;
     P.cnt = cnt;
     P.cand_negv = cnegv;

@@ -91,6 +91,7 @@ struct TcParams {
     float *thr = nullptr;  // per query: rows scoring below it cannot matter (see the epilogue); raised with atomic max
     const float *margin = nullptr;  // per query, in score units: > 2 eps_q (query_bounds_kernel)
     int k = 0;                      // results wanted per query
+    int kk = 64;                    // candidates re-scored per query (64 or 128): thr keeps >= kk emitted rows at or above it
     int tile_stride = 1;   // item j of a unit is row tile j*tile_stride of its list (THRESH samples every 8th tile of a flat list)
     // EMIT
     int cap = 0;

@@ -313,11 +313,11 @@ __global__ void __launch_bounds__(256) rescore_pairs_kernel(const int64_t *__res
     if (q >= nq) return;
     const double nk = k <= kk ? sel_negv[q * kk + k - 1] : INFINITY;  // the list is ascending in -score
     const double lim = nk + (double)margin[q] + 4e-6 * fabs(nk);
-    int row[2] = {-1, -1};
+    int row[4] = {-1, -1, -1, -1};
     int nwant = 0;
-    unsigned bal[2] = {0u, 0u};
+    unsigned bal[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 4; ++h) {
         const int j = h * 32 + lane;
         bool want = false;
         if (j < kk) {
@@ -334,14 +334,16 @@ __global__ void __launch_bounds__(256) rescore_pairs_kernel(const int64_t *__res
     int base = 0;
     if (lane == 0 && nwant > 0) base = atomicAdd(total, nwant);
     base = __shfl_sync(0xffffffffu, base, 0);
+    int before = 0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 4; ++h) {
         if (row[h] >= 0) {
-            const int o = base + (h ? __popc(bal[0]) : 0) + __popc(bal[h] & ((1u << lane) - 1u));
+            const int o = base + before + __popc(bal[h] & ((1u << lane) - 1u));
             pair_query[o] = (int32_t)q;
             pair_row[o] = row[h];
             pair_slot[o] = (int32_t)(q * kk + h * 32 + lane);
         }
+        before += __popc(bal[h]);
     }
 }
 
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(256) cand_select_kernel(const double *__restri
     extern __shared__ uint64_t s_keys[];
     const int64_t q = blockIdx.x;
     const int n = min(cnt[q], cap);
-    int m = 64;
+    int m = kk > 64 ? 128 : 64;
     while (m < n) m <<= 1;
     const double *v = cand_negv + q * cap;
     for (int i = threadIdx.x; i < m; i += blockDim.x)
@@ -626,7 +628,7 @@ __global__ void and_flags_kernel(int32_t *__restrict__ ok, const int32_t *__rest
 void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq, int kk, int cap, double *sel_negv,
                         int64_t *sel_pos) {
     if (nq == 0) return;
-    HB_REQUIRE(cap <= 4096 && kk <= 64, "candidate select: cap <= 4096, kk <= 64");
+    HB_REQUIRE(cap <= 4096 && kk <= 128, "candidate select: cap <= 4096, kk <= 128");
     cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos);
     HB_LAUNCH_CHECK();
 }
@@ -785,7 +787,7 @@ void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const 
                           int k, const float *margin, int32_t *slot_row, double *exact, int32_t *total, int32_t *pair_query,
                           int32_t *pair_row, int32_t *pair_slot) {
     if (nq * kk == 0) return;
-    HB_REQUIRE(kk <= 64, "re-score pairs: kk <= 64");
+    HB_REQUIRE(kk <= 128, "re-score pairs: kk <= 128");
     HB_CUDA(cudaMemsetAsync(total, 0, 4, g_stream));
     rescore_pairs_kernel<<<blocks_for(nq * 32, 256), 256, 0, g_stream>>>(sel_pos, sel_negv, cand_pos, nq, kk, cap, k, margin, slot_row,
                                                                          exact, total, pair_query, pair_row, pair_slot);

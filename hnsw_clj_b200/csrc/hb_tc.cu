@@ -33,7 +33,8 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + EPI_THREADS;
 constexpr int TMEM_COLS = 512;
-constexpr int NB = 16;     // threshold buckets per thread (two best scores each; two threads per query slot: >= 64 rows)
+// threshold buckets per thread (two best scores each; two threads per query slot): NB = 16 bounds the 64th best score
+// (64 candidates re-scored), NB = 32 the 128th (128 re-scored, k > 48)
 constexpr int STASH = 8;   // candidates a thread keeps in shared memory before it appends them to the query's list
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -164,7 +165,7 @@ __device__ __noinline__ void flush_stash(const CandOut C, int qi, int rel0, int6
     }
 }
 
-template <int NS, int MODE>
+template <int NS, int MODE, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P) {
     using Cfg = TcCfg<NS>;
     extern __shared__ uint8_t smem_dyn[];
@@ -283,9 +284,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
         bool have_pend = false;
         // Running lower bounds on the query's best scores.  Bucket b of this thread holds the two best scores among the
         // rows with (column % NB == b) of its column half seen in this unit:
-        //   min_b(b2) has >= 2*NB = 32 rows at or above it, the minimum over the two threads of a slot 64 (all emitted:
-        //   the 64 re-scored candidates can be taken from them);
-        //   min_b(b1) has >= NB = 16 rows at or above it (32 over both threads): for k <= 16 (32) the k-th best score is at
+        //   min_b(b2) has >= 2*NB rows at or above it, the minimum over the two threads of a slot 4*NB = kk (all emitted:
+        //   the kk re-scored candidates can be taken from them);
+        //   min_b(b1) has >= NB rows at or above it (2*NB over both threads): for k <= NB (2*NB) the k-th best score is at
         //   least that, and a row more than `margin` (> 2 eps_q) below it can never enter the exact top-k.
         float b1[NB], b2[NB];
         int it = 0;
@@ -456,9 +457,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
     }
 }
 
-template <int NS, int MODE>
+template <int NS, int MODE, int NB>
 void tc_launch(const TcParams &P, int total_items) {
-    auto kernel = tc_pass_kernel<NS, MODE>;
+    auto kernel = tc_pass_kernel<NS, MODE, NB>;
     HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<NS>::SMEM_BYTES));
     const int grid = std::max(1, std::min(g_num_sms, total_items));
     kernel<<<grid, TC_THREADS, TcCfg<NS>::SMEM_BYTES, g_stream>>>(P);
@@ -471,11 +472,13 @@ void tc_launch(const TcParams &P, int total_items) {
 void launch_tc_pass(const TcParams &P, int ns, int mode) {
     if (P.nunits == 0) return;
     HB_REQUIRE(ns == 2 || ns == 3, "digit count must be 2 or 3");
+    HB_REQUIRE(P.kk == 64 || P.kk == 128 || mode == FAST_DUMP, "candidates re-scored per query must be 64 or 128");
     const int hint = P.nunits * 8;
-#define HB_TC(NS_)                                                        \
-    do {                                                                  \
-        if (mode == FAST_EMIT) tc_launch<NS_, FAST_EMIT>(P, hint);        \
-        else tc_launch<NS_, FAST_DUMP>(P, hint);                          \
+#define HB_TC(NS_)                                                          \
+    do {                                                                    \
+        if (mode == FAST_DUMP) tc_launch<NS_, FAST_DUMP, 16>(P, hint);      \
+        else if (P.kk == 64) tc_launch<NS_, FAST_EMIT, 16>(P, hint);        \
+        else tc_launch<NS_, FAST_EMIT, 32>(P, hint);                        \
     } while (0)
     if (ns == 2) HB_TC(2);
     else HB_TC(3);

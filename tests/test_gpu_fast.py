@@ -112,7 +112,8 @@ def test_tensor_core_scores_bit_exact(hb, ns, n, d, nq, metric):
 
 @pytest.mark.parametrize("ns", [2, 3])
 @pytest.mark.parametrize("n,d,nq,k,metric", [(3000, 96, 70, 10, "cosine"), (2000, 768, 200, 10, "cosine"), (129, 5, 3, 1, "cosine"),
-                                             (5000, 128, 300, 48, "ip"), (40, 16, 9, 10, "cosine"), (700, 64, 130, 10, "ip")])
+                                             (5000, 128, 300, 48, "ip"), (40, 16, 9, 10, "cosine"), (700, 64, 130, 10, "ip"),
+                                             (20000, 128, 200, 100, "ip"), (9000, 96, 130, 64, "cosine"), (300, 64, 40, 112, "ip")])
 def test_flat_fast_equals_exact(hb, ns, n, d, nq, k, metric):
     from hnsw_clj_b200 import _lib
     from hnsw_clj_b200.flat import FlatIndex
@@ -171,6 +172,33 @@ def test_ivf_fast_equals_exact_and_oracle(hb, ns, n, d, nlist, nprobe, nq, k):
     print(f"ivf fast ns={ns} n={n} nlist={nlist}: {int(fell)} of {nq} queries fell back")
     oids, odist = orc.ivf_search(rows, cents, asg, queries[:64], k, nprobe)
     assert fids[:64].tolist() == oids.tolist() and same_bits(fdist[:64], odist)
+
+
+def test_flat_fast_bf16_top100_inner_product(hb):
+    """BASELINE configs[2] in small: bf16 rows, inner product, top-100 -- candidate pass with 128 re-scored candidates."""
+    import torch
+
+    from hnsw_clj_b200 import _lib
+    from hnsw_clj_b200.flat import FlatIndex
+
+    r = np.random.default_rng(77)
+    rows = torch.from_numpy(r.standard_normal((30000, 256)).astype(np.float32)).to(torch.bfloat16)
+    q = torch.from_numpy(r.standard_normal((150, 256)).astype(np.float32)).to(torch.bfloat16).float()
+    want_ids, want_d = orc.exact_knn(rows.float().numpy(), q.numpy(), 100, orc.IP)
+    with FlatIndex(rows.cuda(), distance_fn="ip") as ix:
+        _lib.set_option("profile", 1)
+        _lib.set_mode(_lib.MODE_FAST)
+        try:
+            ids, dist = ix.search_raw(q.cuda(), 100)
+        finally:
+            _lib.set_mode(_lib.MODE_EXACT)
+        served, fell = _lib.get_stat("fast_queries"), _lib.get_stat("fast_fallbacks")
+        _lib.set_option("profile", 0)
+    if hasattr(ids, "cpu"):
+        ids, dist = ids.cpu().numpy(), dist.cpu().numpy()
+    assert ids.tolist() == want_ids.tolist() and same_bits(dist, want_d)
+    assert served == 150
+    assert fell <= 75, f"{fell} of 150 queries fell back to the exact path"
 
 
 def test_fast_duplicates_fall_back_and_stay_exact(hb):

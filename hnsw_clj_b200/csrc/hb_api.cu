@@ -516,6 +516,10 @@ static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int6
 // partition-vectors-kmeans, src/hnsw/ann/partition/ivf_flat.clj:92-131, on device rows.
 // cents [nlist x d] fp64 (device), assign [n] int32 (device); seeds (device int64[nlist]) are filled by
 // k-means++ unless given.
+// assign-to-nearest-centroid over all rows (ivf_flat.clj:79-90); defined with the FAST-mode orchestration below
+static void assign_rows(const void *rows, int dtype, const double *row_norm, int64_t n, int d, const double *cents,
+                        const double *cnorm, int nlist, bool l2, int32_t *assign);
+
 static void kmeans_exact(const void *rows, int dtype, int64_t n, int d, int metric, int nlist, int iters, int64_t seed,
                          const int64_t *seed_rows_dev, double *cents, int32_t *assign, int64_t *seeds_out_dev) {
     HB_REQUIRE(n >= 1 && nlist >= 1, "k-means needs at least one row and one partition");
@@ -564,21 +568,11 @@ static void kmeans_exact(const void *rows, int dtype, int64_t n, int d, int metr
     double *cnorm = g_ws.misc3.as<double>((size_t)nlist + 2 + 2 * (size_t)n);  // reuse: [nlist] norms
     int64_t *list_off = g_ws.lq_off.as<int64_t>(nlist + 1);
     int64_t *list_rows = g_ws.cand_id.as<int64_t>(n);
-    AssignParams A;
-    A.rows = rows;
-    A.row_norm = norm;
-    A.n = n;
-    A.d = d;
-    A.cents = cents;
-    A.cent_norm = cnorm;
-    A.nlist = nlist;
-    A.epi = l2 ? EPI_L2 : EPI_COS_GUARD;
-    A.out_assign = assign;
     for (int it = 0; it <= iters; ++it) {
         launch_row_norms(cents, HB_F64, nlist, d, cnorm);
         {
             Prof pr(PROF_ASSIGN);
-            launch_assign(A, dtype, l2);
+            assign_rows(rows, dtype, norm, n, d, cents, cnorm, nlist, l2, assign);
         }
         if (it == iters) break;  // final assignment pass (:119-131)
         build_lists(assign, n, nlist, list_off, list_rows, g_ws.tmp);
@@ -613,6 +607,7 @@ struct FastWs {
     DevBuf dig, q64, pslot, srow, ptotal, qu, ql1, qscale, qeps, qmargin, thr, cnt, cnegv, crel, cpos, selval, selpos, pq, pr, exact;
     DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_slotq, u_slotrel;
     DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_slotq, t_slotrel;
+    DevBuf a_ids, a_dist, a_norm, a_tmp;
     DevBuf ppos, ppos0, ok_a, ok_b, relk, probes0, pair_out0, qsel0, lq_off0, uprefix0, uprefix, flat_plan, idx, gq, gids, gdist,
         tmp2;
     void release() {
@@ -620,7 +615,7 @@ struct FastWs {
                          &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_slotq, &u_slotrel,
                          &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_slotq, &t_slotrel,
                          &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
-                         &idx, &gq, &gids, &gdist, &tmp2};
+                         &idx, &gq, &gids, &gdist, &tmp2, &a_ids, &a_dist, &a_norm, &a_tmp};
         for (DevBuf *b : all) b->release();
     }
 };
@@ -1002,6 +997,83 @@ static void flat_search_fast(hb_index *ix, const void *queries, int qdtype, int6
                   });
 }
 
+// assign-to-nearest-centroid (ivf_flat.clj:79-90) over all rows.  EXACT mode: the fp64 tile kernel.  FAST mode
+// (cosine): the rows are the queries of a k = 1 candidate pass over the centroids (quantised afresh for every Lloyd
+// round), the surviving centroids are re-scored in fp64 and a row whose nearest centroid is not proven falls back to
+// the fp64 kernel -- same assignments, ties to the lowest centroid index (strict <, :87-89).
+static FastSideBufs g_assign_side;
+static void assign_rows(const void *rows, int dtype, const double *row_norm, int64_t n, int d, const double *cents,
+                        const double *cnorm, int nlist, bool l2, int32_t *assign) {
+    auto exact = [&](const void *r, const double *rn, int64_t cnt, int32_t *out) {
+        AssignParams A;
+        A.rows = r;
+        A.row_norm = rn;
+        A.n = cnt;
+        A.d = d;
+        A.cents = cents;
+        A.cent_norm = cnorm;
+        A.nlist = nlist;
+        A.epi = l2 ? EPI_L2 : EPI_COS_GUARD;
+        A.out_assign = out;
+        launch_assign(A, dtype, l2);
+    };
+    const bool try_fast = g_mode == HB_MODE_FAST && !l2 && (dtype == HB_F32 || dtype == HB_F64) && nlist >= 2 * kFastTile && n >= 1;
+    FastSideBufs &S = g_assign_side;
+    if (try_fast) {
+        int64_t h[2] = {0, nlist};
+        int64_t *lo = S.list_off.as<int64_t>(2);
+        HB_CUDA(cudaMemcpyAsync(lo, h, 16, cudaMemcpyHostToDevice, g_stream));
+        sync_stream();
+        build_fast_side(S, cents, HB_F64, d, 1, lo, cnorm, g_fast_ns);
+    }
+    if (!try_fast || !S.usable) {
+        exact(rows, row_norm, n, assign);
+        return;
+    }
+    const size_t esz = dtype_size(dtype);
+    int64_t *ids64 = g_fw.a_ids.as<int64_t>(n);
+    double *dist64 = g_fw.a_dist.as<double>(n);
+    int32_t *ok = g_fw.ok_a.as<int32_t>(n);
+    const int64_t qc = 16384;
+    for (int64_t q0 = 0; q0 < n; q0 += qc) {
+        const int64_t nqc = std::min(qc, n - q0);
+        const void *qptr = (const char *)rows + (size_t)q0 * d * esz;
+        fast_quant_queries(qptr, dtype, nqc, d);
+        const double *q64 = launch_widen_queries(qptr, dtype, nqc * d, g_fw.q64.as<double>((size_t)nqc * d));
+        FastJob J;
+        J.side = &S;
+        J.list_off = (const int64_t *)S.list_off.p;
+        J.rows_exact = cents;
+        J.rdtype = HB_F64;
+        J.row_norm = cnorm;
+        J.queries = qptr;
+        J.qdtype = dtype;
+        J.q64 = q64;
+        J.nq = nqc;
+        J.qn = row_norm + q0;
+        J.d = d;
+        J.metric = HB_COSINE;
+        J.epi = EPI_COS_GUARD;
+        J.k = 1;
+        J.profile = false;
+        flat_fast_plan(nqc, J.emit, J.thresh, g_fw.flat_plan);
+        J.shared_units = true;
+        J.out_rel = ids64 + q0;
+        J.out_dist = dist64 + q0;
+        J.out_ok = ok + q0;
+        fast_topk(J);
+    }
+    fast_fallback(ok, rows, dtype, n, d, 1, ids64, dist64, [&](const void *gq, int64_t nb, int64_t *gids, double *gdist) {
+        double *gn = g_fw.a_norm.as<double>(nb);
+        int32_t *ga = g_fw.a_tmp.as<int32_t>(nb);
+        launch_row_norms(gq, dtype, nb, d, gn);
+        exact(gq, gn, nb, ga);
+        launch_i32_to_i64(ga, nb, gids);
+        HB_CUDA(cudaMemsetAsync(gdist, 0, (size_t)nb * 8, g_stream));
+    });
+    launch_pos_to_i32(ids64, n, assign);
+}
+
 // search-ivf-flat in FAST mode: coarse routing and the probed-list scan both run the candidate pass
 static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64_t nq, int k, int nprobe, int64_t *ids,
                             double *dist) {
@@ -1281,6 +1353,7 @@ HB_API int hb_shutdown(void) {
         if (g_inited) cudaStreamSynchronize(g_stream);
         g_ws.release();
         g_fw.release();
+        g_assign_side.release();
     });
 }
 HB_API const char *hb_last_error(void) { return t_err.c_str(); }
@@ -1617,17 +1690,10 @@ HB_API int hb_kmeans_assign(const void *rows, int64_t n, int32_t d, int dtype, i
         double *cnorm = g_ws.qnorm.as<double>(nlist);
         launch_row_norms(r, dtype, n, d, norm);
         launch_row_norms(c, HB_F64, nlist, d, cnorm);
-        AssignParams A;
-        A.rows = r;
-        A.row_norm = norm;
-        A.n = n;
-        A.d = d;
-        A.cents = c;
-        A.cent_norm = cnorm;
-        A.nlist = nlist;
-        A.epi = metric == HB_L2 ? EPI_L2 : EPI_COS_GUARD;
-        A.out_assign = (int32_t *)o.dev;
-        launch_assign(A, dtype, metric == HB_L2);
+        {
+            Prof pr(PROF_ASSIGN);
+            assign_rows(r, dtype, norm, n, d, c, cnorm, nlist, metric == HB_L2, (int32_t *)o.dev);
+        }
         finish_out(o);
         sync_stream();
     });

@@ -146,6 +146,7 @@ const double *launch_widen_queries(const void *queries, int qdtype, int64_t coun
 // fallback plumbing: dst[i] = src[idx[i]] (rows of row_bytes, multiple of 4) and dst[idx[i]] = src[i] (rows of k 8-byte words)
 void launch_gather_bytes(const void *src, const int32_t *idx, int64_t n, int64_t row_bytes, void *dst);
 void launch_scatter_rows64(const void *src, const int32_t *idx, int64_t n, int k, void *dst);
+void launch_i32_to_i64(const int32_t *in, int64_t n, int64_t *out);
 // first[q] = pos[q*stride]  (probe rank 0 of every query)
 void launch_first_column(const int64_t *pos, int64_t nq, int stride, int64_t *first);
 // thr[q] = max(thr[q], kk-th best sample candidate) where the sample pass collected kk..cap candidates

@@ -675,6 +675,18 @@ const double *launch_widen_queries(const void *queries, int qdtype, int64_t coun
     return buf;
 }
 
+namespace {
+__global__ void i32_to_i64_kernel(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+}  // namespace
+void launch_i32_to_i64(const int32_t *in, int64_t n, int64_t *out) {
+    if (n == 0) return;
+    i32_to_i64_kernel<<<blocks_for(n, 256), 256, 0, g_stream>>>(in, n, out);
+    HB_LAUNCH_CHECK();
+}
+
 void launch_gather_bytes(const void *src, const int32_t *idx, int64_t n, int64_t row_bytes, void *dst) {
     if (n == 0) return;
     HB_REQUIRE(row_bytes % 4 == 0, "gather rows must be whole 32-bit words");

@@ -201,6 +201,53 @@ def test_flat_fast_bf16_top100_inner_product(hb):
     assert fell <= 75, f"{fell} of 150 queries fell back to the exact path"
 
 
+@pytest.mark.parametrize("n,d,nlist", [(20000, 64, 300), (5000, 768, 256), (40000, 32, 1000)])
+def test_kmeans_assign_fast_equals_exact_and_oracle(hb, n, d, nlist):
+    """assign-to-nearest-centroid through the tensor-core candidate pass (k = 1 over the centroids): same assignments as the
+    fp64 kernel and the oracle, ties to the lowest centroid index."""
+    from hnsw_clj_b200 import _lib, ivf_flat
+
+    rows = clustered(n, d, 3 * n + d, centres=nlist // 2)
+    r = np.random.default_rng(n)
+    cents = rows[r.choice(n, nlist, replace=False)].astype(np.float64) + 1e-3 * r.standard_normal((nlist, d))
+    cents[7] = cents[3]  # duplicate centroid: every row nearest to it must go to the lower index
+    want = orc.assign(rows, cents)
+    exact = ivf_flat.assign_to_nearest_centroid(rows, cents)
+    _lib.set_option("profile", 1)
+    _lib.set_mode(_lib.MODE_FAST)
+    try:
+        fast = ivf_flat.assign_to_nearest_centroid(rows, cents)
+    finally:
+        _lib.set_mode(_lib.MODE_EXACT)
+    served, fell = _lib.get_stat("fast_queries"), _lib.get_stat("fast_fallbacks")
+    _lib.set_option("profile", 0)
+    assert exact.tolist() == want.tolist()
+    assert fast.tolist() == want.tolist()
+    assert served == n
+    assert (fast != 7).all()
+    print(f"k-means assign fast n={n} nlist={nlist}: {int(fell)} rows fell back")
+
+
+def test_ivf_build_in_fast_mode_is_bit_identical(hb):
+    """The whole build (k-means++ seeds, Lloyd rounds, final assignment) with FAST-mode assignment passes gives the centroids
+    and assignments of the exact build, bit for bit."""
+    from hnsw_clj_b200 import _lib, ivf_flat
+
+    rows = clustered(30000, 96, 123, centres=200)
+    a = ivf_flat.build_index(rows, num_partitions=300, max_iterations=3)
+    ca, aa = a.export()
+    a.close()
+    _lib.set_mode(_lib.MODE_FAST)
+    try:
+        b = ivf_flat.build_index(rows, num_partitions=300, max_iterations=3)
+    finally:
+        _lib.set_mode(_lib.MODE_EXACT)
+    cb, ab = b.export()
+    b.close()
+    assert aa.tolist() == ab.tolist()
+    assert same_bits(ca, cb)
+
+
 def test_fast_duplicates_fall_back_and_stay_exact(hb):
     """Exact duplicates make the k-th / (k+1)-th gap zero: the proof must refuse and the exact path answer."""
     from hnsw_clj_b200 import _lib

@@ -692,7 +692,7 @@ struct FastPlan {  // which (query, list) pairs a pass covers
     int nunits = 0;       // unit slots (interleaved layouts pad the real count up to a multiple of the SM count)
     int nunits_real = 0;
     int interleave = 0;
-    int tile_limit = 0, tile_div = 0;
+    int tile_limit = 0, tile_div = 0, tile_start = 0;
 };
 // pads the unit count so that the slots can be interleaved across the persistent CTAs (unit_plan_kernel)
 static void set_units(FastPlan &F, int64_t real, bool interleave) {
@@ -734,8 +734,8 @@ static UnitPlan make_units(const FastPlan &F, DevBuf &b_list, DevBuf &b_sel0, De
     U.unit_item0 = b_item0.as<int32_t>(nu + 1);
     U.slot_query = b_slotq.as<int32_t>(nu * kFastTile);
     U.slot_rel0 = b_slotrel.as<int32_t>(nu * kFastTile);
-    launch_unit_plan(F.nlist, F.lq_off, F.unit_prefix, tile_off, F.nunits, F.nunits_real, F.interleave, F.tile_limit, F.tile_div, F.qsel,
-                     F.pair_out, F.pair_div, nullptr, U);
+    launch_unit_plan(F.nlist, F.lq_off, F.unit_prefix, tile_off, F.nunits, F.nunits_real, F.interleave, F.tile_limit, F.tile_div,
+                     F.tile_start, F.qsel, F.pair_out, F.pair_div, nullptr, U);
     return U;
 }
 
@@ -775,7 +775,7 @@ static void fast_topk(const FastJob &J) {
             T.unit_ntile = W.t_ntile.as<int32_t>((size_t)J.emit.nunits + 1);
             T.unit_item0 = W.t_item0.as<int32_t>((size_t)J.emit.nunits + 1);
             launch_unit_plan(J.thresh.nlist, J.thresh.lq_off, J.thresh.unit_prefix, (const int64_t *)S.tile_off.p, J.thresh.nunits,
-                             J.thresh.nunits_real, J.thresh.interleave, J.thresh.tile_limit, J.thresh.tile_div, J.thresh.qsel,
+                             J.thresh.nunits_real, J.thresh.interleave, J.thresh.tile_limit, J.thresh.tile_div, 0, J.thresh.qsel,
                              J.thresh.pair_out, J.thresh.pair_div, nullptr, T);
             aimg0 = aimg;
         } else {
@@ -807,6 +807,34 @@ static void fast_topk(const FastJob &J) {
         Prof pr(J.profile ? PROF_SELECT : -1);
         launch_cand_select(cnegv, cnt, nq, kk, cap, selval, selpos);
     };
+    // A long flat scan (one list, many row tiles) runs in levels over growing tile ranges [0,2), [2,32), [32,512), ...:
+    // after each level the candidate lists are cut back to their kk best and the thresholds rise to the exact kk-th best
+    // (k-th best - margin) so far, so a level emits about kk * 15 rows per query however long the scan is.
+    const bool leveled = J.shared_units && J.emit.nlist == 1 && S.ntiles > 32;
+    if (leveled) {
+        Prof pr(J.profile ? PROF_TC : -1);
+        P.aimg = aimg;
+        P.nunits = J.emit.nunits;
+        P.unit_list = U.unit_list;
+        P.slot_query = U.slot_query;
+        P.slot_rel0 = U.slot_rel0;
+        P.tile_stride = 1;
+        UnitPlan Lp = U;
+        Lp.unit_ntile = W.t_ntile.as<int32_t>((size_t)J.emit.nunits + 1);
+        Lp.unit_item0 = W.t_item0.as<int32_t>((size_t)J.emit.nunits + 1);
+        for (int64_t t0 = 0; t0 < S.ntiles;) {
+            const int64_t t1 = t0 == 0 ? 2 : std::min<int64_t>(S.ntiles, t0 * 16);
+            launch_unit_plan(J.emit.nlist, J.emit.lq_off, J.emit.unit_prefix, (const int64_t *)S.tile_off.p, J.emit.nunits,
+                             J.emit.nunits_real, J.emit.interleave, (int)(t1 - t0), 1, (int)t0, J.emit.qsel, J.emit.pair_out,
+                             J.emit.pair_div, nullptr, Lp);
+            P.unit_item0 = Lp.unit_item0;
+            P.tile_start = (int)t0;
+            launch_tc_pass(P, ns, FAST_EMIT);
+            launch_cand_compact(cnegv, crel, cpos, cnt, nq, kk, cap, J.k, qmargin, thr, selval, selpos);
+            t0 = t1;
+        }
+        P.tile_start = 0;
+    } else {
     {
         // sample pass: candidates of a subset of the rows (nearest list / every 8th tile) -> their kk-th best
         // score seeds the thresholds of the full pass
@@ -835,6 +863,7 @@ static void fast_topk(const FastJob &J) {
         launch_tc_pass(P, ns, FAST_EMIT);
     }
     select_candidates();
+    }
     double *exact = W.exact.as<double>((size_t)nq * kk);
     {
         Prof pr(J.profile ? PROF_RESCORE : -1);

@@ -68,8 +68,8 @@ struct UnitPlan {
 };
 // nunits = unit slots (>= nunits_real; a multiple of `interleave` when interleave > 0, see unit_plan_kernel)
 void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_prefix, const int64_t *tile_off, int nunits,
-                      int nunits_real, int interleave, int tile_limit, int tile_div, const int32_t *qsel, const int64_t *pair_out,
-                      int pair_div, const int32_t *pair_query, UnitPlan U);
+                      int nunits_real, int interleave, int tile_limit, int tile_div, int tile_start, const int32_t *qsel,
+                      const int64_t *pair_out, int pair_div, const int32_t *pair_query, UnitPlan U);
 // gathers the digits of each unit's queries into A images [nunits][kbn][ns][kFastImg]
 void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int32_t *slot_query, int8_t *aimg);
 
@@ -92,7 +92,8 @@ struct TcParams {
     const float *margin = nullptr;  // per query, in score units: > 2 eps_q (query_bounds_kernel)
     int k = 0;                      // results wanted per query
     int kk = 64;                    // candidates re-scored per query (64 or 128): thr keeps >= kk emitted rows at or above it
-    int tile_stride = 1;   // item j of a unit is row tile j*tile_stride of its list (THRESH samples every 8th tile of a flat list)
+    int tile_stride = 1;   // item j of a unit is row tile tile_start + j*tile_stride of its list (the sample pass of a flat
+    int tile_start = 0;    // scan takes every 8th tile, a level of a long flat scan a range of tiles)
     // EMIT
     int cap = 0;
     int32_t *cnt = nullptr;      // per query
@@ -137,6 +138,10 @@ void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const 
 // kk best of the min(cnt, cap) candidates of every query (ascending -score); unused slots: pos -1, +inf
 void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq, int kk, int cap, double *sel_negv,
                         int64_t *sel_pos);
+// the same selection, then only the kk best stay in the query's candidate list (in place, best first, cnt = min(cnt, kk))
+// and its threshold rises to the kk-th best / the k-th best - margin: the step between two levels of a long flat scan
+void launch_cand_compact(double *cand_negv, int32_t *cand_rel, int32_t *cand_pos, int32_t *cnt, int64_t nq, int kk, int cap, int k,
+                         const float *margin, float *thr, double *sel_negv, int64_t *sel_pos);
 // exact fp64 distance of (query, row) pairs in the reference's summation order (cosine / -dot epilogues, no L2)
 void launch_rescore(const void *rows, int rdtype, const double *row_norm, const double *queries64, bool q_f32_repr,
                     const double *q_norm, int d, const int32_t *pair_query, const int32_t *pair_row, const int32_t *pair_slot,

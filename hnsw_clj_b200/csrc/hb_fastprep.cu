@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) quant_queries_kernel(const T *__restrict_
 
 __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, const int64_t *__restrict__ unit_prefix,
                                  const int64_t *__restrict__ tile_off, int nunits, int nunits_real, int interleave,
-                                 int tile_limit, int tile_div, UnitPlan U) {
+                                 int tile_limit, int tile_div, int tile_start, UnitPlan U) {
     const int slot_u = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot_u > nunits) return;
     if (slot_u == nunits) {
@@ -209,6 +209,7 @@ __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, 
     const int nsel = (int)min((int64_t)kFastTile, lq_off[l + 1] - sel0);
     int nt = (int)(tile_off[l + 1] - tile_off[l]);
     if (tile_div > 1) nt = (nt + tile_div - 1) / tile_div;  // tiles 0, tile_div, 2*tile_div, ...
+    nt = max(nt - tile_start, 0);                           // tiles tile_start .. (tile_div == 1 only)
     if (tile_limit > 0) nt = min(nt, tile_limit);
     U.unit_list[slot_u] = l;
     U.unit_sel0[slot_u] = (int32_t)sel0;
@@ -430,12 +431,21 @@ __device__ __forceinline__ uint32_t f32_desc_key(float v) {  // larger score -> 
     b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // ascending order-preserving
     return ~b;
 }
+struct CompactParams {  // non-null cand_rel: keep only the kk best candidates, in place, and raise the query's threshold
+    double *cand_negv = nullptr;
+    int32_t *cand_rel = nullptr, *cand_pos = nullptr;
+    int32_t *cnt_rw = nullptr;
+    float *thr = nullptr;
+    const float *margin = nullptr;
+    int k = 0;
+};
 __global__ void __launch_bounds__(256) cand_select_kernel(const double *__restrict__ cand_negv, const int32_t *__restrict__ cnt,
                                                           int kk, int cap, double *__restrict__ sel_negv,
-                                                          int64_t *__restrict__ sel_pos) {
+                                                          int64_t *__restrict__ sel_pos, const CompactParams CP) {
     extern __shared__ uint64_t s_keys[];
     const int64_t q = blockIdx.x;
-    const int n = min(cnt[q], cap);
+    const int craw = cnt[q];
+    const int n = min(craw, cap);
     int m = kk > 64 ? 128 : 64;
     while (m < n) m <<= 1;
     const double *v = cand_negv + q * cap;
@@ -457,11 +467,45 @@ __global__ void __launch_bounds__(256) cand_select_kernel(const double *__restri
         }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < kk; j += blockDim.x) {
-        const bool ok = j < n;
-        const int slot = ok ? (int)(uint32_t)s_keys[j] : -1;
-        sel_pos[q * kk + j] = slot;
-        sel_negv[q * kk + j] = ok ? v[slot] : INFINITY;
+    if (CP.cand_rel == nullptr) {
+        for (int j = threadIdx.x; j < kk; j += blockDim.x) {
+            const bool ok = j < n;
+            const int slot = ok ? (int)(uint32_t)s_keys[j] : -1;
+            sel_pos[q * kk + j] = slot;
+            sel_negv[q * kk + j] = ok ? v[slot] : INFINITY;
+        }
+        return;
+    }
+    // compaction (kk <= blockDim.x): the kk best move to the front of the query's candidate list, best first; the
+    // discarded ones score at most the kk-th best, which the threshold now records for the proof
+    const int j = threadIdx.x;
+    const bool ok = j < kk && j < n;
+    const int slot = ok ? (int)(uint32_t)s_keys[j] : -1;
+    double nv = INFINITY;
+    int32_t rel = 0, pos = 0;
+    if (ok) {
+        nv = v[slot];
+        rel = CP.cand_rel[q * cap + slot];
+        pos = CP.cand_pos[q * cap + slot];
+    }
+    __syncthreads();
+    if (j < kk) {
+        if (ok && craw <= cap) {
+            CP.cand_negv[q * cap + j] = nv;
+            CP.cand_rel[q * cap + j] = rel;
+            CP.cand_pos[q * cap + j] = pos;
+        }
+        sel_pos[q * kk + j] = ok ? j : -1;
+        sel_negv[q * kk + j] = nv;
+    }
+    if (craw > cap) return;  // overflowed: the count stays above cap and the query goes to the exact path
+    if (j == 0) CP.cnt_rw[q] = min(n, kk);
+    if (n >= kk && j == kk - 1) CP.thr[q] = fmaxf(CP.thr[q], (float)(-nv));
+    __syncthreads();
+    if (CP.k <= kk && n >= CP.k && j == CP.k - 1) {
+        const float sk = (float)(-nv);
+        const float t = sk - CP.margin[q] - 4e-6f * fabsf(sk);
+        if (t > CP.thr[q]) CP.thr[q] = t;
     }
 }
 
@@ -629,7 +673,22 @@ void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq,
                         int64_t *sel_pos) {
     if (nq == 0) return;
     HB_REQUIRE(cap <= 4096 && kk <= 128, "candidate select: cap <= 4096, kk <= 128");
-    cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos);
+    cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos, CompactParams{});
+    HB_LAUNCH_CHECK();
+}
+void launch_cand_compact(double *cand_negv, int32_t *cand_rel, int32_t *cand_pos, int32_t *cnt, int64_t nq, int kk, int cap, int k,
+                         const float *margin, float *thr, double *sel_negv, int64_t *sel_pos) {
+    if (nq == 0) return;
+    HB_REQUIRE(cap <= 4096 && kk <= 128, "candidate compaction: cap <= 4096, kk <= 128");
+    CompactParams CP;
+    CP.cand_negv = cand_negv;
+    CP.cand_rel = cand_rel;
+    CP.cand_pos = cand_pos;
+    CP.cnt_rw = cnt;
+    CP.thr = thr;
+    CP.margin = margin;
+    CP.k = k;
+    cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos, CP);
     HB_LAUNCH_CHECK();
 }
 
@@ -766,11 +825,11 @@ void launch_quant_queries(const void *queries, int qdtype, int64_t nq, int d, in
 }
 
 void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_prefix, const int64_t *tile_off, int nunits,
-                      int nunits_real, int interleave, int tile_limit, int tile_div, const int32_t *qsel, const int64_t *pair_out,
-                      int pair_div, const int32_t *pair_query, UnitPlan U) {
+                      int nunits_real, int interleave, int tile_limit, int tile_div, int tile_start, const int32_t *qsel,
+                      const int64_t *pair_out, int pair_div, const int32_t *pair_query, UnitPlan U) {
     if (nunits == 0) return;
     unit_plan_kernel<<<blocks_for(nunits + 1, 256), 256, 0, g_stream>>>(nlist, lq_off, unit_prefix, tile_off, nunits, nunits_real,
-                                                                        interleave, tile_limit, tile_div, U);
+                                                                        interleave, tile_limit, tile_div, tile_start, U);
     HB_LAUNCH_CHECK();
     unit_scan_kernel<<<1, 1024, 0, g_stream>>>(U.unit_ntile, nunits + 1, U.unit_item0);
     HB_LAUNCH_CHECK();

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
             int u = find_unit(P.unit_item0, P.nunits, item_begin);
             for (int item = item_begin; item < item_end; ++item) {
                 while (item >= P.unit_item0[u + 1]) ++u;
-                const int t = (item - P.unit_item0[u]) * P.tile_stride;
+                const int t = P.tile_start + (item - P.unit_item0[u]) * P.tile_stride;
                 const int64_t btile = P.tile_off[P.unit_list[u]] + t;
                 const int8_t *asrc = P.aimg + (int64_t)u * kbn * NS * kFastImg;
                 const int8_t *bsrc = P.bimg + btile * kbn * NS * kFastImg;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
         int it = 0;
         for (int item = item_begin; item < item_end; ++item, ++it) {
             while (item >= P.unit_item0[u + 1]) ++u;
-            const int t = (item - P.unit_item0[u]) * P.tile_stride;
+            const int t = P.tile_start + (item - P.unit_item0[u]) * P.tile_stride;
             const bool new_unit = item == item_begin || item == P.unit_item0[u];
             const int l = P.unit_list[u];
             const int64_t btile = P.tile_off[l] + t;

@@ -1,0 +1,306 @@
+"""Measurements of the BASELINE.json configs that are not the bench.py headline (configs[1]):
+
+    python tools/bench_configs.py c1            # 31,173 x 768 fp32 cosine, 1000 queries, flat top-10 (configs[0])
+    python tools/bench_configs.py c3 [--n N]    # flat N x 768 bf16 inner product, 4096 queries, top-100 (configs[2], one GPU's rows)
+    python tools/bench_configs.py c4 [--n N]    # one Lloyd round (assign + update) on one GPU's shard of configs[3]
+    python tools/bench_configs.py c5 [--n N]    # batched HNSW search, M=16 ef=128, 16k queries (configs[4], reduced graph)
+
+Every command prints ONE JSON line (device-resident inputs, CUDA events on the launching stream, inputs larger than L2
+or stated otherwise) and checks the device results against the exact mode / the CPU oracle on a bounded sample.
+The oracle is only the checker here, never the thing measured -- except in the explicitly named cpu_baseline field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def timed(fn, reps=3, warm=1):
+    import torch
+
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def same_bits(a, b):
+    return bool((np.asarray(a).view(np.int64) == np.asarray(b).view(np.int64)).all())
+
+
+def unit_rows(n, d, seed, device):
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    x = torch.randn((n, d), generator=g, device=device)
+    return x / x.norm(dim=1, keepdim=True)
+
+
+def run_c1(args):
+    import torch
+
+    from hnsw_clj_b200 import _lib as hb
+    from hnsw_clj_b200.flat import FlatIndex
+    from oracle import oracle as orc
+
+    dev = torch.device("cuda", 0)
+    n, d, nq, k = 31173, 768, 1000, 10
+    rows = unit_rows(n, d, 42, dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(43)
+    queries = (rows[torch.arange(nq, device=dev) * 31] + 0.1 / d ** 0.5 * torch.randn((nq, d), generator=g, device=dev)).contiguous()
+    out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
+    res = {}
+    with FlatIndex(rows) as ix:
+        for mode, code in (("exact", hb.MODE_EXACT), ("fast", hb.MODE_FAST)):
+            hb.set_mode(code)
+            hb.set_option("profile", 1)
+            ms = timed(lambda: ix.search_raw(queries, k, out_ids=out_ids, out_dist=out_d), reps=5, warm=2)
+            res[mode] = {"ms": ms, "qps": nq / ms * 1e3, "ids": out_ids.cpu().numpy().copy(), "dist": out_d.cpu().numpy().copy(),
+                         "fallbacks": hb.get_stat("fast_fallbacks") if mode == "fast" else None}
+            hb.set_option("profile", 0)
+        hb.set_mode(hb.MODE_EXACT)
+    rows_np, q_np = rows.cpu().numpy(), queries.cpu().numpy()
+    s = 128
+    t0 = time.perf_counter()
+    want_ids, want_d = orc.exact_knn(rows_np, q_np[:s], k)
+    cpu_s = time.perf_counter() - t0
+    flops = 2.0 * nq * n * d
+    pk = peaks()
+    line = {
+        "config": "BASELINE configs[0]: 31,173x768 fp32 cosine, 1000 queries, exact flat top-10 (unit-norm Gaussian rows, queries = rows + noise)",
+        "metric": "queries/s", "value_fast": res["fast"]["qps"], "value_exact": res["exact"]["qps"],
+        "ms_fast": res["fast"]["ms"], "ms_exact": res["exact"]["ms"],
+        "fast_equals_exact": bool((res["fast"]["ids"] == res["exact"]["ids"]).all()) and same_bits(res["fast"]["dist"], res["exact"]["dist"]),
+        "fast_fallbacks_per_7_calls": res["fast"]["fallbacks"],
+        "parity_vs_oracle": {"queries": s, "ids_equal": bool((res["exact"]["ids"][:s] == want_ids).all()),
+                             "dist_bits_equal": same_bits(res["exact"]["dist"][:s], want_d)},
+        "cpu_baseline": {"value": s / cpu_s, "unit": "queries/s", "cores": orc.ncores(), "kind": "port",
+                         "sample": f"first {s} queries, all host threads"},
+        "roofline": {"bound": "tensor", "algorithmic_flops": flops, "achieved_tflops_fast": flops / res["fast"]["ms"] / 1e9,
+                     "achieved_tflops_exact_fp64": flops / res["exact"]["ms"] / 1e9, "peak_bf16_tflops": pk.get("bf16_tflops"),
+                     "note": "index (96 MB) fits L2: not an HBM measurement"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_c3(args):
+    import torch
+
+    from hnsw_clj_b200 import _lib as hb
+    from hnsw_clj_b200.flat import FlatIndex
+
+    dev = torch.device("cuda", 0)
+    n, d, nq, k = args.n or 10_000_000, 768, 4096, 100
+    g = torch.Generator(device=dev)
+    g.manual_seed(42)
+    rows = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
+    for i in range(0, n, 1 << 20):
+        m = min(1 << 20, n - i)
+        rows[i:i + m] = torch.randn((m, d), generator=g, device=dev).to(torch.bfloat16)
+    g.manual_seed(43)
+    queries = torch.randn((nq, d), generator=g, device=dev).to(torch.bfloat16).float().contiguous()
+    out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ix = FlatIndex(rows, "ip")
+    del rows
+    torch.cuda.synchronize()
+    create_s = time.perf_counter() - t0
+    hb.set_mode(hb.MODE_FAST)
+    t0 = time.perf_counter()
+    ix.search_raw(queries, k, out_ids=out_ids, out_dist=out_d)  # first call quantises the rows (digit images)
+    torch.cuda.synchronize()
+    first_s = time.perf_counter() - t0
+    hb.set_option("profile", 1)
+    ms = timed(lambda: ix.search_raw(queries, k, out_ids=out_ids, out_dist=out_d), reps=args.reps, warm=1)
+    stats = {nm: hb.get_stat(nm) / (args.reps + 1) for nm in ("tc_ms", "tc_sample_ms", "select_ms", "pack_ms", "rescore_ms")}
+    served, fell = hb.get_stat("fast_queries"), hb.get_stat("fast_fallbacks")
+    hb.set_option("profile", 0)
+    fast_ids, fast_d = out_ids.cpu().numpy().copy(), out_d.cpu().numpy().copy()
+    # the exact mode (fp64 for every pair) on a sample of the queries
+    hb.set_mode(hb.MODE_EXACT)
+    s = 64
+    e_ids, e_d = ix.search_raw(queries[:s].contiguous(), k)
+    if hasattr(e_ids, "cpu"):
+        e_ids, e_d = e_ids.cpu().numpy(), e_d.cpu().numpy()
+    ms_exact = timed(lambda: ix.search_raw(queries[:s].contiguous(), k), reps=1, warm=0)
+    info = ix.info()
+    ix.close()
+    flops = 2.0 * nq * n * d
+    pk = peaks()
+    bf16 = pk.get("bf16_tflops", 1590.0)
+    line = {
+        "config": f"BASELINE configs[2] on one GPU: flat {n}x{d} bf16 inner product, {nq} queries, top-{k} (Gaussian rows)",
+        "metric": "queries/s", "value": nq / ms * 1e3, "ms_per_batch": ms, "mode": "fast (int8 x2-digit tcgen05 candidate pass, 128 re-scored, proof)",
+        "exact_mode_qps_on_sample": s / ms_exact * 1e3,
+        "parity": {"sample_queries": s, "ids_equal": bool((fast_ids[:s] == e_ids).all()), "dist_bits_equal": same_bits(fast_d[:s], e_d)},
+        "fast_queries": served, "fast_fallbacks": fell, "index_create_s": create_s, "first_call_s": first_s,
+        "device_bytes": info["device_bytes"], "step_breakdown_ms": stats,
+        "roofline": {"bound": "tensor", "algorithmic_flops": flops, "achieved_tflops": flops / ms / 1e9, "peak_bf16_tflops": bf16,
+                     "frac": flops / ms / 1e9 / bf16, "algorithmic_bytes": float(n) * d * 2, "hbm_gbs_at_unique_bytes": n * d * 2 / ms / 1e6},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_c4(args):
+    import torch
+
+    from hnsw_clj_b200 import _lib as hb
+
+    dev = torch.device("cuda", 0)
+    n, d, nlist = args.n or 12_500_000, 768, args.nlist
+    L = hb.lib()
+    hb.check(L.hb_init(0))
+    g = torch.Generator(device=dev)
+    g.manual_seed(42)
+    ncent = max(nlist // 2, 8)
+    centres = torch.randn((ncent, d), generator=g, device=dev)
+    rows = torch.empty((n, d), dtype=torch.float32, device=dev)
+    for i in range(0, n, 1 << 19):
+        m = min(1 << 19, n - i)
+        idx = torch.randint(0, ncent, (m,), generator=g, device=dev)
+        rows[i:i + m] = centres[idx] + 0.1 * torch.randn((m, d), generator=g, device=dev)
+    del centres
+    seeds = torch.randperm(n, generator=g, device=dev)[:nlist]
+    cents = rows[seeds].double().contiguous()  # seeds = data rows, as k-means++ would hand over (ivf_flat.clj:37-41)
+    asg = torch.empty(n, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def assign(r, out):
+        hb.check(L.hb_kmeans_assign(r.data_ptr(), r.shape[0], d, hb.F32, 0, cents.data_ptr(), nlist, out.data_ptr()))
+
+    def update():
+        hb.check(L.hb_kmeans_update(rows.data_ptr(), n, d, hb.F32, asg.data_ptr(), nlist, cents.data_ptr(), None, None))
+
+    hb.set_mode(hb.MODE_FAST)
+    hb.set_option("profile", 1)
+    ms_assign = timed(lambda: assign(rows, asg), reps=args.reps, warm=1)
+    served, fell = hb.get_stat("fast_queries"), hb.get_stat("fast_fallbacks")
+    hb.set_option("profile", 0)
+    # exact mode on a sample of the rows
+    hb.set_mode(hb.MODE_EXACT)
+    s = min(n, 16384)
+    sample = rows[:s].contiguous()
+    e_asg = torch.empty(s, dtype=torch.int32, device=dev)
+    ms_exact = timed(lambda: assign(sample, e_asg), reps=1, warm=0)
+    equal = bool((e_asg == asg[:s]).all().item())
+    c_before = cents.clone()
+    ms_update = timed(update, reps=1, warm=0)
+    moved = float((cents - c_before).abs().max().item())
+    pairs = float(n) * nlist
+    flops = 2.0 * pairs * d
+    pk = peaks()
+    bf16 = pk.get("bf16_tflops", 1590.0)
+    line = {
+        "config": f"BASELINE configs[3], one GPU's shard: k-means on {n}x{d} fp32, nlist={nlist}: one Lloyd round = assign + update "
+                  "(seeds given; configs[3] is 100M rows over 8 GPUs = 12.5M per GPU)",
+        "assign_ms": ms_assign, "update_ms": ms_update, "rows_per_s_assign": n / ms_assign * 1e3,
+        "assign_mode": "fast (k=1 candidate pass over the centroids on tcgen05 + fp64 re-score + proof)",
+        "fast_rows": served, "fast_fallbacks": fell,
+        "exact_assign_ms_on_sample": ms_exact, "exact_rows_per_s": s / ms_exact * 1e3,
+        "parity": {"sample_rows": s, "assignments_equal_exact_mode": equal},
+        "centroids_moved_max_abs": moved,
+        "roofline": {"bound": "tensor", "algorithmic_flops": flops, "achieved_tflops": flops / ms_assign / 1e9, "peak_bf16_tflops": bf16,
+                     "frac": flops / ms_assign / 1e9 / bf16,
+                     "update_hbm_gbs": float(n) * d * 4 / ms_update / 1e6, "hbm_peak_gbs": pk.get("hbm_gbs")},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_c5(args):
+    import torch
+
+    from hnsw_clj_b200 import _lib as hb
+    from oracle import oracle as orc
+
+    dev = torch.device("cuda", 0)
+    n, d, nq, k, ef = args.n or 20000, 768, 16384, 10, 128
+    rows = unit_rows(n, d, 42, dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(43)
+    queries = (rows[torch.randint(0, n, (nq,), generator=g, device=dev)] +
+               0.3 / d ** 0.5 * torch.randn((nq, d), generator=g, device=dev)).contiguous()
+    rows_np = rows.cpu().numpy()
+    t0 = time.perf_counter()
+    graph = orc.Hnsw(rows_np, M=16, ef_construction=200, level_seed=42)
+    build_s = time.perf_counter() - t0
+    from hnsw_clj_b200.ultra_fast import HnswIndex
+
+    adjacency = [graph.export_level(l) for l in range(graph.max_level + 1)]
+    ix = HnswIndex(rows_np, graph.levels(), graph.entry, adjacency, distance_fn="cosine")
+    out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
+    hb.set_option("profile", 1)
+    ms = timed(lambda: ix.search_raw(queries, k, ef, out_ids=out_ids, out_dist=out_d), reps=args.reps, warm=1)
+    scored = hb.get_stat("hnsw_scored") / (args.reps + 1)
+    hb.set_option("profile", 0)
+    ids = out_ids.cpu().numpy()
+    s = 256
+    q_np = queries[:s].cpu().numpy()
+    t0 = time.perf_counter()
+    want_ids, want_d = graph.search(q_np, k, ef)
+    cpu_s = time.perf_counter() - t0
+    from hnsw_clj_b200.flat import FlatIndex, recall_at_k
+
+    with FlatIndex(rows) as fx:
+        ex_ids, _ = fx.search_raw(queries, k)
+    if hasattr(ex_ids, "cpu"):
+        ex_ids = ex_ids.cpu().numpy()
+    pk = peaks()
+    bytes_scored = scored * (d * 4 + 4)
+    line = {
+        "config": f"BASELINE configs[4] on a reduced graph: HNSW M=16 efSearch={ef}, {n}x{d} fp32 unit-norm, {nq} concurrent queries, top-{k} "
+                  f"(graph built on the host by the oracle in {build_s:.0f} s; configs[4] names 1M nodes)",
+        "metric": "queries/s", "value": nq / ms * 1e3, "ms_per_batch": ms, "recall_at_10": recall_at_k(ids, ex_ids),
+        "pairs_scored_per_batch": scored,
+        "parity": {"sample_queries": s, "ids_equal_oracle_traversal": bool((ids[:s] == want_ids).all()),
+                   "dist_bits_equal": same_bits(out_d.cpu().numpy()[:s], want_d)},
+        "cpu_baseline": {"value": s / cpu_s, "unit": "queries/s", "cores": 1, "kind": "port", "sample": f"first {s} queries, one thread"},
+        "roofline": {"bound": "hbm", "achieved": bytes_scored / ms / 1e6, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                     "frac": bytes_scored / ms / 1e6 / pk.get("hbm_gbs", 6500.0), "algorithmic_bytes_per_scored_candidate": d * 4 + 4,
+                     "note": f"the {n * d * 4 / 1e6:.0f} MB of vectors fit L2 at this graph size: the gather is L2-bound here, not HBM-bound"},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--nlist", type=int, default=65536)
+    ap.add_argument("--reps", type=int, default=2)
+    args = ap.parse_args()
+    from hnsw_clj_b200 import _lib as hb
+
+    hb.check(hb.lib().hb_init(0))
+    {"c1": run_c1, "c3": run_c3, "c4": run_c4, "c5": run_c5}[args.config](args)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(128) update_centroids_kernel(const T *__restri
                                                                const int64_t *__restrict__ list_rows, int nlist,
                                                                double *__restrict__ cents, double *__restrict__ out_sums,
                                                                int64_t *__restrict__ out_counts) {
-    const int c = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x;  // clusters on grid.x: nlist can exceed the 65535 limit of grid.y
+    const int j = blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= d) return;
     const int64_t b = list_off[c], e = list_off[c + 1];
     double s = 0.0;
@@ -255,7 +255,7 @@ void launch_init_centroids(const void *rows, int dtype, int d, const int64_t *se
 void launch_update_centroids(const void *rows, int dtype, int d, const int64_t *list_off, const int64_t *list_rows,
                              int nlist, double *cents, double *out_sums, int64_t *out_counts) {
     if (nlist == 0 || d == 0) return;
-    dim3 grid((unsigned)ceil_div(d, 128), (unsigned)nlist);
+    dim3 grid((unsigned)nlist, (unsigned)ceil_div(d, 128));
     if (dtype == HB_F32) update_centroids_kernel<float><<<grid, 128, 0, g_stream>>>((const float *)rows, d, list_off, list_rows, nlist, cents, out_sums, out_counts);
     else if (dtype == HB_BF16) update_centroids_kernel<__nv_bfloat16><<<grid, 128, 0, g_stream>>>((const __nv_bfloat16 *)rows, d, list_off, list_rows, nlist, cents, out_sums, out_counts);
     else update_centroids_kernel<double><<<grid, 128, 0, g_stream>>>((const double *)rows, d, list_off, list_rows, nlist, cents, out_sums, out_counts);

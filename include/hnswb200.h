@@ -55,7 +55,8 @@ enum hb_index_type { HB_INDEX_FLAT = 0, HB_INDEX_IVF_FLAT = 1, HB_INDEX_HNSW = 2
  * pair; HB_MODE_FAST selects candidates on the tensor cores (exact int8-digit dot products, tcgen05), re-scores
  * them in fp64 in the reference's summation order and accepts a query only when an a-priori error bound proves
  * the top-k complete — otherwise the query is recomputed by the exact path.  Both modes return identical ids
- * and distance bits. */
+ * and distance bits.  FAST serves cosine / inner-product searches with k <= 112 and the k-means
+ * assignment passes (hb_kmeans_assign, hb_kmeans, hb_ivf_build); everything else runs the exact kernels. */
 enum hb_mode { HB_MODE_EXACT = 0, HB_MODE_FAST = 1 };
 
 typedef struct hb_info {
@@ -78,7 +79,8 @@ HB_API int hb_set_stream(void *cuda_stream); /* launch on this stream (default: 
 HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches (default EXACT) */
 /* knobs: "scratch_mb" = budget for the transient distance scratch (default 8192); "profile" = 1 records
  * CUDA events around the main kernels (and resets the counters); "fast_digits" = 2 | 3 signed 8-bit digits per
- * element in the HB_MODE_FAST candidate pass (16- or 24-bit block-fixed-point mantissas) */
+ * element in the HB_MODE_FAST candidate pass (16- or 24-bit block-fixed-point mantissas); "fast_sample_tiles" = row
+ * tiles (128 rows) of each query's nearest list scored first to seed the IVF scan's thresholds (default 2) */
 HB_API int hb_set_option(const char *name, int64_t value);
 /* measurements: "scan_ms"/"scan_count" (list/flat scan kernel), "coarse_ms", "select_ms", "plan_ms", "assign_ms",
  * "tc_ms" (tensor-core candidate pass over all probed lists), "tc_sample_ms" (its threshold-seeding pass), "pack_ms",
@@ -136,7 +138,8 @@ HB_API int hb_ivf_probes(hb_index *index, const void *queries, int qdtype, int64
 /* kmeans-plus-plus-init (ivf_flat.clj:32-60): chosen data-row indices, int64 [nlist] */
 HB_API int hb_kmeanspp_init(const void *rows, int64_t n, int32_t d, int dtype, int metric, int32_t nlist,
                             int64_t seed, int64_t *out_seed_rows);
-/* assign-to-nearest-centroid over all rows (ivf_flat.clj:79-90): strict <, lowest index wins */
+/* assign-to-nearest-centroid over all rows (ivf_flat.clj:79-90): strict <, lowest index wins.  In HB_MODE_FAST
+ * (cosine, fp32 / fp64 rows) the rows are the queries of a k = 1 candidate pass over the centroids; same result. */
 HB_API int hb_kmeans_assign(const void *rows, int64_t n, int32_t d, int dtype, int metric,
                             const double *centroids, int32_t nlist, int32_t *out_assign);
 /* compute-centroid per cluster in row order, empty cluster keeps its centroid (ivf_flat.clj:66-77,112-116).

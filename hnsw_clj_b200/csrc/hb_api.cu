@@ -200,7 +200,7 @@ static void check_dtype(int dtype) {
 struct FastSideBufs {
     DevBuf img, rs, ro, tile_off, stats, list_off;
     int ns = 0, kbn = 0;
-    int64_t ntiles = 0;
+    int64_t ntiles = 0, nrows = 0;
     bool built = false, usable = false;
     size_t bytes() const { return img.cap + rs.cap + ro.cap + tile_off.cap + stats.cap + list_off.cap; }
     void release() {
@@ -217,6 +217,8 @@ struct FastSideBufs {
 static bool g_fast_debug = false;
 static bool g_tc_interleave = true;
 static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
+static bool g_fast_dense = true;     // short flat scans (<= 2048 rows) select from the dumped score matrix
+static int g_fast_level_min = 33;     // flat scans of at least this many row tiles run in levels (fast_topk)
 static int g_fast_sample_tiles = 2;  // IVF: row tiles of the nearest list scored by the threshold-seeding pass
 static int64_t g_fast_queries = 0;   // queries answered in FAST mode ...
 static int64_t g_fast_fallbacks = 0; // ... of which recomputed by the exact path (proof failed)
@@ -607,7 +609,7 @@ struct FastWs {
     DevBuf dig, q64, pslot, srow, ptotal, qu, ql1, qscale, qeps, qmargin, thr, cnt, cnegv, crel, cpos, selval, selpos, pq, pr, exact;
     DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_slotq, u_slotrel;
     DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_slotq, t_slotrel;
-    DevBuf a_ids, a_dist, a_norm, a_tmp;
+    DevBuf a_ids, a_dist, a_norm, a_tmp, dump;
     DevBuf ppos, ppos0, ok_a, ok_b, relk, probes0, pair_out0, qsel0, lq_off0, uprefix0, uprefix, flat_plan, idx, gq, gids, gdist,
         tmp2;
     void release() {
@@ -615,7 +617,7 @@ struct FastWs {
                          &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_slotq, &u_slotrel,
                          &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_slotq, &t_slotrel,
                          &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
-                         &idx, &gq, &gids, &gdist, &tmp2, &a_ids, &a_dist, &a_norm, &a_tmp};
+                         &idx, &gq, &gids, &gdist, &tmp2, &a_ids, &a_dist, &a_norm, &a_tmp, &dump};
         for (DevBuf *b : all) b->release();
     }
 };
@@ -632,10 +634,12 @@ static void build_fast_side(FastSideBufs &S, const void *rows, int dtype, int d,
     S.ns = ns;
     int64_t *toff = S.tile_off.as<int64_t>((size_t)nlist + 1);
     launch_tile_offsets(list_off_dev, nlist, toff);
-    int64_t nt = 0;
+    int64_t nt = 0, nr = 0;
     HB_CUDA(cudaMemcpyAsync(&nt, toff + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
+    HB_CUDA(cudaMemcpyAsync(&nr, list_off_dev + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
     sync_stream();
     S.ntiles = nt;
+    S.nrows = nr;
     const size_t img_bytes = (size_t)nt * S.kbn * ns * kFastImg;
     void *img = S.img.get(std::max<size_t>(img_bytes, 16));
     HB_CUDA(cudaMemsetAsync(img, 0, std::max<size_t>(img_bytes, 16), g_stream));
@@ -810,8 +814,25 @@ static void fast_topk(const FastJob &J) {
     // A long flat scan (one list, many row tiles) runs in levels over growing tile ranges [0,2), [2,32), [32,512), ...:
     // after each level the candidate lists are cut back to their kk best and the thresholds rise to the exact kk-th best
     // (k-th best - margin) so far, so a level emits about kk * 15 rows per query however long the scan is.
-    const bool leveled = J.shared_units && J.emit.nlist == 1 && S.ntiles > 32;
-    if (leveled) {
+    const bool leveled = J.shared_units && J.emit.nlist == 1 && S.ntiles >= g_fast_level_min;
+    // A short flat scan (coarse routing, k-means assignment over <= 2048 centroids) dumps its whole score matrix and lets
+    // one warp per query pick the candidates from it: no thresholds, no sample pass, no sort.
+    const int64_t flat_rows = J.emit.nlist == 1 ? S.nrows : 0;
+    const bool dense = g_fast_dense && J.shared_units && J.emit.nlist == 1 && flat_rows >= 1 && flat_rows <= 2048 && !leveled;
+    if (dense) {
+        Prof pr(J.profile ? PROF_TC : -1);
+        P.aimg = aimg;
+        P.nunits = J.emit.nunits;
+        P.unit_list = U.unit_list;
+        P.unit_item0 = U.unit_item0;
+        P.slot_query = U.slot_query;
+        P.slot_rel0 = U.slot_rel0;
+        P.tile_stride = 1;
+        P.dump = W.dump.as<float>((size_t)J.emit.nunits * S.ntiles * kFastTile * kFastTile);
+        launch_tc_pass(P, ns, FAST_DUMP);
+        launch_dense_select(P.dump, (int)S.ntiles, nq, (int)flat_rows, J.k, kk, cap, qmargin, cnegv, crel, cpos, cnt, thr, selval,
+                            selpos);
+    } else if (leveled) {
         Prof pr(J.profile ? PROF_TC : -1);
         P.aimg = aimg;
         P.nunits = J.emit.nunits;
@@ -1409,6 +1430,11 @@ HB_API int hb_set_option(const char *name, int64_t value) {
         } else if (!strcmp(name, "fast_digits")) {
             HB_REQUIRE(value == 2 || value == 3, "fast_digits must be 2 or 3");
             g_fast_ns = (int)value;
+        } else if (!strcmp(name, "fast_dense")) {
+            g_fast_dense = value != 0;
+        } else if (!strcmp(name, "fast_level_min")) {
+            HB_REQUIRE(value >= 3, "fast_level_min must be >= 3");
+            g_fast_level_min = (int)value;
         } else if (!strcmp(name, "fast_sample_tiles")) {
             HB_REQUIRE(value >= 1 && value <= 64, "fast_sample_tiles must be 1..64");
             g_fast_sample_tiles = (int)value;

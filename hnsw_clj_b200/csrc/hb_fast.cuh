@@ -138,6 +138,12 @@ void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const 
 // kk best of the min(cnt, cap) candidates of every query (ascending -score); unused slots: pos -1, +inf
 void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq, int kk, int cap, double *sel_negv,
                         int64_t *sel_pos);
+// short flat scans (<= 2048 rows): from the dumped score matrix [unit][tile][slot][row] of a FAST_DUMP pass, per query the
+// rows within `margin` of its k-th best score become its candidate list (sorted; sel_* filled, cnt = their number, or
+// cap + 1 if more than kk) and thr the best rejected score
+void launch_dense_select(const float *dump, int ntiles, int64_t nq, int nrows, int k, int kk, int cap, const float *margin,
+                         double *cand_negv, int32_t *cand_rel, int32_t *cand_pos, int32_t *cnt, float *thr, double *sel_negv,
+                         int64_t *sel_pos);
 // the same selection, then only the kk best stay in the query's candidate list (in place, best first, cnt = min(cnt, kk))
 // and its threshold rises to the kk-th best / the k-th best - margin: the step between two levels of a long flat scan
 void launch_cand_compact(double *cand_negv, int32_t *cand_rel, int32_t *cand_pos, int32_t *cnt, int64_t nq, int kk, int cap, int k,

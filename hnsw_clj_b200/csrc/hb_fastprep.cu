@@ -509,6 +509,109 @@ __global__ void __launch_bounds__(256) cand_select_kernel(const double *__restri
     }
 }
 
+// ---- dense selection: short flat scans (<= 2048 rows: IVF coarse routing, k-means assignment) --------------------------
+// The candidate pass writes every score of the short list (hb_tc.cu, FAST_DUMP); one warp per query then finds its k-th
+// best score exactly (bisection on the order-preserving bits, counting across the warp), keeps the rows within
+// `margin` of it as the candidate list (sorted, best first) and records the best rejected score as the threshold the
+// proof needs.  Replaces the threshold / emit / sort machinery where the whole score row fits a warp's registers.
+__device__ __forceinline__ uint32_t f32_asc_key(float v) {
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_asc_key(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+template <int NPL>
+__global__ void __launch_bounds__(128) dense_select_kernel(const float *__restrict__ dump, int ntiles, int64_t nq, int nrows, int k,
+                                                           int kk, int cap, const float *__restrict__ margin,
+                                                           double *__restrict__ cand_negv, int32_t *__restrict__ cand_rel,
+                                                           int32_t *__restrict__ cand_pos, int32_t *__restrict__ cnt,
+                                                           float *__restrict__ thr, double *__restrict__ sel_negv,
+                                                           int64_t *__restrict__ sel_pos) {
+    __shared__ uint32_t s_key[4][128];
+    __shared__ int32_t s_row[4][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 4 + warp;
+    if (q >= nq) return;
+    const float *base = dump + ((q >> 7) * ntiles) * (int64_t)(kFastTile * kFastTile) + (q & 127) * kFastTile;
+    uint32_t key[NPL];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        const int r = i * 32 + lane;
+        const float v = r < nrows ? base[(int64_t)(r >> 7) * (kFastTile * kFastTile) + (r & 127)] : -INFINITY;
+        key[i] = f32_asc_key(v);
+    }
+    const uint32_t key_ninf = f32_asc_key(-INFINITY);
+    // k-th largest key: the largest x with count(key >= x) >= k
+    uint32_t x = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t c = x | (1u << bit);
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) n += key[i] >= c;
+        n = __reduce_add_sync(0xffffffffu, n);
+        if (n >= k) x = c;
+    }
+    // cut: rows scoring at least (k-th best - margin) are candidates; fewer than k real rows: all of them
+    float cutf = -FLT_MAX;
+    if (x > key_ninf) {
+        const float sk = f32_from_asc_key(x);
+        cutf = fmaxf(sk - margin[q] - 4e-6f * fabsf(sk), -FLT_MAX);
+    }
+    const uint32_t cut = f32_asc_key(cutf);
+    int m = 0;
+    uint32_t best_rej = 0;  // largest key below the cut
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        const bool in = key[i] >= cut;
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (in) {
+            const int o = m + __popc(bal & ((1u << lane) - 1u));
+            if (o < 128) {
+                s_key[warp][o] = key[i];
+                s_row[warp][o] = i * 32 + lane;
+            }
+        } else {
+            best_rej = max(best_rej, key[i]);
+        }
+        m += __popc(bal);
+    }
+    best_rej = __reduce_max_sync(0xffffffffu, best_rej);
+    __syncwarp();
+    if (m > kk) {  // too many rows within the margin: the exact path answers this query
+        if (lane == 0) cnt[q] = cap + 1;
+        for (int j = lane; j < kk; j += 32) {
+            sel_pos[q * kk + j] = -1;
+            sel_negv[q * kk + j] = INFINITY;
+        }
+        return;
+    }
+    // rank by (score descending, row ascending) and write the candidate list, best first
+    for (int c = lane; c < m; c += 32) {
+        const uint32_t kc = s_key[warp][c];
+        const int rc = s_row[warp][c];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) {
+            const uint32_t kj = s_key[warp][j];
+            rank += (kj > kc) || (kj == kc && s_row[warp][j] < rc);
+        }
+        const double nv = -(double)f32_from_asc_key(kc);
+        cand_negv[q * cap + rank] = nv;
+        cand_rel[q * cap + rank] = rc;
+        cand_pos[q * cap + rank] = rc;
+        sel_negv[q * kk + rank] = nv;
+        sel_pos[q * kk + rank] = rank;
+    }
+    for (int j = m + lane; j < kk; j += 32) {
+        sel_pos[q * kk + j] = -1;
+        sel_negv[q * kk + j] = INFINITY;
+    }
+    if (lane == 0) {
+        cnt[q] = m;
+        thr[q] = best_rej > key_ninf ? f32_from_asc_key(best_rej) : -INFINITY;
+    }
+}
+
 // ---- exact re-score of (query, row) pairs: one thread per pair walks the reference's sequential fp64 sum
 // (src/hnsw/ultra_fast.clj:53-95, ivf_flat.clj:224-226); a warp stages its 32 rows chunk by chunk through shared
 // memory with full-line loads (the rows are scattered, 3-6 KB each); the queries were widened to fp64 once per call
@@ -674,6 +777,19 @@ void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq,
     if (nq == 0) return;
     HB_REQUIRE(cap <= 4096 && kk <= 128, "candidate select: cap <= 4096, kk <= 128");
     cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos, CompactParams{});
+    HB_LAUNCH_CHECK();
+}
+void launch_dense_select(const float *dump, int ntiles, int64_t nq, int nrows, int k, int kk, int cap, const float *margin,
+                         double *cand_negv, int32_t *cand_rel, int32_t *cand_pos, int32_t *cnt, float *thr, double *sel_negv,
+                         int64_t *sel_pos) {
+    if (nq == 0) return;
+    HB_REQUIRE(nrows <= 2048 && kk <= 128 && k >= 1, "dense select: at most 2048 rows, kk <= 128");
+    const int grid = blocks_for(nq, 4);
+#define HB_DS(NPL_) dense_select_kernel<NPL_><<<grid, 128, 0, g_stream>>>(dump, ntiles, nq, nrows, k, kk, cap, margin, cand_negv, cand_rel, cand_pos, cnt, thr, sel_negv, sel_pos)
+    if (nrows <= 512) HB_DS(16);
+    else if (nrows <= 1024) HB_DS(32);
+    else HB_DS(64);
+#undef HB_DS
     HB_LAUNCH_CHECK();
 }
 void launch_cand_compact(double *cand_negv, int32_t *cand_rel, int32_t *cand_pos, int32_t *cnt, int64_t nq, int kk, int cap, int k,

@@ -641,6 +641,7 @@ struct Widen<double> {
     }
 };
 
+constexpr int RS_QSLOTS = 4;  // distinct queries per warp whose chunks are staged in shared memory (others: direct loads)
 template <typename TRow, int ARITH>
 __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ rows, const double *__restrict__ row_norm,
                                                       const double *__restrict__ queries, const double *__restrict__ q_norm, int d,
@@ -650,17 +651,33 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
     constexpr int CH = 128 / (int)sizeof(TRow);  // elements per 128-byte chunk
     constexpr int EPL = 16 / (int)sizeof(TRow);  // elements per lane and round (16 B)
     constexpr int PER = Widen<TRow>::PER;
+    constexpr int QPL = (CH + 31) / 32;          // query elements a lane stages per chunk and slot
     __shared__ __align__(16) unsigned char s_raw[4][32][128 + 16];
+    __shared__ __align__(16) double s_q[4][RS_QSLOTS][CH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npairs = *total;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p - lane >= npairs) return;  // whole warp past the end of the pair list
     const bool live = p < npairs;
-    const int qi = live ? pair_query[p] : 0, ri = live ? pair_row[p] : -1;
-    const double *qp = queries + (int64_t)qi * d;
+    const int qi = live ? pair_query[p] : -1, ri = live ? pair_row[p] : -1;
+    const double *qp = queries + (int64_t)max(qi, 0) * d;
     const int nch = (d + CH - 1) / CH;
     const bool vec = (((size_t)d * sizeof(TRow)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(rows) & 15) == 0);
-    const bool qvec = (d % 2 == 0) && ((reinterpret_cast<uintptr_t>(queries) & 15) == 0);
+    // the pairs of a query are consecutive: number the runs of equal queries in this warp; the chunks of the first
+    // RS_QSLOTS runs are staged in shared memory with one coalesced load each, later runs read their query directly
+    const int qprev = __shfl_up_sync(0xffffffffu, qi, 1);
+    const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || qi != qprev);
+    const int qslot = __popc(heads & ((2u << lane) - 1u)) - 1;
+    const double *qsrc[RS_QSLOTS];
+#pragma unroll
+    for (int sidx = 0; sidx < RS_QSLOTS; ++sidx) {
+        // lane of the sidx-th head
+        unsigned h = heads;
+        for (int t = 0; t < sidx; ++t) h &= h - 1;
+        const int hl = h ? __ffs(h) - 1 : -1;
+        const int qh = __shfl_sync(0xffffffffu, qi, max(hl, 0));
+        qsrc[sidx] = (hl >= 0 && qh >= 0) ? queries + (int64_t)qh * d : nullptr;
+    }
     // cooperative loads: in round r, lanes 8*(j%4) .. +7 fetch the 128-byte chunk of the warp's row j = 4*r + lane/8
     const int part = lane & 7;
     const TRow *src[8];
@@ -670,6 +687,7 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
         src[r] = rj >= 0 ? rows + (int64_t)rj * d : nullptr;
     }
     uint4 pre[8];
+    double preq[RS_QSLOTS][QPL];
     auto fetch = [&](int c) {
         const int e0 = c * CH + part * EPL;
 #pragma unroll
@@ -685,6 +703,14 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
             }
             pre[r] = val;
         }
+#pragma unroll
+        for (int sidx = 0; sidx < RS_QSLOTS; ++sidx) {
+#pragma unroll
+            for (int t = 0; t < QPL; ++t) {
+                const int i = t * 32 + lane;
+                preq[sidx][t] = (qsrc[sidx] != nullptr && i < CH && c * CH + i < d) ? __ldg(qsrc[sidx] + c * CH + i) : 0.0;
+            }
+        }
     };
     fetch(0);
     double s = 0.0;
@@ -692,12 +718,22 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < 8; ++r) *reinterpret_cast<uint4 *>(&s_raw[warp][r * 4 + (lane >> 3)][part * 16]) = pre[r];
+#pragma unroll
+        for (int sidx = 0; sidx < RS_QSLOTS; ++sidx) {
+#pragma unroll
+            for (int t = 0; t < QPL; ++t) {
+                const int i = t * 32 + lane;
+                if (i < CH) s_q[warp][sidx][i] = preq[sidx][t];
+            }
+        }
         __syncwarp();
         if (c + 1 < nch) fetch(c + 1);  // in flight while this chunk is accumulated
         // own row chunk back as 128-bit reads (row stride 144 B: conflict-free per quarter warp)
         const uint4 *mine = reinterpret_cast<const uint4 *>(&s_raw[warp][lane][0]);
         const int kmax = min(CH, d - c * CH);
         if (live) {
+            const bool staged = qslot < RS_QSLOTS;
+            const double *qs = staged ? &s_q[warp][qslot][0] : qp + c * CH;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
                 const uint4 bits = mine[w];
@@ -706,13 +742,13 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
                     const int i0 = w * PER + e;
                     if (i0 < kmax) {
                         double q0, q1 = 0.0;
-                        if (qvec && i0 + 1 < kmax) {
-                            const double2 qq = __ldg(reinterpret_cast<const double2 *>(qp + c * CH + i0));
+                        if (staged) {
+                            const double2 qq = *reinterpret_cast<const double2 *>(qs + i0);  // zero-padded past d
                             q0 = qq.x;
                             q1 = qq.y;
                         } else {
-                            q0 = qp[c * CH + i0];
-                            if (i0 + 1 < kmax) q1 = qp[c * CH + i0 + 1];
+                            q0 = qs[i0];
+                            if (i0 + 1 < kmax) q1 = qs[i0 + 1];
                         }
                         s = mac_seq<ARITH>(q0, Widen<TRow>::at(bits, e), s);
                         if (i0 + 1 < kmax) s = mac_seq<ARITH>(q1, Widen<TRow>::at(bits, e + 1), s);

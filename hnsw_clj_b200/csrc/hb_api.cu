@@ -609,7 +609,7 @@ struct FastWs {
     DevBuf dig, q64, pslot, srow, ptotal, qu, ql1, qscale, qeps, qmargin, thr, cnt, cnegv, crel, cpos, selval, selpos, pq, pr, exact;
     DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_slotq, u_slotrel;
     DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_slotq, t_slotrel;
-    DevBuf a_ids, a_dist, a_norm, a_tmp, dump;
+    DevBuf a_ids, a_dist, a_norm, a_tmp, dump, timing;
     DevBuf ppos, ppos0, ok_a, ok_b, relk, probes0, pair_out0, qsel0, lq_off0, uprefix0, uprefix, flat_plan, idx, gq, gids, gdist,
         tmp2;
     void release() {
@@ -617,7 +617,7 @@ struct FastWs {
                          &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_slotq, &u_slotrel,
                          &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_slotq, &t_slotrel,
                          &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
-                         &idx, &gq, &gids, &gdist, &tmp2, &a_ids, &a_dist, &a_norm, &a_tmp, &dump};
+                         &idx, &gq, &gids, &gdist, &tmp2, &a_ids, &a_dist, &a_norm, &a_tmp, &dump, &timing};
         for (DevBuf *b : all) b->release();
     }
 };
@@ -801,6 +801,10 @@ static void fast_topk(const FastJob &J) {
     P.k = J.k;
     P.kk = kk;
     P.cap = cap;
+    if (g_fast_debug) {
+        P.timing = (long long *)W.timing.get((size_t)g_num_sms * 8 * 8);
+        HB_CUDA(cudaMemsetAsync(P.timing, 0, (size_t)g_num_sms * 8 * 8, g_stream));
+    }
     P.cnt = cnt;
     P.cand_negv = cnegv;
     P.cand_rel = crel;
@@ -913,6 +917,15 @@ static void fast_topk(const FastJob &J) {
         F.out_dist = J.out_dist;
         F.out_ok = J.out_ok;
         launch_fast_final(F);
+    }
+    if (g_fast_debug && P.timing) {
+        std::vector<long long> ht((size_t)g_num_sms * 8);
+        HB_CUDA(cudaMemcpy(ht.data(), P.timing, ht.size() * 8, cudaMemcpyDeviceToHost));
+        double a[6] = {0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < g_num_sms; ++c)
+            for (int j = 0; j < 6; ++j) a[j] += (double)ht[(size_t)c * 8 + j] / g_num_sms;
+        fprintf(stderr, "[hb fast] last tc pass, mean per CTA: items %.1f, mma warp %.0f clk (wait accumulators free %.0f, wait operands %.0f), "
+                        "epilogue: wait accumulators %.0f, phase A %.0f\n", a[3], a[0], a[1], a[2], a[4], a[5]);
     }
     if (g_fast_debug) {
         std::vector<int32_t> hc((size_t)nq), hok((size_t)nq);

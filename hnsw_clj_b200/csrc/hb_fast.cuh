@@ -94,6 +94,7 @@ struct TcParams {
     int kk = 64;                    // candidates re-scored per query (64 or 128): thr keeps >= kk emitted rows at or above it
     int tile_stride = 1;   // item j of a unit is row tile tile_start + j*tile_stride of its list (the sample pass of a flat
     int tile_start = 0;    // scan takes every 8th tile, a level of a long flat scan a range of tiles)
+    long long *timing = nullptr;  // debug: per CTA {mma warp total, wait accumulators free, wait operands, items, epilogue wait, phase A} clocks
     // EMIT
     int cap = 0;
     int32_t *cnt = nullptr;      // per query

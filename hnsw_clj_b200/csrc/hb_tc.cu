@@ -238,11 +238,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
         if (lane == 0 && item_begin < item_end) {
             int stage = 0;
             uint32_t phase = 0, tphase = 0;
+            long long t_tmem = 0, t_full = 0;
+            const long long t_all0 = clock64();
             for (int item = item_begin; item < item_end; ++item) {
+                long long c0 = P.timing ? clock64() : 0;
                 mbar_wait(smem_u32(&s_tmem_empty), tphase ^ 1u);
+                if (P.timing) t_tmem += clock64() - c0;
                 tc_fence_after();
                 for (int kb = 0; kb < kbn; ++kb) {
+                    c0 = P.timing ? clock64() : 0;
                     mbar_wait(smem_u32(&s_full[stage]), phase);
+                    if (P.timing) t_full += clock64() - c0;
                     tc_fence_after();
                     const uint32_t abase = stage0 + (uint32_t)stage * Cfg::STAGE_BYTES;
                     const uint32_t bbase = abase + NS * kFastImg;
@@ -265,6 +271,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
                 }
                 umma_commit(smem_u32(&s_tmem_full));
                 tphase ^= 1u;
+            }
+            if (P.timing) {  // debug: where the issuing thread spent its clocks
+                P.timing[blockIdx.x * 8 + 0] = clock64() - t_all0;
+                P.timing[blockIdx.x * 8 + 1] = t_tmem;
+                P.timing[blockIdx.x * 8 + 2] = t_full;
+                P.timing[blockIdx.x * 8 + 3] = item_end - item_begin;
             }
         }
     } else {
@@ -342,7 +354,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
                     resv_base = resv > 0 ? atomicAdd(&P.cnt[qi], resv) : 0;
                 }
             }
+            const long long e0 = (P.timing && et == 0) ? clock64() : 0;
             mbar_wait(smem_u32(&s_tmem_full), tphase);
+            const long long e1 = (P.timing && et == 0) ? clock64() : 0;
             tc_fence_after();
             tphase ^= 1u;
             const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
@@ -367,6 +381,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_tmem_empty));
+            if (P.timing && et == 0) {
+                const long long e2 = clock64();
+                P.timing[blockIdx.x * 8 + 4] += e1 - e0;  // waiting for the accumulators
+                P.timing[blockIdx.x * 8 + 5] += e2 - e1;  // phase A
+            }
             // phase B: thresholds and candidates
             if (MODE == FAST_EMIT) {
                 const float cut = fmaxf(thr, -FLT_MAX);  // padding rows score -inf: never candidates

@@ -76,6 +76,50 @@ class ShardedIVFFlat:
             self.index = None
 
 
+def row_range(n: int, rank: int, world: int):
+    """Contiguous row block of `rank`: [g*N/G, (g+1)*N/G), so ascending global ids = (rank, local id) order."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+class ShardedFlat:
+    """Row-sharded exact flat search (BASELINE configs[2]): rank g holds rows [g*N/G, (g+1)*N/G) (+ norms), queries are
+    replicated, every rank produces a local top-k with global row ids, one all-gather of G*nq*k (distance, id) pairs and
+    the merge kernel give the global top-k.  Ties across shards resolve by rank = by global row index, like the
+    single-GPU stable sort (src/hnsw/bench.clj:72-84)."""
+
+    def __init__(self, local_rows, first_row: int, rank: int, world: int, distance_fn="cosine", group=None):
+        from .flat import FlatIndex
+
+        self.rank, self.world, self.group, self.first_row = rank, world, group, int(first_row)
+        self.index = FlatIndex(local_rows, distance_fn) if len(local_rows) else None
+
+    def local_search(self, queries, k: int):
+        if hb._is_torch(queries) and queries.is_cuda:
+            import torch
+
+            nq = queries.shape[0]
+            ids = torch.full((nq, k), -1, dtype=torch.int64, device=queries.device)
+            dist = torch.full((nq, k), float("inf"), dtype=torch.float64, device=queries.device)
+            if self.index is not None:
+                self.index.search_raw(queries, k, out_ids=ids, out_dist=dist)
+                ids = torch.where(ids >= 0, ids + self.first_row, ids)
+            return ids, dist
+        q = hb.as_matrix(queries, allow=(hb.F32, hb.F64))
+        if self.index is None:
+            return np.full((q.shape[0], k), -1, np.int64), np.full((q.shape[0], k), np.inf)
+        ids, dist = self.index.search_raw(q, k)
+        return np.where(ids >= 0, ids + self.first_row, -1), dist
+
+    def search(self, queries, k: int):
+        ids, dist = self.local_search(queries, k)
+        return all_gather_merge(ids, dist, self.world, self.group)
+
+    def close(self):
+        if self.index is not None:
+            self.index.close()
+            self.index = None
+
+
 def all_gather_merge(ids, dist, world: int, group=None):
     """All-gather the per-rank (dist, id) blocks and merge them: ties by (rank, position) as in the stable
     sort of the concatenation, src/hnsw/ann/partition/ivf_flat.clj:291-294."""

@@ -58,7 +58,14 @@ def _worker(rank, world, port, ret):
     nz = tc.numpy() > 0
     new[nz] = ts.numpy()[nz] / tc.numpy()[nz, None]
     ok2 = np.allclose(new, orc.update_centroids(rows, asg, cents), rtol=1e-13, atol=0)
-    ret[rank] = (ok, ok2)
+    # row-sharded flat search (configs[2]): contiguous row blocks, local exact top-k, all-gather, merge
+    lo, hi = sharded.row_range(rows.shape[0], rank, world)
+    f_ids, f_dist = orc.exact_knn(rows[lo:hi], q, k)
+    f_ids = np.where(f_ids >= 0, f_ids + lo, -1)
+    m_ids, m_d = sharded.all_gather_merge(f_ids, f_dist, world)
+    w_ids, w_d = orc.exact_knn(rows, q, k)
+    ok3 = m_ids.tolist() == w_ids.tolist() and m_d.tolist() == w_d.tolist()
+    ret[rank] = (ok, ok2 and ok3)
     dist.barrier()
     dist.destroy_process_group()
 

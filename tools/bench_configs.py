@@ -109,63 +109,100 @@ def run_c1(args):
 
 
 def run_c3(args):
+    """One GPU: the whole matrix.  Under torchrun (WORLD_SIZE = G): rows sharded [g*N/G, (g+1)*N/G), queries replicated,
+    local top-100 -> NCCL all-gather -> merge kernel (hnsw_clj_b200/sharded.py: ShardedFlat); strong scaling."""
     import torch
 
     from hnsw_clj_b200 import _lib as hb
-    from hnsw_clj_b200.flat import FlatIndex
+    from hnsw_clj_b200.sharded import ShardedFlat, row_range
 
-    dev = torch.device("cuda", 0)
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    hb.check(hb.lib().hb_init(local))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     n, d, nq, k = args.n or 10_000_000, 768, 4096, 100
+    lo, hi = row_range(n, rank, world)
     g = torch.Generator(device=dev)
-    g.manual_seed(42)
-    rows = torch.empty((n, d), dtype=torch.bfloat16, device=dev)
-    for i in range(0, n, 1 << 20):
-        m = min(1 << 20, n - i)
+    g.manual_seed(42 + rank)
+    rows = torch.empty((hi - lo, d), dtype=torch.bfloat16, device=dev)
+    for i in range(0, hi - lo, 1 << 20):
+        m = min(1 << 20, hi - lo - i)
         rows[i:i + m] = torch.randn((m, d), generator=g, device=dev).to(torch.bfloat16)
     g.manual_seed(43)
     queries = torch.randn((nq, d), generator=g, device=dev).to(torch.bfloat16).float().contiguous()
-    out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    ix = FlatIndex(rows, "ip")
+    sh = ShardedFlat(rows, lo, rank, world, "ip")
     del rows
     torch.cuda.synchronize()
     create_s = time.perf_counter() - t0
     hb.set_mode(hb.MODE_FAST)
     t0 = time.perf_counter()
-    ix.search_raw(queries, k, out_ids=out_ids, out_dist=out_d)  # first call quantises the rows (digit images)
+    sh.search(queries, k)  # first call quantises the rows (digit images)
     torch.cuda.synchronize()
     first_s = time.perf_counter() - t0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
     hb.set_option("profile", 1)
-    ms = timed(lambda: ix.search_raw(queries, k, out_ids=out_ids, out_dist=out_d), reps=args.reps, warm=1)
-    stats = {nm: hb.get_stat(nm) / (args.reps + 1) for nm in ("tc_ms", "tc_sample_ms", "select_ms", "pack_ms", "rescore_ms")}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.reps):
+        out_ids, out_d = sh.search(queries, k)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.reps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    stats = {nm: hb.get_stat(nm) / args.reps for nm in ("tc_ms", "tc_sample_ms", "select_ms", "pack_ms", "rescore_ms")}
     served, fell = hb.get_stat("fast_queries"), hb.get_stat("fast_fallbacks")
     hb.set_option("profile", 0)
     fast_ids, fast_d = out_ids.cpu().numpy().copy(), out_d.cpu().numpy().copy()
-    # the exact mode (fp64 for every pair) on a sample of the queries
+    # the exact mode (fp64 for every pair) on a sample of the queries, through the same sharded path
     hb.set_mode(hb.MODE_EXACT)
     s = 64
-    e_ids, e_d = ix.search_raw(queries[:s].contiguous(), k)
-    if hasattr(e_ids, "cpu"):
-        e_ids, e_d = e_ids.cpu().numpy(), e_d.cpu().numpy()
-    ms_exact = timed(lambda: ix.search_raw(queries[:s].contiguous(), k), reps=1, warm=0)
-    info = ix.info()
-    ix.close()
-    flops = 2.0 * nq * n * d
-    pk = peaks()
-    bf16 = pk.get("bf16_tflops", 1590.0)
-    line = {
-        "config": f"BASELINE configs[2] on one GPU: flat {n}x{d} bf16 inner product, {nq} queries, top-{k} (Gaussian rows)",
-        "metric": "queries/s", "value": nq / ms * 1e3, "ms_per_batch": ms, "mode": "fast (int8 x2-digit tcgen05 candidate pass, 128 re-scored, proof)",
-        "exact_mode_qps_on_sample": s / ms_exact * 1e3,
-        "parity": {"sample_queries": s, "ids_equal": bool((fast_ids[:s] == e_ids).all()), "dist_bits_equal": same_bits(fast_d[:s], e_d)},
-        "fast_queries": served, "fast_fallbacks": fell, "index_create_s": create_s, "first_call_s": first_s,
-        "device_bytes": info["device_bytes"], "step_breakdown_ms": stats,
-        "roofline": {"bound": "tensor", "algorithmic_flops": flops, "achieved_tflops": flops / ms / 1e9, "peak_bf16_tflops": bf16,
-                     "frac": flops / ms / 1e9 / bf16, "algorithmic_bytes": float(n) * d * 2, "hbm_gbs_at_unique_bytes": n * d * 2 / ms / 1e6},
-    }
-    print(json.dumps(line), flush=True)
+    qs = queries[:s].contiguous()
+    e_ids, e_d = sh.search(qs, k)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sh.search(qs, k)
+    torch.cuda.synchronize()
+    ms_exact = (time.perf_counter() - t0) * 1e3
+    e_ids, e_d = e_ids.cpu().numpy(), e_d.cpu().numpy()
+    info = sh.index.info()
+    sh.close()
+    if rank == 0:
+        flops = 2.0 * nq * n * d
+        pk = peaks()
+        bf16 = pk.get("bf16_tflops", 1590.0)
+        line = {
+            "config": f"BASELINE configs[2]: flat {n}x{d} bf16 inner product, {nq} queries, top-{k} (Gaussian rows), rows sharded over {world} GPU(s)",
+            "metric": "queries/s", "value": nq / ms * 1e3, "ms_per_batch": ms, "n_gpus": world, "scaling": "strong",
+            "mode": "fast (int8 x2-digit tcgen05 candidate pass, 128 re-scored, proof)" + ("; NCCL all-gather + merge kernel" if world > 1 else ""),
+            "exact_mode_qps_on_sample": s / ms_exact * 1e3,
+            "parity": {"sample_queries": s, "ids_equal": bool((fast_ids[:s] == e_ids).all()), "dist_bits_equal": same_bits(fast_d[:s], e_d)},
+            "fast_queries_rank0": served, "fast_fallbacks_rank0": fell, "index_create_s": create_s, "first_call_s": first_s,
+            "device_bytes_rank0": info["device_bytes"], "step_breakdown_ms_rank0": stats,
+            "roofline": {"bound": "tensor", "algorithmic_flops": flops, "achieved_tflops": flops / ms / 1e9,
+                         "peak_bf16_tflops_per_gpu": bf16, "frac": flops / ms / 1e9 / (bf16 * world),
+                         "algorithmic_bytes": float(n) * d * 2, "hbm_gbs_at_unique_bytes": n * d * 2 / ms / 1e6},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_c4(args):
@@ -298,7 +335,7 @@ def main():
     args = ap.parse_args()
     from hnsw_clj_b200 import _lib as hb
 
-    hb.check(hb.lib().hb_init(0))
+    hb.check(hb.lib().hb_init(int(os.environ.get("LOCAL_RANK", "0"))))
     {"c1": run_c1, "c3": run_c3, "c4": run_c4, "c5": run_c5}[args.config](args)
 
 

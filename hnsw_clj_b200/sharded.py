@@ -179,3 +179,35 @@ def sharded_kmeans_update(rows, assignments, centroids, group=None):
     nz = tc > 0
     out[nz] = ts[nz] / tc[nz, None].astype(np.float64)
     return out
+
+
+def lloyd_round_device(rows, centroids, assign_out, group=None, world: int = 1):
+    """One Lloyd round of partition-vectors-kmeans (ivf_flat.clj:100-118) on device tensors, rows sharded across ranks:
+    assign this rank's rows (hb_kmeans_assign; FAST mode runs the tensor-core candidate pass), per-cluster fp64 sums and
+    counts of the shard (hb_kmeans_update), all-reduce(sum) over the ranks, divide; an empty cluster keeps its centroid
+    (:112-116).  `centroids` [nlist, d] fp64 is updated in place and identical on every rank afterwards.
+    Returns (assign_ms, update_ms, allreduce_ms) measured with CUDA events."""
+    import torch
+    import torch.distributed as dist_
+
+    L = hb.lib()
+    n, d = rows.shape
+    nlist = centroids.shape[0]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    sums = torch.empty((nlist, d), dtype=torch.float64, device=rows.device)
+    cnt = torch.empty(nlist, dtype=torch.int64, device=rows.device)
+    ev[0].record()
+    hb.check(L.hb_kmeans_assign(rows.data_ptr(), n, d, hb.dtype_code(rows), hb.COSINE, centroids.data_ptr(), nlist,
+                                assign_out.data_ptr()))
+    ev[1].record()
+    hb.check(L.hb_kmeans_update(rows.data_ptr(), n, d, hb.dtype_code(rows), assign_out.data_ptr(), nlist, None,
+                                sums.data_ptr(), cnt.data_ptr()))
+    ev[2].record()
+    if world > 1:
+        dist_.all_reduce(sums, group=group)
+        dist_.all_reduce(cnt, group=group)
+    nz = cnt > 0
+    centroids[nz] = sums[nz] / cnt[nz].to(torch.float64).unsqueeze(1)
+    ev[3].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])

@@ -3,6 +3,7 @@
     python tools/bench_configs.py c1            # 31,173 x 768 fp32 cosine, 1000 queries, flat top-10 (configs[0])
     python tools/bench_configs.py c3 [--n N]    # flat N x 768 bf16 inner product, 4096 queries, top-100 (configs[2], one GPU's rows)
     python tools/bench_configs.py c4 [--n N]    # one Lloyd round (assign + update) on one GPU's shard of configs[3]
+    torchrun ... tools/bench_configs.py c4full  # configs[3] as named: 100 M rows over the GPUs of the box, 10 Lloyd rounds
     python tools/bench_configs.py c5 [--n N]    # batched HNSW search, M=16 ef=128, 16k queries (configs[4], reduced graph)
 
 Every command prints ONE JSON line (device-resident inputs, CUDA events on the launching stream, inputs larger than L2
@@ -270,6 +271,110 @@ def run_c4(args):
     print(json.dumps(line), flush=True)
 
 
+def run_c4_full(args):
+    """BASELINE configs[3] as named: k-means on N x 768 fp32 (default 100 M), nlist 65,536, `--iters` Lloyd rounds + the final
+    assignment, rows sharded over the GPUs of the box (torchrun).  Seeds are given (rows of rank 0's shard): the
+    reference's k-means++ is a sequential O(N) prefix walk per seed and cannot be run at this nlist."""
+    import torch
+    import torch.distributed as dist
+
+    from hnsw_clj_b200 import _lib as hb
+    from hnsw_clj_b200.sharded import lloyd_round_device, row_range
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n, d, nlist, iters = args.n or 100_000_000, 768, args.nlist, args.iters
+    lo, hi = row_range(n, rank, world)
+    nl = hi - lo
+    g = torch.Generator(device=dev)
+    g.manual_seed(42)
+    ncent = max(nlist // 2, 8)
+    centres = torch.randn((ncent, d), generator=g, device=dev)  # same centres on every rank
+    g.manual_seed(1000 + rank)
+    rows = torch.empty((nl, d), dtype=torch.float32, device=dev)
+    for i in range(0, nl, 1 << 19):
+        m = min(1 << 19, nl - i)
+        idx = torch.randint(0, ncent, (m,), generator=g, device=dev)
+        rows[i:i + m] = centres[idx] + 0.1 * torch.randn((m, d), generator=g, device=dev)
+    del centres
+    cents = torch.empty((nlist, d), dtype=torch.float64, device=dev)
+    if rank == 0:
+        cents.copy_(rows[torch.randperm(nl, generator=g, device=dev)[:nlist]].double())
+    if world > 1:
+        dist.broadcast(cents, 0)
+    asg = torch.empty(nl, dtype=torch.int32, device=dev)
+    hb.set_mode(hb.MODE_FAST)
+    hb.set_option("profile", 1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    per_round = []
+    for _ in range(iters):
+        per_round.append(lloyd_round_device(rows, cents, asg, world=world))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    hb.check(hb.lib().hb_kmeans_assign(rows.data_ptr(), nl, d, hb.F32, hb.COSINE, cents.data_ptr(), nlist, asg.data_ptr()))
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_s = time.perf_counter() - t0
+    served, fell = hb.get_stat("fast_queries"), hb.get_stat("fast_fallbacks")
+    hb.set_option("profile", 0)
+    tt = torch.tensor([total_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_s = float(tt.item())
+    # exact mode on a sample of this rank's rows against the final centroids
+    hb.set_mode(hb.MODE_EXACT)
+    s = min(nl, 8192)
+    sample = rows[:s].contiguous()
+    e_asg = torch.empty(s, dtype=torch.int32, device=dev)
+    hb.check(hb.lib().hb_kmeans_assign(sample.data_ptr(), s, d, hb.F32, hb.COSINE, cents.data_ptr(), nlist, e_asg.data_ptr()))
+    equal = torch.tensor([int((e_asg == asg[:s]).all().item())], device=dev)
+    csum = cents.sum(dtype=torch.float64).reshape(1).clone()
+    if world > 1:
+        dist.all_reduce(equal, op=dist.ReduceOp.MIN)
+        gathered = [torch.empty_like(csum) for _ in range(world)]
+        dist.all_gather(gathered, csum)
+        same_c = all(bool((x == gathered[0]).all().item()) for x in gathered)
+    else:
+        same_c = True
+    if rank == 0:
+        a_ms = [r[0] for r in per_round]
+        u_ms = [r[1] for r in per_round]
+        r_ms = [r[2] for r in per_round]
+        flops = 2.0 * n * nlist * d
+        pk = peaks()
+        bf16 = pk.get("bf16_tflops", 1590.0)
+        mean_a = sum(a_ms) / max(len(a_ms), 1)
+        line = {
+            "config": f"BASELINE configs[3]: IVF k-means build {n}x{d} fp32, nlist={nlist}, {iters} Lloyd rounds + final assignment, "
+                      f"rows sharded over {world} GPU(s) ({nl} rows = {nl * d * 4 / 1e9:.1f} GB per GPU); seeds given",
+            "metric": "seconds for the Lloyd rounds + final assignment", "value": total_s, "n_gpus": world, "higher_is_better": False,
+            "assign_ms_per_round_rank0": a_ms, "update_ms_per_round_rank0": u_ms, "allreduce_divide_ms_per_round_rank0": r_ms,
+            "final_assign_ms_rank0": e0.elapsed_time(e1),
+            "assign_mode": "fast (k=1 candidate pass over the centroids on tcgen05 + fp64 re-score + proof)",
+            "fast_rows_rank0": served, "fast_fallbacks_rank0": fell,
+            "parity": {"sample_rows_per_rank": s, "final_assignments_equal_exact_mode_on_every_rank": bool(equal.item()),
+                       "centroids_identical_on_every_rank": same_c},
+            "roofline": {"bound": "tensor", "algorithmic_flops_per_assign_pass": flops,
+                         "achieved_tflops_assign": flops / mean_a / 1e9 if a_ms else None, "peak_bf16_tflops_per_gpu": bf16,
+                         "frac": (flops / mean_a / 1e9 / (bf16 * world)) if a_ms else None,
+                         "allreduce_bytes_per_round": nlist * d * 8 + nlist * 8},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_c5(args):
     import torch
 
@@ -328,7 +433,8 @@ def run_c5(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("config", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("config", choices=["c1", "c3", "c4", "c4full", "c5"])
+    ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--nlist", type=int, default=65536)
     ap.add_argument("--reps", type=int, default=2)
@@ -336,7 +442,7 @@ def main():
     from hnsw_clj_b200 import _lib as hb
 
     hb.check(hb.lib().hb_init(int(os.environ.get("LOCAL_RANK", "0"))))
-    {"c1": run_c1, "c3": run_c3, "c4": run_c4, "c5": run_c5}[args.config](args)
+    {"c1": run_c1, "c3": run_c3, "c4": run_c4, "c4full": run_c4_full, "c5": run_c5}[args.config](args)
 
 
 if __name__ == "__main__":

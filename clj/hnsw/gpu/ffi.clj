@@ -41,6 +41,9 @@
 (defonce hb-search (handle "hb_search" I P P I J I I P P))
 ;; int hb_gather_score(index, queries, qdtype, nq, pair_query, pair_row, npairs, out)
 (defonce hb-gather-score (handle "hb_gather_score" I P P I J P P J P))
+;; int hb_index_save(const hb_index*, const char* path); int hb_index_load(const char* path, hb_index** out)
+(defonce hb-index-save (handle "hb_index_save" I P P))
+(defonce hb-index-load (handle "hb_index_load" I P P))
 ;; int hb_index_free(hb_index*)
 (defonce hb-index-free (handle "hb_index_free" I P))
 

@@ -2,7 +2,8 @@
   "Drop-in for hnsw.ann.partition.ivf-flat (src/hnsw/ann/partition/ivf_flat.clj:300-327): same build-index /
    search-knn / index-info signatures and option keys, device-resident index behind libhnswb200.so.
    Adds search-batch (BatchSearchIndex/search-batch*, src/hnsw/api/protocol.clj:58-67): ONE device call for all queries."
-  (:require [hnsw.gpu.ffi :as ffi]
+  (:require [clojure.edn]
+            [hnsw.gpu.ffi :as ffi]
             [hnsw.api.protocol :as proto])
   (:import [java.lang.foreign Arena MemorySegment ValueLayout]
            [java.lang.invoke MethodHandle]))
@@ -62,6 +63,29 @@
 
 (defn index-info [^GpuIVFFlatIndex index]
   {:type "IVF-FLAT (B200)" :vectors (count (:ids index)) :partitions (:num-partitions index)})
+
+(defn save-index
+  "Device layout -> `filepath` (hb_index_save) + the String ids as EDN beside it.  The reference has no IVF-FLAT
+   persistence; the signature follows hnsw.helper.index-io/save-index (src/hnsw/helper/index_io.clj:10-39)."
+  [^GpuIVFFlatIndex index ^String filepath]
+  (with-open [arena (Arena/ofConfined)]
+    (ffi/check! (.invokeWithArguments ^MethodHandle ffi/hb-index-save
+                                      (object-array [(:handle index) (.allocateFrom arena filepath)]))))
+  (spit (str filepath ".ids.edn") (pr-str {:ids (:ids index) :dim (:dim index) :num-partitions (:num-partitions index)
+                                           :distance-fn (:distance-fn index)}))
+  index)
+
+(defn load-index
+  "nil when the file does not exist, like hnsw.helper.index-io/load-index (src/hnsw/helper/index_io.clj:78-80)."
+  [^String filepath]
+  (when (.exists (java.io.File. filepath))
+    (with-open [arena (Arena/ofConfined)]
+      (let [out (.allocate arena ValueLayout/ADDRESS)
+            meta (clojure.edn/read-string (slurp (str filepath ".ids.edn")))]
+        (ffi/check! (.invokeWithArguments ^MethodHandle ffi/hb-index-load
+                                          (object-array [(.allocateFrom arena filepath) out])))
+        (->GpuIVFFlatIndex (.get out ValueLayout/ADDRESS 0) (:ids meta) (:dim meta) (:num-partitions meta)
+                           (:distance-fn meta))))))
 
 (defn close! [^GpuIVFFlatIndex index]
   (ffi/check! (.invokeWithArguments ^MethodHandle ffi/hb-index-free (object-array [(:handle index)]))))

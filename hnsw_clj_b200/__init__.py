@@ -5,6 +5,7 @@ Python host side of the C ABI (libhnswb200.so); module names follow the referenc
   flat            <- hnsw.bench/compute-exact-knn (exact flat search)
   ivf_flat        <- hnsw.ann.partition.ivf-flat  (build-index / search-knn / index-info)
   ultra_fast      <- hnsw.ultra-fast              (HNSW neighbour-candidate scoring on an uploaded graph)
+  index_io        <- hnsw.helper.index-io         (save-index / load-index of the device layout)
   api             <- hnsw.api + hnsw.api.protocol (index / search, ANNIndex + BatchSearchIndex)
   parallel_search <- hnsw.helper.parallel-search  (batch fan-out, here one batched device call)
   sharded         <- row-sharded multi-GPU search (torch.distributed all-gather + merge kernel)

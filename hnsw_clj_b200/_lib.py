@@ -64,6 +64,8 @@ SIGNATURES = {
     "hb_gather_score": (_int, [_p, _p, _int, _i64, _p, _p, _i64, _p]),
     "hb_fast_scores": (_int, [_p, _p, _int, _i64, _p, _p, _p]),
     "hb_topk_merge": (_int, [_p, _p, _i32, _i64, _i32, _p, _p]),
+    "hb_index_save": (_int, [_p, C.c_char_p]),
+    "hb_index_load": (_int, [C.c_char_p, _pp]),
     "hb_index_info": (_int, [_p, C.POINTER(HbInfo)]),
     "hb_index_free": (_int, [_p]),
 }

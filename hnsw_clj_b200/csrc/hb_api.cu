@@ -1,5 +1,6 @@
 // hb_api.cu — the C ABI of libhnswb200.so (include/hnswb200.h): handles, staging of host/device buffers and
 // the orchestration of the kernels behind hnsw-clj's build-index / search-knn / search-batch* surface.
+#include <errno.h>
 #include <float.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1137,18 +1138,35 @@ static void assign_rows(const void *rows, int dtype, const double *row_norm, int
     launch_pos_to_i32(ids64, n, assign);
 }
 
+// Host queries arrive in blocks on a copy stream while the per-query stages (norms, digits, coarse routing) of the blocks
+// already on the device run: the H2D copy of a 10k x 768 batch is 0.55 ms, as long as the whole coarse stage.
+struct HostFeed {
+    int64_t block = 0;                // queries per block
+    std::vector<cudaEvent_t> ready;   // ready[b]: block b is on the device
+};
+static cudaStream_t g_copy_stream = nullptr;
+// hb_set_option("host_feed", block).  Off by default: measured at configs[1] (10k x 768 fp32 queries) the per-block coarse
+// stage costs more than the hidden copy saves (e2e 3.52 ms with one copy, 3.80 ms in blocks of 2048, 4.67 ms in blocks of 1024).
+static int64_t g_host_feed_block = 0;
+
 // search-ivf-flat in FAST mode: coarse routing and the probed-list scan both run the candidate pass
 static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64_t nq, int k, int nprobe, int64_t *ids,
-                            double *dist) {
+                            double *dist, const HostFeed *feed = nullptr) {
     if (nq == 0 || k == 0) return;
+    auto wait_all = [&] {
+        if (feed)
+            for (cudaEvent_t e : feed->ready) HB_CUDA(cudaStreamWaitEvent(g_stream, e, 0));
+    };
     const int d = ix->d, nlist = ix->nlist;
     const int np_eff = std::min(nprobe, nlist);
     if (ix->n == 0 || nlist == 0 || k > kFastMaxK || ix->n >= (1ll << 31) || np_eff < 1) {
+        wait_all();
         ivf_search_exact(ix, queries, qdtype, nq, k, nprobe, ids, dist, nullptr);
         return;
     }
     FastSideBufs &S = fast_rows_side(ix, true);
     if (!S.usable) {
+        wait_all();
         ivf_search_exact(ix, queries, qdtype, nq, k, nprobe, ids, dist, nullptr);
         return;
     }
@@ -1158,43 +1176,64 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
     const size_t qsz = dtype_size(qdtype);
     int64_t qc = std::max<int64_t>(kFastTile, (1ll << 20) / np_eff);
     qc = std::min(qc, nq);
+    if (feed) {  // query chunks must start on a block boundary of the feed
+        if (qc >= feed->block && qc < nq) qc -= qc % feed->block;
+        else if (qc < feed->block) {
+            wait_all();
+            feed = nullptr;
+        }
+    }
     FastWs &W = g_fw;
     int32_t *ok_all = W.ok_a.as<int32_t>(nq);
     for (int64_t q0 = 0; q0 < nq; q0 += qc) {
         const int64_t nqc = std::min(qc, nq - q0);
         const void *qptr = (const char *)queries + (size_t)q0 * d * qsz;
         double *qn = g_ws.qnorm.as<double>(nqc);
-        launch_row_norms(qptr, qdtype, nqc, d, qn);
-        fast_quant_queries(qptr, qdtype, nqc, d);
-        const double *q64 = launch_widen_queries(qptr, qdtype, nqc * d, g_fw.q64.as<double>((size_t)nqc * d));
+        double *q64buf = g_fw.q64.as<double>((size_t)nqc * d);
+        const double *q64 = qdtype == HB_F64 ? (const double *)qptr : q64buf;
         int64_t *ppos = W.ppos.as<int64_t>((size_t)nqc * np_eff);
         int32_t *ok_c = W.ok_b.as<int32_t>(nqc);
         if (coarse_tc) {
             Prof pr(PROF_COARSE);
-            FastJob J;
-            J.side = C;
-            J.list_off = (const int64_t *)C->list_off.p;
-            J.rows_exact = ix->cents.p;
-            J.rdtype = HB_F64;
-            J.row_norm = (const double *)ix->cent_norm.p;
-            J.queries = qptr;
-            J.qdtype = qdtype;
-            J.q64 = q64;
-            J.nq = nqc;
-            J.qn = qn;
-            J.d = d;
-            J.metric = HB_COSINE;
-            J.epi = EPI_COS_GUARD;
-            J.profile = false;
-            J.k = np_eff;
-            flat_fast_plan(nqc, J.emit, J.thresh, W.flat_plan);
-            J.shared_units = true;
-            J.out_rel = ppos;
-            J.out_dist = W.tmp2.as<double>((size_t)nqc * np_eff);
-            J.out_ok = ok_c;
-            fast_topk(J);
+            // per-query stages in blocks (the blocks of a host batch as they arrive; a device batch is one block)
+            const int64_t blk = (feed && feed->block > 0) ? feed->block : nqc;
+            for (int64_t b0 = 0; b0 < nqc; b0 += blk) {
+                const int64_t nb = std::min(blk, nqc - b0);
+                if (feed) HB_CUDA(cudaStreamWaitEvent(g_stream, feed->ready[(size_t)((q0 + b0) / feed->block)], 0));
+                const void *bptr = (const char *)qptr + (size_t)b0 * d * qsz;
+                launch_row_norms(bptr, qdtype, nb, d, qn + b0);
+                fast_quant_queries(bptr, qdtype, nb, d);
+                const double *b64 = launch_widen_queries(bptr, qdtype, nb * d, q64buf + (size_t)b0 * d);
+                FastJob J;
+                J.side = C;
+                J.list_off = (const int64_t *)C->list_off.p;
+                J.rows_exact = ix->cents.p;
+                J.rdtype = HB_F64;
+                J.row_norm = (const double *)ix->cent_norm.p;
+                J.queries = bptr;
+                J.qdtype = qdtype;
+                J.q64 = b64;
+                J.nq = nb;
+                J.qn = qn + b0;
+                J.d = d;
+                J.metric = HB_COSINE;
+                J.epi = EPI_COS_GUARD;
+                J.profile = false;
+                J.k = np_eff;
+                flat_fast_plan(nb, J.emit, J.thresh, W.flat_plan);
+                J.shared_units = true;
+                J.out_rel = ppos + (size_t)b0 * np_eff;
+                J.out_dist = W.tmp2.as<double>((size_t)nb * np_eff);
+                J.out_ok = ok_c + b0;
+                fast_topk(J);
+            }
+            if (blk < nqc) fast_quant_queries(qptr, qdtype, nqc, d);  // the list scan packs its units from the whole batch's digits
         } else {
             Prof pr(PROF_COARSE);
+            wait_all();
+            launch_row_norms(qptr, qdtype, nqc, d, qn);
+            fast_quant_queries(qptr, qdtype, nqc, d);
+            launch_widen_queries(qptr, qdtype, nqc * d, q64buf);
             bool cl2;
             int cepi;
             metric_to_epi(ix->metric == HB_IP ? HB_COSINE : ix->metric, true, cl2, cepi);
@@ -1462,6 +1501,9 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             for (int i = 0; i < PROF_NTAGS; ++i) g_prof_ms[i] = 0, g_prof_n[i] = 0;
             g_fast_queries = g_fast_fallbacks = 0;
             g_hnsw_scored = g_hnsw_overflows = 0;
+        } else if (!strcmp(name, "host_feed")) {
+            HB_REQUIRE(value == 0 || (value >= 128 && value % 128 == 0), "host_feed must be 0 or a multiple of 128");
+            g_host_feed_block = value;
         } else if (!strcmp(name, "hnsw_cand_cap")) {
             HB_REQUIRE(value >= 0 && value <= 8192, "hnsw_cand_cap must be 0..8192");
             g_hnsw_cand_cap = (int)value;
@@ -1687,7 +1729,34 @@ HB_API int hb_search(hb_index *index, const void *queries, int qdtype, int64_t n
         if (nq == 0 || k == 0) return;
         HB_REQUIRE(queries && out_ids && out_dist, "null buffer");
         HB_REQUIRE(k <= 1024, "k > 1024 is not supported");
-        const void *q = stage_in(queries, (size_t)nq * index->d * dtype_size(qdtype), g_ws.in_b);
+        HostFeed feed;
+        const void *q = nullptr;
+        const size_t qrow = (size_t)index->d * dtype_size(qdtype);
+        if (index->type == HB_INDEX_IVF_FLAT && g_mode == HB_MODE_FAST && !is_device_ptr(queries) && g_host_feed_block > 0 &&
+            nq >= 2 * g_host_feed_block) {
+            // blocks of 2048 queries on a copy stream, one event each (pinned host memory makes the copies asynchronous)
+            if (!g_copy_stream) HB_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+            char *dq = (char *)g_ws.in_b.get((size_t)nq * qrow);
+            feed.block = g_host_feed_block;
+            for (int64_t b0 = 0; b0 < nq; b0 += feed.block) {
+                const int64_t nb = std::min<int64_t>(feed.block, nq - b0);
+                HB_CUDA(cudaMemcpyAsync(dq + (size_t)b0 * qrow, (const char *)queries + (size_t)b0 * qrow, (size_t)nb * qrow,
+                                        cudaMemcpyHostToDevice, g_copy_stream));
+                cudaEvent_t e;
+                HB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                HB_CUDA(cudaEventRecord(e, g_copy_stream));
+                feed.ready.push_back(e);
+            }
+            q = dq;
+        } else {
+            q = stage_in(queries, (size_t)nq * qrow, g_ws.in_b);
+        }
+        struct FeedGuard {
+            HostFeed &f;
+            ~FeedGuard() {
+                for (cudaEvent_t e : f.ready) cudaEventDestroy(e);
+            }
+        } feed_guard{feed};
         OutStage oi = stage_out(out_ids, (size_t)nq * k * 8, g_ws.out_a);
         OutStage od = stage_out(out_dist, (size_t)nq * k * 8, g_ws.out_b);
         if (index->type == HB_INDEX_FLAT) {
@@ -1697,7 +1766,8 @@ HB_API int hb_search(hb_index *index, const void *queries, int qdtype, int64_t n
                                   qdtype, nq, k, (int64_t *)oi.dev, (double *)od.dev);
         } else if (index->type == HB_INDEX_IVF_FLAT) {
             HB_REQUIRE(param >= 1, "num-probes must be >= 1");
-            if (g_mode == HB_MODE_FAST) ivf_search_fast(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev);
+            if (g_mode == HB_MODE_FAST)
+                ivf_search_fast(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev, feed.block ? &feed : nullptr);
             else ivf_search_exact(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev, nullptr);
         } else if (index->type == HB_INDEX_HNSW) {
             HB_REQUIRE(param >= 0, "ef must be >= 0");
@@ -1993,6 +2063,199 @@ HB_API int hb_fast_scores(hb_index *index, const void *queries, int qdtype, int6
         finish_out(oc);
         finish_out(oe);
         sync_stream();
+    });
+}
+
+// ---- persistence of the device layout -----------------------------------------------------------------
+// The reference persists only the HNSW graph, as EDN text (pr-str of every double, src/hnsw/helper/index_io.clj:10-80:
+// 492.9 MB for 31 k vectors, README.md:22) and has no save / load for IVF-FLAT at all.  Here the file is the device layout
+// itself: a fixed header, then tagged sections holding the index's device arrays verbatim (list-major slab, fp64 norms,
+// centroids, list offsets, ...), so loading is file -> pinned staging -> HBM with no re-clustering, no norm pass and no
+// re-ordering.  The FAST-mode digit images are derived data and are rebuilt on first use.
+namespace {
+constexpr uint64_t kFileMagic = 0x3130304958494248ull;  // "HBIXI001" little-endian
+constexpr size_t kIoChunk = 64u << 20;
+struct FileHeader {
+    uint64_t magic;
+    int32_t version, type, dtype, metric, d, nlist, max_level, entry;
+    int64_t n, max_list;
+    int32_t nsections, reserved;
+};
+enum SectionTag : uint32_t { SEC_ROWS = 1, SEC_NORMS, SEC_CENTS, SEC_CENT_NORM, SEC_LIST_OFF, SEC_LIST_ROWS, SEC_ASSIGN, SEC_LEVELS,
+                             SEC_ADJ_OFF = 0x100, SEC_ADJ_IDS = 0x200 };  // + level
+struct SectionHeader {
+    uint32_t tag, reserved;
+    uint64_t bytes;
+};
+struct PinnedChunk {
+    void *p = nullptr;
+    PinnedChunk() {
+        if (cudaMallocHost(&p, kIoChunk) != cudaSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+            throw Error(HB_ERR_OOM, "cudaMallocHost of the I/O staging chunk failed");
+        }
+    }
+    ~PinnedChunk() {
+        if (p) cudaFreeHost(p);
+    }
+};
+struct File {
+    FILE *f = nullptr;
+    File(const char *path, const char *mode) : f(fopen(path, mode)) {
+        if (!f) throw Error(HB_ERR_INVALID, std::string("cannot open ") + path + ": " + strerror(errno));
+    }
+    ~File() {
+        if (f) fclose(f);
+    }
+};
+void write_section(FILE *f, uint32_t tag, const void *dev, size_t bytes, PinnedChunk &pin) {
+    SectionHeader sh{tag, 0, (uint64_t)bytes};
+    if (fwrite(&sh, sizeof(sh), 1, f) != 1) throw Error(HB_ERR_INVALID, "write failed");
+    for (size_t o = 0; o < bytes; o += kIoChunk) {
+        const size_t c = std::min(kIoChunk, bytes - o);
+        HB_CUDA(cudaMemcpyAsync(pin.p, (const char *)dev + o, c, cudaMemcpyDeviceToHost, g_stream));
+        HB_CUDA(cudaStreamSynchronize(g_stream));
+        if (fwrite(pin.p, 1, c, f) != c) throw Error(HB_ERR_INVALID, "write failed (disk full?)");
+    }
+}
+void read_section(FILE *f, void *dev, size_t bytes, PinnedChunk &pin) {
+    for (size_t o = 0; o < bytes; o += kIoChunk) {
+        const size_t c = std::min(kIoChunk, bytes - o);
+        if (fread(pin.p, 1, c, f) != c) throw Error(HB_ERR_INVALID, "index file is truncated");
+        HB_CUDA(cudaMemcpyAsync((char *)dev + o, pin.p, c, cudaMemcpyHostToDevice, g_stream));
+        HB_CUDA(cudaStreamSynchronize(g_stream));
+    }
+}
+}  // namespace
+
+HB_API int hb_index_save(const hb_index *index, const char *path) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(index && path, "null argument");
+        const hb_index &ix = *index;
+        const int64_t n = ix.n;
+        struct Sec {
+            uint32_t tag;
+            const void *p;
+            size_t bytes;
+        };
+        std::vector<Sec> secs;
+        secs.push_back({SEC_ROWS, ix.rows.p, (size_t)n * ix.d * dtype_size(ix.dtype)});
+        secs.push_back({SEC_NORMS, ix.norms.p, (size_t)n * 8});
+        if (ix.type == HB_INDEX_IVF_FLAT) {
+            secs.push_back({SEC_CENTS, ix.cents.p, (size_t)ix.nlist * ix.d * 8});
+            secs.push_back({SEC_CENT_NORM, ix.cent_norm.p, (size_t)ix.nlist * 8});
+            secs.push_back({SEC_LIST_OFF, ix.list_off.p, ((size_t)ix.nlist + 1) * 8});
+            secs.push_back({SEC_LIST_ROWS, ix.list_rows.p, (size_t)n * 8});
+            secs.push_back({SEC_ASSIGN, ix.assign.p, (size_t)n * 4});
+        } else if (ix.type == HB_INDEX_HNSW && n > 0) {
+            secs.push_back({SEC_LEVELS, ix.levels.p, (size_t)n * 4});
+            for (int l = 0; l <= ix.max_level; ++l) {
+                int64_t tot = 0;
+                HB_CUDA(cudaMemcpyAsync(&tot, (const int64_t *)ix.adj_off[l].p + n, 8, cudaMemcpyDeviceToHost, g_stream));
+                sync_stream();
+                secs.push_back({SEC_ADJ_OFF + (uint32_t)l, ix.adj_off[l].p, ((size_t)n + 1) * 8});
+                secs.push_back({SEC_ADJ_IDS + (uint32_t)l, ix.adj_ids[l].p, (size_t)tot * 4});
+            }
+        }
+        FileHeader h{};
+        h.magic = kFileMagic;
+        h.version = 1;
+        h.type = ix.type, h.dtype = ix.dtype, h.metric = ix.metric, h.d = ix.d;
+        h.nlist = ix.nlist, h.max_level = ix.max_level, h.entry = ix.entry;
+        h.n = n, h.max_list = ix.max_list;
+        h.nsections = (int32_t)secs.size();
+        const std::string tmp = std::string(path) + ".tmp";
+        {
+            File f(tmp.c_str(), "wb");
+            PinnedChunk pin;
+            if (fwrite(&h, sizeof(h), 1, f.f) != 1) throw Error(HB_ERR_INVALID, "write failed");
+            for (const Sec &s : secs) write_section(f.f, s.tag, s.p, s.bytes, pin);
+            if (fflush(f.f) != 0) throw Error(HB_ERR_INVALID, "write failed");
+        }
+        if (rename(tmp.c_str(), path) != 0) throw Error(HB_ERR_INVALID, std::string("cannot rename to ") + path);
+    });
+}
+
+HB_API int hb_index_load(const char *path, hb_index **out) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(path && out, "null argument");
+        File f(path, "rb");
+        FileHeader h{};
+        if (fread(&h, sizeof(h), 1, f.f) != 1 || h.magic != kFileMagic) throw Error(HB_ERR_INVALID, "not an hnswb200 index file");
+        HB_REQUIRE(h.version == 1, "unsupported index file version");
+        HB_REQUIRE(h.type >= HB_INDEX_FLAT && h.type <= HB_INDEX_HNSW && h.n >= 0 && h.d >= 1 && h.nlist >= 0 && h.max_level >= 0 &&
+                       h.max_level < 64 && h.nsections >= 0 && h.nsections < 1024,
+                   "corrupt index file header");
+        check_dtype(h.dtype);
+        hb_index *ix = new hb_index();
+        try {
+            ix->type = h.type, ix->dtype = h.dtype, ix->metric = h.metric, ix->d = h.d;
+            ix->n = h.n, ix->nlist = h.nlist, ix->max_list = h.max_list, ix->max_level = h.max_level, ix->entry = h.entry;
+            const int64_t n = h.n;
+            if (ix->type == HB_INDEX_HNSW && n > 0) {
+                ix->adj_off.resize((size_t)h.max_level + 1);
+                ix->adj_ids.resize((size_t)h.max_level + 1);
+            }
+            PinnedChunk pin;
+            uint64_t seen = 0;  // bit per fixed tag
+            std::vector<char> seen_off((size_t)h.max_level + 1, 0), seen_ids((size_t)h.max_level + 1, 0);
+            for (int s = 0; s < h.nsections; ++s) {
+                SectionHeader sh{};
+                if (fread(&sh, sizeof(sh), 1, f.f) != 1) throw Error(HB_ERR_INVALID, "index file is truncated");
+                DevBuf *dst = nullptr;
+                size_t want = 0;
+                switch (sh.tag) {
+                    case SEC_ROWS: dst = &ix->rows, want = (size_t)n * h.d * dtype_size(h.dtype); break;
+                    case SEC_NORMS: dst = &ix->norms, want = (size_t)n * 8; break;
+                    case SEC_CENTS: dst = &ix->cents, want = (size_t)h.nlist * h.d * 8; break;
+                    case SEC_CENT_NORM: dst = &ix->cent_norm, want = (size_t)h.nlist * 8; break;
+                    case SEC_LIST_OFF: dst = &ix->list_off, want = ((size_t)h.nlist + 1) * 8; break;
+                    case SEC_LIST_ROWS: dst = &ix->list_rows, want = (size_t)n * 8; break;
+                    case SEC_ASSIGN: dst = &ix->assign, want = (size_t)n * 4; break;
+                    case SEC_LEVELS: dst = &ix->levels, want = (size_t)n * 4; break;
+                    default: {
+                        const uint32_t l = sh.tag & 0xff;
+                        HB_REQUIRE(ix->type == HB_INDEX_HNSW && n > 0 && l <= (uint32_t)h.max_level, "unknown section in index file");
+                        if ((sh.tag & ~0xffu) == SEC_ADJ_OFF) dst = &ix->adj_off[l], want = ((size_t)n + 1) * 8, seen_off[l] = 1;
+                        else if ((sh.tag & ~0xffu) == SEC_ADJ_IDS) dst = &ix->adj_ids[l], want = sh.bytes, seen_ids[l] = 1;
+                        else throw Error(HB_ERR_INVALID, "unknown section in index file");
+                    }
+                }
+                HB_REQUIRE(sh.bytes == want, "section size does not match the header");
+                if (sh.tag < 64) seen |= 1ull << sh.tag;
+                void *p = dst->get(std::max<size_t>(want, 16));
+                read_section(f.f, p, want, pin);
+            }
+            auto need = [&](uint32_t tag) { HB_REQUIRE(seen >> tag & 1, "index file lacks a required section"); };
+            need(SEC_ROWS), need(SEC_NORMS);
+            if (ix->type == HB_INDEX_IVF_FLAT) {
+                HB_REQUIRE(n >= 1 && h.nlist >= 1, "corrupt index file header");
+                need(SEC_CENTS), need(SEC_CENT_NORM), need(SEC_LIST_OFF), need(SEC_LIST_ROWS), need(SEC_ASSIGN);
+            }
+            if (ix->type == HB_INDEX_HNSW && n > 0) {
+                need(SEC_LEVELS);
+                HB_REQUIRE(h.entry >= 0 && h.entry < n, "corrupt index file header");
+                std::vector<const void *> po((size_t)h.max_level + 1), pi((size_t)h.max_level + 1);
+                for (int l = 0; l <= h.max_level; ++l) {
+                    HB_REQUIRE(seen_off[l] && seen_ids[l], "index file lacks an adjacency level");
+                    po[l] = ix->adj_off[l].p, pi[l] = ix->adj_ids[l].p;
+                }
+                HB_CUDA(cudaMemcpyAsync(ix->adj_off_ptrs.as<const void *>(po.size()), po.data(), po.size() * sizeof(void *),
+                                        cudaMemcpyHostToDevice, g_stream));
+                HB_CUDA(cudaMemcpyAsync(ix->adj_ids_ptrs.as<const void *>(pi.size()), pi.data(), pi.size() * sizeof(void *),
+                                        cudaMemcpyHostToDevice, g_stream));
+                sync_stream();
+            }
+            sync_stream();
+        } catch (...) {
+            ix->release();
+            delete ix;
+            throw;
+        }
+        *out = ix;
     });
 }
 

@@ -33,6 +33,65 @@ class HnswIndex(DeviceIndex):
         return gather_score(self, queries, pair_query, pair_row)
 
 
+def bulk_knn_graph(data, M=16, distance_fn="cosine", level_seed=42, batch=16384):
+    """A layered graph for the batched search, built in bulk on the device by the flat search itself.
+
+    Levels are drawn like random-level (ultra_fast.clj:143-147: (long)(ml * -ln U), ml = 1/ln 2, :133), from a
+    seeded generator.  The neighbour lists are NOT the product of the reference's incremental insert-single
+    (:216-275, host-side graph mutation, out of scope): every member of level l links to its m nearest members of
+    level l (m = 2M at level 0, M above, :131) in ascending (distance, row) order, found by the exact flat search —
+    the list insert-single's (take m candidates) approaches with a large ef-construction.  Used to get a graph of
+    BASELINE configs[4]'s size (1M nodes) in seconds; the traversal over it is the reference's.
+    Returns (levels int32 [n], entry point, adjacency = per level (offsets int64 [n+1], ids int32))."""
+    from .flat import FlatIndex
+
+    _, rows = split_data(data)
+    n = rows.shape[0]
+    u = np.random.default_rng(level_seed).random(n)
+    levels = np.floor(-np.log(np.maximum(u, 1e-300)) / np.log(2.0)).astype(np.int32)
+    max_level = int(levels.max()) if n else 0
+    entry = int(np.flatnonzero(levels == max_level)[0]) if n else -1
+    adjacency = []
+    for l in range(max_level + 1):
+        members = np.flatnonzero(levels >= l)
+        nm = len(members)
+        m = 2 * M if l == 0 else M
+        kk = min(m + 1, nm)
+        off = np.zeros(n + 1, dtype=np.int64)
+        if kk <= 1:
+            adjacency.append((off, np.zeros(0, dtype=np.int32)))
+            continue
+        if l == 0:
+            sub = rows
+        elif hb._is_torch(rows):
+            import torch
+
+            sub = rows[torch.as_tensor(members, device=rows.device)]
+        else:
+            sub = rows[members]
+        nbr = np.empty((nm, kk - 1), dtype=np.int32)
+        with FlatIndex(sub, distance_fn=distance_fn) as fx:
+            for b0 in range(0, nm, batch):
+                b1 = min(b0 + batch, nm)
+                ids, _ = fx.search_raw(sub[b0:b1], kk)
+                keep = ids != np.arange(b0, b1)[:, None]  # drop the node itself (or, among duplicates, the last hit)
+                order = np.argsort(~keep, axis=1, kind="stable")[:, :kk - 1]
+                nbr[b0:b1] = members[np.take_along_axis(ids, order, axis=1)]
+        counts = np.zeros(n, dtype=np.int64)
+        counts[members] = kk - 1
+        np.cumsum(counts, out=off[1:])
+        adjacency.append((off, nbr.reshape(-1)))
+    return levels, entry, adjacency
+
+
+def build_index_bulk(data, M=16, distance_fn="cosine", level_seed=42):
+    """bulk_knn_graph + upload: an HnswIndex whose `graph` attribute keeps (levels, entry, adjacency)."""
+    levels, entry, adjacency = bulk_knn_graph(data, M, distance_fn, level_seed)
+    ix = HnswIndex(data, levels, entry, adjacency, distance_fn=distance_fn)
+    ix.graph = (levels, entry, adjacency)
+    return ix
+
+
 def gather_score(index: DeviceIndex, queries, pair_query, pair_row) -> np.ndarray:
     q = hb.as_matrix(queries, allow=(hb.F32, hb.F64))
     pq = np.ascontiguousarray(pair_query, dtype=np.int32)

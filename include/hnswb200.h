@@ -184,6 +184,17 @@ HB_API int hb_fast_scores(hb_index *index, const void *queries, int qdtype, int6
 HB_API int hb_topk_merge(const double *dist, const int64_t *ids, int32_t nparts, int64_t nq, int32_t k,
                          int64_t *out_ids, double *out_dist);
 
+/* ---- persistence ------------------------------------------------------------------------------- */
+/* save-index / load-index (src/hnsw/api.clj:40-50, src/hnsw/helper/index_io.clj:10-80: EDN text of the HNSW graph
+ * only; IVF-FLAT has no persistence in the reference).  The file is the device layout verbatim (header + tagged
+ * sections: list-major slab, fp64 norms, centroids, list offsets, row ids, assignments / HNSW levels + CSR
+ * adjacency), written atomically (path.tmp + rename); loading streams it into HBM through pinned staging without
+ * re-clustering or re-computing norms, and the loaded index returns the same bits as the saved one.  String ids
+ * stay with the host shim.  A missing / truncated / foreign file is HB_ERR_INVALID (the reference prints and
+ * returns nil, index_io.clj:78-80). */
+HB_API int hb_index_save(const hb_index *index, const char *path);
+HB_API int hb_index_load(const char *path, hb_index **out);
+
 /* ---- bookkeeping -------------------------------------------------------------------------------- */
 HB_API int hb_index_info(const hb_index *index, hb_info *out);
 HB_API int hb_index_free(hb_index *index);

@@ -902,6 +902,32 @@ static void hnsw_insert(orc_hnsw *g, int32_t id) {
 ORC_EXPORT void orc_hnsw_build(orc_hnsw *g) {
     for (int64_t i = 0; i < g->n; ++i) hnsw_insert(g, (int32_t)i);
 }
+/* Replace the graph by a given one (test infrastructure for graphs built elsewhere, e.g. the bulk k-NN graph of the
+ * benchmark): per-node level, entry point and one CSR adjacency per level in neighbour iteration order — the same
+ * arrays orc_hnsw_export_level produces.  The traversal (:151-212, :346-374) then runs on it unchanged. */
+ORC_EXPORT void orc_hnsw_import(orc_hnsw *g, const int32_t *levels, int32_t entry, int32_t max_level,
+                                const int64_t *const *level_offsets, const int32_t *const *level_ids) {
+    for (int64_t i = 0; i < g->n; ++i) {
+        if (g->nbrs[i]) {
+            for (int32_t l = 0; l <= g->level[i]; ++l) free(g->nbrs[i][l].ids);
+            free(g->nbrs[i]);
+        }
+        int32_t lv = levels[i];
+        g->level[i] = lv;
+        g->nbrs[i] = (nbset *)calloc((size_t)lv + 1, sizeof(nbset));
+        for (int32_t l = 0; l <= lv && l <= max_level; ++l) {
+            int64_t a = level_offsets[l][i], b = level_offsets[l][i + 1];
+            nbset *s = &g->nbrs[i][l];
+            s->size = s->cap = (int32_t)(b - a);
+            if (b > a) {
+                s->ids = (int32_t *)malloc(sizeof(int32_t) * (size_t)(b - a));
+                memcpy(s->ids, level_ids[l] + a, sizeof(int32_t) * (size_t)(b - a));
+            }
+        }
+    }
+    g->entry = entry;
+    g->count = g->n;
+}
 ORC_EXPORT int32_t orc_hnsw_entry(const orc_hnsw *g) { return g->entry; }
 ORC_EXPORT int32_t orc_hnsw_max_level(const orc_hnsw *g) { return g->entry < 0 ? -1 : g->level[g->entry]; }
 ORC_EXPORT void orc_hnsw_levels(const orc_hnsw *g, int32_t *out) {

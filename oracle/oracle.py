@@ -73,6 +73,7 @@ def _declare(L):
     L.orc_hnsw_create.restype, L.orc_hnsw_create.argtypes = _p, [_p, _i64, _i64, _int, _i32, _i32, _i64]
     L.orc_hnsw_free.restype, L.orc_hnsw_free.argtypes = None, [_p]
     L.orc_hnsw_build.restype, L.orc_hnsw_build.argtypes = None, [_p]
+    L.orc_hnsw_import.restype, L.orc_hnsw_import.argtypes = None, [_p, _p, _i32, _i32, _p, _p]
     L.orc_hnsw_entry.restype, L.orc_hnsw_entry.argtypes = _i32, [_p]
     L.orc_hnsw_max_level.restype, L.orc_hnsw_max_level.argtypes = _i32, [_p]
     L.orc_hnsw_levels.restype, L.orc_hnsw_levels.argtypes = None, [_p, _p]
@@ -248,6 +249,21 @@ class Hnsw:
         self.n, self.d = self.rows.shape
         self._h = lib().orc_hnsw_create(_ptr(self.rows), self.n, self.d, metric, M, ef_construction, level_seed)
         lib().orc_hnsw_build(self._h)
+
+    @classmethod
+    def from_graph(cls, rows, levels, entry, adjacency, metric=COSINE, M=16):
+        """The oracle traversal over a graph built elsewhere: adjacency = per level (offsets int64 [n+1], ids int32)."""
+        self = cls.__new__(cls)
+        self.rows = _f32(rows)
+        self.n, self.d = self.rows.shape
+        self._h = lib().orc_hnsw_create(_ptr(self.rows), self.n, self.d, metric, M, 200, 42)
+        lv = np.ascontiguousarray(levels, dtype=np.int32)
+        offs = [np.ascontiguousarray(a[0], dtype=np.int64) for a in adjacency]
+        ids = [np.ascontiguousarray(a[1], dtype=np.int32) if len(a[1]) else np.zeros(1, np.int32) for a in adjacency]
+        po = (C.c_void_p * len(offs))(*[o.ctypes.data for o in offs])
+        pi = (C.c_void_p * len(ids))(*[x.ctypes.data for x in ids])
+        lib().orc_hnsw_import(self._h, _ptr(lv), int(entry), len(adjacency) - 1, po, pi)
+        return self
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -137,3 +137,45 @@ def test_search_knn_mirror_returns_maps(hb, graph_case):
         res = ultra_fast.search_knn(ix, rows[0], 5)
     assert [r["id"] for r in res] == want_ids[0].tolist()
     assert [r["distance"] for r in res] == want_d[0].tolist()
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_bulk_knn_graph_and_traversal(hb, mode):
+    """The device-built bulk graph (ultra_fast.bulk_knn_graph): level-l neighbour lists are the m nearest members of the
+    level in the oracle's (distance, row) order, and the batched search over it equals the oracle traversal of the same
+    graph (orc.Hnsw.from_graph)."""
+    from hnsw_clj_b200 import _lib
+    from hnsw_clj_b200.ultra_fast import HnswIndex, bulk_knn_graph
+
+    rows = rows_of(2500, 64, 11, dup=20)
+    _lib.set_mode(_lib.MODE_FAST if mode == "fast" else _lib.MODE_EXACT)
+    try:
+        levels, entry, adjacency = bulk_knn_graph(rows, M=8, level_seed=3, batch=1000)
+    finally:
+        _lib.set_mode(_lib.MODE_EXACT)
+    assert levels.max() == len(adjacency) - 1 and levels[entry] == levels.max()
+    assert entry == int(np.flatnonzero(levels == levels.max())[0])
+    for l, (off, ids) in enumerate(adjacency[:3]):
+        members = np.flatnonzero(levels >= l)
+        m = 16 if l == 0 else 8
+        kk = min(m + 1, len(members))
+        want_ids, _ = orc.exact_knn(rows[members], rows[members], kk)
+        for j in (0, 1, len(members) // 2, len(members) - 1):
+            w = [int(members[x]) for x in want_ids[j] if x != j][: kk - 1]
+            if len(w) < kk - 1:
+                w = [int(members[x]) for x in want_ids[j][: kk - 1]]
+            node = int(members[j])
+            assert ids[off[node]:off[node + 1]].tolist() == w, (l, j)
+        absent = np.flatnonzero(levels < l)
+        if len(absent):
+            assert off[absent[0]] == off[absent[0] + 1]
+    g = orc.Hnsw.from_graph(rows, levels, entry, adjacency, M=8)
+    q = np.concatenate([rows_of(120, 64, 12), rows[:40]])
+    want_ids, want_d = g.search(q, 10, 96)
+    with HnswIndex(rows, levels, entry, adjacency) as ix:
+        ids, dist = ix.search_raw(q, 10, 96)
+    assert ids.tolist() == want_ids.tolist() and same_bits(dist, want_d)
+    from hnsw_clj_b200.flat import recall_at_k
+
+    ex_ids, _ = orc.exact_knn(rows, q, 10)
+    assert recall_at_k(ids, ex_ids) > 0.5

@@ -145,3 +145,21 @@ def test_hnsw_oracle_recall_and_shape():
     s = orc.gather_score(rows, q, pq, pr)
     for t in range(3):
         assert s[t] == orc.cosine_distance(q[pq[t]].astype(np.float64), rows[pr[t]].astype(np.float64))
+
+
+def test_hnsw_oracle_import_round_trip():
+    """from_graph (used to run the oracle traversal over graphs built elsewhere) reproduces the searches of the graph
+    it was exported from."""
+    rows = np.random.default_rng(5).standard_normal((600, 32)).astype(np.float32)
+    g = orc.Hnsw(rows, M=6, ef_construction=40, level_seed=7)
+    adjacency = [g.export_level(l) for l in range(g.max_level + 1)]
+    g2 = orc.Hnsw.from_graph(rows, g.levels(), g.entry, adjacency, M=6)
+    assert g2.entry == g.entry and g2.max_level == g.max_level
+    for l in range(g.max_level + 1):
+        o1, i1 = g.export_level(l)
+        o2, i2 = g2.export_level(l)
+        assert o1.tolist() == o2.tolist() and i1.tolist() == i2.tolist()
+    q = rows[:40] + 0.01
+    a_ids, a_d = g.search(q, 5, 30)
+    b_ids, b_d = g2.search(q, 5, 30)
+    assert a_ids.tolist() == b_ids.tolist() and (a_d.view(np.int64) == b_d.view(np.int64)).all()

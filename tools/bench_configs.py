@@ -4,7 +4,7 @@
     python tools/bench_configs.py c3 [--n N]    # flat N x 768 bf16 inner product, 4096 queries, top-100 (configs[2], one GPU's rows)
     python tools/bench_configs.py c4 [--n N]    # one Lloyd round (assign + update) on one GPU's shard of configs[3]
     torchrun ... tools/bench_configs.py c4full  # configs[3] as named: 100 M rows over the GPUs of the box, 10 Lloyd rounds
-    python tools/bench_configs.py c5 [--n N]    # batched HNSW search, M=16 ef=128, 16k queries (configs[4], reduced graph)
+    python tools/bench_configs.py c5 [--n N]    # batched HNSW search, M=16 ef=128, 16k queries (configs[4]; --n 1000000 --graph bulk = as named)
 
 Every command prints ONE JSON line (device-resident inputs, CUDA events on the launching stream, inputs larger than L2
 or stated otherwise) and checks the device results against the exact mode / the CPU oracle on a bounded sample.
@@ -389,13 +389,24 @@ def run_c5(args):
     queries = (rows[torch.randint(0, n, (nq,), generator=g, device=dev)] +
                0.3 / d ** 0.5 * torch.randn((nq, d), generator=g, device=dev)).contiguous()
     rows_np = rows.cpu().numpy()
-    t0 = time.perf_counter()
-    graph = orc.Hnsw(rows_np, M=16, ef_construction=200, level_seed=42)
-    build_s = time.perf_counter() - t0
-    from hnsw_clj_b200.ultra_fast import HnswIndex
+    from hnsw_clj_b200.ultra_fast import HnswIndex, bulk_knn_graph
 
-    adjacency = [graph.export_level(l) for l in range(graph.max_level + 1)]
-    ix = HnswIndex(rows_np, graph.levels(), graph.entry, adjacency, distance_fn="cosine")
+    t0 = time.perf_counter()
+    if args.graph == "oracle":
+        # the reference's incremental insert-single, restated on the host (feasible up to a few 10k nodes)
+        graph = orc.Hnsw(rows_np, M=16, ef_construction=200, level_seed=42)
+        levels, entry = graph.levels(), graph.entry
+        adjacency = [graph.export_level(l) for l in range(graph.max_level + 1)]
+        how = "graph built on the host by the oracle (insert-single, efConstruction=200)"
+    else:
+        # bulk k-NN graph built on the device by the flat search (FAST mode): configs[4]'s 1M nodes in seconds
+        hb.set_mode(hb.MODE_FAST)
+        levels, entry, adjacency = bulk_knn_graph(rows, M=16, level_seed=42)
+        hb.set_mode(hb.MODE_EXACT)
+        graph = orc.Hnsw.from_graph(rows_np, levels, entry, adjacency)
+        how = "bulk k-NN graph (32 nearest per node at level 0, 16 above, reference level distribution) built on the device by the flat search"
+    build_s = time.perf_counter() - t0
+    ix = HnswIndex(rows, levels, entry, adjacency, distance_fn="cosine")
     out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
     out_d = torch.empty((nq, k), dtype=torch.float64, device=dev)
     hb.set_option("profile", 1)
@@ -417,8 +428,8 @@ def run_c5(args):
     pk = peaks()
     bytes_scored = scored * (d * 4 + 4)
     line = {
-        "config": f"BASELINE configs[4] on a reduced graph: HNSW M=16 efSearch={ef}, {n}x{d} fp32 unit-norm, {nq} concurrent queries, top-{k} "
-                  f"(graph built on the host by the oracle in {build_s:.0f} s; configs[4] names 1M nodes)",
+        "config": f"BASELINE configs[4]{'' if n >= 1000000 else ' on a reduced graph'}: HNSW M=16 efSearch={ef}, {n}x{d} fp32 unit-norm, {nq} concurrent queries, top-{k} "
+                  f"({how}, {build_s:.0f} s)",
         "metric": "queries/s", "value": nq / ms * 1e3, "ms_per_batch": ms, "recall_at_10": recall_at_k(ids, ex_ids),
         "pairs_scored_per_batch": scored,
         "parity": {"sample_queries": s, "ids_equal_oracle_traversal": bool((ids[:s] == want_ids).all()),
@@ -426,7 +437,9 @@ def run_c5(args):
         "cpu_baseline": {"value": s / cpu_s, "unit": "queries/s", "cores": 1, "kind": "port", "sample": f"first {s} queries, one thread"},
         "roofline": {"bound": "hbm", "achieved": bytes_scored / ms / 1e6, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
                      "frac": bytes_scored / ms / 1e6 / pk.get("hbm_gbs", 6500.0), "algorithmic_bytes_per_scored_candidate": d * 4 + 4,
-                     "note": f"the {n * d * 4 / 1e6:.0f} MB of vectors fit L2 at this graph size: the gather is L2-bound here, not HBM-bound"},
+                     "note": (f"the {n * d * 4 / 1e6:.0f} MB of vectors fit L2 at this graph size: the gather is L2-bound here, not HBM-bound"
+                              if n * d * 4 < 120e6 else f"random {d * 4}-byte row gathers over {n * d * 4 / 1e9:.2f} GB of vectors")},
+        "graph": {"max_level": int(levels.max()), "edges_level0": int(adjacency[0][0][-1])},
     }
     print(json.dumps(line), flush=True)
 
@@ -438,6 +451,7 @@ def main():
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--nlist", type=int, default=65536)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--graph", choices=["oracle", "bulk"], default="bulk")
     args = ap.parse_args()
     from hnsw_clj_b200 import _lib as hb
 

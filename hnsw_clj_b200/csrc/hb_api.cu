@@ -218,6 +218,7 @@ struct FastSideBufs {
 static bool g_fast_debug = false;
 static bool g_tc_interleave = true;
 static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
+static bool g_fast_set_only = true;  // IVF coarse routing proves the probed set only (FastJob::set_only)
 static bool g_fast_dense = true;     // short flat scans (<= 2048 rows) select from the dumped score matrix
 static int g_fast_level_min = 33;     // flat scans of at least this many row tiles run in levels (fast_topk)
 static int g_fast_sample_tiles = 2;  // IVF: row tiles of the nearest list scored by the threshold-seeding pass
@@ -723,6 +724,11 @@ struct FastJob {
     FastPlan emit, thresh;
     bool shared_units = false;  // thresh covers the same units as emit (fewer tiles)
     bool profile = true;        // record the per-stage events (the coarse job is timed as a whole by its caller)
+    // The caller needs the exact top-k SET only (IVF coarse routing: which lists to probe): candidates that are in it by
+    // their bounds alone are not re-scored, out_rel lists them first, out_dist is not meaningful.
+    bool set_only = false;
+    const int64_t *tie_list_off = nullptr;  // see FinalParams
+    int tie_nlist = 0;
     int64_t *out_rel = nullptr;
     double *out_dist = nullptr;
     int32_t *out_ok = nullptr;
@@ -896,7 +902,7 @@ static void fast_topk(const FastJob &J) {
         int32_t *pq = W.pq.as<int32_t>((size_t)nq * kk), *prow = W.pr.as<int32_t>((size_t)nq * kk);
         int32_t *pslot = W.pslot.as<int32_t>((size_t)nq * kk), *srow = W.srow.as<int32_t>((size_t)nq * kk);
         int32_t *ptotal = W.ptotal.as<int32_t>(1);
-        launch_rescore_pairs(selpos, selval, cpos, nq, kk, cap, J.k, qmargin, srow, exact, ptotal, pq, prow, pslot);
+        launch_rescore_pairs(selpos, selval, cpos, nq, kk, cap, J.k, qmargin, srow, exact, ptotal, pq, prow, pslot, J.set_only);
         launch_rescore(J.rows_exact, J.rdtype, J.row_norm, J.q64, J.qdtype == HB_F32, J.qn, J.d, pq, prow, pslot, ptotal, nq * kk, J.epi,
                        exact);
         FinalParams F;
@@ -917,6 +923,8 @@ static void fast_topk(const FastJob &J) {
         F.out_rel = J.out_rel;
         F.out_dist = J.out_dist;
         F.out_ok = J.out_ok;
+        F.tie_list_off = J.tie_list_off;
+        F.tie_nlist = J.tie_nlist;
         launch_fast_final(F);
     }
     if (g_fast_debug && P.timing) {
@@ -1220,6 +1228,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
                 J.epi = EPI_COS_GUARD;
                 J.profile = false;
                 J.k = np_eff;
+                J.set_only = g_fast_set_only;  // which lists to probe; their order only numbers the candidates (ties: tie_list_off below)
                 flat_fast_plan(nb, J.emit, J.thresh, W.flat_plan);
                 J.shared_units = true;
                 J.out_rel = ppos + (size_t)b0 * np_eff;
@@ -1333,6 +1342,10 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         J.out_rel = relk;
         J.out_dist = dist + (size_t)q0 * k;
         J.out_ok = ok_all + q0;
+        if (coarse_tc && g_fast_set_only) {  // probe order is approximate: cross-list distance ties go to the exact path
+            J.tie_list_off = (const int64_t *)ix->list_off.p;
+            J.tie_nlist = nlist;
+        }
         fast_topk(J);
         launch_ivf_resolve(relk, nqc, k, np_eff, probes, pair_out, (const int64_t *)ix->list_off.p, (const int64_t *)ix->list_rows.p,
                            ids + (size_t)q0 * k);
@@ -1501,6 +1514,8 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             for (int i = 0; i < PROF_NTAGS; ++i) g_prof_ms[i] = 0, g_prof_n[i] = 0;
             g_fast_queries = g_fast_fallbacks = 0;
             g_hnsw_scored = g_hnsw_overflows = 0;
+        } else if (!strcmp(name, "fast_set_only")) {
+            g_fast_set_only = value != 0;
         } else if (!strcmp(name, "host_feed")) {
             HB_REQUIRE(value == 0 || (value >= 128 && value % 128 == 0), "host_feed must be 0 or a multiple of 128");
             g_host_feed_block = value;

@@ -125,17 +125,22 @@ struct FinalParams {
     int64_t *out_rel = nullptr;         // [nq][k] rel of the winners (-1 unused)
     double *out_dist = nullptr;         // [nq][k]
     int32_t *out_ok = nullptr;          // [nq] 1 = proven exact
+    // non-NULL (IVF list scan over an approximately ordered probe list): first slab row of each list; a distance tie
+    // between rows of different lists among the k + 1 best fails the query (the reference breaks it by probe rank)
+    const int64_t *tie_list_off = nullptr;
+    int tie_nlist = 0;
 };
 void launch_fast_final(const FinalParams &P);
 
 // per query: q_scale = u_q / ||q|| (cosine) or u_q (ip); q_eps from the index stats
 void launch_query_bounds(const double *qu, const double *ql1, const double *qnorm, int64_t nq, int ns, int d, int metric,
                          const float *stats, double *q_scale, double *q_eps, float *q_margin);
-// pairs for the exact re-score: per selected slot the row or -1 (slot_row), exact = +inf where not re-scored, and the
+// pairs for the exact re-score: per selected slot the row or -1 (slot_row), exact = +inf where not re-scored (set_only:
+// slot_row -2 and exact -inf for a candidate that is in the top-k set without a re-score), and the
 // dense list of wanted (query, row, slot) triples with its length in *total
 void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const int32_t *cand_pos, int64_t nq, int kk, int cap,
                           int k, const float *margin, int32_t *slot_row, double *exact, int32_t *total, int32_t *pair_query,
-                          int32_t *pair_row, int32_t *pair_slot);
+                          int32_t *pair_row, int32_t *pair_slot, bool set_only = false);
 // kk best of the min(cnt, cap) candidates of every query (ascending -score); unused slots: pos -1, +inf
 void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq, int kk, int cap, double *sel_negv,
                         int64_t *sel_pos);

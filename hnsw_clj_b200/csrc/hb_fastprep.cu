@@ -308,12 +308,16 @@ __global__ void __launch_bounds__(256) rescore_pairs_kernel(const int64_t *__res
                                                             const float *__restrict__ margin, int32_t *__restrict__ slot_row,
                                                             double *__restrict__ exact, int32_t *__restrict__ total,
                                                             int32_t *__restrict__ pair_query, int32_t *__restrict__ pair_row,
-                                                            int32_t *__restrict__ pair_slot) {
+                                                            int32_t *__restrict__ pair_slot, int set_only) {
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
     const double nk = k <= kk ? sel_negv[q * kk + k - 1] : INFINITY;  // the list is ascending in -score
     const double lim = nk + (double)margin[q] + 4e-6 * fabs(nk);
+    // set_only (the caller wants the top-k SET, not its order or distances): a candidate more than `margin` (> 2 eps_q)
+    // above the k-th approximate score is in the exact top-k whatever its exact distance is -- fewer than k rows can
+    // reach its lower bound -- so only the candidates within `margin` of the k-th on either side are re-scored
+    const double sure = set_only && nk < INFINITY ? nk - (double)margin[q] - 4e-6 * fabs(nk) : -INFINITY;
     int row[4] = {-1, -1, -1, -1};
     int nwant = 0;
     unsigned bal[4] = {0u, 0u, 0u, 0u};
@@ -325,9 +329,11 @@ __global__ void __launch_bounds__(256) rescore_pairs_kernel(const int64_t *__res
             const int64_t p = sel_pos[q * kk + j];
             const double nv = sel_negv[q * kk + j];
             want = p >= 0 && nv < INFINITY && (j < k || !(nk < INFINITY) || nv <= lim);
+            const bool certain = want && nv < sure;
+            if (certain) want = false;
             if (want) row[h] = cand_pos[q * cap + p];
-            slot_row[q * kk + j] = row[h];
-            if (!want) exact[q * kk + j] = INFINITY;
+            slot_row[q * kk + j] = certain ? -2 : row[h];
+            if (!want) exact[q * kk + j] = certain ? -INFINITY : INFINITY;
         }
         bal[h] = __ballot_sync(0xffffffffu, want);
         nwant += __popc(bal[h]);
@@ -354,6 +360,9 @@ __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
     __shared__ int32_t s_rel[128];
     __shared__ double s_kth;
     __shared__ int s_skipped;
+    __shared__ uint64_t s_okey[129];  // the k + 1 best in rank order: ties across lists (tie_list_off)
+    __shared__ int32_t s_orow[129];
+    __shared__ int s_tie;
     const int64_t q = blockIdx.x;
     const int j = threadIdx.x;
     const int kk = P.kk, k = P.k;
@@ -364,14 +373,19 @@ __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
     if (j == 0) {
         s_kth = INFINITY;
         s_skipped = INT_MAX;
+        s_tie = 0;
     }
+    int32_t prow = -1;
     __syncthreads();
     if (j < kk) {
         const int64_t p = P.sel_pos[q * kk + j];
         if (p >= 0 && P.sel_negv[q * kk + j] < INFINITY) {
-            if (P.pair_row[q * kk + j] >= 0) {
+            prow = P.pair_row[q * kk + j];
+            if (prow >= 0 || prow == -2) {  // re-scored, or (set_only) certainly in the top-k: exact reads -inf
                 dist = P.exact[q * kk + j];
-                key = dist_key(dist);
+                // a certain candidate keeps its approximate rank j (the selection is best-first), ahead of every re-scored one:
+                // column 0 stays the (approximately) nearest row, which seeds the IVF scan's thresholds
+                key = prow == -2 ? (uint64_t)j : dist_key(dist);
                 rel = P.cand_rel[q * P.cap + p];
             } else {
                 atomicMin(&s_skipped, j);  // selected but not re-scored: the best of them bounds the others
@@ -393,6 +407,24 @@ __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
         P.out_dist[q * k + rank] = dist;
         if (rank == min(k, nvalid) - 1) s_kth = dist;
     }
+    if (P.tie_list_off) {
+        // The caller's `rel` order across lists is not the reference's (approximate probe order, see set_only): equal
+        // distances inside a list still fall in row order, but a tie between rows of different lists among the k + 1 best
+        // would be broken by probe rank in the reference (ivf_flat.clj:281-294) -- such a query goes to the exact path.
+        if (j < kk && key != kKeyEmpty && rank <= k) s_okey[rank] = key, s_orow[rank] = prow;
+        __syncthreads();
+        if (j < k && j + 1 < nvalid && s_okey[j] == s_okey[j + 1]) {
+            auto list_of = [&](int32_t row) {
+                int lo = 0, hi = P.tie_nlist;  // last l with list_off[l] <= row
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (P.tie_list_off[mid] <= row) lo = mid; else hi = mid;
+                }
+                return lo;
+            };
+            if (list_of(s_orow[j]) != list_of(s_orow[j + 1])) s_tie = 1;
+        }
+    }
     for (int r = nvalid + j; r < k; r += blockDim.x) {
         P.out_rel[q * k + r] = -1;
         P.out_dist[q * k + r] = INFINITY;
@@ -401,7 +433,7 @@ __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
     if (j == 0) {
         // rejected rows: selected but not re-scored (score <= the best of them), emitted but not selected (score <= worst
         // selected) or never emitted (score < thr)
-        bool ok = cnt <= P.cap;
+        bool ok = cnt <= P.cap && !s_tie;
         const float thr = P.thr[q];
         const int skipped = s_skipped;
         const bool none_rejected = cnt <= kk && thr == -INFINITY && skipped == INT_MAX;
@@ -1008,12 +1040,12 @@ void launch_query_bounds(const double *qu, const double *ql1, const double *qnor
 
 void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const int32_t *cand_pos, int64_t nq, int kk, int cap,
                           int k, const float *margin, int32_t *slot_row, double *exact, int32_t *total, int32_t *pair_query,
-                          int32_t *pair_row, int32_t *pair_slot) {
+                          int32_t *pair_row, int32_t *pair_slot, bool set_only) {
     if (nq * kk == 0) return;
     HB_REQUIRE(kk <= 128, "re-score pairs: kk <= 128");
     HB_CUDA(cudaMemsetAsync(total, 0, 4, g_stream));
     rescore_pairs_kernel<<<blocks_for(nq * 32, 256), 256, 0, g_stream>>>(sel_pos, sel_negv, cand_pos, nq, kk, cap, k, margin, slot_row,
-                                                                         exact, total, pair_query, pair_row, pair_slot);
+                                                                         exact, total, pair_query, pair_row, pair_slot, set_only ? 1 : 0);
     HB_LAUNCH_CHECK();
 }
 

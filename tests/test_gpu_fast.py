@@ -270,3 +270,39 @@ def test_fast_duplicates_fall_back_and_stay_exact(hb):
     assert fell == 20
     oids, _ = orc.exact_knn(rows, queries, 10)
     assert fids.tolist() == oids.tolist()
+
+
+def test_ivf_fast_cross_list_ties_follow_probe_rank(hb):
+    """The FAST coarse stage proves the probed SET and leaves the probe ORDER approximate (set_only); the reference breaks
+    a distance tie between rows of different lists by probe rank (ivf_flat.clj:281-294), so such queries must be handed
+    to the exact path.  Rows and their duplicates are planted in different lists (hb_ivf_import takes any assignment)."""
+    from hnsw_clj_b200 import _lib, ivf_flat
+
+    n, d, nlist, nprobe, k = 12000, 64, 256, 8, 3  # nlist >= 256: the coarse stage runs the candidate pass
+    base = clustered(n, d, 77, centres=150)
+    cents, asg = orc.kmeans(base, nlist, iters=3, seed=42)
+    dmat = np.stack([[orc.cosine_distance(base[i].astype(np.float64), c) for c in cents] for i in range(200)])
+    second = np.argsort(dmat, axis=1, kind="stable")[:, 1].astype(np.int32)
+    rows = np.concatenate([base, base[:200]])  # row n + i duplicates row i ...
+    asg2 = np.concatenate([asg, asg[:200]]).astype(np.int32)  # ... and takes its place in the nearest list,
+    asg2[:200] = second  # while row i itself moves to its second-nearest list: probe rank and row order now disagree
+    queries = (base[:200] + np.float32(1e-3)).astype(np.float32)
+    want_ids, want_d = orc.ivf_search(rows, cents, asg2, queries, k, nprobe)
+    assert (want_ids[:, :2] % n == np.arange(200)[:, None]).all() and (want_d[:, 0] == want_d[:, 1]).all()
+    assert (want_ids[:, 0] >= n).sum() > 150  # the pair leads every result, the copy in the nearer list first
+    ix = ivf_flat.import_index(rows, cents, asg2)
+    try:
+        eids, edist = ix.search_raw(queries, k, nprobe)
+        _lib.set_option("profile", 1)
+        _lib.set_mode(_lib.MODE_FAST)
+        try:
+            fids, fdist = ix.search_raw(queries, k, nprobe)
+        finally:
+            _lib.set_mode(_lib.MODE_EXACT)
+        fell = _lib.get_stat("fast_fallbacks")
+        _lib.set_option("profile", 0)
+    finally:
+        ix.close()
+    assert eids.tolist() == want_ids.tolist() and same_bits(edist, want_d)
+    assert fids.tolist() == want_ids.tolist() and same_bits(fdist, want_d)
+    assert fell == 200

@@ -37,6 +37,8 @@
 (defonce hb-flat-create (handle "hb_flat_create" I P J I I I P))
 ;; int hb_ivf_build(rows, n, d, dtype, metric, nlist, iters, seed, hb_index** out)
 (defonce hb-ivf-build (handle "hb_ivf_build" I P J I I I I I J P))
+;; int hb_lightning_build(rows, n, d, dtype, metric, nlist, seed, hb_index** out)
+(defonce hb-lightning-build (handle "hb_lightning_build" I P J I I I I J P))
 ;; int hb_search(index, queries, qdtype, nq, k, param, int64* out_ids, double* out_dist)
 (defonce hb-search (handle "hb_search" I P P I J I I P P))
 ;; int hb_gather_score(index, queries, qdtype, nq, pair_query, pair_row, npairs, out)

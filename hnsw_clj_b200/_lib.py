@@ -52,6 +52,7 @@ SIGNATURES = {
     "hb_pairwise": (_int, [_p, _i64, _int, _p, _i64, _int, _i32, _int, _p]),
     "hb_flat_create": (_int, [_p, _i64, _i32, _int, _int, _pp]),
     "hb_ivf_build": (_int, [_p, _i64, _i32, _int, _int, _i32, _i32, _i64, _pp]),
+    "hb_lightning_build": (_int, [_p, _i64, _i32, _int, _int, _i32, _i64, _pp]),
     "hb_ivf_import": (_int, [_p, _i64, _i32, _int, _int, _p, _i32, _p, _pp]),
     "hb_ivf_export": (_int, [_p, _p, _p]),
     "hb_search": (_int, [_p, _p, _int, _i64, _i32, _i32, _p, _p]),

@@ -524,6 +524,43 @@ static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int6
 static void assign_rows(const void *rows, int dtype, const double *row_norm, int64_t n, int d, const double *cents,
                         const double *cnorm, int nlist, bool l2, int32_t *assign);
 
+// kmeans-plus-plus-init (ivf_flat.clj:32-60; linear: Lightning's d_i-weighted walk, lightning.clj:86-109): `seeds` receives
+// the nlist chosen rows (device int64).  norm = fp64 row norms (device).
+static void kpp_seeds(const void *rows, int dtype, int64_t n, int d, const double *norm, bool l2, int nlist, int64_t seed, bool linear,
+                      int64_t *seeds) {
+    JavaRandom rng(seed);
+    std::vector<double> u((size_t)nlist);
+    const int64_t first = rng.next_int((int32_t)n);
+    for (int t = 1; t < nlist; ++t) u[t] = rng.next_double();
+    double *ud = g_ws.misc3.as<double>((size_t)nlist + 2 + 2 * (size_t)n);
+    double *total = ud + nlist;
+    double *mind = ud + nlist + 2;
+    double *cum = mind + n;
+    int64_t *pick = g_ws.misc4.as<int64_t>(1);
+    HB_CUDA(cudaMemcpyAsync(ud, u.data(), (size_t)nlist * 8, cudaMemcpyHostToDevice, g_stream));
+    HB_CUDA(cudaMemcpyAsync(pick, &first, 8, cudaMemcpyHostToDevice, g_stream));
+    HB_CUDA(cudaMemcpyAsync(seeds, &first, 8, cudaMemcpyHostToDevice, g_stream));
+    launch_fill_f64(mind, n, DBL_MAX);
+    KppParams K;
+    K.rows = rows;
+    K.dtype = dtype;
+    K.n = n;
+    K.d = d;
+    K.row_norm = norm;
+    K.l2 = l2;
+    K.linear = linear;
+    K.mind = mind;
+    K.cum = cum;
+    K.total = total;
+    K.pick = pick;
+    for (int t = 1; t < nlist; ++t) {
+        K.u = ud + t;
+        K.out_seed = seeds + t;
+        launch_kpp_step(K);
+    }
+    sync_stream();  // u (host vector) must outlive the copy; also bounds queue depth
+}
+
 static void kmeans_exact(const void *rows, int dtype, int64_t n, int d, int metric, int nlist, int iters, int64_t seed,
                          const int64_t *seed_rows_dev, double *cents, int32_t *assign, int64_t *seeds_out_dev) {
     HB_REQUIRE(n >= 1 && nlist >= 1, "k-means needs at least one row and one partition");
@@ -536,37 +573,7 @@ static void kmeans_exact(const void *rows, int dtype, int64_t n, int d, int metr
     if (seed_rows_dev) {
         if (seeds != seed_rows_dev) HB_CUDA(cudaMemcpyAsync(seeds, seed_rows_dev, (size_t)nlist * 8, cudaMemcpyDeviceToDevice, g_stream));
     } else {
-        // kmeans-plus-plus-init (:32-60)
-        JavaRandom rng(seed);
-        std::vector<double> u((size_t)nlist);
-        const int64_t first = rng.next_int((int32_t)n);
-        for (int t = 1; t < nlist; ++t) u[t] = rng.next_double();
-        double *ud = g_ws.misc3.as<double>((size_t)nlist + 2 + 2 * (size_t)n);
-        double *total = ud + nlist;
-        double *mind = ud + nlist + 2;
-        double *cum = mind + n;
-        int64_t *pick = g_ws.misc4.as<int64_t>(1);
-        HB_CUDA(cudaMemcpyAsync(ud, u.data(), (size_t)nlist * 8, cudaMemcpyHostToDevice, g_stream));
-        HB_CUDA(cudaMemcpyAsync(pick, &first, 8, cudaMemcpyHostToDevice, g_stream));
-        HB_CUDA(cudaMemcpyAsync(seeds, &first, 8, cudaMemcpyHostToDevice, g_stream));
-        launch_fill_f64(mind, n, DBL_MAX);
-        KppParams K;
-        K.rows = rows;
-        K.dtype = dtype;
-        K.n = n;
-        K.d = d;
-        K.row_norm = norm;
-        K.l2 = l2;
-        K.mind = mind;
-        K.cum = cum;
-        K.total = total;
-        K.pick = pick;
-        for (int t = 1; t < nlist; ++t) {
-            K.u = ud + t;
-            K.out_seed = seeds + t;
-            launch_kpp_step(K);
-        }
-        sync_stream();  // u (host vector) must outlive the copy; also bounds queue depth
+        kpp_seeds(rows, dtype, n, d, norm, l2, nlist, seed, false, seeds);
     }
     launch_init_centroids(rows, dtype, d, seeds, nlist, cents);
     double *cnorm = g_ws.misc3.as<double>((size_t)nlist + 2 + 2 * (size_t)n);  // reuse: [nlist] norms
@@ -1682,6 +1689,50 @@ HB_API int hb_ivf_build(const void *rows, int64_t n, int32_t d, int dtype, int m
             int32_t *assign = ix->assign.as<int32_t>(n);
             kmeans_exact(r, dtype, n, d, metric, nlist, iters, seed, nullptr, cents, assign, nullptr);
             ivf_finalize(ix, r, (const double *)g_ws.misc.p);
+        } catch (...) {
+            ix->release();
+            delete ix;
+            throw;
+        }
+        *out = ix;
+    });
+}
+
+// build-lightning-index with :smart-partition? true (src/hnsw/ann/partition/lightning.clj:84-130)
+HB_API int hb_lightning_build(const void *rows, int64_t n, int32_t d, int dtype, int metric, int32_t nlist, int64_t seed,
+                              hb_index **out) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(out, "null out");
+        ivf_common_checks(rows, n, d, dtype, metric, nlist);
+        HB_REQUIRE(n < (1ll << 31), "n must be < 2^31");
+        hb_index *ix = new hb_index();
+        try {
+            ix->type = HB_INDEX_IVF_FLAT;
+            ix->dtype = dtype;
+            ix->metric = metric;
+            ix->d = d;
+            ix->n = n;
+            ix->nlist = nlist;
+            const bool l2 = metric == HB_L2;
+            const void *r = stage_in(rows, (size_t)n * d * dtype_size(dtype), g_ws.in_a);
+            double *norm = g_ws.misc.as<double>(n);
+            launch_row_norms(r, dtype, n, d, norm);
+            int64_t *seeds = g_ws.misc2.as<int64_t>(nlist);
+            kpp_seeds(r, dtype, n, d, norm, l2, nlist, seed, true, seeds);  // :86-109
+            double *cents = ix->cents.as<double>((size_t)nlist * d);
+            int32_t *assign = ix->assign.as<int32_t>(n);
+            launch_init_centroids(r, dtype, d, seeds, nlist, cents);
+            double *cnorm = g_ws.misc3.as<double>((size_t)nlist + 2 + 2 * (size_t)n);
+            launch_row_norms(cents, HB_F64, nlist, d, cnorm);
+            assign_rows(r, dtype, norm, n, d, cents, cnorm, nlist, l2, assign);  // assign-to-partition over the seeds, :111-115
+            int64_t *list_off = g_ws.lq_off.as<int64_t>(nlist + 1);
+            int64_t *list_rows = g_ws.cand_id.as<int64_t>(n);
+            build_lists(assign, n, nlist, list_off, list_rows, g_ws.tmp);
+            // routing centroids = partition means, an empty partition gets the zero vector (:122-126)
+            HB_CUDA(cudaMemsetAsync(cents, 0, (size_t)nlist * d * 8, g_stream));
+            launch_update_centroids(r, dtype, d, list_off, list_rows, nlist, cents, nullptr, nullptr);
+            ivf_finalize(ix, r, norm);
         } catch (...) {
             ix->release();
             delete ix;

@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(128) kpp_update_kernel(const T *__restrict__ r
 
 // S = sum_i mind_i^2 in row order (ivf_flat.clj:51-52): an ordered fp64 sum has no parallel form that
 // is bit-identical, so one thread walks it while the CTA streams the data through shared memory.
+// SQ = false: the weights are d_i themselves (Lightning's seeding, lightning.clj:100-106).
 constexpr int PFX_NT = 256, PFX_CH = 4096;
+template <bool SQ>
 __global__ void __launch_bounds__(PFX_NT) kpp_prefix_kernel(const double *__restrict__ mind, int64_t n,
                                                             double *__restrict__ cum, double *__restrict__ total) {
     __shared__ double sq[PFX_CH];
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(PFX_NT) kpp_prefix_kernel(const double *__rest
         const int m = (int)min((int64_t)PFX_CH, n - base);
         for (int j = threadIdx.x; j < m; j += PFX_NT) {
             const double v = mind[base + j];
-            sq[j] = __dmul_rn(v, v);
+            sq[j] = SQ ? __dmul_rn(v, v) : v;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -101,6 +103,7 @@ __global__ void __launch_bounds__(PFX_NT) kpp_prefix_kernel(const double *__rest
 
 // first i with cum_i + mind_i^2 >= r (ivf_flat.clj:54-58); the running sum is monotone, so the
 // predicate flips exactly once.
+template <bool SQ>
 __global__ void kpp_pick_kernel(const double *__restrict__ mind, const double *__restrict__ cum, int64_t n,
                                 const double *__restrict__ total, const double *__restrict__ u,
                                 int64_t *__restrict__ pick) {
@@ -108,11 +111,11 @@ __global__ void kpp_pick_kernel(const double *__restrict__ mind, const double *_
     if (i >= n) return;
     const double r = __dmul_rn(*u, *total);
     const double v = mind[i];
-    const bool here = __dadd_rn(cum[i], __dmul_rn(v, v)) >= r;
+    const bool here = __dadd_rn(cum[i], SQ ? __dmul_rn(v, v) : v) >= r;
     bool prev = false;
     if (i > 0) {
         const double w = mind[i - 1];
-        prev = __dadd_rn(cum[i - 1], __dmul_rn(w, w)) >= r;
+        prev = __dadd_rn(cum[i - 1], SQ ? __dmul_rn(w, w) : w) >= r;
     }
     if (here && !prev) *pick = i;
 }
@@ -274,11 +277,13 @@ void launch_kpp_step(const KppParams &P) {
     else HB_KPP(double);
 #undef HB_KPP
     HB_LAUNCH_CHECK();
-    kpp_prefix_kernel<<<1, PFX_NT, 0, g_stream>>>(P.mind, P.n, P.cum, P.total);
+    if (P.linear) kpp_prefix_kernel<false><<<1, PFX_NT, 0, g_stream>>>(P.mind, P.n, P.cum, P.total);
+    else kpp_prefix_kernel<true><<<1, PFX_NT, 0, g_stream>>>(P.mind, P.n, P.cum, P.total);
     HB_LAUNCH_CHECK();
     kpp_prepick_kernel<<<1, 1, 0, g_stream>>>(P.n, P.pick);
     HB_LAUNCH_CHECK();
-    kpp_pick_kernel<<<blocks_for(P.n, 256), 256, 0, g_stream>>>(P.mind, P.cum, P.n, P.total, P.u, P.pick);
+    if (P.linear) kpp_pick_kernel<false><<<blocks_for(P.n, 256), 256, 0, g_stream>>>(P.mind, P.cum, P.n, P.total, P.u, P.pick);
+    else kpp_pick_kernel<true><<<blocks_for(P.n, 256), 256, 0, g_stream>>>(P.mind, P.cum, P.n, P.total, P.u, P.pick);
     HB_LAUNCH_CHECK();
     kpp_record_kernel<<<1, 1, 0, g_stream>>>(P.pick, P.out_seed);
     HB_LAUNCH_CHECK();

@@ -23,6 +23,7 @@ struct KppParams {
     int d = 0;
     const double *row_norm = nullptr;
     bool l2 = false;
+    bool linear = false;        // weights d_i instead of d_i^2 (Lightning, lightning.clj:100-106)
     double *mind = nullptr;     // [n]
     double *cum = nullptr;      // [n] scratch
     double *total = nullptr;    // [1] scratch

@@ -115,6 +115,15 @@ HB_API int hb_flat_create(const void *rows, int64_t n, int32_t d, int dtype, int
  * cosine, as in the reference (:217-234). */
 HB_API int hb_ivf_build(const void *rows, int64_t n, int32_t d, int dtype, int metric, int32_t nlist,
                         int32_t iters, int64_t seed, hb_index **out);
+/* build-lightning-index with :smart-partition? true (src/hnsw/ann/partition/lightning.clj:46-160): seeds by the
+ * k-means++ walk weighted with d_i (not d_i^2, :86-109, java.util.Random(seed)), every row to its nearest seed
+ * (assign-to-partition :31-44), routing centroids = partition means, zero vector for an empty partition
+ * (:122-126); no Lloyd rounds.  The result is an IVF-FLAT-type index: search-lightning (:184-298) is hb_search with
+ * nprobe = max(1, (int)(partitions * percent)) (:262) — centroid routing, per-list cosine scan, stable merge.
+ * The reference's default (:smart-partition? false) is an unseeded shuffle split (:132-137): pass such a partition
+ * through hb_ivf_import. */
+HB_API int hb_lightning_build(const void *rows, int64_t n, int32_t d, int dtype, int metric, int32_t nlist,
+                              int64_t seed, hb_index **out);
 /* Same index from given centroids (fp64 [nlist x d]) and per-row assignments: parity mode for
  * oracle-built partitions, and the load path for a persisted index. */
 HB_API int hb_ivf_import(const void *rows, int64_t n, int32_t d, int dtype, int metric,

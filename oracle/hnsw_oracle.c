@@ -405,8 +405,8 @@ static void kpp_task(void *p, int64_t b, int64_t e) {
 /* Incremental form: d_i = min(prev d_i, dist(x_i, newest centroid)).  `min` is exact, so this is
  * bit-identical to the reference's min over ALL chosen centroids (:43-49) at O(N*k*D) instead of
  * O(N*k^2*D).  orc_kmeanspp_init_literal below is the literal form, kept for cross-checking. */
-ORC_EXPORT void orc_kmeanspp_init(const float *rows, int64_t n, int64_t d, int32_t nlist, int metric,
-                                  int64_t seed, int64_t *out_seed_rows, int nthreads) {
+static void kmeanspp_weighted(const float *rows, int64_t n, int64_t d, int32_t nlist, int metric, int64_t seed,
+                              int squared, int64_t *out_seed_rows, int nthreads) {
     orc_rng r;
     orc_rng_init(&r, seed); /* (Random. 42) :37 */
     double *mind = (double *)malloc(sizeof(double) * (size_t)n);
@@ -419,14 +419,14 @@ ORC_EXPORT void orc_kmeanspp_init(const float *rows, int64_t n, int64_t d, int32
         kpp_ctx c = {rows, d, cvec, metric, mind};
         parallel_for(n, nthreads, 4096, kpp_task, &c);
         double sum = 0.0; /* :51-52, row order */
-        for (int64_t i = 0; i < n; ++i) sum = sum + mind[i] * mind[i];
+        for (int64_t i = 0; i < n; ++i) sum = sum + (squared ? mind[i] * mind[i] : mind[i]);
         double rr = orc_rng_next_double(&r) * sum; /* :53 */
         double cum = 0.0;
         int64_t i = 0;
         for (;; ++i) { /* :54-58 */
-            double dsq = mind[i] * mind[i];
-            if (cum + dsq >= rr) break;
-            cum = cum + dsq;
+            double w = squared ? mind[i] * mind[i] : mind[i];
+            if (cum + w >= rr) break;
+            cum = cum + w;
             if (i == n - 1) break; /* reference would throw ArrayIndexOutOfBounds; clamp */
         }
         pick = i;
@@ -434,6 +434,16 @@ ORC_EXPORT void orc_kmeanspp_init(const float *rows, int64_t n, int64_t d, int32
     }
     free(mind);
     free(cvec);
+}
+ORC_EXPORT void orc_kmeanspp_init(const float *rows, int64_t n, int64_t d, int32_t nlist, int metric,
+                                  int64_t seed, int64_t *out_seed_rows, int nthreads) {
+    kmeanspp_weighted(rows, n, d, nlist, metric, seed, 1, out_seed_rows, nthreads);
+}
+/* Lightning's seeding (src/hnsw/ann/partition/lightning.clj:86-109): the same walk with the weights d_i instead of
+ * d_i^2 (:100-106) and the minimum taken over all chosen centroids (:93-97; the incremental min is bit-identical). */
+ORC_EXPORT void orc_lightning_seeds(const float *rows, int64_t n, int64_t d, int32_t nlist, int metric,
+                                    int64_t seed, int64_t *out_seed_rows, int nthreads) {
+    kmeanspp_weighted(rows, n, d, nlist, metric, seed, 0, out_seed_rows, nthreads);
 }
 
 ORC_EXPORT void orc_kmeanspp_init_literal(const float *rows, int64_t n, int64_t d, int32_t nlist,
@@ -542,6 +552,25 @@ ORC_EXPORT void orc_kmeans(const float *rows, int64_t n, int64_t d, int32_t nlis
         orc_update_centroids(rows, n, d, out_assign, nlist, out_cents);
     }
     orc_assign(rows, n, d, out_cents, nlist, metric, out_assign, nthreads); /* :119-131 */
+}
+
+/* build-lightning-index with :smart-partition? true (src/hnsw/ann/partition/lightning.clj:84-130): seeds as above,
+ * every row goes to its nearest SEED (assign-to-partition :31-44: strict <, first minimum), partitions keep data order
+ * (:117-120), the routing centroids are the partition means (compute-centroid :17-29), a zero vector for an empty
+ * partition (:123-126).  No Lloyd rounds.  Search is search-lightning (:184-298) = the IVF-FLAT search with
+ * nprobe = max(1, (int)(partitions * percent)) (:262) and centroid routing (:265-274). */
+ORC_EXPORT void orc_lightning_build(const float *rows, int64_t n, int64_t d, int32_t nlist, int metric, int64_t seed,
+                                    double *out_cents, int32_t *out_assign, int nthreads) {
+    int64_t *sr = (int64_t *)malloc(sizeof(int64_t) * (size_t)nlist);
+    orc_lightning_seeds(rows, n, d, nlist, metric, seed, sr, nthreads);
+    double *seeds = (double *)malloc(sizeof(double) * (size_t)nlist * (size_t)d);
+    for (int32_t c = 0; c < nlist; ++c)
+        for (int64_t j = 0; j < d; ++j) seeds[(int64_t)c * d + j] = (double)rows[sr[c] * d + j];
+    orc_assign(rows, n, d, seeds, nlist, metric, out_assign, nthreads);
+    for (int64_t x = 0; x < (int64_t)nlist * d; ++x) out_cents[x] = 0.0;
+    orc_update_centroids(rows, n, d, out_assign, nlist, out_cents); /* empty keeps what is there: the zero vector */
+    free(seeds);
+    free(sr);
 }
 
 /* ------------------------------------------------------------------------------------------

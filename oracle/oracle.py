@@ -73,6 +73,8 @@ def _declare(L):
     L.orc_hnsw_create.restype, L.orc_hnsw_create.argtypes = _p, [_p, _i64, _i64, _int, _i32, _i32, _i64]
     L.orc_hnsw_free.restype, L.orc_hnsw_free.argtypes = None, [_p]
     L.orc_hnsw_build.restype, L.orc_hnsw_build.argtypes = None, [_p]
+    L.orc_lightning_seeds.restype, L.orc_lightning_seeds.argtypes = None, [_p, _i64, _i64, _i32, _int, _i64, _p, _int]
+    L.orc_lightning_build.restype, L.orc_lightning_build.argtypes = None, [_p, _i64, _i64, _i32, _int, _i64, _p, _p, _int]
     L.orc_hnsw_import.restype, L.orc_hnsw_import.argtypes = None, [_p, _p, _i32, _i32, _p, _p]
     L.orc_hnsw_entry.restype, L.orc_hnsw_entry.argtypes = _i32, [_p]
     L.orc_hnsw_max_level.restype, L.orc_hnsw_max_level.argtypes = _i32, [_p]
@@ -186,6 +188,24 @@ def kmeanspp_init(rows, nlist, metric=COSINE, seed=42, nthreads=None, literal=Fa
         lib().orc_kmeanspp_init(_ptr(rows), rows.shape[0], rows.shape[1], nlist, metric, seed, _ptr(out),
                                 nthreads or ncores())
     return out
+
+
+def lightning_seeds(rows, nlist, metric=COSINE, seed=42, nthreads=None) -> np.ndarray:
+    """src/hnsw/ann/partition/lightning.clj:86-109: k-means++ walk weighted by d_i (not d_i^2)."""
+    rows = _f32(rows)
+    out = np.empty(nlist, dtype=np.int64)
+    lib().orc_lightning_seeds(_ptr(rows), rows.shape[0], rows.shape[1], nlist, metric, seed, _ptr(out), nthreads or ncores())
+    return out
+
+
+def lightning_build(rows, nlist, metric=COSINE, seed=42, nthreads=None):
+    """build-lightning-index :smart-partition? true (lightning.clj:84-130) -> (centroids fp64 [nlist, d], assignments)."""
+    rows = _f32(rows)
+    n, d = rows.shape
+    cents = np.empty((nlist, d), dtype=np.float64)
+    asg = np.empty(n, dtype=np.int32)
+    lib().orc_lightning_build(_ptr(rows), n, d, nlist, metric, seed, _ptr(cents), _ptr(asg), nthreads or ncores())
+    return cents, asg
 
 
 def assign(rows, centroids, metric=COSINE, nthreads=None) -> np.ndarray:

@@ -72,3 +72,15 @@ def test_host_helpers(lib):
     assert ivf_flat._num_probes("custom", 32) == 32 and ivf_flat._num_probes("custom", None) == 4
     assert flat.calc_recall([{"id": 1}, {"id": 2}], [{"id": 2}, {"id": 3}]) == 0.5
     assert flat.recall_at_k(np.array([[1, 2, -1]]), np.array([[2, 3, -1]])) == 0.5
+
+
+def test_lightning_probe_counts_follow_the_reference_tables():
+    """(max 1 (int (* num-partitions percent))) with the per-size mode tables of src/hnsw/ann/partition/lightning.clj:193-262."""
+    from hnsw_clj_b200.lightning import num_partitions_to_search as nps
+
+    assert nps(64, "balanced") == 6 and nps(100, "precise") == 25 and nps(64, "turbo") == 1
+    assert nps(32, "balanced") == 4 and nps(48, "accurate") == 12
+    assert nps(24, "balanced") == 4 and nps(24, "precise") == 12 and nps(24, ":fast") == 2
+    assert nps(16, "balanced") == 4 and nps(8, "turbo") == 1 and nps(20, "precise") == 12
+    assert nps(24) == 4 and nps(16) == 4 and nps(32) == 4 and nps(64) == 6 and nps(200) == 16  # dynamic default (:253-260)
+    assert nps(40, search_percent=0.01) == 1 and nps(40, search_percent=0.5) == 20

@@ -163,3 +163,58 @@ def test_hnsw_oracle_import_round_trip():
     a_ids, a_d = g.search(q, 5, 30)
     b_ids, b_d = g2.search(q, 5, 30)
     assert a_ids.tolist() == b_ids.tolist() and (a_d.view(np.int64) == b_d.view(np.int64)).all()
+
+
+def test_lightning_seeding_matches_a_literal_python_walk():
+    """orc.lightning_seeds against a direct Python restatement of src/hnsw/ann/partition/lightning.clj:86-109
+    (min over ALL chosen centroids, weights d_i, first i with cumsum + d_i >= r)."""
+    r = np.random.default_rng(3)
+    rows = r.standard_normal((120, 12)).astype(np.float32)
+    got = orc.lightning_seeds(rows, 7, seed=42)
+    state = (42 ^ 0x5DEECE66D) & ((1 << 48) - 1)
+
+    def nxt(bits):
+        nonlocal state
+        state = (state * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+        v = state >> (48 - bits)
+        return v - (1 << bits) if bits == 32 and v >= (1 << 31) else v
+
+    def next_int(bound):
+        rr = nxt(31)
+        m = bound - 1
+        if bound & m == 0:
+            return (bound * rr) >> 31
+        u = rr
+        while True:
+            rr = u % bound
+            if u - rr + m < (1 << 31):
+                return rr
+            u = nxt(31)
+
+    def next_double():
+        return ((nxt(26) << 27) + nxt(27)) * (1.0 / (1 << 53))
+
+    chosen = [next_int(len(rows))]
+    for _ in range(6):
+        dist = [min([1.7976931348623157e308] + [orc.cosine_distance(rows[i].astype(np.float64), rows[c].astype(np.float64))
+                                                 for c in chosen]) for i in range(len(rows))]
+        s = 0.0
+        for v in dist:
+            s = s + v
+        rr = next_double() * s
+        cum, i = 0.0, 0
+        while not (cum + dist[i] >= rr):
+            cum = cum + dist[i]
+            i += 1
+        chosen.append(i)
+    assert got.tolist() == chosen
+    cents, asg = orc.lightning_build(rows, 7)
+    seeds = rows[got].astype(np.float64)
+    want_a = [int(np.argmin([orc.cosine_distance(rows[i].astype(np.float64), s_) for s_ in seeds])) for i in range(len(rows))]
+    assert asg.tolist() == want_a
+    for c in range(7):
+        members = rows[asg == c].astype(np.float64)
+        acc = np.zeros(12)
+        for v in members:
+            acc = acc + v
+        assert (cents[c] == (acc / len(members) if len(members) else acc)).all()

@@ -4,10 +4,12 @@ Python host side of the C ABI (libhnswb200.so); module names follow the referenc
   simd_optimized  <- hnsw.simd-optimized          (pairwise distances, norms, top-k)
   flat            <- hnsw.bench/compute-exact-knn (exact flat search)
   ivf_flat        <- hnsw.ann.partition.ivf-flat  (build-index / search-knn / index-info)
+  lightning       <- hnsw.ann.partition.lightning (k-means++-seeded partitions, percentage probing; the IVF-FLAT scan)
   ultra_fast      <- hnsw.ultra-fast              (HNSW neighbour-candidate scoring on an uploaded graph)
   index_io        <- hnsw.helper.index-io         (save-index / load-index of the device layout)
+  data_loader     <- hnsw.helper.data-loader      (embeddings JSON -> ids + one pinned fp32 / fp64 matrix)
   api             <- hnsw.api + hnsw.api.protocol (index / search, ANNIndex + BatchSearchIndex)
-  parallel_search <- hnsw.helper.parallel-search  (batch fan-out, here one batched device call)
+  parallel_search <- hnsw.helper.parallel-search  (batch fan-out = one device call; MicroBatcher for concurrent single-query callers)
   sharded         <- row-sharded multi-GPU search (torch.distributed all-gather + merge kernel)
 """
 from . import _lib

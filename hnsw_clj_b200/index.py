@@ -37,7 +37,13 @@ def split_data(data):
     first = data[0]
     if isinstance(first, (tuple, list)) and len(first) == 2 and not np.isscalar(first[1]):
         ids = [p[0] for p in data]
-        return ids, hb.as_matrix(np.stack([np.asarray(p[1]) for p in data]))
+        rows = [p[1] for p in data]
+        base = getattr(rows[0], "base", None)
+        if (isinstance(base, np.ndarray) and base.ndim == 2 and base.shape[0] == len(rows) and base.flags.c_contiguous
+                and all(getattr(r, "base", None) is base for r in rows)
+                and all(r.ctypes.data == base.ctypes.data + i * base.strides[0] for i, r in enumerate(rows))):
+            return ids, hb.as_matrix(base)  # the rows of one matrix, in order (data_loader.as_data): no copy
+        return ids, hb.as_matrix(np.stack([np.asarray(r) for r in rows]))
     return None, hb.as_matrix(np.asarray(data))
 
 

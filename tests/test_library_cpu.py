@@ -84,3 +84,35 @@ def test_lightning_probe_counts_follow_the_reference_tables():
     assert nps(16, "balanced") == 4 and nps(8, "turbo") == 1 and nps(20, "precise") == 12
     assert nps(24) == 4 and nps(16) == 4 and nps(32) == 4 and nps(64) == 6 and nps(200) == 16  # dynamic default (:253-260)
     assert nps(40, search_percent=0.01) == 1 and nps(40, search_percent=0.5) == 20
+
+
+def test_data_loader_reads_the_reference_json_layout(tmp_path):
+    """src/hnsw/helper/data_loader.clj:7-45: {"verses": [{"id", "text", "embedding"}]} -> ids + one matrix; fp32-exact
+    and unit-norm detection; an unreadable file gives None (nil)."""
+    import json
+
+    import numpy as np
+
+    from hnsw_clj_b200 import data_loader
+    from hnsw_clj_b200.index import split_data
+
+    r = np.random.default_rng(0)
+    emb = r.standard_normal((7, 12)).astype(np.float32)
+    emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+    verses = [{"id": f"Gen_1:{i + 1}", "text": f"verse {i}", "embedding": [float(x) for x in emb[i].astype(np.float32)]}
+              for i in range(7)]
+    path = tmp_path / "bible_embeddings.json"
+    path.write_text(json.dumps({"verses": verses}))
+    got = data_loader.load_bible_vectors(str(path))
+    m = got["vectors"]["matrix"]
+    assert m.dtype == np.float32 and (m == emb.astype(np.float32)).all()
+    assert got["metadata"]["fp32-exact"] and got["metadata"]["unit-norm"]
+    assert got["metadata"]["count"] == 7 and got["metadata"]["dimension"] == 12
+    assert got["text-map"]["Gen_1:3"] == "verse 2"
+    ids, rows = split_data(data_loader.as_data(got))
+    assert ids[0] == "Gen_1:1" and rows.ctypes.data == m.ctypes.data  # zero-copy hand-over to build_index
+    verses[2]["embedding"][0] = 0.1  # not fp32-representable, not unit norm
+    path.write_text(json.dumps({"verses": verses}))
+    got = data_loader.load_bible_vectors(str(path))
+    assert got["vectors"]["matrix"].dtype == np.float64 and not got["metadata"]["fp32-exact"]
+    assert data_loader.load_bible_vectors(str(tmp_path / "missing.json")) is None

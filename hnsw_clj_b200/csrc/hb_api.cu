@@ -218,6 +218,7 @@ struct FastSideBufs {
 static bool g_fast_debug = false;
 static bool g_tc_interleave = true;
 static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
+static int g_hnsw_prefetch = -1;     // hb_set_option("hnsw_prefetch", lines): -1 = sized to the L2 (hnsw_search)
 static bool g_fast_set_only = true;  // IVF coarse routing proves the probed set only (FastJob::set_only)
 static bool g_fast_dense = true;     // short flat scans (<= 2048 rows) select from the dumped score matrix
 static int g_fast_level_min = 33;     // flat scans of at least this many row tiles run in levels (fast_topk)
@@ -1412,6 +1413,12 @@ static void hnsw_search(hb_index *ix, const void *queries, int qdtype, int64_t n
     HB_REQUIRE((size_t)W * P.warp_smem <= 227 * 1024, "ef too large for the shared-memory queues");
     const int ctas_per_sm = std::max<int>(1, std::min<size_t>(4, (220 * 1024) / ((size_t)W * P.warp_smem + 1024)));
     const int grid = (int)std::min<int64_t>((int64_t)g_num_sms * ctas_per_sm, ceil_div(nq, W));
+    // rows in flight: every resident warp gathers up to 32 rows at once; keep their prefetched lines within ~48 MB of the L2
+    {
+        const int64_t warps = (int64_t)grid * W;
+        const int64_t lines = (48ll << 20) / (warps * 32 * 128);
+        P.pf_window = g_hnsw_prefetch >= 0 ? g_hnsw_prefetch : (int)std::max<int64_t>(2, std::min<int64_t>(lines, 32));
+    }
     const int64_t slots = (int64_t)g_num_sms * 4 * W;  // upper bound of grid * W, so the buffers are allocated once
     P.vwords = ceil_div(ix->n, 32);
     P.vcap = 8192;
@@ -1521,6 +1528,9 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             for (int i = 0; i < PROF_NTAGS; ++i) g_prof_ms[i] = 0, g_prof_n[i] = 0;
             g_fast_queries = g_fast_fallbacks = 0;
             g_hnsw_scored = g_hnsw_overflows = 0;
+        } else if (!strcmp(name, "hnsw_prefetch")) {
+            HB_REQUIRE(value >= -1 && value <= 64, "hnsw_prefetch must be -1..64");
+            g_hnsw_prefetch = (int)value;
         } else if (!strcmp(name, "fast_set_only")) {
             g_fast_set_only = value != 0;
         } else if (!strcmp(name, "host_feed")) {

@@ -90,19 +90,25 @@ __device__ __forceinline__ void heap_poll(Heap &h, double &rd, int32_t &ri) {
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // distance-fn(query, row[my_row]) for the m rows held by lanes 0..m-1 (my_row < 0 on the others): the gather-dot.
+// Row chunks (128 bytes of each of the <= 32 rows) are staged through shared memory with full-line loads; the matching
+// query chunk is loaded once per warp (one coalesced load, software-pipelined with the rows), widened to fp64 once and
+// broadcast from shared memory -- a per-element global load of the query inside the sequential sum left the warp waiting
+// on its scoreboard for half of the kernel (ncu, profiles/r01f_hnsw_1m_*).
 template <typename TRow, typename TQry, int ARITH>
 __device__ __forceinline__ double warp_gather_dot(const TRow *__restrict__ rows, int d, bool vec, const TQry *__restrict__ qp,
-                                                  int my_row, int m, unsigned char *stage, int lane) {
+                                                  int my_row, int m, unsigned char *stage, double *qstage, int lane, int pf_window) {
     constexpr int CH = 128 / (int)sizeof(TRow);  // elements per 128-byte chunk
     constexpr int PER = 16 / (int)sizeof(TRow);  // elements per 16-byte part
+    constexpr int QPL = (CH + 31) / 32;          // query elements a lane stages per chunk
     const int nch = (d + CH - 1) / CH;
     const int nr = (m + 3) >> 2;  // staging rounds: 4 rows per round, 8 lanes x 16 B per row chunk
     const int sub = lane >> 3, part = lane & 7;
-    if (my_row >= 0) {
-        const char *line = reinterpret_cast<const char *>(rows + (int64_t)my_row * d);
-        const int nline = (int)(((size_t)d * sizeof(TRow) + 127) >> 7);
-        for (int i = 0; i < nline; ++i) prefetch_l2(line + (size_t)i * 128);
-    }
+    // Rolling L2 prefetch of the lane's own row, pf_window lines ahead of the chunk being staged.  Prefetching whole rows
+    // up front put 32 rows x 3 KB per warp in flight -- 227 MB over the 2368 resident warps, more than the 126 MB L2, so
+    // lines were evicted before use and fetched twice (ncu: 416 GB of DRAM reads for 262 GB of rows at configs[4]).
+    const char *line = reinterpret_cast<const char *>(rows + (int64_t)max(my_row, 0) * d);
+    const int nline = my_row >= 0 ? (int)(((size_t)d * sizeof(TRow) + 127) >> 7) : 0;
+    for (int i = 0; i < min(pf_window, nline); ++i) prefetch_l2(line + (size_t)i * 128);
     // the rows this lane helps to stage: round r -> slot r*4 + sub
     int64_t src_row[8];
 #pragma unroll
@@ -110,7 +116,7 @@ __device__ __forceinline__ double warp_gather_dot(const TRow *__restrict__ rows,
         const int rj = __shfl_sync(0xffffffffu, my_row, (r * 4 + sub) & 31);
         src_row[r] = (r < nr && rj >= 0) ? (int64_t)rj : -1;
     }
-    auto load_chunk = [&](int c, uint4(&buf)[8]) {
+    auto load_chunk = [&](int c, uint4(&buf)[8], TQry(&qbuf)[QPL]) {
         const int e0 = c * CH + part * PER;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -127,28 +133,51 @@ __device__ __forceinline__ double warp_gather_dot(const TRow *__restrict__ rows,
             }
             buf[r] = val;
         }
+#pragma unroll
+        for (int t = 0; t < QPL; ++t) {
+            const int i = t * 32 + lane;
+            qbuf[t] = (i < CH && c * CH + i < d) ? __ldg(qp + c * CH + i) : TQry(0);
+        }
     };
     uint4 nxt[8];
-    load_chunk(0, nxt);
+    TQry qnxt[QPL];
+    load_chunk(0, nxt, qnxt);
     double s = 0.0;
     for (int c = 0; c < nch; ++c) {
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < 8; ++r)
             if (r < nr) *reinterpret_cast<uint4 *>(stage + (r * 4 + sub) * STAGE_ROW + part * 16) = nxt[r];
+#pragma unroll
+        for (int t = 0; t < QPL; ++t)
+            if (t * 32 + lane < CH) qstage[t * 32 + lane] = to_f64(qnxt[t]);
         __syncwarp();
-        if (c + 1 < nch) load_chunk(c + 1, nxt);
+        if (c + 1 < nch) load_chunk(c + 1, nxt, qnxt);
+        if (c + pf_window < nline) prefetch_l2(line + (size_t)(c + pf_window) * 128);
         if (lane < m) {
             const uint4 *mine = reinterpret_cast<const uint4 *>(stage + lane * STAGE_ROW);
             const int kmax = min(CH, d - c * CH);
-            const TQry *qc = qp + c * CH;
+            if (kmax == CH) {  // full chunk: no per-element predicates in the sequential sum
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const uint4 bits = mine[w];
-                const TRow *el = reinterpret_cast<const TRow *>(&bits);
+                for (int w = 0; w < 8; ++w) {
+                    const uint4 bits = mine[w];
+                    const TRow *el = reinterpret_cast<const TRow *>(&bits);
 #pragma unroll
-                for (int e = 0; e < PER; ++e)
-                    if (w * PER + e < kmax) s = mac_seq<ARITH>(to_f64(__ldg(qc + w * PER + e)), to_f64(el[e]), s);
+                    for (int e = 0; e < PER; e += 2) {
+                        const double2 qq = *reinterpret_cast<const double2 *>(qstage + w * PER + e);  // warp-uniform: broadcast
+                        s = mac_seq<ARITH>(qq.x, to_f64(el[e]), s);
+                        s = mac_seq<ARITH>(qq.y, to_f64(el[e + 1]), s);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    const uint4 bits = mine[w];
+                    const TRow *el = reinterpret_cast<const TRow *>(&bits);
+#pragma unroll
+                    for (int e = 0; e < PER; ++e)
+                        if (w * PER + e < kmax) s = mac_seq<ARITH>(qstage[w * PER + e], to_f64(el[e]), s);
+                }
             }
         }
     }
@@ -156,13 +185,14 @@ __device__ __forceinline__ double warp_gather_dot(const TRow *__restrict__ rows,
 }
 
 template <typename TRow, typename TQry, int ARITH>
-__global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(const HnswSearchParams P) {
+__global__ void __launch_bounds__(HN_THREADS, 4) hnsw_search_kernel(const HnswSearchParams P) {
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int efc = P.ef_cap;  // slots of the nearest queue / entry list (>= ef + 1)
     unsigned char *wb = smem_dyn + (size_t)warp * P.warp_smem;
     unsigned char *stage = wb;
-    double *near_d = reinterpret_cast<double *>(wb + 32 * STAGE_ROW);
+    double *qstage = reinterpret_cast<double *>(wb + 32 * STAGE_ROW);  // the query chunk in fp64, 64 slots
+    double *near_d = qstage + 64;
     double *sd = near_d + efc;
     double *cand_d_s = sd + 32;
     int32_t *near_i = reinterpret_cast<int32_t *>(cand_d_s + P.cand_cap_smem);
@@ -215,7 +245,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(const HnswSearc
                     if (p < P.vcap) vlist[p] = id;
                 }
                 vcount += m;
-                const double acc = warp_gather_dot<TRow, TQry, ARITH>(rows, d, vec, qp, id, m, stage, lane);
+                const double acc = warp_gather_dot<TRow, TQry, ARITH>(rows, d, vec, qp, id, m, stage, qstage, lane, P.pf_window);
                 if (lane < m) {
                     sd[lane] = apply_epi(P.epi, acc, qn, P.row_norm ? P.row_norm[id] : 0.0);
                     sid[lane] = id;
@@ -275,7 +305,7 @@ __global__ void __launch_bounds__(HN_THREADS) hnsw_search_kernel(const HnswSearc
                     vcount += m;
                     __syncwarp();
                     const int my = lane < m ? sid[lane] : -1;
-                    const double acc = warp_gather_dot<TRow, TQry, ARITH>(rows, d, vec, qp, my, m, stage, lane);
+                    const double acc = warp_gather_dot<TRow, TQry, ARITH>(rows, d, vec, qp, my, m, stage, qstage, lane, P.pf_window);
                     scored += (unsigned)m;
                     double dist = 0.0;
                     if (lane < m) dist = apply_epi(P.epi, acc, qn, P.row_norm ? P.row_norm[my] : 0.0);
@@ -377,7 +407,7 @@ void hnsw_arith(const HnswSearchParams &P, bool l2, int grid, size_t smem) {
 int hnsw_warps_per_cta() { return HN_WARPS; }
 
 size_t hnsw_warp_smem(int ef_cap, int cand_cap_smem) {
-    size_t b = 32 * STAGE_ROW;
+    size_t b = 32 * STAGE_ROW + 64 * 8;
     b += (size_t)(ef_cap + 32 + cand_cap_smem) * 8;
     b += (size_t)(ef_cap + ef_cap + 32 + cand_cap_smem) * 4;
     return (b + 15) & ~(size_t)15;

@@ -20,6 +20,7 @@ struct HnswSearchParams {
     const int32_t *work_list = nullptr;  // work item -> query index (NULL: identity)
     int32_t *next_work = nullptr;        // work counter (zeroed by the caller)
     int ef = 0, k = 0, epi = EPI_COS_GUARD;
+    int pf_window = 6;  // 128-byte lines of each gathered row prefetched to L2 ahead of the chunk being staged
     // per-warp state
     int ef_cap = 0;         // slots of the `nearest` queue and of the entry list (>= ef + 1)
     int cand_cap_smem = 0;  // slots of the candidate queue in shared memory

@@ -442,6 +442,14 @@ def run_c5(args):
         "graph": {"max_level": int(levels.max()), "edges_level0": int(adjacency[0][0][-1])},
     }
     print(json.dumps(line), flush=True)
+    if args.sweep:
+        name, _, vals = args.sweep.partition("=")
+        for v in vals.split(","):
+            hb.set_option(name, int(v))
+            ms_v = timed(lambda: ix.search_raw(queries, k, ef, out_ids=out_ids, out_dist=out_d), reps=args.reps, warm=1)
+            same = bool((out_ids.cpu().numpy() == ids).all())
+            print(json.dumps({"sweep": name, "value": int(v), "ms_per_batch": ms_v, "queries_per_s": nq / ms_v * 1e3,
+                              "gather_gbs": bytes_scored / ms_v / 1e6, "ids_unchanged": same}), flush=True)
 
 
 def main():
@@ -452,10 +460,15 @@ def main():
     ap.add_argument("--nlist", type=int, default=65536)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--graph", choices=["oracle", "bulk"], default="bulk")
+    ap.add_argument("--opt", action="append", default=[], help="library knob name=value (hb_set_option), repeatable")
+    ap.add_argument("--sweep", default="", help="c5: name=v1,v2,... re-times the search for each value of a library knob")
     args = ap.parse_args()
     from hnsw_clj_b200 import _lib as hb
 
     hb.check(hb.lib().hb_init(int(os.environ.get("LOCAL_RANK", "0"))))
+    for kv in args.opt:
+        name, _, val = kv.partition("=")
+        hb.set_option(name, int(val))
     {"c1": run_c1, "c3": run_c3, "c4": run_c4, "c4full": run_c4_full, "c5": run_c5}[args.config](args)
 
 

@@ -446,10 +446,13 @@ def run_c5(args):
         name, _, vals = args.sweep.partition("=")
         for v in vals.split(","):
             hb.set_option(name, int(v))
+            hb.set_option("profile", 1)
             ms_v = timed(lambda: ix.search_raw(queries, k, ef, out_ids=out_ids, out_dist=out_d), reps=args.reps, warm=1)
             same = bool((out_ids.cpu().numpy() == ids).all())
             print(json.dumps({"sweep": name, "value": int(v), "ms_per_batch": ms_v, "queries_per_s": nq / ms_v * 1e3,
-                              "gather_gbs": bytes_scored / ms_v / 1e6, "ids_unchanged": same}), flush=True)
+                              "gather_gbs": bytes_scored / ms_v / 1e6, "ids_unchanged": same,
+                              "queue_overflows_per_batch": hb.get_stat("hnsw_overflows") / (args.reps + 1)}), flush=True)
+            hb.set_option("profile", 0)
 
 
 def main():

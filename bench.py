@@ -213,6 +213,11 @@ def run_reference(args, w, key):
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum of one tc_pass_kernel<2,EMIT> list-scan launch, from `ncu --set full` captures of
+# this command: (workload, digits, probe pruning on) -> bytes.  profiles/r01c_tc_pass_ncu_raw.csv (5.42 GB + 0.03 GB, no pruning)
+TRAFFIC = {("c2", 2, False): 5.45e9}
+
+
 def run_ours(args, w, key):
     import torch
     import torch.distributed as dist
@@ -313,6 +318,11 @@ def run_ours(args, w, key):
                                                          "pack_ms", "rescore_ms")}
     tc_ms, tc_n = hb.get_stat("tc_ms"), max(hb.get_stat("tc_count"), 1.0)
     fast_served, fast_fell = hb.get_stat("fast_queries"), hb.get_stat("fast_fallbacks")
+    # (query, probed list) pairs the scan dropped by the angle bound, and the rows they held, per step
+    pruned_pairs = hb.get_stat("fast_pruned_pairs") / args.steps
+    pruned_rows = hb.get_stat("fast_pruned_rows") / args.steps
+    probe_pairs = hb.get_stat("fast_probe_pairs") / args.steps
+    hb_stats = {n: hb.get_stat(n) for n in ("tc_units", "tc_items", "tc_tiles")}
     hb.set_option("profile", 0)
     if world > 1:
         t = torch.tensor([ms], device=device)
@@ -402,18 +412,49 @@ def run_ours(args, w, key):
         t_tc = (tc_ms / tc_n) * 1e-3
         nprod = 4 if args.digits == 2 else 6
         dpad = -(-w["d"] // 128) * 128
+        # What the launch covered, counted by the library while profiling: units (<= 128 query slots of one list), items
+        # (unit x row tile = one 128 x 128 x dpad block of digit products) and the distinct row tiles they read.  With probe
+        # pruning the kernel only sees the (query, list) pairs that survive: its roofline is quoted on the rows it actually
+        # scores and the bytes it has to read; the step's algorithmic work (every probed row, as the reference scans them)
+        # stands beside it.
+        algorithmic_pairs = pairs
+        pairs = pairs - pruned_rows
+        flops = 2.0 * pairs * w["d"]
+        tc_units, tc_items, tc_tiles = (hb_stats[n] / args.steps for n in ("tc_units", "tc_items", "tc_tiles"))
+        if tc_items > 0:
+            items = tc_items
         int8_ops = 2.0 * items * 128 * 128 * dpad * nprod if items else None
-        img_bytes = float(w["n"]) * dpad * args.digits + nq * nprobe * dpad * args.digits  # digit images read once
+        # digit images read once: the row tiles some unit scans + the units' query images (128 slots each)
+        img_bytes = (tc_tiles * 128.0 * dpad * args.digits + tc_units * 128.0 * dpad * args.digits) if tc_items > 0 else (
+            float(w["n"]) * dpad * args.digits + nq * nprobe * dpad * args.digits)
+        hbm_peak = peaks.get("hbm_gbs", 7700.0)
+        t_flops, t_bytes = flops / (bf16_peak * 1e12), img_bytes / (hbm_peak * 1e9)
+        hbm_bound = t_bytes > t_flops  # the binding roofline is the larger of the two lower bounds on the launch time
+        tensor = {"achieved_tflops": flops / t_tc / 1e12 if single else None, "peak_tflops": bf16_peak,
+                  "frac": (flops / t_tc / 1e12 / bf16_peak) if single else None}
+        hbm = {"achieved_gbs": img_bytes / t_tc / 1e9 if single else None, "peak_gbs": hbm_peak,
+               "frac": (img_bytes / t_tc / 1e9 / hbm_peak) if single else None}
         roofline = {
             "kernel": f"tc_pass_kernel<{args.digits},EMIT> (tcgen05.mma kind::i8, IVF list scan candidate pass)",
-            "bound": "tensor", "achieved": flops / t_tc / 1e12 if single else None, "peak": bf16_peak, "unit": "TFLOP/s",
-            "frac": (flops / t_tc / 1e12 / bf16_peak) if single else None, "peak_source": peak_src,
+            "bound": "hbm" if hbm_bound else "tensor",
+            "achieved": (hbm["achieved_gbs"] if hbm_bound else tensor["achieved_tflops"]),
+            "peak": hbm_peak if hbm_bound else bf16_peak, "unit": "GB/s" if hbm_bound else "TFLOP/s",
+            "frac": hbm["frac"] if hbm_bound else tensor["frac"],
+            "peak_source": ("MEASURED_PEAKS.json " + ("hbm_gbs" if hbm_bound else "bf16_tflops (burst)")) if peaks else "fallback",
+            "why_this_bound": f"lower bounds on the launch: unique digit-image bytes / HBM peak = {t_bytes * 1e3:.3f} ms, "
+                              f"algorithmic flops / bf16 peak = {t_flops * 1e3:.3f} ms",
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel's launch, ncu --set full capture of this very
-            # command (profiles/r01c_tc_pass_ncu_raw.csv): 5.42 GB + 0.03 GB
-            "traffic": 5.45e9 if (key == "c2" and args.digits == 2) else None,
+            # command (see TRAFFIC below)
+            "traffic": TRAFFIC.get((key, args.digits, pruned_rows > 0)),
             "launch_ms": t_tc * 1e3, "launches_per_step": tc_n / args.steps,
             "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": img_bytes,
-            "hbm_gbs_at_unique_bytes": img_bytes / t_tc / 1e9 if single else None,
+            "tensor": tensor, "hbm": hbm,
+            "units_per_launch": tc_units, "items_per_launch": items, "row_tiles_read_per_launch": tc_tiles,
+            "scored_pairs_per_launch": pairs, "algorithmic_pairs_per_step": algorithmic_pairs,
+            "probe_pruning": {"probe_pairs": probe_pairs, "pruned_probe_pairs": pruned_pairs, "pruned_rows": pruned_rows,
+                              "note": "exact: a probed list is dropped for a query when cos(angle(q, centroid) - list radius) "
+                                      "cannot reach the query's candidate threshold (results stay bit-identical); "
+                                      "--opt fast_prune=0 scans every probed list"},
             "int8_pipe": {"executed_tops": int8_ops / t_tc / 1e12 if int8_ops else None,
                           "nominal_peak_tops": 2.0 * bf16_peak, "frac": (int8_ops / t_tc / 1e12 / (2.0 * bf16_peak)) if int8_ops else None,
                           "note": "executed = digit products on padded tiles; peak = 2 x measured bf16 (int8 runs at twice the "

@@ -219,6 +219,9 @@ static bool g_fast_debug = false;
 static bool g_tc_interleave = true;
 static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
 static int g_hnsw_prefetch = -1;     // hb_set_option("hnsw_prefetch", lines): -1 = sized to the L2 (hnsw_search)
+static bool g_fast_prune = true;     // IVF scan: drop (query, probed list) pairs that cannot reach the query's threshold
+static int64_t g_fast_pruned_pairs = 0, g_fast_pruned_rows = 0, g_fast_probe_pairs = 0;
+static int64_t g_tc_units = 0, g_tc_items = 0, g_tc_tiles = 0;  // IVF main candidate pass, accumulated while profiling
 static bool g_fast_set_only = true;  // IVF coarse routing proves the probed set only (FastJob::set_only)
 static bool g_fast_dense = true;     // short flat scans (<= 2048 rows) select from the dumped score matrix
 static int g_fast_level_min = 33;     // flat scans of at least this many row tiles run in levels (fast_topk)
@@ -251,13 +254,15 @@ struct hb_index {
     int64_t hn_slots = 0;
     // HB_MODE_FAST: digit images of the rows (all index types) and of the centroids (IVF), built on first use
     hb::FastSideBufs fast_rows, fast_cents;
+    DevBuf radius;  // IVF, built on first use: per list the largest angle between a row and the centroid (probe pruning)
+    bool radius_built = false;
     int64_t device_bytes() const {
         size_t b = rows.cap + norms.cap + cents.cap + cent_norm.cap + list_off.cap + list_rows.cap + assign.cap + levels.cap;
         for (auto &x : adj_off) b += x.cap;
         for (auto &x : adj_ids) b += x.cap;
         b += adj_off_ptrs.cap + adj_ids_ptrs.cap + hn_visited.cap + hn_vlist.cap + hn_ctrl.cap + hn_over.cap + hn_gcand_d.cap +
              hn_gcand_i.cap;
-        b += fast_rows.bytes() + fast_cents.bytes();
+        b += fast_rows.bytes() + fast_cents.bytes() + radius.cap;
         return (int64_t)b;
     }
     void release() {
@@ -275,6 +280,8 @@ struct hb_index {
         hn_slots = 0;
         fast_rows.release();
         fast_cents.release();
+        radius.release();
+        radius_built = false;
     }
 };
 
@@ -619,7 +626,7 @@ struct FastWs {
     DevBuf dig, q64, pslot, srow, ptotal, qu, ql1, qscale, qeps, qmargin, thr, cnt, cnegv, crel, cpos, selval, selpos, pq, pr, exact;
     DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_slotq, u_slotrel;
     DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_slotq, t_slotrel;
-    DevBuf a_ids, a_dist, a_norm, a_tmp, dump, timing;
+    DevBuf a_ids, a_dist, a_norm, a_tmp, dump, timing, simub, pruned;
     DevBuf ppos, ppos0, ok_a, ok_b, relk, probes0, pair_out0, qsel0, lq_off0, uprefix0, uprefix, flat_plan, idx, gq, gids, gdist,
         tmp2;
     void release() {
@@ -627,7 +634,7 @@ struct FastWs {
                          &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_slotq, &u_slotrel,
                          &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_slotq, &t_slotrel,
                          &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
-                         &idx, &gq, &gids, &gdist, &tmp2, &a_ids, &a_dist, &a_norm, &a_tmp, &dump, &timing};
+                         &idx, &gq, &gids, &gdist, &tmp2, &a_ids, &a_dist, &a_norm, &a_tmp, &dump, &timing, &simub, &pruned};
         for (DevBuf *b : all) b->release();
     }
 };
@@ -696,6 +703,16 @@ static FastSideBufs &fast_cents_side(hb_index *ix) {
     return S;
 }
 
+static const double *list_radius(hb_index *ix) {
+    double *r = ix->radius.as<double>((size_t)std::max(ix->nlist, 1));
+    if (!ix->radius_built) {
+        launch_list_radius(ix->rows.p, ix->dtype, (const double *)ix->norms.p, (const double *)ix->cents.p,
+                           (const double *)ix->cent_norm.p, (const int64_t *)ix->list_off.p, ix->nlist, ix->n, ix->d, r);
+        ix->radius_built = true;
+    }
+    return r;
+}
+
 struct FastPlan {  // which (query, list) pairs a pass covers
     int nlist = 0;
     const int64_t *lq_off = nullptr;       // [nlist+1] selections per list
@@ -737,6 +754,10 @@ struct FastJob {
     bool set_only = false;
     const int64_t *tie_list_off = nullptr;  // see FinalParams
     int tie_nlist = 0;
+    double *out_simub = nullptr;  // see FinalParams
+    // 0: the whole job.  IVF list scan with probe pruning: 1 = query bounds + threshold sample only (needs `thresh`),
+    // 2 = everything after it (needs `emit`, planned after the pruning; thresholds and bounds stay from phase 1)
+    int phase = 0;
     int64_t *out_rel = nullptr;
     double *out_dist = nullptr;
     int32_t *out_ok = nullptr;
@@ -770,26 +791,33 @@ static void fast_topk(const FastJob &J) {
     const FastSideBufs &S = *J.side;
     const int ns = S.ns, kbn = S.kbn, kk = fast_kk(J.k), cap = fast_cap(J.k);
     const int64_t nq = J.nq;
+    const bool do_sample = J.phase != 2, do_main = J.phase != 1;
+    HB_REQUIRE(J.phase == 0 || !J.shared_units, "phased jobs need their own threshold plan");
     double *qscale = W.qscale.as<double>(nq), *qeps = W.qeps.as<double>(nq);
     float *qmargin = W.qmargin.as<float>(nq);
-    launch_query_bounds((const double *)W.qu.p, (const double *)W.ql1.p, J.qn, nq, ns, J.d, J.metric, (const float *)S.stats.p, qscale,
-                        qeps, qmargin);
     float *thr = W.thr.as<float>(nq);
     int32_t *cnt = W.cnt.as<int32_t>(nq);
     double *cnegv = W.cnegv.as<double>((size_t)nq * cap);
     int32_t *crel = W.crel.as<int32_t>((size_t)nq * cap);
     int32_t *cpos = W.cpos.as<int32_t>((size_t)nq * cap);
-    launch_fill_f32(thr, nq, -INFINITY);
-    HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
+    if (do_sample) {
+        launch_query_bounds((const double *)W.qu.p, (const double *)W.ql1.p, J.qn, nq, ns, J.d, J.metric, (const float *)S.stats.p, qscale,
+                            qeps, qmargin);
+        launch_fill_f32(thr, nq, -INFINITY);
+        HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
+    }
 
     UnitPlan U, T;
     int8_t *aimg = nullptr, *aimg0 = nullptr;
     {
         Prof pr(J.profile ? PROF_PACK : -1);
-        U = make_units(J.emit, W.u_list, W.u_sel0, W.u_nsel, W.u_ntile, W.u_item0, W.u_slotq, W.u_slotrel, (const int64_t *)S.tile_off.p);
-        aimg = W.aimg.as<int8_t>((size_t)std::max(J.emit.nunits, 1) * kbn * ns * kFastImg);
-        launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.emit.nunits, U.slot_query, aimg);
-        if (J.shared_units) {
+        if (do_main) {
+            U = make_units(J.emit, W.u_list, W.u_sel0, W.u_nsel, W.u_ntile, W.u_item0, W.u_slotq, W.u_slotrel, (const int64_t *)S.tile_off.p);
+            aimg = W.aimg.as<int8_t>((size_t)std::max(J.emit.nunits, 1) * kbn * ns * kFastImg);
+            launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.emit.nunits, U.slot_query, aimg);
+        }
+        if (!do_sample) {
+        } else if (J.shared_units) {
             T = U;
             T.unit_ntile = W.t_ntile.as<int32_t>((size_t)J.emit.nunits + 1);
             T.unit_item0 = W.t_item0.as<int32_t>((size_t)J.emit.nunits + 1);
@@ -833,11 +861,11 @@ static void fast_topk(const FastJob &J) {
     // A long flat scan (one list, many row tiles) runs in levels over growing tile ranges [0,2), [2,32), [32,512), ...:
     // after each level the candidate lists are cut back to their kk best and the thresholds rise to the exact kk-th best
     // (k-th best - margin) so far, so a level emits about kk * 15 rows per query however long the scan is.
-    const bool leveled = J.shared_units && J.emit.nlist == 1 && S.ntiles >= g_fast_level_min;
+    const bool leveled = J.phase == 0 && J.shared_units && J.emit.nlist == 1 && S.ntiles >= g_fast_level_min;
     // A short flat scan (coarse routing, k-means assignment over <= 2048 centroids) dumps its whole score matrix and lets
     // one warp per query pick the candidates from it: no thresholds, no sample pass, no sort.
     const int64_t flat_rows = J.emit.nlist == 1 ? S.nrows : 0;
-    const bool dense = g_fast_dense && J.shared_units && J.emit.nlist == 1 && flat_rows >= 1 && flat_rows <= 2048 && !leveled;
+    const bool dense = J.phase == 0 && g_fast_dense && J.shared_units && J.emit.nlist == 1 && flat_rows >= 1 && flat_rows <= 2048 && !leveled;
     if (dense) {
         Prof pr(J.profile ? PROF_TC : -1);
         P.aimg = aimg;
@@ -875,6 +903,7 @@ static void fast_topk(const FastJob &J) {
         }
         P.tile_start = 0;
     } else {
+    if (do_sample) {
     {
         // sample pass: candidates of a subset of the rows (nearest list / every 8th tile) -> their kk-th best
         // score seeds the thresholds of the full pass
@@ -891,6 +920,8 @@ static void fast_topk(const FastJob &J) {
     select_candidates();
     launch_thr_from_sample(selval, cnt, nq, kk, cap, J.k, qmargin, thr);
     HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
+    }
+    if (!do_main) return;
     {
         Prof pr(J.profile ? PROF_TC : -1);
         P.tile_stride = 1;
@@ -933,6 +964,7 @@ static void fast_topk(const FastJob &J) {
         F.out_ok = J.out_ok;
         F.tie_list_off = J.tie_list_off;
         F.tie_nlist = J.tie_nlist;
+        F.out_simub = J.out_simub;
         launch_fast_final(F);
     }
     if (g_fast_debug && P.timing) {
@@ -1208,6 +1240,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         double *q64buf = g_fw.q64.as<double>((size_t)nqc * d);
         const double *q64 = qdtype == HB_F64 ? (const double *)qptr : q64buf;
         int64_t *ppos = W.ppos.as<int64_t>((size_t)nqc * np_eff);
+        double *simub = W.simub.as<double>((size_t)nqc * np_eff);
         int32_t *ok_c = W.ok_b.as<int32_t>(nqc);
         if (coarse_tc) {
             Prof pr(PROF_COARSE);
@@ -1236,6 +1269,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
                 J.epi = EPI_COS_GUARD;
                 J.profile = false;
                 J.k = np_eff;
+                J.out_simub = simub + (size_t)b0 * np_eff;
                 J.set_only = g_fast_set_only;  // which lists to probe; their order only numbers the candidates (ties: tie_list_off below)
                 flat_fast_plan(nb, J.emit, J.thresh, W.flat_plan);
                 J.shared_units = true;
@@ -1303,16 +1337,22 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         int32_t *qsel0 = W.qsel0.as<int32_t>(nqc);
         int64_t *lq_off0 = W.lq_off0.as<int64_t>(nlist + 1);
         int64_t *uprefix0 = W.uprefix0.as<int64_t>(nlist + 1);
-        {
-            Prof prp(PROF_PLAN);
+        // Probe pruning (needs the coarse stage's similarity bounds): sample the nearest list first, then drop every
+        // (query, probed list) pair whose rows cannot reach the query's threshold, and plan the scan over the rest.
+        const bool prune = coarse_tc && g_fast_prune && np_eff > 1;
+        auto plan_emit = [&] {
             ivf_plan(ppos, np, nlist, (const int64_t *)ix->list_off.p, probes, pair_out, qsel, lq_off, uprefix, 1 << 30, kFastTile,
                      g_ws.tmp);
+        };
+        {
+            Prof prp(PROF_PLAN);
+            if (!prune) plan_emit();
             launch_first_column(ppos, nqc, np_eff, ppos0);
             ivf_plan(ppos0, nqc, nlist, (const int64_t *)ix->list_off.p, probes0, pair_out0, qsel0, lq_off0, uprefix0, 1 << 30,
                      kFastTile, g_ws.tmp);
         }
         int64_t nu = 0, nu0 = 0;
-        HB_CUDA(cudaMemcpyAsync(&nu, uprefix + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
+        if (!prune) HB_CUDA(cudaMemcpyAsync(&nu, uprefix + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
         HB_CUDA(cudaMemcpyAsync(&nu0, uprefix0 + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
         sync_stream();
         int64_t *relk = W.relk.as<int64_t>((size_t)nqc * k);
@@ -1337,7 +1377,6 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         J.emit.qsel = qsel;
         J.emit.pair_out = pair_out;
         J.emit.pair_div = np_eff;
-        set_units(J.emit, nu, g_tc_interleave);
         J.thresh.nlist = nlist;
         J.thresh.lq_off = lq_off0;
         J.thresh.unit_prefix = uprefix0;
@@ -1354,7 +1393,43 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
             J.tie_list_off = (const int64_t *)ix->list_off.p;
             J.tie_nlist = nlist;
         }
-        fast_topk(J);
+        if (prune) {
+            J.phase = 1;
+            fast_topk(J);  // query bounds + thresholds from the nearest list
+            {
+                Prof prp(PROF_PLAN);
+                unsigned long long *npruned = (unsigned long long *)W.pruned.get(16);
+                HB_CUDA(cudaMemsetAsync(npruned, 0, 16, g_stream));
+                launch_prune_probes(ppos, simub, list_radius(ix), (const float *)W.thr.p, (const double *)W.qscale.p,
+                                    (const double *)W.qeps.p, nqc, np_eff, (const int64_t *)ix->list_off.p, npruned);
+                plan_emit();
+                unsigned long long hp[2] = {0, 0};
+                HB_CUDA(cudaMemcpyAsync(&nu, uprefix + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
+                HB_CUDA(cudaMemcpyAsync(hp, npruned, 16, cudaMemcpyDeviceToHost, g_stream));
+                sync_stream();
+                g_fast_pruned_pairs += (int64_t)hp[0];
+                g_fast_pruned_rows += (int64_t)hp[1];
+                g_fast_probe_pairs += np;
+            }
+            set_units(J.emit, nu, g_tc_interleave);
+            J.phase = 2;
+            fast_topk(J);
+        } else {
+            set_units(J.emit, nu, g_tc_interleave);
+            fast_topk(J);
+        }
+        if (g_profile) {  // what the main candidate pass covered: units, items (unit x row tile), distinct row tiles
+            std::vector<int64_t> hu((size_t)nlist + 1), ht((size_t)nlist + 1);
+            HB_CUDA(cudaMemcpyAsync(hu.data(), uprefix, hu.size() * 8, cudaMemcpyDeviceToHost, g_stream));
+            HB_CUDA(cudaMemcpyAsync(ht.data(), S.tile_off.p, ht.size() * 8, cudaMemcpyDeviceToHost, g_stream));
+            sync_stream();
+            for (int l = 0; l < nlist; ++l) {
+                const int64_t units = hu[l + 1] - hu[l], tiles = ht[l + 1] - ht[l];
+                g_tc_units += units;
+                g_tc_items += units * tiles;
+                if (units > 0) g_tc_tiles += tiles;
+            }
+        }
         launch_ivf_resolve(relk, nqc, k, np_eff, probes, pair_out, (const int64_t *)ix->list_off.p, (const int64_t *)ix->list_rows.p,
                            ids + (size_t)q0 * k);
         launch_and_flags(ok_all + q0, ok_c, nqc);
@@ -1527,10 +1602,14 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             g_profile = value != 0;
             for (int i = 0; i < PROF_NTAGS; ++i) g_prof_ms[i] = 0, g_prof_n[i] = 0;
             g_fast_queries = g_fast_fallbacks = 0;
+            g_fast_pruned_pairs = g_fast_pruned_rows = g_fast_probe_pairs = 0;
+            g_tc_units = g_tc_items = g_tc_tiles = 0;
             g_hnsw_scored = g_hnsw_overflows = 0;
         } else if (!strcmp(name, "hnsw_prefetch")) {
             HB_REQUIRE(value >= -1 && value <= 64, "hnsw_prefetch must be -1..64");
             g_hnsw_prefetch = (int)value;
+        } else if (!strcmp(name, "fast_prune")) {
+            g_fast_prune = value != 0;
         } else if (!strcmp(name, "fast_set_only")) {
             g_fast_set_only = value != 0;
         } else if (!strcmp(name, "host_feed")) {
@@ -1556,6 +1635,12 @@ HB_API int hb_get_stat(const char *name, double *out) {
         }
         if (!strcmp(name, "fast_queries")) { *out = (double)g_fast_queries; return; }
         if (!strcmp(name, "fast_fallbacks")) { *out = (double)g_fast_fallbacks; return; }
+        if (!strcmp(name, "fast_pruned_pairs")) { *out = (double)g_fast_pruned_pairs; return; }
+        if (!strcmp(name, "tc_units")) { *out = (double)g_tc_units; return; }
+        if (!strcmp(name, "tc_items")) { *out = (double)g_tc_items; return; }
+        if (!strcmp(name, "tc_tiles")) { *out = (double)g_tc_tiles; return; }
+        if (!strcmp(name, "fast_pruned_rows")) { *out = (double)g_fast_pruned_rows; return; }
+        if (!strcmp(name, "fast_probe_pairs")) { *out = (double)g_fast_probe_pairs; return; }
         if (!strcmp(name, "hnsw_scored")) { *out = (double)g_hnsw_scored; return; }
         if (!strcmp(name, "hnsw_overflows")) { *out = (double)g_hnsw_overflows; return; }
         if (!strncmp(name, "mma_clocks_", 11)) {

@@ -125,6 +125,7 @@ struct FinalParams {
     int64_t *out_rel = nullptr;         // [nq][k] rel of the winners (-1 unused)
     double *out_dist = nullptr;         // [nq][k]
     int32_t *out_ok = nullptr;          // [nq] 1 = proven exact
+    double *out_simub = nullptr;        // optional [nq][k]: upper bound of each winner's similarity (probe pruning)
     // non-NULL (IVF list scan over an approximately ordered probe list): first slab row of each list; a distance tie
     // between rows of different lists among the k + 1 best fails the query (the reference breaks it by probe rank)
     const int64_t *tie_list_off = nullptr;
@@ -169,6 +170,12 @@ void launch_first_column(const int64_t *pos, int64_t nq, int stride, int64_t *fi
 // thr[q] = max(thr[q], kk-th best sample candidate) where the sample pass collected kk..cap candidates
 void launch_thr_from_sample(const double *sel_negv, const int32_t *cnt, int64_t nq, int kk, int cap, int k, const float *margin,
                             float *thr);
+// Exact pruning of probed lists (triangle inequality on angles, see hb_fastprep.cu): radius[l] = largest angle between a
+// row of list l and its centroid; probe_pos[q][p >= 1] = -1 where no row of the list can reach the query's threshold
+void launch_list_radius(const void *slab, int dtype, const double *slab_norm, const double *cents, const double *cent_norm,
+                        const int64_t *list_off, int nlist, int64_t n, int d, double *radius);
+void launch_prune_probes(int64_t *probe_pos, const double *sim_ub, const double *radius, const float *thr, const double *q_scale,
+                         const double *q_eps, int64_t nq, int np, const int64_t *list_off, unsigned long long *pruned /*[2]*/);
 // ok[q] &= other[q]
 void launch_and_flags(int32_t *ok, const int32_t *other, int64_t nq);
 

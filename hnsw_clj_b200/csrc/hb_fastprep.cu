@@ -406,6 +406,10 @@ __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
         P.out_rel[q * k + rank] = rel;
         P.out_dist[q * k + rank] = dist;
         if (rank == min(k, nvalid) - 1) s_kth = dist;
+        if (P.out_simub) {  // upper bound of the winner's similarity: exact if re-scored, approximate score + eps_q if certain
+            const double sim = prow == -2 ? -P.sel_negv[q * kk + j] * P.q_scale[q] + P.q_eps[q] : (P.metric == HB_COSINE ? 1.0 - dist : -dist);
+            P.out_simub[q * k + rank] = sim + 1e-9 * (1.0 + fabs(sim));
+        }
     }
     if (P.tie_list_off) {
         // The caller's `rel` order across lists is not the reference's (approximate probe order, see set_only): equal
@@ -428,6 +432,7 @@ __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
     for (int r = nvalid + j; r < k; r += blockDim.x) {
         P.out_rel[q * k + r] = -1;
         P.out_dist[q * k + r] = INFINITY;
+        if (P.out_simub) P.out_simub[q * k + r] = INFINITY;
     }
     __syncthreads();
     if (j == 0) {
@@ -833,6 +838,73 @@ __global__ void thr_from_sample_kernel(const double *__restrict__ sel_negv, cons
     }
     thr[q] = t;
 }
+// ---- exact pruning of probed lists by the triangle inequality on angles ------------------------------------------------
+// radius[l] = max over the rows r of list l of angle(r, centroid_l) (+ a rounding margin).  For any query q,
+// angle(q, r) >= angle(q, c) - angle(r, c), so every row of list l has cosine similarity <= cos(angle(q, c_l) - radius[l])
+// when the query is farther from the centroid than the list's radius.  One warp per slab row.
+template <typename T>
+__global__ void __launch_bounds__(256) list_radius_kernel(const T *__restrict__ slab, const double *__restrict__ slab_norm,
+                                                          const double *__restrict__ cents, const double *__restrict__ cent_norm,
+                                                          const int64_t *__restrict__ list_off, int nlist, int64_t n, int d,
+                                                          unsigned long long *__restrict__ radius_bits) {
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    int lo = 0, hi = nlist;  // last l with list_off[l] <= r
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (list_off[mid] <= r) lo = mid; else hi = mid;
+    }
+    const T *x = slab + r * d;
+    const double *c = cents + (int64_t)lo * d;
+    double s = 0.0;
+    for (int i = lane; i < d; i += 32) s += to_f64(x[i]) * c[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const double den = slab_norm[r] * cent_norm[lo];
+        double ang = 3.141592653589794;  // zero / non-finite norms: the list is never pruned
+        if (den > 0.0 && isfinite(den) && isfinite(s)) ang = acos(fmin(1.0, fmax(-1.0, s / den))) + 1e-7;
+        atomicMax(&radius_bits[lo], (unsigned long long)__double_as_longlong(ang));  // positive doubles order like their bits
+    }
+}
+
+// probe_pos[q][p] (list id, p >= 1) becomes -1 when no row of the list can reach the query's threshold:
+//   cos(angle_lb(q, c) - radius) < thr[q] * q_scale[q] - q_eps[q],
+// i.e. even the approximate score of every such row would lie below the threshold the candidate pass applies (and the
+// proof of fast_final_kernel accounts for: rows "never emitted").  sim_ub = upper bound of cos(q, c) from the coarse stage.
+__global__ void prune_probes_kernel(int64_t *__restrict__ probe_pos, const double *__restrict__ sim_ub,
+                                    const double *__restrict__ radius, const float *__restrict__ thr,
+                                    const double *__restrict__ q_scale, const double *__restrict__ q_eps, int64_t nq, int np,
+                                    const int64_t *__restrict__ list_off, unsigned long long *__restrict__ pruned) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool cut = false;
+    unsigned rows_cut = 0;
+    if (i < nq * np && (i % np) != 0) {
+        const int64_t q = i / np;
+        const int64_t l = probe_pos[i];
+        const float t = thr[q];
+        if (l >= 0 && t > -INFINITY) {
+            const double ub = fmin(1.0, fmax(-1.0, sim_ub[i]));
+            const double a = acos(ub) - 1e-7;  // lower bound of angle(q, c)
+            const double rad = radius[l];
+            if (a > rad) {
+                const double best = cos(a - rad) + 1e-9;  // no row of the list is more similar to q than this
+                if (best < (double)t * q_scale[q] - q_eps[q]) {
+                    probe_pos[i] = -1;
+                    cut = true;
+                    rows_cut = (unsigned)(list_off[l + 1] - list_off[l]);
+                }
+            }
+        }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, cut);
+    const unsigned rows = __reduce_add_sync(0xffffffffu, rows_cut);
+    if ((threadIdx.x & 31) == 0 && b) {  // pruned[0] = (query, list) pairs, pruned[1] = (query, row) pairs
+        atomicAdd(pruned, (unsigned long long)__popc(b));
+        atomicAdd(pruned + 1, (unsigned long long)rows);
+    }
+}
+
 __global__ void and_flags_kernel(int32_t *__restrict__ ok, const int32_t *__restrict__ other, int64_t nq) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q < nq) ok[q] = ok[q] & other[q];
@@ -951,6 +1023,24 @@ void launch_thr_from_sample(const double *sel_negv, const int32_t *cnt, int64_t 
                             float *thr) {
     if (nq == 0) return;
     thr_from_sample_kernel<<<blocks_for(nq, 256), 256, 0, g_stream>>>(sel_negv, cnt, nq, kk, cap, k, margin, thr);
+    HB_LAUNCH_CHECK();
+}
+void launch_list_radius(const void *slab, int dtype, const double *slab_norm, const double *cents, const double *cent_norm,
+                        const int64_t *list_off, int nlist, int64_t n, int d, double *radius) {
+    HB_CUDA(cudaMemsetAsync(radius, 0, (size_t)nlist * 8, g_stream));
+    if (n == 0) return;
+    const int grid = blocks_for(n * 32, 256);
+    unsigned long long *rb = reinterpret_cast<unsigned long long *>(radius);
+    if (dtype == HB_F32) list_radius_kernel<float><<<grid, 256, 0, g_stream>>>((const float *)slab, slab_norm, cents, cent_norm, list_off, nlist, n, d, rb);
+    else if (dtype == HB_BF16) list_radius_kernel<__nv_bfloat16><<<grid, 256, 0, g_stream>>>((const __nv_bfloat16 *)slab, slab_norm, cents, cent_norm, list_off, nlist, n, d, rb);
+    else list_radius_kernel<double><<<grid, 256, 0, g_stream>>>((const double *)slab, slab_norm, cents, cent_norm, list_off, nlist, n, d, rb);
+    HB_LAUNCH_CHECK();
+}
+void launch_prune_probes(int64_t *probe_pos, const double *sim_ub, const double *radius, const float *thr, const double *q_scale,
+                         const double *q_eps, int64_t nq, int np, const int64_t *list_off, unsigned long long *pruned) {
+    if (nq * np == 0) return;
+    prune_probes_kernel<<<blocks_for(nq * np, 256), 256, 0, g_stream>>>(probe_pos, sim_ub, radius, thr, q_scale, q_eps, nq, np, list_off,
+                                                                        pruned);
     HB_LAUNCH_CHECK();
 }
 void launch_and_flags(int32_t *ok, const int32_t *other, int64_t nq) {

@@ -306,3 +306,52 @@ def test_ivf_fast_cross_list_ties_follow_probe_rank(hb):
     assert eids.tolist() == want_ids.tolist() and same_bits(edist, want_d)
     assert fids.tolist() == want_ids.tolist() and same_bits(fdist, want_d)
     assert fell == 200
+
+
+@pytest.mark.parametrize("data", ["clustered", "gaussian", "boundary"])
+def test_ivf_fast_probe_pruning_is_exact(hb, data):
+    """Probed lists whose rows cannot reach a query's candidate threshold (cos(angle(q, centroid) - list radius) below it)
+    are dropped before the scan.  Clustered rows: nearly every non-nearest list goes; structureless rows: the true
+    neighbours sit in many lists and none of those may go; queries half-way between two clusters need both lists."""
+    from hnsw_clj_b200 import _lib, ivf_flat
+
+    n, d, nlist, nprobe, nq, k = 20000, 96, 256, 16, 500, 10
+    r = np.random.default_rng(17)
+    if data == "gaussian":
+        rows = r.standard_normal((n, d)).astype(np.float32)
+        queries = r.standard_normal((nq, d)).astype(np.float32)
+    else:
+        c = r.standard_normal((300, d))
+        rows = (c[r.integers(0, 300, n)] + 0.1 * r.standard_normal((n, d))).astype(np.float32)
+        if data == "clustered":
+            queries = (c[r.integers(0, 300, nq)] + 0.1 * r.standard_normal((nq, d))).astype(np.float32)
+        else:
+            a, b = r.integers(0, 300, nq), r.integers(0, 300, nq)
+            queries = (0.5 * (c[a] + c[b]) + 0.05 * r.standard_normal((nq, d))).astype(np.float32)
+    ix = ivf_flat.build_index(rows, num_partitions=nlist, max_iterations=3)
+    try:
+        eids, edist = ix.search_raw(queries, k, nprobe)
+        _lib.set_mode(_lib.MODE_FAST)
+        try:
+            _lib.set_option("fast_prune", 0)
+            uids, udist = ix.search_raw(queries, k, nprobe)
+            _lib.set_option("fast_prune", 1)
+            _lib.set_option("profile", 1)
+            fids, fdist = ix.search_raw(queries, k, nprobe)
+            pruned, total = _lib.get_stat("fast_pruned_pairs"), _lib.get_stat("fast_probe_pairs")
+            fell = _lib.get_stat("fast_fallbacks")
+            _lib.set_option("profile", 0)
+        finally:
+            _lib.set_option("fast_prune", 1)
+            _lib.set_mode(_lib.MODE_EXACT)
+        cents, asg = ix.export()
+    finally:
+        ix.close()
+    assert total == nq * nprobe
+    assert fids.tolist() == eids.tolist() and same_bits(fdist, edist)
+    assert uids.tolist() == eids.tolist() and same_bits(udist, edist)
+    oids, odist = orc.ivf_search(rows, cents, asg, queries[:64], k, nprobe)
+    assert fids[:64].tolist() == oids.tolist() and same_bits(fdist[:64], odist)
+    print(f"probe pruning on {data} rows: {int(pruned)} of {int(total)} (query, list) pairs dropped, {int(fell)} fallbacks")
+    if data == "clustered":
+        assert pruned > 0.5 * total

@@ -214,8 +214,9 @@ def run_reference(args, w, key):
 # our arm
 # ---------------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of one tc_pass_kernel<2,EMIT> list-scan launch, from `ncu --set full` captures of
-# this command: (workload, digits, probe pruning on) -> bytes.  profiles/r01c_tc_pass_ncu_raw.csv (5.42 GB + 0.03 GB, no pruning)
-TRAFFIC = {("c2", 2, False): 5.45e9}
+# this command: (workload, digits, probe pruning on) -> bytes.  profiles/r01c_tc_pass_ncu_raw.csv (5.42 GB + 0.03 GB, no pruning),
+# profiles/r01j_tc_pass_ncu_raw.csv (1.936 GB + 0.022 GB with probe pruning: 1.07x the unique digit-image bytes)
+TRAFFIC = {("c2", 2, False): 5.45e9, ("c2", 2, True): 1.958e9}
 
 
 def run_ours(args, w, key):

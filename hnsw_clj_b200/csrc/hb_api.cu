@@ -337,6 +337,11 @@ static void flat_search_exact(const void *rows, int rdtype, const double *row_no
         sub_len = ceil_div(rc, nsub);
         nsub = (int)ceil_div(rc, sub_len);
     }
+    if (nq <= kSmallScanQ && rc > 2048) {  // a small batch: the select is latency-bound per CTA, use many short sub-ranges
+        nsub = (int)std::min<int64_t>(ceil_div(4 * g_num_sms, nq), ceil_div(rc, 1024));
+        sub_len = ceil_div(rc, nsub);
+        nsub = (int)ceil_div(rc, sub_len);
+    }
     const int64_t parts = npass * nsub;
     double *scratch = g_ws.scratch.as<double>((size_t)nq * rc);
     double *cval = parts > 1 ? g_ws.cand_val.as<double>((size_t)nq * parts * k) : dist;
@@ -367,7 +372,7 @@ static void flat_search_exact(const void *rows, int rdtype, const double *row_no
         S.epi = epi;
         {
             Prof pr(PROF_SCAN);
-            launch_pairscan(S, rdtype, qdtype, l2);
+            launch_pairscan(S, rdtype, qdtype, l2, (int)std::min<int64_t>(nq, 1 << 20));
         }
         Prof pr2(PROF_SELECT);
         SelectParams L;
@@ -458,7 +463,7 @@ static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int6
             S.out = coarse;
             S.epi = cepi;
             Prof pr(PROF_COARSE);
-            launch_pairscan(S, HB_F64, qdtype, cl2);
+            launch_pairscan(S, HB_F64, qdtype, cl2, (int)std::min<int64_t>(nqc, 1 << 20));
             SelectParams L;
             L.vals = coarse;
             L.nseg = nqc;
@@ -507,7 +512,7 @@ static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int6
         S.epi = EPI_COS;
         {
             Prof pr(PROF_SCAN);
-            launch_pairscan(S, ix->dtype, qdtype, false);
+            launch_pairscan(S, ix->dtype, qdtype, false, (int)std::min<int64_t>(nqc, 1 << 20));  // a query probes a list once
         }
         Prof prs(PROF_SELECT);
         // merge (:291-294): stable sort of the concatenation in probe order, take k
@@ -519,7 +524,35 @@ static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int6
         L.k = k;
         L.out_val = dist + (size_t)q0 * k;
         L.out_pos = ppos;
-        launch_select(L);
+        const int64_t max_seg = (int64_t)np_eff * std::max<int64_t>(ix->max_list, 1);
+        if (nqc <= kSmallScanQ && max_seg > 2048) {
+            // a small batch: one CTA per concatenation is latency-bound; short sub-ranges first (their k best in
+            // (distance, position) order), then the same selection over the [nsub x k] survivors, which are again in
+            // position order among equal distances
+            const int nsub = (int)std::min<int64_t>(ceil_div(4 * g_num_sms, nqc), ceil_div(max_seg, 1024));
+            const int64_t sub_len = ceil_div(max_seg, nsub);
+            double *cval = g_ws.misc3.as<double>((size_t)nqc * nsub * k);
+            int64_t *cpos = g_ws.misc4.as<int64_t>((size_t)nqc * nsub * k);
+            L.nsub = nsub;
+            L.sub_len = sub_len;
+            L.out_seg_stride = nsub;
+            L.out_val = cval;
+            L.out_pos = cpos;
+            launch_select(L);
+            SelectParams M;
+            M.vals = cval;
+            M.nseg = nqc;
+            M.seg_stride = (int64_t)nsub * k;
+            M.seg_len_const = (int64_t)nsub * k;
+            M.k = k;
+            M.out_val = dist + (size_t)q0 * k;
+            int64_t *mpos = g_ws.misc2.as<int64_t>((size_t)nqc * k);
+            M.out_pos = mpos;
+            launch_select(M);
+            launch_lookup_ids(mpos, nqc, k, cpos, (int64_t)nsub * k, ppos);
+        } else {
+            launch_select(L);
+        }
         launch_ivf_resolve(ppos, nqc, k, np_eff, probes, pair_out, (const int64_t *)ix->list_off.p,
                            (const int64_t *)ix->list_rows.p, ids + (size_t)q0 * k);
     }
@@ -1061,7 +1094,8 @@ static bool fast_metric_ok(int metric) { return metric == HB_COSINE || metric ==
 static void flat_search_fast(hb_index *ix, const void *queries, int qdtype, int64_t nq, int k, int64_t *ids, double *dist) {
     const bool cosine = ix->metric == HB_COSINE;
     if (nq == 0 || k == 0) return;
-    if (ix->n == 0 || k > kFastMaxK || !fast_metric_ok(ix->metric) || ix->n >= (1ll << 31)) {
+    // a small batch fills at most 8 of a unit's 128 query slots: the HBM-bound exact scan (smallscan_kernel) is the faster path
+    if (ix->n == 0 || k > kFastMaxK || !fast_metric_ok(ix->metric) || ix->n >= (1ll << 31) || nq <= kSmallScanQ) {
         flat_search_exact(ix->rows.p, ix->dtype, (const double *)ix->norms.p, ix->n, ix->d, ix->metric, queries, qdtype, nq, k, ids, dist);
         return;
     }
@@ -1207,8 +1241,8 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
     };
     const int d = ix->d, nlist = ix->nlist;
     const int np_eff = std::min(nprobe, nlist);
-    if (ix->n == 0 || nlist == 0 || k > kFastMaxK || ix->n >= (1ll << 31) || np_eff < 1) {
-        wait_all();
+    if (ix->n == 0 || nlist == 0 || k > kFastMaxK || ix->n >= (1ll << 31) || np_eff < 1 || nq <= kSmallScanQ) {
+        wait_all();  // (small batches: see flat_search_fast)
         ivf_search_exact(ix, queries, qdtype, nq, k, nprobe, ids, dist, nullptr);
         return;
     }

@@ -30,7 +30,10 @@ struct ScanParams {
     double *out = nullptr;                 // distances
     int epi = EPI_COS;
 };
-void launch_pairscan(const ScanParams &P, int rdtype, int qdtype, bool l2);
+// max_sel: the caller's upper bound on the selections of any one list (0: unknown).  Up to kSmallScanQ the scan runs as the
+// HBM-bound thread-per-row kernel (smallscan_kernel) instead of 128 x 64 fp64 tiles; the results are the same bits.
+constexpr int kSmallScanQ = 8;
+void launch_pairscan(const ScanParams &P, int rdtype, int qdtype, bool l2, int max_sel = 0);
 
 // k-means assignment (hb_pairscan.cu): argmin over centroids of the same exact distances, strict <,
 // lowest index wins (ivf_flat.clj:79-90).

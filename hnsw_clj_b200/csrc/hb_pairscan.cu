@@ -208,6 +208,139 @@ __global__ void __launch_bounds__(NT, 2) pairscan_kernel(const ScanParams P) {
     }
 }
 
+// ---- small-batch scan: lists with at most NQ <= 8 selections (search-knn with one query per call, the reference's own
+// calling pattern: src/hnsw/ann/partition/ivf_flat.clj:300-317, src/hnsw/bench.clj:72-84) -------------------------------
+// The 128 x 64 tile of pairscan_kernel would spend 63/64 of its DFMAs on padding; this scan is bound by HBM instead: a CTA
+// owns 128 consecutive rows of a list, THREAD = ROW streams its own row with 128-bit loads (two 128-byte chunks in flight
+// per thread: every sector it touches is consumed whole, no shared-memory staging, no barrier in the loop) and advances
+// one sequential fp64 sum per selection -- the same mac_seq chain as pairscan_kernel, so the results are bit-identical.
+// The selections' queries sit in shared memory as fp64, [k][NQ], read by broadcast.  Same ScanParams / tile numbering
+// as pairscan_kernel (a tile = 128 rows of a list x all of its <= NQ selections).
+template <typename TRow, typename TQry, int ARITH, int NQ>
+__global__ void __launch_bounds__(TR) smallscan_kernel(const ScanParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *qs = reinterpret_cast<double *>(smem_raw);  // [d][NQ]
+    __shared__ int s_tile[3];
+    __shared__ long long s_row0, s_sel0;
+    __shared__ int s_qidx[NQ];
+    __shared__ long long s_qout[NQ];
+    __shared__ double s_qn[NQ];
+    constexpr int CH = sizeof(TRow) == 2 ? 32 : 128 / (int)sizeof(TRow);  // elements per chunk: 128 bytes (bf16: 64)
+
+    const int tid = threadIdx.x;
+    const int d = P.d;
+    const int64_t total = P.tile_prefix[P.nlist];
+    const TRow *rows = static_cast<const TRow *>(P.rows);
+    const TQry *queries = static_cast<const TQry *>(P.queries);
+    int loaded_list = -1;  // block-uniform: the list whose queries are in shared memory
+
+    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) {
+            int lo = 0, hi = P.nlist;  // last l with tile_prefix[l] <= t
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (P.tile_prefix[mid] <= t) lo = mid;
+                else hi = mid;
+            }
+            const int64_t rt = t - P.tile_prefix[lo];
+            const int64_t len = P.list_off[lo + 1] - P.list_off[lo];
+            s_tile[0] = lo;
+            s_tile[1] = (int)min((int64_t)TR, len - rt * TR);
+            s_tile[2] = (int)min((int64_t)NQ, P.lq_off[lo + 1] - P.lq_off[lo]);
+            s_row0 = P.list_off[lo] + rt * TR;
+            s_sel0 = P.lq_off[lo];
+        }
+        __syncthreads();
+        const int l = s_tile[0], nrows = s_tile[1], nqt = s_tile[2];
+        const int64_t row0 = s_row0, sel0 = s_sel0;
+        const int64_t rt_off = row0 - P.list_off[l];
+        if (l != loaded_list) {
+            if (tid < NQ) {
+                int qi = -1;
+                long long ob = 0;
+                double qn = 0.0;
+                if (tid < nqt) {
+                    const int64_t p = P.qsel ? (int64_t)P.qsel[sel0 + tid] : sel0 + tid;
+                    qi = P.pair_query ? P.pair_query[p] : (P.pair_div > 0 ? (int)(p / P.pair_div) : (int)p);
+                    ob = P.pair_out ? P.pair_out[p] : p * P.out_stride;
+                    qn = P.q_norm ? P.q_norm[qi] : 0.0;
+                }
+                s_qidx[tid] = qi;
+                s_qout[tid] = ob;
+                s_qn[tid] = qn;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+                const int qi = s_qidx[j];
+                const TQry *qp = queries + (int64_t)max(qi, 0) * d;
+                for (int k = tid; k < d; k += TR) qs[(int64_t)k * NQ + j] = qi >= 0 ? to_f64(qp[k]) : 0.0;
+            }
+            loaded_list = l;
+            __syncthreads();
+        }
+        if (tid < nrows) {
+            const TRow *rp = rows + (row0 + tid) * (int64_t)d;
+            double acc[NQ];
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) acc[j] = 0.0;
+            auto consume = [&](const Run<TRow, CH> &v, int c) {
+                const int kbase = c * CH;
+                const double *qk = qs + (int64_t)kbase * NQ;
+                if (kbase + CH <= d) {
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        const double x = to_f64(v[i]);
+#pragma unroll
+                        for (int j = 0; j < NQ; ++j) acc[j] = mac_seq<ARITH>(qk[i * NQ + j], x, acc[j]);
+                    }
+                } else {
+                    const int kmax = d - kbase;
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        if (i < kmax) {
+                            const double x = to_f64(v[i]);
+#pragma unroll
+                            for (int j = 0; j < NQ; ++j) acc[j] = mac_seq<ARITH>(qk[i * NQ + j], x, acc[j]);
+                        }
+                    }
+                }
+            };
+            const int nch = (d + CH - 1) / CH;
+            Run<TRow, CH> a, b;
+            load_run<TRow, CH, true>(rp, 0, d, true, a);
+            for (int c = 0; c < nch; c += 2) {
+                if (c + 1 < nch) load_run<TRow, CH, true>(rp, (c + 1) * CH, d, true, b);
+                consume(a, c);
+                if (c + 2 < nch) load_run<TRow, CH, true>(rp, (c + 2) * CH, d, true, a);
+                if (c + 1 < nch) consume(b, c + 1);
+            }
+            const double rn = P.row_norm ? P.row_norm[row0 + tid] : 0.0;
+#pragma unroll
+            for (int j = 0; j < NQ; ++j)
+                if (j < nqt) P.out[s_qout[j] + rt_off + tid] = apply_epi(P.epi, acc[j], s_qn[j], rn);
+        }
+    }
+}
+
+// sqrt(sum v^2) for a handful of rows (the queries of a small batch): one warp per row stages it in shared memory with
+// coalesced loads, lane 0 walks the sequential sum (one thread per row would wait on d dependent global loads).
+template <typename T>
+__global__ void __launch_bounds__(32) row_norms_warp_kernel(const T *__restrict__ rows, int d, double *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *v = reinterpret_cast<double *>(smem_raw);
+    const T *p = rows + (int64_t)blockIdx.x * d;
+    for (int k = threadIdx.x; k < d; k += 32) v[k] = to_f64(p[k]);
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < d; ++k) s = mac_seq<is_f32_repr<T>::value ? ARITH_FMA : ARITH_MULADD>(v[k], v[k], s);
+        out[blockIdx.x] = __dsqrt_rn(s);
+    }
+}
+
 // assign-to-nearest-centroid, src/hnsw/ann/partition/ivf_flat.clj:79-90: centroids scanned in index
 // order from Double/MAX_VALUE with strict <, so the lowest index wins ties and NaN never wins.
 template <typename TRow, int ARITH, bool VEC>
@@ -363,8 +496,29 @@ void pairscan_dispatch(const ScanParams &P, bool vec) {
     else go(pairscan_kernel<TRow, TQry, ARITH, false>);
 }
 
+template <typename TRow, typename TQry, int ARITH>
+void smallscan_dispatch(const ScanParams &P, int max_sel) {
+    auto go = [&](auto kernel, int nq) {
+        const size_t smem = (size_t)P.d * nq * sizeof(double);
+        HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = resident_grid(kernel, TR, smem);
+        kernel<<<grid, TR, smem, g_stream>>>(P);
+        HB_LAUNCH_CHECK();
+    };
+    if (max_sel <= 1) go(smallscan_kernel<TRow, TQry, ARITH, 1>, 1);
+    else if (max_sel <= 4) go(smallscan_kernel<TRow, TQry, ARITH, 4>, 4);
+    else go(smallscan_kernel<TRow, TQry, ARITH, 8>, 8);
+}
+
 template <typename TRow, typename TQry>
-void pairscan_arith(const ScanParams &P, bool l2, bool vec) {
+void pairscan_arith(const ScanParams &P, bool l2, bool vec, int max_sel) {
+    // small batches (every list has at most kSmallScanQ selections): the HBM-bound thread-per-row scan
+    if (max_sel >= 1 && max_sel <= kSmallScanQ && vec && (size_t)P.d * 8 * sizeof(double) <= 96 * 1024) {
+        if (l2) smallscan_dispatch<TRow, TQry, ARITH_L2>(P, max_sel);
+        else if (is_f32_repr<TRow>::value && is_f32_repr<TQry>::value) smallscan_dispatch<TRow, TQry, ARITH_FMA>(P, max_sel);
+        else smallscan_dispatch<TRow, TQry, ARITH_MULADD>(P, max_sel);
+        return;
+    }
     if (l2) pairscan_dispatch<TRow, TQry, ARITH_L2>(P, vec);
     else if (is_f32_repr<TRow>::value && is_f32_repr<TQry>::value) pairscan_dispatch<TRow, TQry, ARITH_FMA>(P, vec);
     else pairscan_dispatch<TRow, TQry, ARITH_MULADD>(P, vec);
@@ -385,15 +539,15 @@ void assign_dispatch(const AssignParams &P, bool vec) {
 
 }  // namespace
 
-void launch_pairscan(const ScanParams &P, int rdtype, int qdtype, bool l2) {
+void launch_pairscan(const ScanParams &P, int rdtype, int qdtype, bool l2, int max_sel) {
     HB_REQUIRE(qdtype == HB_F32 || qdtype == HB_F64, "queries must be fp32 or fp64");
     const bool vec = vec_ok(P.rows, P.d, dtype_size(rdtype)) && vec_ok(P.queries, P.d, dtype_size(qdtype));
-    if (rdtype == HB_F32 && qdtype == HB_F32) pairscan_arith<float, float>(P, l2, vec);
-    else if (rdtype == HB_F32 && qdtype == HB_F64) pairscan_arith<float, double>(P, l2, vec);
-    else if (rdtype == HB_BF16 && qdtype == HB_F32) pairscan_arith<__nv_bfloat16, float>(P, l2, vec);
-    else if (rdtype == HB_BF16 && qdtype == HB_F64) pairscan_arith<__nv_bfloat16, double>(P, l2, vec);
-    else if (rdtype == HB_F64 && qdtype == HB_F32) pairscan_arith<double, float>(P, l2, vec);
-    else if (rdtype == HB_F64 && qdtype == HB_F64) pairscan_arith<double, double>(P, l2, vec);
+    if (rdtype == HB_F32 && qdtype == HB_F32) pairscan_arith<float, float>(P, l2, vec, max_sel);
+    else if (rdtype == HB_F32 && qdtype == HB_F64) pairscan_arith<float, double>(P, l2, vec, max_sel);
+    else if (rdtype == HB_BF16 && qdtype == HB_F32) pairscan_arith<__nv_bfloat16, float>(P, l2, vec, max_sel);
+    else if (rdtype == HB_BF16 && qdtype == HB_F64) pairscan_arith<__nv_bfloat16, double>(P, l2, vec, max_sel);
+    else if (rdtype == HB_F64 && qdtype == HB_F32) pairscan_arith<double, float>(P, l2, vec, max_sel);
+    else if (rdtype == HB_F64 && qdtype == HB_F64) pairscan_arith<double, double>(P, l2, vec, max_sel);
     else throw Error(HB_ERR_INVALID, "unsupported row dtype");
 }
 
@@ -414,6 +568,15 @@ void launch_assign(const AssignParams &P, int rdtype, bool l2) {
 
 void launch_row_norms(const void *rows, int dtype, int64_t n, int d, double *out) {
     if (n == 0) return;
+    if (n <= 64 && (size_t)d * 8 <= 48 * 1024) {  // a small batch of queries: one warp per row (row_norms_warp_kernel)
+        const size_t smem = (size_t)d * 8;
+        if (dtype == HB_F32) row_norms_warp_kernel<float><<<(int)n, 32, smem, g_stream>>>((const float *)rows, d, out);
+        else if (dtype == HB_BF16) row_norms_warp_kernel<__nv_bfloat16><<<(int)n, 32, smem, g_stream>>>((const __nv_bfloat16 *)rows, d, out);
+        else if (dtype == HB_F64) row_norms_warp_kernel<double><<<(int)n, 32, smem, g_stream>>>((const double *)rows, d, out);
+        else throw Error(HB_ERR_INVALID, "unsupported dtype");
+        HB_LAUNCH_CHECK();
+        return;
+    }
     const int grid = (int)ceil_div(n, 128);
     const bool vec = vec_ok(rows, d, dtype_size(dtype));
 #define HB_RN(T)                                                                                  \

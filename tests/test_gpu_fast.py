@@ -134,7 +134,7 @@ def test_flat_fast_equals_exact(hb, ns, n, d, nq, k, metric):
         _lib.set_option("profile", 0)
     assert fids.tolist() == eids.tolist()
     assert same_bits(fdist, edist)
-    assert served == nq
+    assert served == (nq if nq > 8 else 0)  # batches of <= 8 queries take the HBM-bound exact scan (smallscan_kernel)
     if metric == "cosine" and n >= 1000:
         assert fell <= 0.5 * nq, f"{fell} of {nq} queries fell back to the exact path"
     if metric == "cosine":

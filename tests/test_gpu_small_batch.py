@@ -1,0 +1,141 @@
+"""Small batches (1..8 queries per call — the reference's own calling pattern, `search-knn` with one query:
+src/hnsw/ann/partition/ivf_flat.clj:300-317, src/hnsw/bench.clj:72-84) take the HBM-bound thread-per-row scan
+(`smallscan_kernel`) and a split selection instead of the 128 x 64 fp64 tiles.  Same bits as the oracle and as the
+large-batch path, in EXACT and FAST mode."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hb():
+    import hnsw_clj_b200 as pkg
+    from hnsw_clj_b200 import _lib
+
+    _lib.check(_lib.lib().hb_init(0))
+    return pkg
+
+
+def rng_rows(n, d, seed, clustered=0):
+    r = np.random.default_rng(seed)
+    if clustered:
+        c = r.standard_normal((clustered, d))
+        x = c[r.integers(0, clustered, n)] + 0.1 * r.standard_normal((n, d))
+    else:
+        x = r.standard_normal((n, d))
+    return x.astype(np.float32)
+
+
+def same_bits(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and bool((a.view(np.int64) == b.view(np.int64)).all())
+
+
+@pytest.mark.parametrize("n,d,k", [(5000, 768, 10), (300, 100, 7), (129, 4, 1), (9000, 36, 100)])
+@pytest.mark.parametrize("nq", [1, 2, 4, 5, 8])
+@pytest.mark.parametrize("metric", ["cosine", "euclidean", "ip"])
+def test_flat_small_batch_parity(hb, n, d, k, nq, metric):
+    from hnsw_clj_b200.flat import FlatIndex
+
+    rows, q = rng_rows(n, d, 10 + nq), rng_rows(nq, d, 11)
+    code = {"cosine": orc.COSINE, "euclidean": orc.L2, "ip": orc.IP}[metric]
+    want_ids, want_d = orc.exact_knn(rows, q, k, code)
+    with FlatIndex(rows, distance_fn=metric) as ix:
+        ids, dist = ix.search_raw(q, k)
+    assert ids.tolist() == want_ids.tolist()
+    assert same_bits(dist, want_d)
+
+
+def test_flat_small_batch_dtypes_and_unaligned_rows(hb):
+    import torch
+
+    from hnsw_clj_b200.flat import FlatIndex
+
+    # bf16 rows, fp64 queries (the reference's double[]), inner product
+    rows = torch.from_numpy(rng_rows(4100, 64, 5)).to(torch.bfloat16)
+    q = torch.from_numpy(rng_rows(3, 64, 6)).to(torch.bfloat16).float()
+    want_ids, want_d = orc.exact_knn(rows.float().numpy(), q.numpy(), 50, orc.IP)
+    with FlatIndex(rows.cuda(), distance_fn="ip") as ix:
+        ids, dist = ix.search_raw(q.cuda(), 50)
+        ids2, dist2 = ix.search_raw(q.numpy().astype(np.float64), 50)
+    assert ids.tolist() == want_ids.tolist() and same_bits(dist, want_d)
+    assert ids2.tolist() == want_ids.tolist() and same_bits(dist2, want_d)
+    # fp64 rows whose values are not fp32-representable: separately rounded product (mul, then add)
+    r64 = np.random.default_rng(7).standard_normal((3000, 40))
+    q64 = np.random.default_rng(8).standard_normal((2, 40))
+    with FlatIndex(r64) as ix:
+        ids, dist = ix.search_raw(q64, 10)
+    for qi, qv in enumerate(q64):
+        dd = np.array([orc.cosine_distance(qv, r) for r in r64])
+        order = np.argsort(dd, kind="stable")[:10]
+        assert ids[qi].tolist() == order.tolist() and same_bits(dist[qi], dd[order])
+    # a row length that is not a multiple of 16 bytes: the vectorised scan does not apply, the tiled kernel answers
+    rows = rng_rows(2500, 7, 9)
+    q = rng_rows(1, 7, 10)
+    want_ids, want_d = orc.exact_knn(rows, q, 10)
+    with FlatIndex(rows) as ix:
+        ids, dist = ix.search_raw(q, 10)
+    assert ids.tolist() == want_ids.tolist() and same_bits(dist, want_d)
+
+
+def test_flat_small_batch_ties_and_k_larger_than_n(hb):
+    from hnsw_clj_b200.flat import FlatIndex
+
+    dup = np.repeat(rng_rows(700, 16, 2), 5, axis=0)  # 3500 rows: the split selection sees ties across sub-ranges
+    q = dup[[0, 1700]]
+    want_ids, want_d = orc.exact_knn(dup, q, 12)
+    with FlatIndex(dup) as ix:
+        ids, dist = ix.search_raw(q, 12)
+    assert ids.tolist() == want_ids.tolist() and same_bits(dist, want_d)
+    assert ids[0, :5].tolist() == [0, 1, 2, 3, 4]
+    rows = rng_rows(6, 8, 3)
+    with FlatIndex(rows) as ix:
+        ids, dist = ix.search_raw(rows[:1], 9)
+    assert ids[0, 6:].tolist() == [-1, -1, -1] and np.isinf(dist[0, 6:]).all()
+
+
+@pytest.mark.parametrize("nq", [1, 3, 8])
+@pytest.mark.parametrize("nprobe", [1, 8, 16])
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_ivf_small_batch_parity(hb, nq, nprobe, mode):
+    from hnsw_clj_b200 import _lib, ivf_flat
+
+    rows = rng_rows(20000, 64, 40, clustered=30)
+    q = rng_rows(nq, 64, 41 + nq, clustered=30)
+    cents, asg = orc.kmeans(rows, 16, iters=2, seed=42)
+    want_ids, want_d, want_p = orc.ivf_search(rows, cents, asg, q, 10, nprobe, return_probes=True)
+    with ivf_flat.import_index(rows, cents, asg) as ix:
+        _lib.set_mode(_lib.MODE_FAST if mode == "fast" else _lib.MODE_EXACT)
+        try:
+            ids, dist = ix.search_raw(q, 10, nprobe)  # 8 x ~1250 rows per query: split selection + merge
+        finally:
+            _lib.set_mode(_lib.MODE_EXACT)
+        probes = ix.probes(q, nprobe)
+    assert probes.tolist() == want_p.tolist()
+    assert ids.tolist() == want_ids.tolist()
+    assert same_bits(dist, want_d)
+
+
+def test_small_batch_equals_large_batch(hb):
+    """The first rows of a 200-query call and the same queries asked 1, 3 and 8 at a time: identical ids and bits."""
+    from hnsw_clj_b200 import _lib, ivf_flat
+    from hnsw_clj_b200.flat import FlatIndex
+
+    rows = rng_rows(30000, 128, 50, clustered=64)
+    q = rng_rows(200, 128, 51, clustered=64)
+    with FlatIndex(rows) as fx, ivf_flat.build_index(rows, num_partitions=32, max_iterations=2) as ix:
+        big_f = fx.search_raw(q, 10)
+        big_i = ix.search_raw(q, 10, 8)
+        for mode in (_lib.MODE_EXACT, _lib.MODE_FAST):
+            _lib.set_mode(mode)
+            try:
+                for nq in (1, 3, 8):
+                    f = fx.search_raw(q[:nq], 10)
+                    i = ix.search_raw(q[:nq], 10, 8)
+                    assert f[0].tolist() == big_f[0][:nq].tolist() and same_bits(f[1], big_f[1][:nq])
+                    assert i[0].tolist() == big_i[0][:nq].tolist() and same_bits(i[1], big_i[1][:nq])
+            finally:
+                _lib.set_mode(_lib.MODE_EXACT)

@@ -490,9 +490,13 @@ static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int6
             }
         }
         if (k == 0) continue;
-        int64_t total = 0;
-        HB_CUDA(cudaMemcpyAsync(&total, pair_out + np, 8, cudaMemcpyDeviceToHost, g_stream));
-        sync_stream();
+        // candidates of the chunk: read back to size the scratch, unless the bound nprobe x longest list is small anyway
+        // (small batches: one host round trip less per call)
+        int64_t total = np * std::max<int64_t>(ix->max_list, 1);
+        if (total > (1ll << 22)) {
+            HB_CUDA(cudaMemcpyAsync(&total, pair_out + np, 8, cudaMemcpyDeviceToHost, g_stream));
+            sync_stream();
+        }
         double *scratch = g_ws.scratch.as<double>((size_t)std::max<int64_t>(total, 1));
         // list scan (:217-234): always cosine via precomputed norms, no zero guard; lists in probe order (:281-288)
         ScanParams S;
@@ -1642,6 +1646,10 @@ HB_API int hb_set_option(const char *name, int64_t value) {
         } else if (!strcmp(name, "hnsw_prefetch")) {
             HB_REQUIRE(value >= -1 && value <= 64, "hnsw_prefetch must be -1..64");
             g_hnsw_prefetch = (int)value;
+        } else if (!strcmp(name, "rowstream")) {
+            g_use_rowstream = value != 0;
+        } else if (!strncmp(name, "stream_", 7)) {
+            set_rowstream_option(name, (int)value);
         } else if (!strcmp(name, "fast_prune")) {
             g_fast_prune = value != 0;
         } else if (!strcmp(name, "fast_set_only")) {

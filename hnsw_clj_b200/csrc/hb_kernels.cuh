@@ -34,6 +34,11 @@ struct ScanParams {
 // HBM-bound thread-per-row kernel (smallscan_kernel) instead of 128 x 64 fp64 tiles; the results are the same bits.
 constexpr int kSmallScanQ = 8;
 void launch_pairscan(const ScanParams &P, int rdtype, int qdtype, bool l2, int max_sel = 0);
+// hb_rowstream.cu: the same small-batch scan for ONE list (flat search, coarse routing) fed by per-row bulk copies into
+// shared-memory stages; launch_pairscan picks it when it applies.  false: does not fit, nothing was launched.
+bool launch_rowstream(const ScanParams &P, int rdtype, int qdtype, bool l2, int max_sel);
+void set_rowstream_option(const char *name, int value);  // "stream_seg" | "stream_stages" | "stream_warps"
+extern int g_use_rowstream;                              // hb_set_option("rowstream", 0/1)
 
 // k-means assignment (hb_pairscan.cu): argmin over centroids of the same exact distances, strict <,
 // lowest index wins (ivf_flat.clj:79-90).

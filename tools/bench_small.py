@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--opt", action="append", default=[])
     ap.add_argument("--batches", default="1,8,64")
+    ap.add_argument("--indexes", default="flat31k,flat1m,ivf")
+    ap.add_argument("--modes", default="exact,fast")
+    ap.add_argument("--grid", default="", help="name=v1,v2;name2=... : repeat every sweep for each combination of library knobs")
     ap.add_argument("--ncu-region", action="store_true", help="cudaProfilerStart/Stop around ONE call per (index, mode, batch)")
     args = ap.parse_args()
     hb.check(hb.lib().hb_init(0))
@@ -66,7 +69,14 @@ def main():
         want_ids = np.empty((nbig, k), dtype=np.int64)
         want_d = np.empty((nbig, k), dtype=np.float64)
         hb.check(hb.lib().hb_search(ix._h, q_host.ctypes.data, hb.F32, nbig, k, nprobe, want_ids.ctypes.data, want_d.ctypes.data))
-        for mode, code in (("exact", hb.MODE_EXACT), ("fast", hb.MODE_FAST)):
+        import itertools
+        axes = [(a.split("=")[0], [int(v) for v in a.split("=")[1].split(",")]) for a in args.grid.split(";") if a]
+        combos = list(itertools.product(*[[(nm, v) for v in vals] for nm, vals in axes])) or [()]
+        for combo, (mode, code) in itertools.product(combos, (("exact", hb.MODE_EXACT), ("fast", hb.MODE_FAST))):
+            if mode not in args.modes.split(","):
+                continue
+            for nm, v in combo:
+                hb.set_option(nm, v)
             hb.set_mode(code)
             for nq in [int(x) for x in args.batches.split(',')]:
                 med, best, ids, dist = lat(ix, q_host, nq, nprobe)
@@ -78,7 +88,7 @@ def main():
                 scan_ms, sel_ms = hb.get_stat("scan_ms"), hb.get_stat("select_ms")
                 hb.set_option("profile", 0)
                 same = bool((ids == want_ids[:nq]).all() and (dist.view(np.int64) == want_d[:nq].view(np.int64)).all())
-                print(json.dumps({"index": name, "mode": mode, "queries_per_call": nq, "median_us": med, "best_us": best,
+                print(json.dumps({"index": name, "mode": mode, "knobs": dict(combo), "queries_per_call": nq, "median_us": med, "best_us": best,
                                   "qps": nq / med * 1e6, "equals_large_batch_exact": same,
                                   "hbm_floor_us": unique_bytes(nq) / 6562.6e3,
                                                                     "scan_us_per_call": scan_ms / calls * 1e3, "select_us_per_call": sel_ms / calls * 1e3,
@@ -92,16 +102,20 @@ def main():
     rows = torch.randn((n, d), generator=g, device=dev)
     rows = rows / rows.norm(dim=1, keepdim=True)
     q = (rows[torch.arange(64, device=dev) * 31] + 0.1 / d ** 0.5 * torch.randn((64, d), generator=g, device=dev)).contiguous()
-    with FlatIndex(rows) as fx:
-        sweep("flat 31173x768 fp32 cosine top-10", fx, q.cpu().numpy(), 0, lambda nq: n * d * 4.0)
+    if "flat31k" in args.indexes:
+        with FlatIndex(rows) as fx:
+            sweep("flat 31173x768 fp32 cosine top-10", fx, q.cpu().numpy(), 0, lambda nq: n * d * 4.0)
     del rows
     # a flat index far larger than the L2 (3.07 GB): the small-batch scan against the HBM roofline
     n = args.n_ivf
-    rows = torch.randn((n, d), generator=g, device=dev)
-    q = torch.randn((64, d), generator=g, device=dev)
-    with FlatIndex(rows) as fx:
-        sweep(f"flat {n}x768 fp32 cosine top-10", fx, q.cpu().numpy(), 0, lambda nq: n * d * 4.0)
-    del rows
+    if "flat1m" in args.indexes:
+        rows = torch.randn((n, d), generator=g, device=dev)
+        q = torch.randn((64, d), generator=g, device=dev)
+        with FlatIndex(rows) as fx:
+            sweep(f"flat {n}x768 fp32 cosine top-10", fx, q.cpu().numpy(), 0, lambda nq: n * d * 4.0)
+        del rows
+    if "ivf" not in args.indexes:
+        return
     # configs[1]: IVF-FLAT, nlist 1024, nprobe 32
     n = args.n_ivf
     c = torch.randn((2048, d), generator=g, device=dev)

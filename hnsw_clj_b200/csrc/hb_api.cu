@@ -220,8 +220,23 @@ static bool g_tc_interleave = true;
 static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
 static int g_hnsw_prefetch = -1;     // hb_set_option("hnsw_prefetch", lines): -1 = sized to the L2 (hnsw_search)
 static bool g_fast_prune = true;     // IVF scan: drop (query, probed list) pairs that cannot reach the query's threshold
-static int64_t g_fast_pruned_pairs = 0, g_fast_pruned_rows = 0, g_fast_probe_pairs = 0;
-static int64_t g_tc_units = 0, g_tc_items = 0, g_tc_tiles = 0;  // IVF main candidate pass, accumulated while profiling
+static int64_t g_fast_probe_pairs = 0;
+// profiling counters that live on the device (a search makes no host round trip for them): [pruned (query, list) pairs,
+// rows they held, units / items / row tiles of the IVF main candidate pass]
+enum { DS_PRUNED_PAIRS = 0, DS_PRUNED_ROWS = 1, DS_TC_UNITS = 2, DS_TC_ITEMS = 3, DS_TC_TILES = 4, DS_COUNT = 8 };
+static DevBuf g_dev_stats;
+static unsigned long long *dev_stats() {
+    const bool fresh = g_dev_stats.p == nullptr;
+    unsigned long long *p = g_dev_stats.as<unsigned long long>(DS_COUNT);
+    if (fresh) HB_CUDA(cudaMemsetAsync(p, 0, DS_COUNT * 8, g_stream));
+    return p;
+}
+static double dev_stat(int i) {
+    unsigned long long h[DS_COUNT];
+    HB_CUDA(cudaMemcpyAsync(h, dev_stats(), sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+    HB_CUDA(cudaStreamSynchronize(g_stream));
+    return (double)h[i];
+}
 static bool g_fast_set_only = true;  // IVF coarse routing proves the probed set only (FastJob::set_only)
 static bool g_fast_dense = true;     // short flat scans (<= 2048 rows) select from the dumped score matrix
 static int g_fast_level_min = 33;     // flat scans of at least this many row tiles run in levels (fast_topk)
@@ -768,6 +783,14 @@ static void set_units(FastPlan &F, int64_t real, bool interleave) {
     F.interleave = (interleave && real > 2 * g_num_sms) ? g_num_sms : 0;
     F.nunits = F.interleave ? (int)(ceil_div(real, F.interleave) * F.interleave) : (int)real;
 }
+// The host only knows an upper bound of the unit count (the plan lives on the device): ceil(pairs / 128) full units plus
+// one partial unit per list that has a selection.  unit_plan_kernel reads the real count; slots beyond it stay empty.
+static void set_units_bound(FastPlan &F, int64_t pairs, int nlist, bool interleave) {
+    const int64_t bound = ceil_div(pairs, kFastTile) + std::min<int64_t>(nlist, pairs);
+    F.interleave = (interleave && bound > 2 * g_num_sms) ? g_num_sms : 0;
+    F.nunits = F.interleave ? (int)(ceil_div(bound, F.interleave) * F.interleave) : (int)bound;
+    F.nunits_real = -1;
+}
 struct FastJob {
     FastSideBufs *side = nullptr;
     const int64_t *list_off = nullptr;  // slab rows per list (B side)
@@ -1055,8 +1078,7 @@ static void fast_topk(const FastJob &J) {
 static void flat_fast_plan(int64_t nq, FastPlan &E, FastPlan &T, DevBuf &buf) {
     int64_t h[4] = {0, nq, 0, ceil_div(nq, kFastTile)};
     int64_t *dptr = buf.as<int64_t>(4);
-    HB_CUDA(cudaMemcpyAsync(dptr, h, sizeof(h), cudaMemcpyHostToDevice, g_stream));
-    sync_stream();  // h is a stack array
+    launch_set_i64x4(dptr, h[0], h[1], h[2], h[3]);  // kernel arguments: no host buffer to keep alive, no sync
     E.nlist = 1;
     E.lq_off = dptr;
     E.unit_prefix = dptr + 2;
@@ -1389,10 +1411,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
             ivf_plan(ppos0, nqc, nlist, (const int64_t *)ix->list_off.p, probes0, pair_out0, qsel0, lq_off0, uprefix0, 1 << 30,
                      kFastTile, g_ws.tmp);
         }
-        int64_t nu = 0, nu0 = 0;
-        if (!prune) HB_CUDA(cudaMemcpyAsync(&nu, uprefix + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
-        HB_CUDA(cudaMemcpyAsync(&nu0, uprefix0 + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
-        sync_stream();
+        // no host round trip: unit counts stay on the device, the host sizes buffers and grids by their bounds
         int64_t *relk = W.relk.as<int64_t>((size_t)nqc * k);
         FastJob J;
         J.side = &S;
@@ -1421,7 +1440,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         J.thresh.qsel = qsel0;
         J.thresh.pair_out = nullptr;
         J.thresh.pair_div = 1;
-        set_units(J.thresh, nu0, false);
+        set_units_bound(J.thresh, nqc, nlist, false);
         J.thresh.tile_limit = g_fast_sample_tiles;
         J.shared_units = false;
         J.out_rel = relk;
@@ -1441,33 +1460,20 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
                 launch_prune_probes(ppos, simub, list_radius(ix), (const float *)W.thr.p, (const double *)W.qscale.p,
                                     (const double *)W.qeps.p, nqc, np_eff, (const int64_t *)ix->list_off.p, npruned);
                 plan_emit();
-                unsigned long long hp[2] = {0, 0};
-                HB_CUDA(cudaMemcpyAsync(&nu, uprefix + nlist, 8, cudaMemcpyDeviceToHost, g_stream));
-                HB_CUDA(cudaMemcpyAsync(hp, npruned, 16, cudaMemcpyDeviceToHost, g_stream));
-                sync_stream();
-                g_fast_pruned_pairs += (int64_t)hp[0];
-                g_fast_pruned_rows += (int64_t)hp[1];
-                g_fast_probe_pairs += np;
+                if (g_profile) {
+                    launch_accumulate_u64(dev_stats() + DS_PRUNED_PAIRS, npruned, 2);
+                    g_fast_probe_pairs += np;
+                }
             }
-            set_units(J.emit, nu, g_tc_interleave);
+            set_units_bound(J.emit, np, nlist, g_tc_interleave);
             J.phase = 2;
             fast_topk(J);
         } else {
-            set_units(J.emit, nu, g_tc_interleave);
+            set_units_bound(J.emit, np, nlist, g_tc_interleave);
             fast_topk(J);
         }
-        if (g_profile) {  // what the main candidate pass covered: units, items (unit x row tile), distinct row tiles
-            std::vector<int64_t> hu((size_t)nlist + 1), ht((size_t)nlist + 1);
-            HB_CUDA(cudaMemcpyAsync(hu.data(), uprefix, hu.size() * 8, cudaMemcpyDeviceToHost, g_stream));
-            HB_CUDA(cudaMemcpyAsync(ht.data(), S.tile_off.p, ht.size() * 8, cudaMemcpyDeviceToHost, g_stream));
-            sync_stream();
-            for (int l = 0; l < nlist; ++l) {
-                const int64_t units = hu[l + 1] - hu[l], tiles = ht[l + 1] - ht[l];
-                g_tc_units += units;
-                g_tc_items += units * tiles;
-                if (units > 0) g_tc_tiles += tiles;
-            }
-        }
+        // what the main candidate pass covered: units, items (unit x row tile), distinct row tiles
+        if (g_profile) launch_tc_cover(uprefix, (const int64_t *)S.tile_off.p, nlist, dev_stats() + DS_TC_UNITS);
         launch_ivf_resolve(relk, nqc, k, np_eff, probes, pair_out, (const int64_t *)ix->list_off.p, (const int64_t *)ix->list_rows.p,
                            ids + (size_t)q0 * k);
         launch_and_flags(ok_all + q0, ok_c, nqc);
@@ -1595,6 +1601,7 @@ HB_API int hb_shutdown(void) {
         if (g_inited) cudaStreamSynchronize(g_stream);
         g_ws.release();
         g_fw.release();
+        g_dev_stats.release();
         g_assign_side.release();
     });
 }
@@ -1640,8 +1647,8 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             g_profile = value != 0;
             for (int i = 0; i < PROF_NTAGS; ++i) g_prof_ms[i] = 0, g_prof_n[i] = 0;
             g_fast_queries = g_fast_fallbacks = 0;
-            g_fast_pruned_pairs = g_fast_pruned_rows = g_fast_probe_pairs = 0;
-            g_tc_units = g_tc_items = g_tc_tiles = 0;
+            g_fast_probe_pairs = 0;
+            HB_CUDA(cudaMemsetAsync(dev_stats(), 0, DS_COUNT * 8, g_stream));
             g_hnsw_scored = g_hnsw_overflows = 0;
         } else if (!strcmp(name, "hnsw_prefetch")) {
             HB_REQUIRE(value >= -1 && value <= 64, "hnsw_prefetch must be -1..64");
@@ -1677,11 +1684,11 @@ HB_API int hb_get_stat(const char *name, double *out) {
         }
         if (!strcmp(name, "fast_queries")) { *out = (double)g_fast_queries; return; }
         if (!strcmp(name, "fast_fallbacks")) { *out = (double)g_fast_fallbacks; return; }
-        if (!strcmp(name, "fast_pruned_pairs")) { *out = (double)g_fast_pruned_pairs; return; }
-        if (!strcmp(name, "tc_units")) { *out = (double)g_tc_units; return; }
-        if (!strcmp(name, "tc_items")) { *out = (double)g_tc_items; return; }
-        if (!strcmp(name, "tc_tiles")) { *out = (double)g_tc_tiles; return; }
-        if (!strcmp(name, "fast_pruned_rows")) { *out = (double)g_fast_pruned_rows; return; }
+        if (!strcmp(name, "fast_pruned_pairs")) { *out = dev_stat(DS_PRUNED_PAIRS); return; }
+        if (!strcmp(name, "tc_units")) { *out = dev_stat(DS_TC_UNITS); return; }
+        if (!strcmp(name, "tc_items")) { *out = dev_stat(DS_TC_ITEMS); return; }
+        if (!strcmp(name, "tc_tiles")) { *out = dev_stat(DS_TC_TILES); return; }
+        if (!strcmp(name, "fast_pruned_rows")) { *out = dev_stat(DS_PRUNED_ROWS); return; }
         if (!strcmp(name, "fast_probe_pairs")) { *out = (double)g_fast_probe_pairs; return; }
         if (!strcmp(name, "hnsw_scored")) { *out = (double)g_hnsw_scored; return; }
         if (!strcmp(name, "hnsw_overflows")) { *out = (double)g_hnsw_overflows; return; }

@@ -66,7 +66,8 @@ struct UnitPlan {
     int32_t *slot_query = nullptr;  // [nunits*128] query index or -1
     int32_t *slot_rel0 = nullptr;   // [nunits*128] position of the (query, list) segment inside the query's concatenation
 };
-// nunits = unit slots (>= nunits_real; a multiple of `interleave` when interleave > 0, see unit_plan_kernel)
+// nunits = unit slots (>= nunits_real; a multiple of `interleave` when interleave > 0, see unit_plan_kernel);
+// nunits_real < 0: read the real count from unit_prefix[nlist] on the device (nunits is then an upper bound)
 void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_prefix, const int64_t *tile_off, int nunits,
                       int nunits_real, int interleave, int tile_limit, int tile_div, int tile_start, const int32_t *qsel,
                       const int64_t *pair_out, int pair_div, const int32_t *pair_query, UnitPlan U);
@@ -176,6 +177,10 @@ void launch_list_radius(const void *slab, int dtype, const double *slab_norm, co
                         const int64_t *list_off, int nlist, int64_t n, int d, double *radius);
 void launch_prune_probes(int64_t *probe_pos, const double *sim_ub, const double *radius, const float *thr, const double *q_scale,
                          const double *q_eps, int64_t nq, int np, const int64_t *list_off, unsigned long long *pruned /*[2]*/);
+// profiling counters accumulated on the device (read by hb_get_stat), and a 4-word plan written without host memory
+void launch_accumulate_u64(unsigned long long *acc, const unsigned long long *src, int n);
+void launch_tc_cover(const int64_t *unit_prefix, const int64_t *tile_off, int nlist, unsigned long long *acc /*[3]*/);
+void launch_set_i64x4(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d);
 // ok[q] &= other[q]
 void launch_and_flags(int32_t *ok, const int32_t *other, int64_t nq);
 

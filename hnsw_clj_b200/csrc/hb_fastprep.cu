@@ -182,6 +182,9 @@ __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, 
         U.unit_ntile[slot_u] = 0;
         return;
     }
+    // nunits_real < 0: `nunits` is the host's upper bound, the real count is the plan's unit_prefix[nlist] (device) --
+    // a search then needs no host round trip between planning and the candidate pass
+    if (nunits_real < 0) nunits_real = (int)unit_prefix[nlist];
     // interleave > 0: unit slots are laid out so that the contiguous item ranges the CTAs take visit the real units
     // round-robin (slot c*rows + r <- real unit r*interleave + c): the units of one list then run on neighbouring
     // CTAs at the same time and share their row tiles through L2.
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(256) pack_units_kernel(const int8_t *__restric
                                                          const int32_t *__restrict__ slot_query, int8_t *__restrict__ aimg) {
     const int u = blockIdx.x, kb = blockIdx.y;
     const int dpad = kbn * kFastKB;
+    if (slot_query[(int64_t)u * kFastTile] < 0) return;  // slots fill from 0: an empty unit (padding / bound) has no items
     int8_t *dst = aimg + ((int64_t)u * kbn + kb) * NS * kFastImg;
     for (int i = threadIdx.x; i < NS * kFastTile * 8; i += blockDim.x) {
         const int ch = i & 7, slot = (i >> 3) % kFastTile, s = i / (8 * kFastTile);
@@ -905,6 +909,35 @@ __global__ void prune_probes_kernel(int64_t *__restrict__ probe_pos, const doubl
     }
 }
 
+// acc[0..n) += src[0..n)  (profiling counters kept on the device: no host round trip inside a search)
+__global__ void accumulate_u64_kernel(unsigned long long *__restrict__ acc, const unsigned long long *__restrict__ src, int n) {
+    if ((int)threadIdx.x < n) acc[threadIdx.x] += src[threadIdx.x];
+}
+// what a candidate pass covers: acc[0] += units, acc[1] += items (unit x row tile), acc[2] += row tiles of lists with units
+__global__ void tc_cover_kernel(const int64_t *__restrict__ unit_prefix, const int64_t *__restrict__ tile_off, int nlist,
+                                unsigned long long *__restrict__ acc) {
+    unsigned long long u = 0, it = 0, t = 0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < nlist; l += gridDim.x * blockDim.x) {
+        const unsigned long long units = (unsigned long long)(unit_prefix[l + 1] - unit_prefix[l]);
+        const unsigned long long tiles = (unsigned long long)(tile_off[l + 1] - tile_off[l]);
+        u += units;
+        it += units * tiles;
+        if (units > 0) t += tiles;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        u += __shfl_xor_sync(0xffffffffu, u, o);
+        it += __shfl_xor_sync(0xffffffffu, it, o);
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc, u);
+        atomicAdd(acc + 1, it);
+        atomicAdd(acc + 2, t);
+    }
+}
+__global__ void set_i64x4_kernel(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d) {
+    p[0] = a, p[1] = b, p[2] = c, p[3] = d;
+}
 __global__ void and_flags_kernel(int32_t *__restrict__ ok, const int32_t *__restrict__ other, int64_t nq) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q < nq) ok[q] = ok[q] & other[q];
@@ -1041,6 +1074,19 @@ void launch_prune_probes(int64_t *probe_pos, const double *sim_ub, const double 
     if (nq * np == 0) return;
     prune_probes_kernel<<<blocks_for(nq * np, 256), 256, 0, g_stream>>>(probe_pos, sim_ub, radius, thr, q_scale, q_eps, nq, np, list_off,
                                                                         pruned);
+    HB_LAUNCH_CHECK();
+}
+void launch_accumulate_u64(unsigned long long *acc, const unsigned long long *src, int n) {
+    accumulate_u64_kernel<<<1, 32, 0, g_stream>>>(acc, src, n);
+    HB_LAUNCH_CHECK();
+}
+void launch_tc_cover(const int64_t *unit_prefix, const int64_t *tile_off, int nlist, unsigned long long *acc) {
+    if (nlist == 0) return;
+    tc_cover_kernel<<<blocks_for(nlist, 256), 256, 0, g_stream>>>(unit_prefix, tile_off, nlist, acc);
+    HB_LAUNCH_CHECK();
+}
+void launch_set_i64x4(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d) {
+    set_i64x4_kernel<<<1, 1, 0, g_stream>>>(p, a, b, c, d);
     HB_LAUNCH_CHECK();
 }
 void launch_and_flags(int32_t *ok, const int32_t *other, int64_t nq) {

@@ -352,9 +352,15 @@ static void flat_search_exact(const void *rows, int rdtype, const double *row_no
         sub_len = ceil_div(rc, nsub);
         nsub = (int)ceil_div(rc, sub_len);
     }
-    if (nq <= kSmallScanQ && rc > 2048) {  // a small batch: the select is latency-bound per CTA, use many short sub-ranges
-        nsub = (int)std::min<int64_t>(ceil_div(4 * g_num_sms, nq), ceil_div(rc, 1024));
-        sub_len = ceil_div(rc, nsub);
+    if (nq <= kSmallScanQ && rc > select_small_max()) {
+        // a small batch: sub-ranges short enough for the shared-memory selection (select_small_kernel), as long as possible
+        // so that the merge of their [nsub x k] survivors fits it too
+        const int64_t sl = (rc / 2048 + 1) * k <= select_small_max() ? 2048 : select_small_max();
+        if (nq * ceil_div(rc, sl) <= 4 * g_num_sms) {
+            sub_len = sl;
+        } else {  // too many sub-ranges for one wave of CTAs: the streaming selection over ~4 CTAs per SM
+            sub_len = ceil_div(rc, std::min<int64_t>(ceil_div(4 * g_num_sms, nq), ceil_div(rc, 1024)));
+        }
         nsub = (int)ceil_div(rc, sub_len);
     }
     const int64_t parts = npass * nsub;
@@ -531,7 +537,8 @@ static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int6
         S.epi = EPI_COS;
         {
             Prof pr(PROF_SCAN);
-            launch_pairscan(S, ix->dtype, qdtype, false, (int)std::min<int64_t>(nqc, 1 << 20));  // a query probes a list once
+            // a query probes a list once; a small batch's queries are rows 0..nqc-1 of qptr
+            launch_pairscan(S, ix->dtype, qdtype, false, (int)std::min<int64_t>(nqc, 1 << 20), nqc <= kSmallScanQ ? (int)nqc : 0);
         }
         Prof prs(PROF_SELECT);
         // merge (:291-294): stable sort of the concatenation in probe order, take k
@@ -544,12 +551,14 @@ static void ivf_search_exact(hb_index *ix, const void *queries, int qdtype, int6
         L.out_val = dist + (size_t)q0 * k;
         L.out_pos = ppos;
         const int64_t max_seg = (int64_t)np_eff * std::max<int64_t>(ix->max_list, 1);
-        if (nqc <= kSmallScanQ && max_seg > 2048) {
+        if (nqc <= kSmallScanQ && max_seg > select_small_max()) {
             // a small batch: one CTA per concatenation is latency-bound; short sub-ranges first (their k best in
-            // (distance, position) order), then the same selection over the [nsub x k] survivors, which are again in
-            // position order among equal distances
-            const int nsub = (int)std::min<int64_t>(ceil_div(4 * g_num_sms, nqc), ceil_div(max_seg, 1024));
-            const int64_t sub_len = ceil_div(max_seg, nsub);
+            // (distance, position) order, select_small_kernel), then the same selection over the [nsub x k] survivors,
+            // which are again in position order among equal distances
+            int64_t sub_len = (max_seg / 2048 + 1) * k <= select_small_max() ? 2048 : select_small_max();
+            if (nqc * ceil_div(max_seg, sub_len) > 4 * g_num_sms)  // more than a wave: the streaming selection, ~4 CTAs per SM
+                sub_len = ceil_div(max_seg, std::min<int64_t>(ceil_div(4 * g_num_sms, nqc), ceil_div(max_seg, 1024)));
+            const int nsub = (int)ceil_div(max_seg, sub_len);
             double *cval = g_ws.misc3.as<double>((size_t)nqc * nsub * k);
             int64_t *cpos = g_ws.misc4.as<int64_t>((size_t)nqc * nsub * k);
             L.nsub = nsub;

@@ -33,10 +33,14 @@ struct ScanParams {
 // max_sel: the caller's upper bound on the selections of any one list (0: unknown).  Up to kSmallScanQ the scan runs as the
 // HBM-bound thread-per-row kernel (smallscan_kernel) instead of 128 x 64 fp64 tiles; the results are the same bits.
 constexpr int kSmallScanQ = 8;
-void launch_pairscan(const ScanParams &P, int rdtype, int qdtype, bool l2, int max_sel = 0);
+// batch_nq > 0 (with many lists): P.queries holds exactly that many queries and every selection refers to one of them
+void launch_pairscan(const ScanParams &P, int rdtype, int qdtype, bool l2, int max_sel = 0, int batch_nq = 0);
 // hb_rowstream.cu: the same small-batch scan for ONE list (flat search, coarse routing) fed by per-row bulk copies into
 // shared-memory stages; launch_pairscan picks it when it applies.  false: does not fit, nothing was launched.
 bool launch_rowstream(const ScanParams &P, int rdtype, int qdtype, bool l2, int max_sel);
+// ... and for the probed lists of a small-batch IVF scan (many lists; the batch's nq <= kSmallScanQ queries are rows
+// 0..nq-1 of P.queries, every selection refers to one of them)
+bool launch_liststream(const ScanParams &P, int rdtype, int qdtype, bool l2, int nq);
 void set_rowstream_option(const char *name, int value);  // "stream_seg" | "stream_stages" | "stream_warps"
 extern int g_use_rowstream;                              // hb_set_option("rowstream", 0/1)
 
@@ -89,6 +93,7 @@ struct SelectParams {
     int64_t *out_pos = nullptr;  // [slots, k] position within the segment (-1: unused)
 };
 void launch_select(const SelectParams &P);
+int select_small_max();  // longest (sub-)range the shared-memory selection (select_small_kernel) takes
 
 
 }  // namespace hb

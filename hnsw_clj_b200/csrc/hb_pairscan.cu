@@ -541,11 +541,14 @@ void assign_dispatch(const AssignParams &P, bool vec) {
 
 int g_use_rowstream = 1;
 
-void launch_pairscan(const ScanParams &P, int rdtype, int qdtype, bool l2, int max_sel) {
+void launch_pairscan(const ScanParams &P, int rdtype, int qdtype, bool l2, int max_sel, int batch_nq) {
     HB_REQUIRE(qdtype == HB_F32 || qdtype == HB_F64, "queries must be fp32 or fp64");
     const bool vec = vec_ok(P.rows, P.d, dtype_size(rdtype)) && vec_ok(P.queries, P.d, dtype_size(qdtype));
     if (g_use_rowstream && vec && P.nlist == 1 && max_sel >= 1 && max_sel <= kSmallScanQ &&
         launch_rowstream(P, rdtype, qdtype, l2, max_sel))
+        return;
+    if (g_use_rowstream && vec && P.nlist > 1 && batch_nq >= 1 && batch_nq <= kSmallScanQ &&
+        launch_liststream(P, rdtype, qdtype, l2, batch_nq))
         return;
     if (rdtype == HB_F32 && qdtype == HB_F32) pairscan_arith<float, float>(P, l2, vec, max_sel);
     else if (rdtype == HB_F32 && qdtype == HB_F64) pairscan_arith<float, double>(P, l2, vec, max_sel);

@@ -80,7 +80,11 @@ HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches 
 /* knobs: "scratch_mb" = budget for the transient distance scratch (default 8192); "profile" = 1 records
  * CUDA events around the main kernels (and resets the counters); "fast_digits" = 2 | 3 signed 8-bit digits per
  * element in the HB_MODE_FAST candidate pass (16- or 24-bit block-fixed-point mantissas); "fast_sample_tiles" = row
- * tiles (128 rows) of each query's nearest list scored first to seed the IVF scan's thresholds (default 2) */
+ * tiles (128 rows) of each query's nearest list scored first to seed the IVF scan's thresholds (default 2);
+ * "fast_prune" = 0 scans every probed list in HB_MODE_FAST (default 1: lists that provably hold no top-k row of a query are
+ * dropped, same results); "rowstream" = 0 keeps small batches (<= 8 queries) on the register-buffered scan instead of
+ * the bulk-copy ring, "stream_seg" (256 | 384 | 512 bytes per row and stage), "stream_stages" (2..4), "stream_warps"
+ * (0 = as many as fit) shape that ring.  Results never depend on a knob. */
 HB_API int hb_set_option(const char *name, int64_t value);
 /* measurements: "scan_ms"/"scan_count" (list/flat scan kernel), "coarse_ms", "select_ms", "plan_ms", "assign_ms",
  * "tc_ms" (tensor-core candidate pass over all probed lists), "tc_sample_ms" (its threshold-seeding pass), "pack_ms",

@@ -219,6 +219,7 @@ static bool g_fast_debug = false;
 static bool g_tc_interleave = true;
 static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
 static int g_hnsw_prefetch = -1;     // hb_set_option("hnsw_prefetch", lines): -1 = sized to the L2 (hnsw_search)
+static bool g_tc_half_m = true;      // EMIT passes: units with <= 64 selections run with M = 64 (hb_tc.cu)
 static bool g_fast_prune = true;     // IVF scan: drop (query, probed list) pairs that cannot reach the query's threshold
 static int64_t g_fast_probe_pairs = 0;
 // profiling counters that live on the device (a search makes no host round trip for them): [pruned (query, list) pairs,
@@ -940,6 +941,7 @@ static void fast_topk(const FastJob &J) {
         P.aimg = aimg;
         P.nunits = J.emit.nunits;
         P.unit_list = U.unit_list;
+        P.unit_nsel = g_tc_half_m ? U.unit_nsel : nullptr;
         P.unit_item0 = U.unit_item0;
         P.slot_query = U.slot_query;
         P.slot_rel0 = U.slot_rel0;
@@ -953,6 +955,7 @@ static void fast_topk(const FastJob &J) {
         P.aimg = aimg;
         P.nunits = J.emit.nunits;
         P.unit_list = U.unit_list;
+        P.unit_nsel = g_tc_half_m ? U.unit_nsel : nullptr;
         P.slot_query = U.slot_query;
         P.slot_rel0 = U.slot_rel0;
         P.tile_stride = 1;
@@ -980,6 +983,7 @@ static void fast_topk(const FastJob &J) {
         P.aimg = aimg0;
         P.nunits = J.thresh.nunits;
         P.unit_list = T.unit_list;
+        P.unit_nsel = g_tc_half_m ? T.unit_nsel : nullptr;
         P.unit_item0 = T.unit_item0;
         P.slot_query = T.slot_query;
         P.slot_rel0 = T.slot_rel0;
@@ -997,6 +1001,7 @@ static void fast_topk(const FastJob &J) {
         P.aimg = aimg;
         P.nunits = J.emit.nunits;
         P.unit_list = U.unit_list;
+        P.unit_nsel = g_tc_half_m ? U.unit_nsel : nullptr;
         P.unit_item0 = U.unit_item0;
         P.slot_query = U.slot_query;
         P.slot_rel0 = U.slot_rel0;
@@ -1662,6 +1667,8 @@ HB_API int hb_set_option(const char *name, int64_t value) {
         } else if (!strcmp(name, "hnsw_prefetch")) {
             HB_REQUIRE(value >= -1 && value <= 64, "hnsw_prefetch must be -1..64");
             g_hnsw_prefetch = (int)value;
+        } else if (!strcmp(name, "tc_half_m")) {
+            g_tc_half_m = value != 0;
         } else if (!strcmp(name, "rowstream")) {
             g_use_rowstream = value != 0;
         } else if (!strncmp(name, "stream_", 7)) {
@@ -2267,6 +2274,7 @@ HB_API int hb_fast_scores(hb_index *index, const void *queries, int qdtype, int6
         P.kbn = S.kbn;
         P.nunits = E.nunits;
         P.unit_list = U.unit_list;
+        P.unit_nsel = g_tc_half_m ? U.unit_nsel : nullptr;
         P.unit_item0 = U.unit_item0;
         P.tile_off = (const int64_t *)S.tile_off.p;
         P.list_off = (const int64_t *)S.list_off.p;

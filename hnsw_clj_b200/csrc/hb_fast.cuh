@@ -87,6 +87,8 @@ struct TcParams {
     const int64_t *list_off = nullptr;  // first slab row of each list
     const int32_t *slot_query = nullptr;
     const int32_t *slot_rel0 = nullptr;
+    // optional [nunits] selections per unit: EMIT passes run a unit of <= 64 selections with M = 64 (half the A operand)
+    const int32_t *unit_nsel = nullptr;
     const float *rs = nullptr;
     const float *ro = nullptr;
     float *thr = nullptr;  // per query: rows scoring below it cannot matter (see the epilogue); raised with atomic max

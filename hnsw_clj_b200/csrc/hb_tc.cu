@@ -93,6 +93,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
 }
 // instruction descriptor: D = S32 (2 @bit4), A = B = signed int8 (1 @bit7, 1 @bit10), K-major both, N>>3 @bit17, M>>4 @bit24
 constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kFastTile >> 3) << 17) | ((uint32_t)(kFastTile >> 4) << 24);
+// the same with M = 64: a unit with <= 64 query slots in use.  The accumulator rows then sit in TMEM lanes 0-15 of each
+// 32-lane quadrant (row r -> lane 32 * (r / 16) + r % 16), the A operand is the first 8 KB of each 16 KB image.
+constexpr uint32_t kIdescI8M64 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kFastTile >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -219,12 +222,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
                 const int64_t btile = P.tile_off[P.unit_list[u]] + t;
                 const int8_t *asrc = P.aimg + (int64_t)u * kbn * NS * kFastImg;
                 const int8_t *bsrc = P.bimg + btile * kbn * NS * kFastImg;
+                const bool hm = MODE == FAST_EMIT && P.unit_nsel != nullptr && P.unit_nsel[u] <= 64;
                 for (int kb = 0; kb < kbn; ++kb) {
                     mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
                     const uint32_t full = smem_u32(&s_full[stage]);
                     const uint32_t dst = stage0 + (uint32_t)stage * Cfg::STAGE_BYTES;
-                    mbar_expect_tx(full, Cfg::STAGE_BYTES);
-                    bulk_g2s(dst, asrc + (int64_t)kb * NS * kFastImg, NS * kFastImg, full);
+                    if (hm) {  // M = 64: the first 64 slots = the first 8 row groups (8 KB) of each digit image
+                        mbar_expect_tx(full, NS * (kFastImg / 2) + NS * kFastImg);
+#pragma unroll
+                        for (int sl = 0; sl < NS; ++sl)
+                            bulk_g2s(dst + sl * kFastImg, asrc + ((int64_t)kb * NS + sl) * kFastImg, kFastImg / 2, full);
+                    } else {
+                        mbar_expect_tx(full, Cfg::STAGE_BYTES);
+                        bulk_g2s(dst, asrc + (int64_t)kb * NS * kFastImg, NS * kFastImg, full);
+                    }
                     bulk_g2s(dst + NS * kFastImg, bsrc + (int64_t)kb * NS * kFastImg, NS * kFastImg, full);
                     if (++stage == Cfg::NSTAGE) {
                         stage = 0;
@@ -240,7 +251,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
             uint32_t phase = 0, tphase = 0;
             long long t_tmem = 0, t_full = 0;
             const long long t_all0 = clock64();
+            int u = find_unit(P.unit_item0, P.nunits, item_begin);
             for (int item = item_begin; item < item_end; ++item) {
+                while (item >= P.unit_item0[u + 1]) ++u;
+                const uint32_t idesc = (MODE == FAST_EMIT && P.unit_nsel != nullptr && P.unit_nsel[u] <= 64) ? kIdescI8M64 : kIdescI8;
                 long long c0 = P.timing ? clock64() : 0;
                 mbar_wait(smem_u32(&s_tmem_empty), tphase ^ 1u);
                 if (P.timing) t_tmem += clock64() - c0;
@@ -260,7 +274,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
                             const uint64_t ad = smem_desc(abase + sa * kFastImg + k4 * 32);
                             const uint64_t bd = smem_desc(bbase + sb * kFastImg + k4 * 32);
                             const uint32_t acc = (kb == 0 && k4 == 0 && Prod<NS>::first(p)) ? 0u : 1u;
-                            umma_i8(tmem_base + (uint32_t)(sa + sb) * kFastTile, ad, bd, kIdescI8, acc);
+                            umma_i8(tmem_base + (uint32_t)(sa + sb) * kFastTile, ad, bd, idesc, acc);
                         }
                     }
                     umma_commit(smem_u32(&s_empty[stage]));
@@ -283,7 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
         // ===== epilogue: 8 warps; thread = (query slot = TMEM lane, half of the tile's 128 columns) =====
         const int quarter = warp & 3;              // TMEM lanes this warp may touch: 32*quarter ..
         const int half = (warp - 2) >> 2;          // columns 64*half ..
-        const int slot = quarter * 32 + lane;
+        int slot = quarter * 32 + lane;  // query slot of this thread's TMEM lane (M = 64 units: see new_unit below)
         const int et = (warp - 2) * 32 + lane;     // 0..255
         const uint2 *my_stash = &s_stash[0][et];
         const CandOut C{P.cnt, P.cand_negv, P.cand_rel, P.cand_pos, P.cap};
@@ -332,6 +346,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
                 if (new_unit) {
                     if (nst > 0) flush_stash(C, qi, rel0, list_row0, nst, -1, my_stash);
                     nst = 0;
+                    // M = 64 unit: accumulator row r lives in lane 32 * (r / 16) + r % 16; lanes 16-31 of a quadrant hold
+                    // nothing and are pointed at the unit's unused slots 64.. (slot_query = -1 there)
+                    const bool hm = P.unit_nsel != nullptr && P.unit_nsel[u] <= 64;
+                    slot = hm ? ((lane < 16 ? 0 : 64) + quarter * 16 + (lane & 15)) : quarter * 32 + lane;
                     qi = P.slot_query[(int64_t)u * kFastTile + slot];
                     rel0 = P.slot_rel0[(int64_t)u * kFastTile + slot];
                     list_row0 = P.list_off[l];

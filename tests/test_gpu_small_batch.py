@@ -139,3 +139,58 @@ def test_small_batch_equals_large_batch(hb):
                     assert i[0].tolist() == big_i[0][:nq].tolist() and same_bits(i[1], big_i[1][:nq])
             finally:
                 _lib.set_mode(_lib.MODE_EXACT)
+
+
+def test_knobs_never_change_results(hb):
+    """hb_set_option knobs pick kernels, never results: the bulk-copy ring in every shape (segment bytes, stages, warps),
+    the register-buffered scan (rowstream = 0), M = 64 / M = 128 tensor-core units, probe pruning on / off."""
+    from hnsw_clj_b200 import _lib, ivf_flat
+    from hnsw_clj_b200.flat import FlatIndex
+
+    rows = rng_rows(12000, 200, 60, clustered=40)  # 800-byte rows: segments of 256 / 384 / 512 bytes all end in a partial one
+    q = rng_rows(150, 200, 61, clustered=40)
+    defaults = {"rowstream": 1, "stream_seg": 256, "stream_stages": 2, "stream_warps": 0, "tc_half_m": 1, "fast_prune": 1}
+    with FlatIndex(rows) as fx, ivf_flat.build_index(rows, num_partitions=256, max_iterations=2) as ix:
+        want_f = fx.search_raw(q[:5], 10)
+        want_i = ix.search_raw(q[:5], 10, 8)
+        want_big = ix.search_raw(q, 10, 8)
+        try:
+            for knobs in ({"stream_seg": 384}, {"stream_seg": 512, "stream_stages": 3}, {"stream_stages": 4, "stream_warps": 3},
+                          {"stream_warps": 1}, {"rowstream": 0}):
+                for name, v in {**defaults, **knobs}.items():
+                    _lib.set_option(name, v)
+                for nq in (1, 5):
+                    f = fx.search_raw(q[:nq], 10)
+                    i = ix.search_raw(q[:nq], 10, 8)
+                    assert f[0].tolist() == want_f[0][:nq].tolist() and same_bits(f[1], want_f[1][:nq]), knobs
+                    assert i[0].tolist() == want_i[0][:nq].tolist() and same_bits(i[1], want_i[1][:nq]), knobs
+            _lib.set_mode(_lib.MODE_FAST)
+            for knobs in ({"tc_half_m": 0}, {"tc_half_m": 1, "fast_prune": 0}, {"tc_half_m": 0, "fast_prune": 0}, {}):
+                for name, v in {**defaults, **knobs}.items():
+                    _lib.set_option(name, v)
+                got = ix.search_raw(q, 10, 8)  # 150 queries over 256 lists: almost every unit holds <= 64 selections
+                assert got[0].tolist() == want_big[0].tolist() and same_bits(got[1], want_big[1]), knobs
+        finally:
+            _lib.set_mode(_lib.MODE_EXACT)
+            for name, v in defaults.items():
+                _lib.set_option(name, v)
+
+
+def test_more_lists_than_queries_and_full_units(hb):
+    """Unit counts stay on the device (the host sizes by a bound): plans with far more lists than queries, and a plan whose
+    units are all full (every query probes the same few lists)."""
+    from hnsw_clj_b200 import _lib, ivf_flat
+
+    rows = rng_rows(9000, 64, 70, clustered=3)
+    q = rng_rows(700, 64, 71, clustered=3)
+    for nlist, nprobe in ((600, 5), (4, 3)):
+        with ivf_flat.build_index(rows, num_partitions=nlist, max_iterations=2) as ix:
+            want = ix.search_raw(q, 10, nprobe)
+            _lib.set_mode(_lib.MODE_FAST)
+            try:
+                got = ix.search_raw(q, 10, nprobe)
+                got9 = ix.search_raw(q[:9], 10, nprobe)
+            finally:
+                _lib.set_mode(_lib.MODE_EXACT)
+        assert got[0].tolist() == want[0].tolist() and same_bits(got[1], want[1]), (nlist, nprobe)
+        assert got9[0].tolist() == want[0][:9].tolist() and same_bits(got9[1], want[1][:9]), (nlist, nprobe)

@@ -57,6 +57,7 @@ SIGNATURES = {
     "hb_ivf_export": (_int, [_p, _p, _p]),
     "hb_search": (_int, [_p, _p, _int, _i64, _i32, _i32, _p, _p]),
     "hb_ivf_probes": (_int, [_p, _p, _int, _i64, _i32, _p]),
+    "hb_lsh_matrices": (_int, [_i32, _i32, _i32, _i64, _p]),
     "hb_kmeanspp_init": (_int, [_p, _i64, _i32, _int, _int, _i32, _i64, _p]),
     "hb_kmeans_assign": (_int, [_p, _i64, _i32, _int, _int, _p, _i32, _p]),
     "hb_kmeans_update": (_int, [_p, _i64, _i32, _int, _p, _i32, _p, _p, _p]),

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "--fmad=true",  # fp32 paths only; every fp64 parity path uses explicit __dmul_rn/__dadd_rn/__fma_rn
-    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2,-ffp-contract=off",  # host fp64 (java.util.Random, StrictMath.log) must not be contracted
     "--expt-relaxed-constexpr",
     "-I", INCLUDE,
 ]

@@ -2,6 +2,7 @@
 // the orchestration of the kernels behind hnsw-clj's build-index / search-knn / search-batch* surface.
 #include <errno.h>
 #include <float.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -183,6 +184,75 @@ struct JavaRandom {
     double next_double() {
         const int64_t hi = next(26), lo = next(27);
         return (double)((hi << 27) + lo) * 0x1.0p-53;
+    }
+};
+
+// StrictMath.log, i.e. fdlibm's __ieee754_log (e_log.c): java.util.Random.nextGaussian goes through it, and the LSH
+// projection matrices (src/hnsw/ann/hash/hybrid_lsh.clj:24-31) are nextGaussian draws.  libm's log is not bit-identical.
+static double strict_log(double x) {
+    static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                        two54 = 1.80143985094819840000e+16, Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
+                        Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01,
+                        Lg6 = 1.531383769920937332e-01, Lg7 = 1.479819860511658591e-01;
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    int32_t hx = (int32_t)(u >> 32), k = 0;
+    const uint32_t lx = (uint32_t)u;
+    if (hx < 0x00100000) {
+        if (((hx & 0x7fffffff) | lx) == 0) return -INFINITY;
+        if (hx < 0) return NAN;
+        k -= 54;
+        x *= two54;
+        memcpy(&u, &x, 8);
+        hx = (int32_t)(u >> 32);
+    }
+    if (hx >= 0x7ff00000) return x + x;
+    k += (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    int32_t i = (hx + 0x95f64) & 0x100000;
+    memcpy(&u, &x, 8);
+    u = (u & 0xffffffffull) | ((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32);
+    memcpy(&x, &u, 8);
+    k += (i >> 20);
+    const double f = x - 1.0, dk = (double)k;
+    if ((0x000fffff & (2 + hx)) < 3) {
+        if (f == 0.0) return k == 0 ? 0.0 : dk * ln2_hi + dk * ln2_lo;
+        const double R = f * f * (0.5 - 0.33333333333333333 * f);
+        return k == 0 ? f - R : dk * ln2_hi - ((R - dk * ln2_lo) - f);
+    }
+    const double s = f / (2.0 + f), z = s * s, w = z * z;
+    i = hx - 0x6147a;
+    const int32_t j = 0x6b851 - hx;
+    const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6)), t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    i |= j;
+    const double R = t2 + t1;
+    if (i > 0) {
+        const double hfsq = 0.5 * f * f;
+        return k == 0 ? f - (hfsq - s * (hfsq + R)) : dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+    }
+    return k == 0 ? f - s * (f - R) : dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+}
+// java.util.Random.nextGaussian: Marsaglia's polar method, one spare value kept
+struct JavaGaussian {
+    JavaRandom rng;
+    bool have = false;
+    double spare = 0.0;
+    explicit JavaGaussian(int64_t seed) : rng(seed) {}
+    double next() {
+        if (have) {
+            have = false;
+            return spare;
+        }
+        double v1, v2, s;
+        do {
+            v1 = 2.0 * rng.next_double() - 1.0;
+            v2 = 2.0 * rng.next_double() - 1.0;
+            s = v1 * v1 + v2 * v2;
+        } while (s >= 1.0 || s == 0.0);
+        const double mul = std::sqrt(-2.0 * strict_log(s) / s);
+        spare = v2 * mul;
+        have = true;
+        return v1 * mul;
     }
 };
 
@@ -2237,6 +2307,15 @@ HB_API int hb_topk_merge(const double *dist, const int64_t *ids, int32_t nparts,
         finish_out(oi);
         finish_out(od);
         sync_stream();
+    });
+}
+
+HB_API int hb_lsh_matrices(int32_t d, int32_t ntables, int32_t proj_dim, int64_t seed, double *out) {
+    return guarded([&] {
+        HB_REQUIRE(d >= 1 && ntables >= 1 && proj_dim >= 1 && out, "bad arguments");
+        JavaGaussian g(seed);  // host arithmetic only: no device is needed
+        const int64_t count = (int64_t)ntables * proj_dim * d;
+        for (int64_t i = 0; i < count; ++i) out[i] = g.next();
     });
 }
 

@@ -180,6 +180,14 @@ HB_API int hb_gather_score(hb_index *index, const void *queries, int qdtype, int
                            const int32_t *pair_query, const int32_t *pair_row, int64_t npairs,
                            double *out_scores);
 
+/* ---- LSH projections ------------------------------------------------------------------------------ */
+/* generate-random-matrix x NUM-HASH-TABLES (src/hnsw/ann/hash/hybrid_lsh.clj:24-31, :77-81): ntables matrices of
+ * proj_dim x d doubles drawn in order from ONE java.util.Random(seed).nextGaussian stream (polar method over
+ * StrictMath.log / sqrt, restated bit for bit), out [ntables][proj_dim][d] on the HOST.  The hashing itself
+ * (compute-hash-vector, :33-45) is hb_pairwise with HB_IP against these rows, the bucket scan
+ * (search-bucket-brute-force, :147-193) is hb_gather_score, the final sort + take k is hb_topk_merge. */
+HB_API int hb_lsh_matrices(int32_t d, int32_t ntables, int32_t proj_dim, int64_t seed, double *out);
+
 /* ---- FAST-mode diagnostics ----------------------------------------------------------------------- */
 /* The candidate pass of HB_MODE_FAST on a flat index, unfiltered: for every (query, row) the tensor-core score
  * (exact integer dot product of the quantised digits times the row scale).  Batched form of

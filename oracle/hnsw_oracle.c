@@ -168,9 +168,71 @@ ORC_EXPORT double orc_rng_next_double(orc_rng *r) {
     int64_t lo = (int64_t)jr_next(r, 27);
     return (double)((hi << 27) + lo) * 0x1.0p-53;
 }
-/* Marsaglia polar method as in java.util.Random.nextGaussian.  Java uses StrictMath (fdlibm) log
- * and sqrt; libm's log may differ from fdlibm by 1 ulp on rare inputs.  That only affects
- * generated TEST DATA, never the parity path (which uses nextInt/nextDouble only). */
+/* StrictMath.log = fdlibm's __ieee754_log (e_log.c, "FreeBSD msun / Sun fdlibm 5.3"; the JDK ships a port of it,
+ * java.lang.FdLibm since JDK 21, the C original before): argument reduction x = 2^k (1+f), s = f/(2+f),
+ * log(1+f) = f - (hfsq - s (hfsq + R(s^2))) with the degree-14 Remez polynomial Lg1..Lg7.  Restated here because
+ * java.util.Random.nextGaussian (the LSH projection matrices, src/hnsw/ann/hash/hybrid_lsh.clj:24-31) goes through
+ * it and libm's log is only faithfully rounded, not bit-identical.  Pinned by new Random(42).nextGaussian() ==
+ * 1.1419053154730547 (tests/test_oracle.py). */
+ORC_EXPORT double orc_strict_log(double x) {
+    static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+                        two54 = 1.80143985094819840000e+16, Lg1 = 6.666666666666735130e-01,
+                        Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+                        Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01, Lg7 = 1.479819860511658591e-01;
+    union { double f; uint64_t u; } c;
+    c.f = x;
+    int32_t hx = (int32_t)(c.u >> 32);
+    uint32_t lx = (uint32_t)c.u;
+    int32_t k = 0, i, j;
+    if (hx < 0x00100000) { /* x < 2^-1022 */
+        if (((hx & 0x7fffffff) | lx) == 0) return -INFINITY;
+        if (hx < 0) return NAN;
+        k -= 54;
+        x *= two54;
+        c.f = x;
+        hx = (int32_t)(c.u >> 32);
+    }
+    if (hx >= 0x7ff00000) return x + x;
+    k += (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    i = (hx + 0x95f64) & 0x100000;
+    c.f = x;
+    c.u = (c.u & 0xffffffffull) | ((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32); /* normalize x or x/2 */
+    x = c.f;
+    k += (i >> 20);
+    double f = x - 1.0, dk, R, s, z, w, t1, t2, hfsq;
+    if ((0x000fffff & (2 + hx)) < 3) { /* |f| < 2^-20 */
+        if (f == 0.0) {
+            if (k == 0) return 0.0;
+            dk = (double)k;
+            return dk * ln2_hi + dk * ln2_lo;
+        }
+        R = f * f * (0.5 - 0.33333333333333333 * f);
+        if (k == 0) return f - R;
+        dk = (double)k;
+        return dk * ln2_hi - ((R - dk * ln2_lo) - f);
+    }
+    s = f / (2.0 + f);
+    dk = (double)k;
+    z = s * s;
+    i = hx - 0x6147a;
+    w = z * z;
+    j = 0x6b851 - hx;
+    t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    i |= j;
+    R = t2 + t1;
+    if (i > 0) {
+        hfsq = 0.5 * f * f;
+        if (k == 0) return f - (hfsq - s * (hfsq + R));
+        return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+    }
+    if (k == 0) return f - s * (f - R);
+    return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+}
+
+/* Marsaglia polar method as in java.util.Random.nextGaussian: StrictMath.log (above) and StrictMath.sqrt
+ * (correctly rounded, = C sqrt). */
 ORC_EXPORT double orc_rng_next_gaussian(orc_rng *r) {
     if (r->have_next_gaussian) {
         r->have_next_gaussian = 0;
@@ -182,7 +244,7 @@ ORC_EXPORT double orc_rng_next_gaussian(orc_rng *r) {
         v2 = 2.0 * orc_rng_next_double(r) - 1.0;
         s = v1 * v1 + v2 * v2;
     } while (s >= 1.0 || s == 0.0);
-    double mul = sqrt(-2.0 * log(s) / s);
+    double mul = sqrt(-2.0 * orc_strict_log(s) / s);
     r->next_gaussian = v2 * mul;
     r->have_next_gaussian = 1;
     return v1 * mul;
@@ -1037,4 +1099,118 @@ ORC_EXPORT void orc_gather_score(const float *rows, int64_t d, const float *quer
         else out[p] = dist_fn_fq(metric, v, q, d);
     }
     free(q);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Hybrid LSH (src/hnsw/ann/hash/hybrid_lsh.clj) — §8 f3: its bucket scan is search-partition's arithmetic (A.2) over a
+ * candidate set chosen by hashing.  8 tables x 12 bits (:12-14); only the first 12 of the 64 projection rows of a table
+ * reach the bucket id (hash-to-bucket-id, :47-55).
+ * ---------------------------------------------------------------------------------------- */
+enum { ORC_LSH_TABLES = 8, ORC_LSH_BITS = 12, ORC_LSH_PROJ = 64 };
+
+/* generate-random-matrix x NUM-HASH-TABLES from one Random(42) (:24-31, :77-81): table by table, row by row.
+ * out: [8][64][d] fp64. */
+ORC_EXPORT void orc_lsh_matrices(int64_t d, int64_t seed, double *out) {
+    orc_rng r;
+    orc_rng_init(&r, seed);
+    for (int64_t i = 0; i < (int64_t)ORC_LSH_TABLES * ORC_LSH_PROJ * d; ++i) out[i] = orc_rng_next_gaussian(&r);
+}
+
+/* compute-hash-vector + hash-to-bucket-id (:33-55): bit i = (sum_j v[j] * row_i[j] >= 0.0), i < 12. */
+static int32_t lsh_bucket(const double *v, const double *table, int64_t d) {
+    int32_t id = 0;
+    for (int i = 0; i < ORC_LSH_BITS; ++i) {
+        const double *row = table + (int64_t)i * d;
+        double sum = 0.0;
+        for (int64_t j = 0; j < d; ++j) sum = sum + v[j] * row[j];
+        if (sum >= 0.0) id |= 1 << i;
+    }
+    return id;
+}
+/* bucket ids of every row in every table: out [n][8] int32 */
+ORC_EXPORT void orc_lsh_hash(const float *rows, int64_t n, int64_t d, const double *matrices, int32_t *out) {
+    double *v = (double *)malloc(sizeof(double) * (size_t)d);
+    for (int64_t r = 0; r < n; ++r) {
+        for (int64_t j = 0; j < d; ++j) v[j] = (double)rows[r * d + j];
+        for (int t = 0; t < ORC_LSH_TABLES; ++t)
+            out[r * ORC_LSH_TABLES + t] = lsh_bucket(v, matrices + (int64_t)t * ORC_LSH_PROJ * d, d);
+    }
+    free(v);
+}
+
+/* search-bucket-brute-force (:147-193) appended to `res`: every member if the bucket holds <= limit rows (bucket order),
+ * else the stable sort by distance cut to limit.  members = row ids of the bucket in insertion (data) order. */
+static int64_t lsh_scan_bucket(const float *rows, int64_t d, const double *norms, const int64_t *members, int64_t size,
+                               const double *q, double qnorm, int64_t limit, orc_hit *res, orc_hit *tmp) {
+    for (int64_t i = 0; i < size; ++i) {
+        const float *v = rows + members[i] * d;
+        double dot = 0.0;
+        for (int64_t j = 0; j < d; ++j) dot = dot + (double)v[j] * q[j];
+        res[i].dist = 1.0 - dot / (qnorm * norms[members[i]]);
+        res[i].id = members[i];
+    }
+    if (size <= limit) return size;
+    stable_sort_hits(res, size, tmp);
+    return limit;
+}
+
+/* search-hybrid (:195-259; multiprobe = 0) and search-hybrid-multiprobe (:261-342; multiprobe = 1) for one query.
+ * Candidates are concatenated table by table (the sequential branch; the parallel branch of search-hybrid adds them in
+ * the same order, :217-220, with k*3 instead of k*2 per bucket — pass main_mult = 3; the parallel branch of the
+ * multi-probe search lets its tasks interleave, which only reorders equal distances of different rows), then
+ * deduplicated by id keeping the first, stable-sorted, cut to k.
+ * bucket CSR per table: off [8][4097], members [8][n]. */
+ORC_EXPORT void orc_lsh_search(const float *rows, int64_t n, int64_t d, const double *norms, const double *matrices,
+                               const int64_t *bucket_off, const int64_t *bucket_members, const float *queries, int64_t nq,
+                               int64_t k, int32_t num_probes, int32_t probe_radius, int multiprobe, int32_t main_mult,
+                               int64_t *out_ids, double *out_dist) {
+    const int64_t nb = (int64_t)1 << ORC_LSH_BITS;
+    const int probes = num_probes < ORC_LSH_TABLES ? num_probes : ORC_LSH_TABLES;
+    const int radius = probe_radius < ORC_LSH_BITS ? probe_radius : ORC_LSH_BITS;
+    double *q = (double *)malloc(sizeof(double) * (size_t)d);
+    orc_hit *cand = (orc_hit *)malloc(sizeof(orc_hit) * (size_t)(n * (1 + ORC_LSH_BITS) * ORC_LSH_TABLES + 1));
+    orc_hit *buf = (orc_hit *)malloc(sizeof(orc_hit) * (size_t)(n + 1));
+    orc_hit *tmp = (orc_hit *)malloc(sizeof(orc_hit) * (size_t)(n * (1 + ORC_LSH_BITS) * ORC_LSH_TABLES + 1));
+    unsigned char *seen = (unsigned char *)malloc((size_t)n + 1);
+    for (int64_t qi = 0; qi < nq; ++qi) {
+        for (int64_t j = 0; j < d; ++j) q[j] = (double)queries[qi * d + j];
+        const double qnorm = sqrt(sumsq_d(q, d)); /* compute-vector-norm, :57-64 */
+        int64_t nc = 0;
+        for (int t = 0; t < probes; ++t) {
+            const int32_t base = lsh_bucket(q, matrices + (int64_t)t * ORC_LSH_PROJ * d, d);
+            const int64_t *off = bucket_off + (int64_t)t * (nb + 1);
+            const int64_t *mem = bucket_members + (int64_t)t * n;
+            int64_t got = lsh_scan_bucket(rows, d, norms, mem + off[base], off[base + 1] - off[base], q, qnorm,
+                                          k * (multiprobe ? 2 : main_mult), buf, tmp);
+            if (off[base + 1] > off[base]) { /* (when bucket ...): an absent bucket adds nothing */
+                memcpy(cand + nc, buf, sizeof(orc_hit) * (size_t)got);
+                nc += got;
+            }
+            if (multiprobe)
+                for (int bit = 0; bit < radius; ++bit) { /* :301-308 */
+                    const int32_t nbk = (base ^ (1 << bit)) & (int32_t)(nb - 1);
+                    if (off[nbk + 1] == off[nbk]) continue;
+                    got = lsh_scan_bucket(rows, d, norms, mem + off[nbk], off[nbk + 1] - off[nbk], q, qnorm, k, buf, tmp);
+                    memcpy(cand + nc, buf, sizeof(orc_hit) * (size_t)got);
+                    nc += got;
+                }
+        }
+        memset(seen, 0, (size_t)n);
+        int64_t nu = 0;
+        for (int64_t i = 0; i < nc; ++i)
+            if (!seen[cand[i].id]) {
+                seen[cand[i].id] = 1;
+                cand[nu++] = cand[i];
+            }
+        stable_sort_hits(cand, nu, tmp);
+        for (int64_t j = 0; j < k; ++j) {
+            out_ids[qi * k + j] = j < nu ? cand[j].id : -1;
+            out_dist[qi * k + j] = j < nu ? cand[j].dist : INFINITY;
+        }
+    }
+    free(q);
+    free(cand);
+    free(buf);
+    free(tmp);
+    free(seen);
 }

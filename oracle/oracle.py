@@ -68,6 +68,11 @@ def _declare(L):
     L.orc_kmeans.restype = None
     L.orc_kmeans.argtypes = [_p, _i64, _i64, _i32, _i32, _int, _i64, _p, _p, _p, _int]
     L.orc_build_lists.restype, L.orc_build_lists.argtypes = None, [_p, _i64, _i32, _p, _p]
+    L.orc_strict_log.restype, L.orc_strict_log.argtypes = _f64, [_f64]
+    L.orc_lsh_matrices.restype, L.orc_lsh_matrices.argtypes = None, [_i64, _i64, _p]
+    L.orc_lsh_hash.restype, L.orc_lsh_hash.argtypes = None, [_p, _i64, _i64, _p, _p]
+    L.orc_lsh_search.restype = None
+    L.orc_lsh_search.argtypes = [_p, _i64, _i64, _p, _p, _p, _p, _p, _i64, _i64, _i32, _i32, _int, _i32, _p, _p]
     L.orc_ivf_search.restype = None
     L.orc_ivf_search.argtypes = [_p, _i64, _i64, _p, _i32, _p, _p, _p, _p, _i64, _i64, _i32, _int, _p, _p, _p, _int]
     L.orc_hnsw_create.restype, L.orc_hnsw_create.argtypes = _p, [_p, _i64, _i64, _int, _i32, _i32, _i64]
@@ -258,6 +263,56 @@ def ivf_search(rows, centroids, assign_, queries, k, nprobe, coarse_metric=COSIN
                          _ptr(queries), nq, k, nprobe, coarse_metric, _ptr(ids), _ptr(dist),
                          None if probes is None else _ptr(probes), nthreads or ncores())
     return (ids, dist, probes) if return_probes else (ids, dist)
+
+
+# ---- Hybrid LSH (src/hnsw/ann/hash/hybrid_lsh.clj) ---------------------------------------------
+LSH_TABLES, LSH_BITS, LSH_PROJ = 8, 12, 64
+
+
+def strict_log(x: float) -> float:
+    return lib().orc_strict_log(float(x))
+
+
+def lsh_matrices(d: int, seed: int = 42) -> np.ndarray:
+    """The 8 projection matrices [8, 64, d] fp64 drawn from one java.util.Random(seed).nextGaussian stream (:24-31, :77-81)."""
+    out = np.empty((LSH_TABLES, LSH_PROJ, d), dtype=np.float64)
+    lib().orc_lsh_matrices(d, seed, _ptr(out))
+    return out
+
+
+def lsh_hash(rows, matrices) -> np.ndarray:
+    """Bucket id of every row in every table, [n, 8] int32 (:33-55, :107-111)."""
+    rows, matrices = _f32(rows), _d64(matrices)
+    out = np.empty((rows.shape[0], LSH_TABLES), dtype=np.int32)
+    lib().orc_lsh_hash(_ptr(rows), rows.shape[0], rows.shape[1], _ptr(matrices), _ptr(out))
+    return out
+
+
+def lsh_buckets(bucket_ids):
+    """Per table the buckets as CSR over 4096 ids, members in insertion (data) order: (off [8, 4097], members [8, n])."""
+    b = np.asarray(bucket_ids)
+    n = b.shape[0]
+    off = np.zeros((LSH_TABLES, (1 << LSH_BITS) + 1), dtype=np.int64)
+    mem = np.empty((LSH_TABLES, n), dtype=np.int64)
+    for t in range(LSH_TABLES):
+        off[t, 1:] = np.cumsum(np.bincount(b[:, t], minlength=1 << LSH_BITS))
+        mem[t] = np.argsort(b[:, t], kind="stable")
+    return off, mem
+
+
+def lsh_search(rows, matrices, bucket_ids, queries, k, num_probes=6, probe_radius=2, multiprobe=True, main_mult=3):
+    """search-hybrid-multiprobe (:261-342) / search-hybrid (:195-259, multiprobe=False; main_mult = 3 for its parallel
+    branch, 2 for the sequential one)."""
+    rows, queries, matrices = _f32(rows), _f32(queries), _d64(matrices)
+    n, d = rows.shape
+    off, mem = lsh_buckets(bucket_ids)
+    norms = row_norms(rows)
+    nq = queries.shape[0]
+    ids = np.empty((nq, k), dtype=np.int64)
+    dist = np.empty((nq, k), dtype=np.float64)
+    lib().orc_lsh_search(_ptr(rows), n, d, _ptr(norms), _ptr(matrices), _ptr(off), _ptr(mem), _ptr(queries), nq, k,
+                         num_probes, probe_radius, 1 if multiprobe else 0, main_mult, _ptr(ids), _ptr(dist))
+    return ids, dist
 
 
 # ---- HNSW ---------------------------------------------------------------------------------

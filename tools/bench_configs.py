@@ -455,9 +455,58 @@ def run_c5(args):
             hb.set_option("profile", 0)
 
 
+def run_lsh(args):
+    """Hybrid LSH (src/hnsw/ann/hash/hybrid_lsh.clj; reference README: 0.5-1 s build, 2-5 ms per query, ~45 % recall) on
+    configs[0]'s shape: 31,173 x 768 unit-norm rows, 1000 noisy queries, search-knn's default mode (6 tables, radius 2)."""
+    import torch
+
+    from hnsw_clj_b200 import hybrid_lsh
+    from hnsw_clj_b200.flat import FlatIndex
+    from oracle import oracle as orc
+
+    dev = torch.device("cuda", 0)
+    n, d, nq, k = args.n or 31173, 768, 1000, 10
+    rows = unit_rows(n, d, 42, dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(43)
+    queries = (rows[torch.arange(nq, device=dev) * (n // nq)] + 0.1 / d ** 0.5 * torch.randn((nq, d), generator=g, device=dev)).contiguous()
+    rows_np, q_np = rows.cpu().numpy(), queries.cpu().numpy()
+    t0 = time.perf_counter()
+    ix = hybrid_lsh.build_index(rows_np)
+    build_s = time.perf_counter() - t0
+    res = {}
+    for mode in ("turbo", "balanced", "precise"):
+        p, r = hybrid_lsh._MODES[mode]
+        hybrid_lsh.search_hybrid_multiprobe_raw(ix, q_np, k, p, r)
+        t0 = time.perf_counter()
+        for _ in range(args.reps):
+            ids, dist = hybrid_lsh.search_hybrid_multiprobe_raw(ix, q_np, k, p, r)
+        ms = (time.perf_counter() - t0) * 1e3 / args.reps
+        res[mode] = (ms, ids, dist)
+    with FlatIndex(rows) as fx:
+        exact_ids, _ = fx.search_raw(queries, k)
+    s = 64
+    t0 = time.perf_counter()
+    want_ids, want_d = orc.lsh_search(rows_np, orc.lsh_matrices(d), ix.buckets, q_np[:s], k, 6, 2, True, 2)
+    cpu_s = time.perf_counter() - t0
+    info = hybrid_lsh.index_info(ix)
+    ix.close()
+    line = {
+        "config": f"Hybrid LSH {n}x768 fp32 cosine, 8 tables x 12 bits, {nq} queries per batch, top-10 (host buffers, host-side bucket tables)",
+        "build_s": build_s, "index_info": info,
+        "modes": {m: {"ms_per_batch": v[0], "queries_per_s": nq / v[0] * 1e3,
+                      "recall_at_10": orc.recall(v[1], exact_ids)} for m, v in res.items()},
+        "parity_vs_oracle": {"queries": s, "mode": "balanced", "ids_equal": bool((res["balanced"][1][:s] == want_ids).all()),
+                             "dist_bits_equal": same_bits(res["balanced"][2][:s], want_d)},
+        "cpu_baseline": {"value": s / cpu_s, "unit": "queries/s", "cores": 1, "kind": "port",
+                         "sample": f"first {s} queries, one thread, balanced mode"},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("config", choices=["c1", "c3", "c4", "c4full", "c5"])
+    ap.add_argument("config", choices=["c1", "c3", "c4", "c4full", "c5", "lsh"])
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--nlist", type=int, default=65536)
@@ -472,7 +521,7 @@ def main():
     for kv in args.opt:
         name, _, val = kv.partition("=")
         hb.set_option(name, int(val))
-    {"c1": run_c1, "c3": run_c3, "c4": run_c4, "c4full": run_c4_full, "c5": run_c5}[args.config](args)
+    {"c1": run_c1, "c3": run_c3, "c4": run_c4, "c4full": run_c4_full, "c5": run_c5, "lsh": run_lsh}[args.config](args)
 
 
 if __name__ == "__main__":

@@ -215,8 +215,8 @@ def run_reference(args, w, key):
 # ---------------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum of one tc_pass_kernel<2,EMIT> list-scan launch, from `ncu --set full` captures of
 # this command: (workload, digits, probe pruning on) -> bytes.  profiles/r01c_tc_pass_ncu_raw.csv (5.42 GB + 0.03 GB, no pruning),
-# profiles/r01j_tc_pass_ncu_raw.csv (1.936 GB + 0.022 GB with probe pruning: 1.07x the unique digit-image bytes)
-TRAFFIC = {("c2", 2, False): 5.45e9, ("c2", 2, True): 1.958e9}
+# profiles/r01v_tc_pass_ncu_raw.csv (final build, probe pruning and M = 64 units on: 1.760 GB + 0.023 GB)
+TRAFFIC = {("c2", 2, False): 5.45e9, ("c2", 2, True): 1.783e9}
 
 
 def run_ours(args, w, key):
@@ -323,7 +323,7 @@ def run_ours(args, w, key):
     pruned_pairs = hb.get_stat("fast_pruned_pairs") / args.steps
     pruned_rows = hb.get_stat("fast_pruned_rows") / args.steps
     probe_pairs = hb.get_stat("fast_probe_pairs") / args.steps
-    hb_stats = {n: hb.get_stat(n) for n in ("tc_units", "tc_items", "tc_tiles")}
+    hb_stats = {n: hb.get_stat(n) for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units")}
     hb.set_option("profile", 0)
     if world > 1:
         t = torch.tensor([ms], device=device)
@@ -421,12 +421,13 @@ def run_ours(args, w, key):
         algorithmic_pairs = pairs
         pairs = pairs - pruned_rows
         flops = 2.0 * pairs * w["d"]
-        tc_units, tc_items, tc_tiles = (hb_stats[n] / args.steps for n in ("tc_units", "tc_items", "tc_tiles"))
+        tc_units, tc_items, tc_tiles, tc_half = (hb_stats[n] / args.steps for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units"))
         if tc_items > 0:
             items = tc_items
         int8_ops = 2.0 * items * 128 * 128 * dpad * nprod if items else None
-        # digit images read once: the row tiles some unit scans + the units' query images (128 slots each)
-        img_bytes = (tc_tiles * 128.0 * dpad * args.digits + tc_units * 128.0 * dpad * args.digits) if tc_items > 0 else (
+        # digit images read once: the row tiles some unit scans + the units' query images (128 slots each, 64 for the
+        # units that run with M = 64)
+        img_bytes = (tc_tiles * 128.0 * dpad * args.digits + (tc_units - 0.5 * tc_half) * 128.0 * dpad * args.digits) if tc_items > 0 else (
             float(w["n"]) * dpad * args.digits + nq * nprobe * dpad * args.digits)
         hbm_peak = peaks.get("hbm_gbs", 7700.0)
         t_flops, t_bytes = flops / (bf16_peak * 1e12), img_bytes / (hbm_peak * 1e9)
@@ -450,7 +451,8 @@ def run_ours(args, w, key):
             "launch_ms": t_tc * 1e3, "launches_per_step": tc_n / args.steps,
             "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": img_bytes,
             "tensor": tensor, "hbm": hbm,
-            "units_per_launch": tc_units, "items_per_launch": items, "row_tiles_read_per_launch": tc_tiles,
+            "units_per_launch": tc_units, "m64_units_per_launch": tc_half, "items_per_launch": items,
+            "row_tiles_read_per_launch": tc_tiles,
             "scored_pairs_per_launch": pairs, "algorithmic_pairs_per_step": algorithmic_pairs,
             "probe_pruning": {"probe_pairs": probe_pairs, "pruned_probe_pairs": pruned_pairs, "pruned_rows": pruned_rows,
                               "note": "exact: a probed list is dropped for a query when cos(angle(q, centroid) - list radius) "

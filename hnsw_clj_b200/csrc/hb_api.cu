@@ -294,7 +294,7 @@ static bool g_fast_prune = true;     // IVF scan: drop (query, probed list) pair
 static int64_t g_fast_probe_pairs = 0;
 // profiling counters that live on the device (a search makes no host round trip for them): [pruned (query, list) pairs,
 // rows they held, units / items / row tiles of the IVF main candidate pass]
-enum { DS_PRUNED_PAIRS = 0, DS_PRUNED_ROWS = 1, DS_TC_UNITS = 2, DS_TC_ITEMS = 3, DS_TC_TILES = 4, DS_COUNT = 8 };
+enum { DS_PRUNED_PAIRS = 0, DS_PRUNED_ROWS = 1, DS_TC_UNITS = 2, DS_TC_ITEMS = 3, DS_TC_TILES = 4, DS_TC_HALF_UNITS = 5, DS_COUNT = 8 };
 static DevBuf g_dev_stats;
 static unsigned long long *dev_stats() {
     const bool fresh = g_dev_stats.p == nullptr;
@@ -1557,7 +1557,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
             fast_topk(J);
         }
         // what the main candidate pass covered: units, items (unit x row tile), distinct row tiles
-        if (g_profile) launch_tc_cover(uprefix, (const int64_t *)S.tile_off.p, nlist, dev_stats() + DS_TC_UNITS);
+        if (g_profile) launch_tc_cover(uprefix, (const int64_t *)S.tile_off.p, g_tc_half_m ? lq_off : nullptr, nlist, dev_stats() + DS_TC_UNITS);
         launch_ivf_resolve(relk, nqc, k, np_eff, probes, pair_out, (const int64_t *)ix->list_off.p, (const int64_t *)ix->list_rows.p,
                            ids + (size_t)q0 * k);
         launch_and_flags(ok_all + q0, ok_c, nqc);
@@ -1774,6 +1774,7 @@ HB_API int hb_get_stat(const char *name, double *out) {
         if (!strcmp(name, "tc_units")) { *out = dev_stat(DS_TC_UNITS); return; }
         if (!strcmp(name, "tc_items")) { *out = dev_stat(DS_TC_ITEMS); return; }
         if (!strcmp(name, "tc_tiles")) { *out = dev_stat(DS_TC_TILES); return; }
+        if (!strcmp(name, "tc_half_units")) { *out = dev_stat(DS_TC_HALF_UNITS); return; }
         if (!strcmp(name, "fast_pruned_rows")) { *out = dev_stat(DS_PRUNED_ROWS); return; }
         if (!strcmp(name, "fast_probe_pairs")) { *out = (double)g_fast_probe_pairs; return; }
         if (!strcmp(name, "hnsw_scored")) { *out = (double)g_hnsw_scored; return; }

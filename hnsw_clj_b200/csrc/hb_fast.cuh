@@ -181,7 +181,8 @@ void launch_prune_probes(int64_t *probe_pos, const double *sim_ub, const double 
                          const double *q_eps, int64_t nq, int np, const int64_t *list_off, unsigned long long *pruned /*[2]*/);
 // profiling counters accumulated on the device (read by hb_get_stat), and a 4-word plan written without host memory
 void launch_accumulate_u64(unsigned long long *acc, const unsigned long long *src, int n);
-void launch_tc_cover(const int64_t *unit_prefix, const int64_t *tile_off, int nlist, unsigned long long *acc /*[3]*/);
+void launch_tc_cover(const int64_t *unit_prefix, const int64_t *tile_off, const int64_t *lq_off /*NULL: M = 64 units off*/,
+                     int nlist, unsigned long long *acc /*[4]: units, items, row tiles, M = 64 units*/);
 void launch_set_i64x4(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d);
 // ok[q] &= other[q]
 void launch_and_flags(int32_t *ok, const int32_t *other, int64_t nq);

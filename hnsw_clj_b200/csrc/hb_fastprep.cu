@@ -914,25 +914,29 @@ __global__ void accumulate_u64_kernel(unsigned long long *__restrict__ acc, cons
     if ((int)threadIdx.x < n) acc[threadIdx.x] += src[threadIdx.x];
 }
 // what a candidate pass covers: acc[0] += units, acc[1] += items (unit x row tile), acc[2] += row tiles of lists with units
-__global__ void tc_cover_kernel(const int64_t *__restrict__ unit_prefix, const int64_t *__restrict__ tile_off, int nlist,
-                                unsigned long long *__restrict__ acc) {
-    unsigned long long u = 0, it = 0, t = 0;
+// acc[3] += units whose selections fit 64 slots (run with M = 64: half of the query image is staged), counted if lq_off
+__global__ void tc_cover_kernel(const int64_t *__restrict__ unit_prefix, const int64_t *__restrict__ tile_off,
+                                const int64_t *__restrict__ lq_off, int nlist, unsigned long long *__restrict__ acc) {
+    unsigned long long u = 0, it = 0, t = 0, h = 0;
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < nlist; l += gridDim.x * blockDim.x) {
         const unsigned long long units = (unsigned long long)(unit_prefix[l + 1] - unit_prefix[l]);
         const unsigned long long tiles = (unsigned long long)(tile_off[l + 1] - tile_off[l]);
         u += units;
         it += units * tiles;
         if (units > 0) t += tiles;
+        if (lq_off != nullptr && units > 0 && (lq_off[l + 1] - lq_off[l]) - (int64_t)(units - 1) * kFastTile <= 64) h += 1;
     }
     for (int o = 16; o > 0; o >>= 1) {
         u += __shfl_xor_sync(0xffffffffu, u, o);
         it += __shfl_xor_sync(0xffffffffu, it, o);
         t += __shfl_xor_sync(0xffffffffu, t, o);
+        h += __shfl_xor_sync(0xffffffffu, h, o);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(acc, u);
         atomicAdd(acc + 1, it);
         atomicAdd(acc + 2, t);
+        atomicAdd(acc + 3, h);
     }
 }
 __global__ void set_i64x4_kernel(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d) {
@@ -1080,9 +1084,10 @@ void launch_accumulate_u64(unsigned long long *acc, const unsigned long long *sr
     accumulate_u64_kernel<<<1, 32, 0, g_stream>>>(acc, src, n);
     HB_LAUNCH_CHECK();
 }
-void launch_tc_cover(const int64_t *unit_prefix, const int64_t *tile_off, int nlist, unsigned long long *acc) {
+void launch_tc_cover(const int64_t *unit_prefix, const int64_t *tile_off, const int64_t *lq_off, int nlist,
+                     unsigned long long *acc) {
     if (nlist == 0) return;
-    tc_cover_kernel<<<blocks_for(nlist, 256), 256, 0, g_stream>>>(unit_prefix, tile_off, nlist, acc);
+    tc_cover_kernel<<<blocks_for(nlist, 256), 256, 0, g_stream>>>(unit_prefix, tile_off, lq_off, nlist, acc);
     HB_LAUNCH_CHECK();
 }
 void launch_set_i64x4(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d) {

@@ -954,7 +954,9 @@ static void fast_topk(const FastJob &J) {
         if (do_main) {
             U = make_units(J.emit, W.u_list, W.u_sel0, W.u_nsel, W.u_ntile, W.u_item0, W.u_slotq, W.u_slotrel, (const int64_t *)S.tile_off.p);
             aimg = W.aimg.as<int8_t>((size_t)std::max(J.emit.nunits, 1) * kbn * ns * kFastImg);
-            launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.emit.nunits, U.slot_query, aimg);
+            // an IVF list scan runs EMIT passes only: its M = 64 units (<= 64 selections) need half an image
+            launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.emit.nunits, U.slot_query, aimg,
+                              (g_tc_half_m && !J.shared_units) ? U.unit_nsel : nullptr);
         }
         if (!do_sample) {
         } else if (J.shared_units) {
@@ -969,7 +971,8 @@ static void fast_topk(const FastJob &J) {
             T = make_units(J.thresh, W.t_list, W.t_sel0, W.t_nsel, W.t_ntile, W.t_item0, W.t_slotq, W.t_slotrel,
                            (const int64_t *)S.tile_off.p);
             aimg0 = W.aimg0.as<int8_t>((size_t)std::max(J.thresh.nunits, 1) * kbn * ns * kFastImg);
-            launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.thresh.nunits, T.slot_query, aimg0);
+            launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.thresh.nunits, T.slot_query, aimg0,
+                              g_tc_half_m ? T.unit_nsel : nullptr);
         }
     }
     TcParams P;

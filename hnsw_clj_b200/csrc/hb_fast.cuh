@@ -72,7 +72,9 @@ void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_pref
                       int nunits_real, int interleave, int tile_limit, int tile_div, int tile_start, const int32_t *qsel,
                       const int64_t *pair_out, int pair_div, const int32_t *pair_query, UnitPlan U);
 // gathers the digits of each unit's queries into A images [nunits][kbn][ns][kFastImg]
-void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int32_t *slot_query, int8_t *aimg);
+// unit_nsel (optional): units with <= 64 selections get only slots 0..63 packed (the M = 64 candidate pass reads no more)
+void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int32_t *slot_query, int8_t *aimg,
+                       const int32_t *unit_nsel = nullptr);
 
 // ---- the tensor-core pass (hb_tc.cu) -------------------------------------------------------------------
 enum FastMode { FAST_EMIT = 1, FAST_DUMP = 2 };

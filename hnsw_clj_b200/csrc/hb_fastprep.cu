@@ -265,13 +265,15 @@ __global__ void unit_slots_kernel(int nunits, const int32_t *__restrict__ unit_s
 // grid (nunits, kbn): copies the 16-byte chunks of the unit's query digits into swizzled images
 template <int NS>
 __global__ void __launch_bounds__(256) pack_units_kernel(const int8_t *__restrict__ dig, int kbn,
-                                                         const int32_t *__restrict__ slot_query, int8_t *__restrict__ aimg) {
+                                                         const int32_t *__restrict__ slot_query, int8_t *__restrict__ aimg,
+                                                         const int32_t *__restrict__ unit_nsel) {
     const int u = blockIdx.x, kb = blockIdx.y;
     const int dpad = kbn * kFastKB;
     if (slot_query[(int64_t)u * kFastTile] < 0) return;  // slots fill from 0: an empty unit (padding / bound) has no items
+    const int nslots = (unit_nsel != nullptr && unit_nsel[u] <= 64) ? 64 : kFastTile;  // M = 64 units: first 8 row groups
     int8_t *dst = aimg + ((int64_t)u * kbn + kb) * NS * kFastImg;
-    for (int i = threadIdx.x; i < NS * kFastTile * 8; i += blockDim.x) {
-        const int ch = i & 7, slot = (i >> 3) % kFastTile, s = i / (8 * kFastTile);
+    for (int i = threadIdx.x; i < NS * nslots * 8; i += blockDim.x) {
+        const int ch = i & 7, slot = (i >> 3) % nslots, s = i / (8 * nslots);
         const int q = slot_query[(int64_t)u * kFastTile + slot];
         uint4 v = make_uint4(0, 0, 0, 0);
         if (q >= 0) v = *reinterpret_cast<const uint4 *>(dig + ((int64_t)q * NS + s) * dpad + kb * kFastKB + ch * 16);
@@ -1163,11 +1165,12 @@ void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_pref
     HB_LAUNCH_CHECK();
 }
 
-void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int32_t *slot_query, int8_t *aimg) {
+void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int32_t *slot_query, int8_t *aimg,
+                       const int32_t *unit_nsel) {
     if (nunits == 0) return;
     dim3 grid((unsigned)nunits, (unsigned)kbn);
-    if (ns == 2) pack_units_kernel<2><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg);
-    else pack_units_kernel<3><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg);
+    if (ns == 2) pack_units_kernel<2><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg, unit_nsel);
+    else pack_units_kernel<3><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg, unit_nsel);
     HB_LAUNCH_CHECK();
 }
 

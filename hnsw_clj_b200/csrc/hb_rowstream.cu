@@ -339,11 +339,20 @@ __global__ void __launch_bounds__(32 * kMaxWarps) liststream_kernel(const ScanPa
 // defaults from the sweep in profiles/r01m_rowstream_sweep.txt: 256-byte segments, 2 stages, as many warps as fit (12 at d = 768)
 int g_stream_seg = 256, g_stream_stages = 2, g_stream_warps = 0;  // hb_set_option("stream_seg" / "stream_stages" / "stream_warps")
 
+// opt-in shared memory per block of the process's device (one process per GPU: asked once)
+int max_optin_smem() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0;
+        HB_CUDA(cudaGetDevice(&dev));
+        HB_CUDA(cudaDeviceGetAttribute(&cached, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    }
+    return cached;
+}
+
 template <typename TRow, typename TQry, int ARITH, int NQ, int SEG>
 bool rowstream_go(const ScanParams &P) {
-    int dev = 0, max_smem = 0;
-    HB_CUDA(cudaGetDevice(&dev));
-    HB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int max_smem = max_optin_smem();
     const int stages = std::min(std::max(g_stream_stages, 2), kMaxStages);
     const size_t qbytes = ((size_t)P.d * NQ * sizeof(double) + 127) & ~(size_t)127;
     const size_t per_warp = (size_t)stages * 32 * (SEG + 16);
@@ -382,9 +391,7 @@ bool rowstream_arith(const ScanParams &P, bool l2, int max_sel) {
 
 template <typename TRow, typename TQry, int ARITH, int SEG>
 bool liststream_go(const ScanParams &P, int nq) {
-    int dev = 0, max_smem = 0;
-    HB_CUDA(cudaGetDevice(&dev));
-    HB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int max_smem = max_optin_smem();
     const int stages = std::min(std::max(g_stream_stages, 2), kMaxStages);
     const size_t qbytes = ((size_t)P.d * nq * sizeof(double) + 127) & ~(size_t)127;
     const size_t per_warp = (size_t)stages * 32 * (SEG + 16);

@@ -1,14 +1,20 @@
 #!/usr/bin/env python
-"""bench.py — QPS@recall@10 of the IVF-FLAT batched search (BASELINE.json configs[1]) on B200.
+"""bench.py — QPS@recall@10 of the IVF-FLAT batched search on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|small]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|small] [--shard rows|replicas|lists]
 
 A step = one pass of the hot path over one batch: coarse quantiser -> list-major scan of the probed lists ->
 per-query top-k, for the whole 10k-query batch.  `value` is measured with the index and the queries resident in
-HBM; `e2e` goes through the C ABI with HOST (pinned) query buffers and host result buffers.  N > 1 (torchrun):
-the lists of ONE global index are sharded across ranks (list l on rank l mod N), every rank scans its lists
-for all queries, then an NCCL all-gather of the local top-k and the merge kernel give the global top-k
-(strong scaling: the database is fixed, per-GPU rows shrink as N grows).
+HBM; `e2e` goes through the C ABI with HOST (pinned) query buffers and host result buffers.
+
+N = 1: BASELINE.json configs[1] (IVF-FLAT 1M x 768, nlist 1024, nprobe 32, 10k queries, top-10).
+N > 1 (torchrun, one process per GPU): ONE global IVF-FLAT index of N x 12.5M rows (100M x 768 at N = 8, nlist =
+8192 N = 65,536 at N = 8: configs[3]'s build), rows sharded in contiguous blocks.  Build = data-parallel k-means inside the
+library (hb_sharded_ivf_build: one NCCL all-reduce per Lloyd round); a step = hb_sharded_search on every rank: coarse
+routing (replicated centroids), scan of this rank's part of every probed list, exchange of the local top-k over NVLink peer
+windows fused with the merge (one kernel; `--opt comm_p2p=0`: ncclAllGather + merge kernel).  Weak scaling: rows per GPU are
+fixed, the database grows with N.  The r01 layout (every GPU a replica of configs[1], no collective) is kept as the
+secondary key `replicas`.
 """
 from __future__ import annotations
 
@@ -26,12 +32,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# per-GPU shard of the N > 1 workload: N x 12.5M rows = 100M at N = 8; nlist = 8192 per GPU (65,536 at N = 8, configs[3])
+SHARD = dict(n_per=12_500_000, d=768, nlist_per=8192, nprobe=32, nq=10_000, k=10, centres_per=16384, noise=0.1, iters=10,
+             truth_queries=1024)
+SHARD_SMALL = dict(n_per=500_000, d=768, nlist_per=512, nprobe=16, nq=4_000, k=10, centres_per=1024, noise=0.1, iters=4,
+                   truth_queries=512)
 WORKLOADS = {
     # BASELINE.json configs[1]: IVF-FLAT 1M x 768 fp32 cosine, nlist=1024, nprobe=32, 10k-query batch, top-10
     "c2": dict(n=1_000_000, d=768, nlist=1024, nprobe=32, nq=10_000, k=10, centres=2048, noise=0.1, iters=10),
     "small": dict(n=100_000, d=768, nlist=256, nprobe=16, nq=2_000, k=10, centres=512, noise=0.1, iters=5),
 }
 METRIC = "QPS@recall@10 (IVF-FLAT 1Mx768 fp32 cosine, nlist=1024, nprobe=32, 10k-query batch, top-10)"
+METRIC_SHARDED = "QPS@recall@10 (IVF-FLAT Nx12.5Mx768 fp32 cosine row-sharded over N GPUs, 100Mx768 at N=8, nprobe=32, 10k-query batch, top-10)"
 
 
 def workload_name(w, key):
@@ -219,14 +231,12 @@ def run_reference(args, w, key):
 TRAFFIC = {("c2", 2, False): 5.45e9, ("c2", 2, True): 1.783e9}
 
 
-def run_ours(args, w, key):
+def setup(args):
+    """One process per GPU: device, library, process group (NCCL) and the library's own communicator."""
     import torch
     import torch.distributed as dist
 
     from hnsw_clj_b200 import _lib as hb
-    from hnsw_clj_b200 import ivf_flat
-    from hnsw_clj_b200.flat import FlatIndex, recall_at_k
-    from hnsw_clj_b200.sharded import ShardedIVFFlat
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -239,22 +249,38 @@ def run_ours(args, w, key):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-
-    fast = args.mode == "fast"
     hb.set_option("fast_digits", args.digits)
     for kv in args.opt:
         name, _, val = kv.partition("=")
         hb.set_option(name, int(val))
+    return rank, world, local, device
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def run_ours(args, w, key, ctx, replicas_only=False):
+    import torch
+    import torch.distributed as dist
+
+    from hnsw_clj_b200 import _lib as hb
+    from hnsw_clj_b200 import ivf_flat
+    from hnsw_clj_b200.flat import FlatIndex, recall_at_k
+    from hnsw_clj_b200.sharded import ShardedIVFFlat
+
+    rank, world, local, device = ctx
+    peaks = load_peaks()
+
+    fast = args.mode == "fast"
     k, nprobe, nq = w["k"], w["nprobe"], w["nq"]
     # N > 1: "replicas" = every GPU holds the whole index (3 GB of 180 GB) and answers its OWN batch of nq queries: no
     # data-path collective, weak scaling, value = N * nq / t.  "lists" = ONE batch against the lists of the index
     # sharded l mod N, all-gather + merge kernel: strong scaling (the layout for an index larger than one GPU).
-    replicas = world > 1 and args.shard == "replicas"
+    replicas = world > 1 and (args.shard == "replicas" or replicas_only)
     rows, queries = gen_gpu(w, device, query_seed=43 + (rank if replicas else 0))
     torch.cuda.synchronize()
 
@@ -366,11 +392,13 @@ def run_ours(args, w, key):
            "h2d_bytes_per_step": int(hq.numel() * 4) * (world if world > 1 else 1),
            "d2h_bytes_per_step": int(h_ids.numel() * 8 + h_dist.numel() * 8) * jobs}
 
-    if rank != 0:
+    if replicas_only or rank != 0:
+        gix.close() if (world == 1 or replicas) else shard.close()
         if world > 1:
             dist.barrier()
-            dist.destroy_process_group()
-        return
+        return {"value": value, "unit": "queries/s", "ms_per_step": ms, "e2e": e2e, "gpu_launches": int(launches),
+                "build_s": build_s, "workload": workload_name(w, key),
+                "sharding": f"replicas: the whole index on each of {world} GPUs, one {nq}-query batch per GPU per step, no collective"}
 
     # ---- recall@10 against the exact flat search of the same rows (device, exact path) ----------------
     hb.set_mode(hb.MODE_EXACT)
@@ -511,10 +539,229 @@ def run_ours(args, w, key):
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         "fast_vs_exact": fast_vs_exact,
     }
-    print(json.dumps(line), flush=True)
+    gix.close() if (world == 1 or replicas) else shard.close()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    return line
+
+
+# ---------------------------------------------------------------------------------------------------------
+# N > 1: one global index, rows sharded, data plane inside the library
+# ---------------------------------------------------------------------------------------------------------
+def gen_shard(S, device, rank, world):
+    """This rank's rows of the global clustered data set (centres and queries identical on every rank; SURVEY §8d C4:
+    generated on the device per shard)."""
+    import torch
+
+    d, n, nq = S["d"], S["n_per"], S["nq"]
+    ncent = S["centres_per"] * world
+    g = torch.Generator(device=device)
+    g.manual_seed(42)
+    centres = torch.randn((ncent, d), generator=g, device=device)
+    g.manual_seed(43)
+    idx = torch.randint(0, ncent, (nq,), generator=g, device=device)
+    queries = (centres[idx] + S["noise"] * torch.randn((nq, d), generator=g, device=device)).contiguous()
+    g.manual_seed(1000 + rank)
+    rows = torch.empty((n, d), dtype=torch.float32, device=device)
+    step = 131072
+    for i in range(0, n, step):
+        m = min(step, n - i)
+        idx = torch.randint(0, ncent, (m,), generator=g, device=device)
+        rows[i:i + m] = centres[idx] + S["noise"] * torch.randn((m, d), generator=g, device=device)
+    del centres
+    return rows, queries
+
+
+def draw_seed_rows(n_total, nlist, seed=42):
+    """nlist distinct global rows in draw order (seeding of the sharded k-means; see config.seeding)."""
+    r = np.random.default_rng(seed)
+    out, seen = [], set()
+    while len(out) < nlist:
+        for v in r.integers(0, n_total, size=2 * nlist).tolist():
+            if v not in seen:
+                seen.add(v)
+                out.append(v)
+                if len(out) == nlist:
+                    break
+    return np.asarray(out, dtype=np.int64)
+
+
+def run_sharded(args, S, ctx):
+    import torch
+    import torch.distributed as dist
+
+    from hnsw_clj_b200 import _lib as hb
+    from hnsw_clj_b200 import sharded
+    from hnsw_clj_b200.flat import recall_at_k
+    from oracle import oracle as orc
+
+    rank, world, local, device = ctx
+    peaks = load_peaks()
+    sharded.comm_init(rank, world)  # the 128-byte id travels over torch.distributed; everything else is the library's
+    d, n_per, nq, k, nprobe = S["d"], S["n_per"], S["nq"], S["k"], S["nprobe"]
+    nlist, n_total, first_row = S["nlist_per"] * world, S["n_per"] * world, rank * S["n_per"]
+    fast = args.mode == "fast"
+    t0 = time.perf_counter()
+    rows, queries = gen_shard(S, device, rank, world)
+    torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t0
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        return float(sharded.comm_allreduce([x], "max")[0])
+
+    hb.set_mode(hb.MODE_FAST if fast else hb.MODE_EXACT)
+    # ---- ground truth for recall@10: exact flat search of a query sample over all shards (sharded flat index, freed again) ----
+    T = min(S["truth_queries"], nq)
+    t0 = time.perf_counter()
+    with sharded.RowShardedFlat(rows, first_row) as fx:
+        truth_ids, _ = fx.search_raw(queries[:T], k)
+    truth_s = time.perf_counter() - t0
+    truth_ids = truth_ids.copy()
+
+    # ---- build (untimed setup; reported): data-parallel k-means + local slabs, inside the library ----------------------
+    seeds = draw_seed_rows(n_total, nlist)
+    hb.set_option("profile", 1)
+    barrier()
+    t0 = time.perf_counter()
+    ix = sharded.RowShardedIVFFlat(rows, first_row, nlist, seeds, max_iterations=S["iters"])
+    barrier()
+    build_s = time.perf_counter() - t0
+    build = {"build_s": build_s, "lloyd_rounds": S["iters"], "assign_ms": hb.get_stat("assign_ms"), "update_ms": hb.get_stat("update_ms"),
+             "allreduce_ms": hb.get_stat("allreduce_ms"), "allreduce_bytes_per_round": nlist * d * 8 + nlist * 8,
+             "seeding": "nlist distinct random global rows (numpy default_rng(42)); the reference's k-means++ "
+                        "(ivf_flat.clj:32-60) walks all rows once per seed"}
+    hb.set_option("profile", 0)
+
+    out_ids = torch.empty((nq, k), dtype=torch.int64, device=device)
+    out_dist = torch.empty((nq, k), dtype=torch.float64, device=device)
+    search = lambda q: ix.search_raw(q, k, nprobe, out_ids=out_ids, out_dist=out_dist)  # noqa: E731
+
+    # ---- timed region: device-resident inputs ------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        search(queries)
+    barrier()
+    hb.set_option("profile", 1)
+    hb.launch_count(reset=True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        search(queries)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = hb.launch_count()
+    clk = clocks.stop() if rank == 0 else {}
+    names = ("coarse_ms", "plan_ms", "pack_ms", "tc_sample_ms", "tc_ms", "select_ms", "rescore_ms", "scan_ms", "exchange_ms", "merge_ms")
+    stats = {n: hb.get_stat(n) / args.steps for n in names}
+    tc_ms, tc_n = hb.get_stat("tc_ms"), max(hb.get_stat("tc_count"), 1.0)
+    fast_served, fast_fell = hb.get_stat("fast_queries"), hb.get_stat("fast_fallbacks")
+    pruned_pairs = hb.get_stat("fast_pruned_pairs") / args.steps
+    pruned_rows = hb.get_stat("fast_pruned_rows") / args.steps
+    probe_pairs = hb.get_stat("fast_probe_pairs") / args.steps
+    tc = {n: hb.get_stat(n) / args.steps for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units")}
+    hb.set_option("profile", 0)
+    # the slowest rank's share of the step spent in the exchange + merge (what the collective costs)
+    comm_ms = max_over_ranks(stats["exchange_ms"] + stats["merge_ms"])
+    value = nq / (ms * 1e-3)
+    ids_np, dist_np = out_ids.cpu().numpy(), out_dist.cpu().numpy()
+
+    # ---- e2e: pinned host queries in, host results out, one C-ABI call per rank ---------------------------------------
+    hq = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
+    hq.copy_(queries)
+    h_ids = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+    h_dist = torch.empty((nq, k), dtype=torch.float64, pin_memory=True)
+    for _ in range(max(1, args.warmup // 2)):
+        ix.search_raw(hq, k, nprobe, out_ids=h_ids, out_dist=h_dist)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ix.search_raw(hq, k, nprobe, out_ids=h_ids, out_dist=h_dist)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    e2e = {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(hq.numel() * 4) * world, "d2h_bytes_per_step": int(h_ids.numel() * 16) * world,
+           "note": "every rank copies the whole query batch in and the merged results out"}
+    e2e_same = bool((h_ids.numpy() == ids_np).all())
+
+    # ---- parity: (1) the same search in EXACT mode (fp64 for every pair) on a query sample — collective;
+    #              (2) the returned distances recomputed by the oracle's pairwise arithmetic from the rows each rank holds ----
+    P = min(256, nq)
+    fast_vs_exact = None
+    if fast:
+        hb.check(hb.lib().hb_index_set_mode(ix._h, hb.MODE_EXACT))
+        x_ids, x_dist = ix.search_raw(queries[:P], k, nprobe)
+        hb.check(hb.lib().hb_index_set_mode(ix._h, -1))
+        fast_vs_exact = {"queries": P, "ids_equal": bool((x_ids == ids_np[:P]).all()),
+                         "dist_bits_equal": bool((x_dist.view(np.int64) == dist_np[:P].view(np.int64)).all()),
+                         "exact_fallbacks_per_step": fast_fell / max(args.steps + 0, 1), "served_per_step": fast_served / args.steps}
+    O = min(64, nq)
+    mine = (ids_np[:O] >= first_row) & (ids_np[:O] < first_row + n_per)
+    qi, ji = np.nonzero(mine)
+    loc = torch.from_numpy(ids_np[:O][mine] - first_row).to(device)
+    vec = rows[loc].cpu().numpy()
+    q_np = queries[:O].cpu().numpy()
+    same = sum(1 for t in range(len(qi))
+               if np.float64(orc.cosine_distance_direct(q_np[qi[t]], vec[t])).view(np.int64) == dist_np[qi[t], ji[t]].view(np.int64))
+    tot = sharded.comm_allreduce([same, len(qi)], "sum")
+    oracle_parity = {"queries": O, "results_checked": int(tot[1]), "dist_bits_equal_oracle": int(tot[0]),
+                     "what": "distance bits of the returned (query, row) pairs vs the oracle's pairwise restatement, each rank "
+                             "checking the rows it holds"}
+    recall = recall_at_k(ids_np[:T], truth_ids)
+    info = sharded.comm_info()
+    ix.close()
+    del rows
+    torch.cuda.empty_cache()
+    barrier()
+    if rank != 0:
+        return None
+
+    # ---- roofline of the dominant kernel on this rank (tc_pass_kernel, the candidate pass over the probed lists) --------
+    dpad = -(-d // 128) * 128
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = None
+    if fast and tc["tc_items"] > 0:
+        t_tc = (tc_ms / tc_n) * 1e-3
+        img_bytes = tc["tc_tiles"] * 128.0 * dpad * args.digits + (tc["tc_units"] - 0.5 * tc["tc_half_units"]) * 128.0 * dpad * args.digits
+        roofline = {"kernel": f"tc_pass_kernel<{args.digits},EMIT> (rank 0's shard)", "bound": "hbm",
+                    "achieved": img_bytes / t_tc / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": img_bytes / t_tc / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s", "traffic": None,
+                    "launch_ms": t_tc * 1e3, "launches_per_step": tc_n / args.steps, "algorithmic_bytes_per_launch": img_bytes,
+                    "units_per_launch": tc["tc_units"], "items_per_launch": tc["tc_items"], "row_tiles_read_per_launch": tc["tc_tiles"],
+                    "probe_pruning": {"probe_pairs": probe_pairs, "pruned_probe_pairs": pruned_pairs, "pruned_rows": pruned_rows},
+                    "step_breakdown_ms": stats}
+    exchange_bytes = nq * k * 16
+    line = {
+        "metric": METRIC_SHARDED, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"ivf-flat {n_total}x{d} fp32 cosine ({world} x {n_per} rows, contiguous row blocks) nlist={nlist} "
+                               f"nprobe={nprobe} nq={nq} k={k}" + (" (100M x 768: BASELINE metric, configs[3]'s index)" if n_total == 100_000_000 else ""),
+                   "recall_at_10": recall, "recall_queries": T,
+                   "mode": (f"fast: tcgen05 int8 x{args.digits}-digit candidate pass + fp64 re-score + proof, exact fallback") if fast else "exact",
+                   "l2": f"inputs_larger_than_l2 (slab {n_per * d * 4 / 1e9:.1f} GB per GPU vs 126 MB L2)",
+                   "sharding": ("rows: one global index, rank g holds rows [g*n_per, (g+1)*n_per) of every list; centroids replicated; "
+                                "per search one collective step: " +
+                                ("peer-window exchange fused with the merge (exchange_merge_kernel<P2P>: stores to cudaIpc-mapped peer "
+                                 "memory over NVLink, release/acquire flags, merge)" if info["p2p"] else
+                                 "ncclAllGather of the packed local top-k + merge kernel")),
+                   "collective": {"kind": "p2p-window" if info["p2p"] else "nccl-allgather", "bytes_per_rank_per_step": exchange_bytes,
+                                  "exchange_ms": stats["exchange_ms"], "merge_ms": stats["merge_ms"],
+                                  "allgather_ms": None if info["p2p"] else stats["exchange_ms"],
+                                  "slowest_rank_exchange_plus_merge_ms": comm_ms,
+                                  "note": "p2p-window: the exchange happens inside the merge kernel (merge_ms covers push + wait + merge, "
+                                          "exchange_ms is 0); wait time includes the skew between ranks"},
+                   "build": build, "gen_s": gen_s, "truth_s": truth_s, "e2e_results_equal_device_results": e2e_same},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": None,
+        "parity": oracle_parity, "fast_vs_exact": fast_vs_exact,
+    }
+    return line
 
 
 def main():
@@ -525,9 +772,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--shard", default="replicas", choices=["replicas", "lists"],
-                    help="N > 1: replicas (whole index per GPU, one batch per GPU, weak scaling) or lists (one batch, lists "
-                         "sharded l mod N, all-gather + merge, strong scaling)")
+    ap.add_argument("--shard", default="rows", choices=["rows", "replicas", "lists"],
+                    help="N > 1: rows (ONE global index of N x 12.5M rows, contiguous row blocks, data plane inside the library: "
+                         "hb_sharded_ivf_build / hb_sharded_search; weak scaling), replicas (whole configs[1] index per GPU, one "
+                         "batch per GPU, no collective) or lists (configs[1], lists sharded l mod N, host-orchestrated all-gather + merge)")
+    ap.add_argument("--shard-workload", default="c100m", choices=["c100m", "small"],
+                    help="--shard rows: c100m = 12.5M rows per GPU (100M x 768 at N = 8), small = 0.5M rows per GPU (smoke runs)")
+    ap.add_argument("--no-replicas", action="store_true", help="--shard rows: skip the secondary replicas measurement")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
                     help="fast: tensor-core candidate pass + fp64 re-score + proof (same results); exact: fp64 for every pair")
     ap.add_argument("--opt", action="append", default=[], help="library knob name=value (hb_set_option), repeatable")
@@ -539,8 +790,24 @@ def main():
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w, args.workload)
+        return
+    ctx = setup(args)
+    rank, world = ctx[0], ctx[1]
+    if world > 1 and args.shard == "rows":
+        line = run_sharded(args, SHARD if args.shard_workload == "c100m" else SHARD_SMALL, ctx)
+        if not args.no_replicas:
+            rep = run_ours(args, w, args.workload, ctx, replicas_only=True)
+            if rank == 0:
+                line["replicas"] = rep
     else:
-        run_ours(args, w, args.workload)
+        line = run_ours(args, w, args.workload, ctx)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

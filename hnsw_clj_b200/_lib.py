@@ -66,6 +66,17 @@ SIGNATURES = {
     "hb_gather_score": (_int, [_p, _p, _int, _i64, _p, _p, _i64, _p]),
     "hb_fast_scores": (_int, [_p, _p, _int, _i64, _p, _p, _p]),
     "hb_topk_merge": (_int, [_p, _p, _i32, _i64, _i32, _p, _p]),
+    "hb_comm_unique_id": (_int, [_p]),
+    "hb_comm_init": (_int, [_p, _i32, _i32]),
+    "hb_comm_info": (_int, [C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "hb_comm_shutdown": (_int, []),
+    "hb_comm_broadcast": (_int, [_p, _i64, _i32]),
+    "hb_comm_allreduce_f64": (_int, [_p, _i64, _i32]),
+    "hb_index_set_id_base": (_int, [_p, _i64]),
+    "hb_index_set_mode": (_int, [_p, _int]),
+    "hb_sharded_search": (_int, [_p, _p, _int, _i64, _i32, _i32, _p, _p]),
+    "hb_sharded_kmeans": (_int, [_p, _i64, _i32, _int, _int, _i32, _i32, _p, _i64, _p, _p]),
+    "hb_sharded_ivf_build": (_int, [_p, _i64, _i32, _int, _int, _i32, _i32, _p, _i64, _pp]),
     "hb_index_save": (_int, [_p, C.c_char_p]),
     "hb_index_load": (_int, [C.c_char_p, _pp]),
     "hb_index_info": (_int, [_p, C.POINTER(HbInfo)]),

@@ -2,7 +2,7 @@
 (src/hnsw/api/protocol.clj:9-28,58-67) for the device-resident index types."""
 from __future__ import annotations
 
-from . import flat, ivf_flat, ultra_fast
+from . import flat, hybrid_lsh, ivf_flat, lightning, ultra_fast
 from .index import DeviceIndex
 
 INDEX_TYPES = {0: "FLAT", 1: "IVF-FLAT", 2: "HNSW"}
@@ -15,6 +15,10 @@ def index(data, index_type="ivf-flat", metric="cosine", **opts) -> DeviceIndex:
         return flat.FlatIndex(data, distance_fn=metric)
     if t in ("ivf-flat", "ivf_flat", "ivf"):
         return ivf_flat.build_index(data, distance_fn=metric, **opts)
+    if t == "lightning":
+        return lightning.build_index(data, distance_fn=metric, **opts)
+    if t in ("hybrid-lsh", "lsh"):
+        return hybrid_lsh.build_index(data, distance_fn=metric, **opts)
     raise ValueError(f"unknown index type {index_type!r}")
 
 
@@ -26,6 +30,12 @@ def search(idx: DeviceIndex, query, k, mode="balanced", **opts):
 # ---- ANNIndex -----------------------------------------------------------------------------------------
 def search_knn_(idx: DeviceIndex, query, k, mode="balanced", **opts):
     """ANNIndex/search-knn* [this query k mode]."""
+    # Lightning first: it shares the IVF-FLAT device layout (subclass) but probes by its own percentage tables
+    # (src/hnsw/ann/partition/lightning.clj:193-262), not the IVF mode table
+    if isinstance(idx, lightning.LightningIndex):
+        return lightning.search_knn(idx, query, k, opts.get("search_percent"), mode=mode)
+    if isinstance(idx, hybrid_lsh.HybridIndex):
+        return hybrid_lsh.search_knn(idx, query, k, mode)
     if isinstance(idx, ivf_flat.IVFFlatIndex):
         return ivf_flat.search_knn(idx, query, k, mode, opts.get("num_probes"))
     if isinstance(idx, ultra_fast.HnswIndex):
@@ -34,6 +44,10 @@ def search_knn_(idx: DeviceIndex, query, k, mode="balanced", **opts):
 
 
 def index_info_(idx: DeviceIndex) -> dict:
+    if isinstance(idx, lightning.LightningIndex):
+        return lightning.index_info(idx)
+    if isinstance(idx, hybrid_lsh.HybridIndex):
+        return hybrid_lsh.index_info(idx)
     if isinstance(idx, ivf_flat.IVFFlatIndex):
         return ivf_flat.index_info(idx)
     i = idx.info()
@@ -41,6 +55,10 @@ def index_info_(idx: DeviceIndex) -> dict:
 
 
 def index_type_(idx: DeviceIndex) -> str:
+    if isinstance(idx, lightning.LightningIndex):
+        return "LIGHTNING"
+    if isinstance(idx, hybrid_lsh.HybridIndex):
+        return "HYBRID-LSH"
     return INDEX_TYPES[idx.info()["type"]]
 
 
@@ -48,6 +66,10 @@ def index_type_(idx: DeviceIndex) -> str:
 def search_batch_(idx: DeviceIndex, queries, k, mode="balanced", **opts):
     """BatchSearchIndex/search-batch* [this queries k mode] -> vector of result vectors.  The reference's
     default is (mapv #(search-knn* ...)) (protocol.clj:92-95); here it is ONE batched device call."""
+    if isinstance(idx, lightning.LightningIndex):
+        return lightning.search_batch(idx, queries, k, opts.get("search_percent"), mode=mode)
+    if isinstance(idx, hybrid_lsh.HybridIndex):
+        return hybrid_lsh.search_batch(idx, queries, k, mode)
     if isinstance(idx, ivf_flat.IVFFlatIndex):
         return ivf_flat.search_batch(idx, queries, k, mode, opts.get("num_probes"))
     if isinstance(idx, ultra_fast.HnswIndex):

@@ -6,17 +6,21 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <cuda_profiler_api.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <vector>
 
 #include "hb_build.cuh"
+#include "hb_comm.cuh"
 #include "hb_fast.cuh"
 #include "hb_hnsw.cuh"
 #include "hb_kernels.cuh"
+#include "hb_validate.cuh"
 
 namespace hb {
 
@@ -95,10 +99,11 @@ static void ensure_init(int device = -1) {
 struct Workspace {
     DevBuf in_a, in_b, in_c, in_d, out_a, out_b, out_c;
     DevBuf qnorm, scratch, sel_val, sel_pos, cand_val, cand_id, plan, probes, pair_out, qsel, lq_off, tile_prefix, tmp,
-        misc, misc2, misc3, misc4;
+        misc, misc2, misc3, misc4, vflag, sh_ids, sh_dist, sh_sums, sh_counts, sh_small;
     void release() {
         DevBuf *all[] = {&in_a, &in_b, &in_c, &in_d, &out_a, &out_b, &out_c, &qnorm, &scratch, &sel_val, &sel_pos, &cand_val,
-                         &cand_id, &plan, &probes, &pair_out, &qsel, &lq_off, &tile_prefix, &tmp, &misc, &misc2, &misc3, &misc4};
+                         &cand_id, &plan, &probes, &pair_out, &qsel, &lq_off, &tile_prefix, &tmp, &misc, &misc2, &misc3, &misc4, &vflag,
+                         &sh_ids, &sh_dist, &sh_sums, &sh_counts, &sh_small};
         for (DevBuf *b : all) b->release();
     }
 };
@@ -108,6 +113,9 @@ template <typename F>
 static int guarded(F &&f) {
     try {
         std::lock_guard<std::mutex> lk(g_mu);
+        // the CUDA current device is per host thread: a caller thread that did not run hb_init (JVM pool threads, the
+        // micro-batcher's leader of the moment) would otherwise allocate and launch on device 0
+        if (g_inited) HB_CUDA(cudaSetDevice(g_device));
         f();
         return HB_OK;
     } catch (const Error &e) {
@@ -121,8 +129,29 @@ static int guarded(F &&f) {
 
 static void sync_stream() { HB_CUDA(cudaStreamSynchronize(g_stream)); }
 
+// Range checks of caller-supplied index arrays (hb_validate.cu): the checks OR into one device flag, require() reads it.
+struct Validator {
+    int32_t *flag;
+    Validator() : flag(g_ws.vflag.as<int32_t>(1)) { HB_CUDA(cudaMemsetAsync(flag, 0, 4, g_stream)); }
+    void range_i32(const int32_t *p, int64_t n, int64_t lo, int64_t hi) { launch_check_range_i32(p, n, lo, hi, flag); }
+    void range_i64(const int64_t *p, int64_t n, int64_t lo, int64_t hi) { launch_check_range_i64(p, n, lo, hi, flag); }
+    void offsets(const int64_t *off, int64_t count, int64_t total) { launch_check_offsets(off, count, total, flag); }
+    void csr(const int64_t *off, const int32_t *ids, int64_t n) { launch_check_csr(off, ids, n, 0, flag); }
+    bool ok() {
+        int32_t h = 0;
+        HB_CUDA(cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, g_stream));
+        HB_CUDA(cudaStreamSynchronize(g_stream));
+        HB_CUDA(cudaMemsetAsync(flag, 0, 4, g_stream));
+        return h == 0;
+    }
+    void require(const char *msg) {
+        if (!ok()) throw Error(HB_ERR_INVALID, msg);
+    }
+};
+
 // ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ------
-enum ProfTag { PROF_SCAN = 0, PROF_COARSE = 1, PROF_SELECT = 2, PROF_PLAN = 3, PROF_ASSIGN = 4, PROF_TC = 5, PROF_PACK = 6, PROF_RESCORE = 7, PROF_TC_SAMPLE = 8, PROF_HNSW = 9, PROF_NTAGS = 10 };
+enum ProfTag { PROF_SCAN = 0, PROF_COARSE = 1, PROF_SELECT = 2, PROF_PLAN = 3, PROF_ASSIGN = 4, PROF_TC = 5, PROF_PACK = 6, PROF_RESCORE = 7, PROF_TC_SAMPLE = 8, PROF_HNSW = 9,
+               PROF_EXCHANGE = 10, PROF_MERGE = 11, PROF_ALLREDUCE = 12, PROF_UPDATE = 13, PROF_NTAGS = 14 };
 static bool g_profile = false;
 struct ProfSpan {
     cudaEvent_t a, b;
@@ -317,6 +346,9 @@ static int64_t g_fast_fallbacks = 0; // ... of which recomputed by the exact pat
 static int64_t g_hnsw_scored = 0;    // (query, row) pairs scored by the HNSW search since "profile" was set
 static int64_t g_hnsw_overflows = 0; // queries re-run with their candidate queue in global memory
 static int g_hnsw_cand_cap = 0;      // shared-memory candidate queue slots (0: 4 * ef, at least 256)
+static int g_micro_batch = 64;       // hb_set_option("micro_batch", n): queries per combined batch of concurrent small calls, 0 = off
+static int64_t g_mb_batches = 0, g_mb_requests = 0;
+static int g_comm_p2p = 1;           // hb_set_option("comm_p2p", 0): exchange the local top-k by ncclAllGather instead of peer windows (2: the peer-window kernel even with one rank)
 
 }  // namespace hb
 
@@ -325,6 +357,8 @@ using namespace hb;
 struct hb_index {
     int type = HB_INDEX_FLAT, dtype = HB_F32, metric = HB_COSINE, d = 0;
     int64_t n = 0;
+    int mode = -1;        // hb_index_set_mode: HB_MODE_EXACT / HB_MODE_FAST for searches of this index, -1 = the process default
+    int64_t id_base = 0;  // multi-GPU: global row of local row 0 (hb_sharded_search returns id_base + local row)
     // rows as given (flat / hnsw) or list-major slab (ivf)
     DevBuf rows, norms;
     // ivf
@@ -728,6 +762,47 @@ static void kmeans_exact(const void *rows, int dtype, int64_t n, int d, int metr
         if (it == iters) break;  // final assignment pass (:119-131)
         build_lists(assign, n, nlist, list_off, list_rows, g_ws.tmp);
         launch_update_centroids(rows, dtype, d, list_off, list_rows, nlist, cents, nullptr, nullptr);
+    }
+}
+
+// partition-vectors-kmeans with the rows sharded over the ranks (contiguous global row blocks, this rank holds
+// [first_row, first_row + n)): centroids replicated; per round every rank assigns its rows, sums its members per cluster in
+// row order, one all-reduce(sum) of [nlist x d] fp64 sums + [nlist] counts, divide (an empty cluster keeps its centroid).
+// Everything is enqueued on the library's stream: no host synchronisation inside a round.  The all-reduce regroups the
+// reference's row-order sum, so a centroid can differ from the single-GPU build in the last ulp.
+static void kmeans_sharded(const void *rows, int dtype, int64_t n, int d, int metric, int nlist, int iters,
+                           const int64_t *seed_rows_dev, int64_t first_row, double *cents, int32_t *assign) {
+    HB_REQUIRE(n >= 1 && nlist >= 1, "k-means needs at least one row per shard and one partition");
+    HB_REQUIRE(n < (1ll << 31), "rows per shard must be < 2^31");
+    HB_REQUIRE(metric == HB_COSINE || metric == HB_L2, "k-means distance-fn must be cosine or euclidean");
+    HB_REQUIRE(seed_rows_dev, "sharded k-means needs seed rows");
+    const bool l2 = metric == HB_L2;
+    double *norm = g_ws.misc.as<double>(n);
+    launch_row_norms(rows, dtype, n, d, norm);
+    // centroids start as data rows (ivf_flat.clj:40,58): the owner of a seed row contributes it, the others zeros
+    launch_init_centroids_sharded(rows, dtype, d, seed_rows_dev, nlist, first_row, n, cents);
+    comm_allreduce_sum_f64(cents, (int64_t)nlist * d);
+    double *cnorm = g_ws.misc3.as<double>((size_t)nlist + 2 + 2 * (size_t)n);
+    int64_t *list_off = g_ws.lq_off.as<int64_t>(nlist + 1);
+    int64_t *list_rows = g_ws.cand_id.as<int64_t>(n);
+    double *sums = g_ws.sh_sums.as<double>((size_t)nlist * d);
+    int64_t *counts = g_ws.sh_counts.as<int64_t>((size_t)nlist);
+    for (int it = 0; it <= iters; ++it) {
+        launch_row_norms(cents, HB_F64, nlist, d, cnorm);
+        {
+            Prof pr(PROF_ASSIGN);
+            assign_rows(rows, dtype, norm, n, d, cents, cnorm, nlist, l2, assign);
+        }
+        if (it == iters) break;
+        {
+            Prof pr(PROF_UPDATE);
+            build_lists(assign, n, nlist, list_off, list_rows, g_ws.tmp);
+            launch_update_centroids(rows, dtype, d, list_off, list_rows, nlist, nullptr, sums, counts);
+        }
+        Prof pr(PROF_ALLREDUCE);
+        comm_allreduce_sum_f64(sums, (int64_t)nlist * d);
+        comm_allreduce_sum_i64(counts, nlist);
+        launch_divide_centroids(sums, counts, nlist, d, cents);
     }
 }
 
@@ -1753,6 +1828,12 @@ HB_API int hb_set_option(const char *name, int64_t value) {
         } else if (!strcmp(name, "host_feed")) {
             HB_REQUIRE(value == 0 || (value >= 128 && value % 128 == 0), "host_feed must be 0 or a multiple of 128");
             g_host_feed_block = value;
+        } else if (!strcmp(name, "comm_p2p")) {
+            HB_REQUIRE(value >= 0 && value <= 2, "comm_p2p must be 0, 1 or 2");
+            g_comm_p2p = (int)value;
+        } else if (!strcmp(name, "micro_batch")) {
+            HB_REQUIRE(value >= 0 && value <= 4096, "micro_batch must be 0..4096");
+            g_micro_batch = (int)value;
         } else if (!strcmp(name, "hnsw_cand_cap")) {
             HB_REQUIRE(value >= 0 && value <= 8192, "hnsw_cand_cap must be 0..8192");
             g_hnsw_cand_cap = (int)value;
@@ -1764,8 +1845,10 @@ HB_API int hb_set_option(const char *name, int64_t value) {
 HB_API int hb_get_stat(const char *name, double *out) {
     return guarded([&] {
         HB_REQUIRE(name && out, "null argument");
-        static const char *ms_names[PROF_NTAGS] = {"scan_ms", "coarse_ms", "select_ms", "plan_ms", "assign_ms", "tc_ms", "pack_ms", "rescore_ms", "tc_sample_ms", "hnsw_ms"};
-        static const char *n_names[PROF_NTAGS] = {"scan_count", "coarse_count", "select_count", "plan_count", "assign_count", "tc_count", "pack_count", "rescore_count", "tc_sample_count", "hnsw_count"};
+        static const char *ms_names[PROF_NTAGS] = {"scan_ms", "coarse_ms", "select_ms", "plan_ms", "assign_ms", "tc_ms", "pack_ms", "rescore_ms", "tc_sample_ms", "hnsw_ms",
+                                                   "exchange_ms", "merge_ms", "allreduce_ms", "update_ms"};
+        static const char *n_names[PROF_NTAGS] = {"scan_count", "coarse_count", "select_count", "plan_count", "assign_count", "tc_count", "pack_count", "rescore_count", "tc_sample_count", "hnsw_count",
+                                                  "exchange_count", "merge_count", "allreduce_count", "update_count"};
         prof_collect();
         for (int i = 0; i < PROF_NTAGS; ++i) {
             if (!strcmp(name, ms_names[i])) { *out = g_prof_ms[i]; return; }
@@ -1782,6 +1865,8 @@ HB_API int hb_get_stat(const char *name, double *out) {
         if (!strcmp(name, "fast_probe_pairs")) { *out = (double)g_fast_probe_pairs; return; }
         if (!strcmp(name, "hnsw_scored")) { *out = (double)g_hnsw_scored; return; }
         if (!strcmp(name, "hnsw_overflows")) { *out = (double)g_hnsw_overflows; return; }
+        if (!strcmp(name, "micro_batches")) { *out = (double)g_mb_batches; return; }
+        if (!strcmp(name, "micro_batch_requests")) { *out = (double)g_mb_requests; return; }
         if (!strncmp(name, "mma_clocks_", 11)) {
             ensure_init();
             const char *k = name + 11;
@@ -1995,6 +2080,11 @@ HB_API int hb_ivf_import(const void *rows, int64_t n, int32_t d, int dtype, int 
             int32_t *assign = ix->assign.as<int32_t>(n);
             HB_CUDA(cudaMemcpyAsync(cents, centroids, (size_t)nlist * d * 8, cudaMemcpyDefault, g_stream));
             HB_CUDA(cudaMemcpyAsync(assign, assignments, (size_t)n * 4, cudaMemcpyDefault, g_stream));
+            {
+                Validator v;
+                v.range_i32(assign, n, 0, nlist);
+                v.require("hb_ivf_import: assignment out of range");
+            }
             double *norm = g_ws.misc.as<double>(n);
             launch_row_norms(r, dtype, n, d, norm);
             ivf_finalize(ix, r, norm);
@@ -2019,65 +2109,308 @@ HB_API int hb_ivf_export(const hb_index *index, double *out_centroids, int32_t *
     });
 }
 
+// The search behind hb_search / hb_sharded_search: stages the queries (host batches of an IVF FAST search optionally in
+// blocks on a copy stream), dispatches on the index type and the effective mode, results into device buffers [nq x k].
+static int effective_mode(const hb_index *index) { return index->mode >= 0 ? index->mode : g_mode; }
+static void check_search_args(const hb_index *index, const void *queries, int qdtype, int64_t nq, int32_t k, const void *out_ids,
+                              const void *out_dist) {
+    HB_REQUIRE(index, "null index");
+    HB_REQUIRE(qdtype == HB_F32 || qdtype == HB_F64, "queries must be fp32 or fp64");
+    HB_REQUIRE(nq >= 0 && k >= 0, "bad arguments");
+    if (nq == 0 || k == 0) return;
+    HB_REQUIRE(queries && out_ids && out_dist, "null buffer");
+    HB_REQUIRE(k <= 1024, "k > 1024 is not supported");
+}
+static void search_core(hb_index *index, const void *queries, int qdtype, int64_t nq, int32_t k, int32_t param, int64_t *ids_dev,
+                        double *dist_dev) {
+    const int mode = effective_mode(index);
+    HostFeed feed;
+    const void *q = nullptr;
+    const size_t qrow = (size_t)index->d * dtype_size(qdtype);
+    if (index->type == HB_INDEX_IVF_FLAT && mode == HB_MODE_FAST && !is_device_ptr(queries) && g_host_feed_block > 0 &&
+        nq >= 2 * g_host_feed_block) {
+        // blocks of 2048 queries on a copy stream, one event each (pinned host memory makes the copies asynchronous)
+        if (!g_copy_stream) HB_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        char *dq = (char *)g_ws.in_b.get((size_t)nq * qrow);
+        feed.block = g_host_feed_block;
+        for (int64_t b0 = 0; b0 < nq; b0 += feed.block) {
+            const int64_t nb = std::min<int64_t>(feed.block, nq - b0);
+            HB_CUDA(cudaMemcpyAsync(dq + (size_t)b0 * qrow, (const char *)queries + (size_t)b0 * qrow, (size_t)nb * qrow,
+                                    cudaMemcpyHostToDevice, g_copy_stream));
+            cudaEvent_t e;
+            HB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            HB_CUDA(cudaEventRecord(e, g_copy_stream));
+            feed.ready.push_back(e);
+        }
+        q = dq;
+    } else {
+        q = stage_in(queries, (size_t)nq * qrow, g_ws.in_b);
+    }
+    struct FeedGuard {
+        HostFeed &f;
+        ~FeedGuard() {
+            for (cudaEvent_t e : f.ready) cudaEventDestroy(e);
+        }
+    } feed_guard{feed};
+    const int saved_mode = g_mode;
+    struct ModeGuard {  // the orchestration below reads g_mode (assign_rows etc.): make the index's mode the current one
+        int saved;
+        ~ModeGuard() { g_mode = saved; }
+    } mode_guard{saved_mode};
+    g_mode = mode;
+    if (index->type == HB_INDEX_FLAT) {
+        if (mode == HB_MODE_FAST) flat_search_fast(index, q, qdtype, nq, k, ids_dev, dist_dev);
+        else
+            flat_search_exact(index->rows.p, index->dtype, (const double *)index->norms.p, index->n, index->d, index->metric, q,
+                              qdtype, nq, k, ids_dev, dist_dev);
+    } else if (index->type == HB_INDEX_IVF_FLAT) {
+        HB_REQUIRE(param >= 1, "num-probes must be >= 1");
+        if (mode == HB_MODE_FAST) ivf_search_fast(index, q, qdtype, nq, k, param, ids_dev, dist_dev, feed.block ? &feed : nullptr);
+        else ivf_search_exact(index, q, qdtype, nq, k, param, ids_dev, dist_dev, nullptr);
+    } else if (index->type == HB_INDEX_HNSW) {
+        HB_REQUIRE(param >= 0, "ef must be >= 0");
+        hnsw_search(index, q, qdtype, nq, k, param, ids_dev, dist_dev);
+    } else {
+        throw Error(HB_ERR_UNSUPPORTED, "search on this index type is not implemented");
+    }
+}
+
+static void search_call(hb_index *index, const void *queries, int qdtype, int64_t nq, int32_t k, int32_t param, int64_t *out_ids,
+                        double *out_dist) {
+    ensure_init();
+    check_search_args(index, queries, qdtype, nq, k, out_ids, out_dist);
+    if (nq == 0 || k == 0) return;
+    OutStage oi = stage_out(out_ids, (size_t)nq * k * 8, g_ws.out_a);
+    OutStage od = stage_out(out_dist, (size_t)nq * k * 8, g_ws.out_b);
+    search_core(index, queries, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev);
+    finish_out(oi);
+    finish_out(od);
+    sync_stream();
+}
+
+// ---- micro-batching of concurrent small calls (src/hnsw/helper/parallel_search.clj:15-49) ---------------------------------
+// The reference fans single-query searches out over a thread pool (up to 50 threads on one index,
+// src/hnsw/wip/31k-multithread-sb.clj:127-134).  On the device one query costs as much as eight, so concurrent small
+// calls on HOST buffers are combined: while a search is in flight the callers that arrive queue up; the next leader takes
+// every queued request that matches its index / k / param / dtype and answers them with ONE batched search (group commit,
+// no timer: an idle library answers a lone caller at once).  Every path returns the same bits whatever the batch is.
+struct PendingSearch {
+    hb_index *index;
+    const void *queries;
+    int qdtype;
+    int64_t nq;
+    int32_t k, param;
+    int64_t *out_ids;
+    double *out_dist;
+    int status = HB_OK;
+    std::string err;
+    bool done = false;
+};
+static std::mutex q_mu;
+static std::condition_variable q_cv;
+static std::vector<PendingSearch *> q_pending;
+static bool q_leader = false;
+static std::vector<char> g_mb_q;  // host staging of a combined batch
+static std::vector<int64_t> g_mb_ids;
+static std::vector<double> g_mb_dist;
+
+static void run_batch(std::vector<PendingSearch *> &batch) {
+    PendingSearch &f = *batch[0];
+    int status = HB_OK;
+    std::string err;
+    if (batch.size() == 1) {
+        status = guarded([&] { search_call(f.index, f.queries, f.qdtype, f.nq, f.k, f.param, f.out_ids, f.out_dist); });
+        if (status != HB_OK) err = t_err;
+    } else {
+        status = guarded([&] {
+            ensure_init();
+            const size_t qrow = (size_t)f.index->d * dtype_size(f.qdtype);
+            int64_t total = 0;
+            for (PendingSearch *r : batch) total += r->nq;
+            g_mb_q.resize((size_t)total * qrow);
+            g_mb_ids.resize((size_t)total * f.k);
+            g_mb_dist.resize((size_t)total * f.k);
+            int64_t o = 0;
+            for (PendingSearch *r : batch) {
+                memcpy(g_mb_q.data() + (size_t)o * qrow, r->queries, (size_t)r->nq * qrow);
+                o += r->nq;
+            }
+            search_call(f.index, g_mb_q.data(), f.qdtype, total, f.k, f.param, g_mb_ids.data(), g_mb_dist.data());
+            o = 0;
+            for (PendingSearch *r : batch) {
+                memcpy(r->out_ids, g_mb_ids.data() + (size_t)o * f.k, (size_t)r->nq * f.k * 8);
+                memcpy(r->out_dist, g_mb_dist.data() + (size_t)o * f.k, (size_t)r->nq * f.k * 8);
+                o += r->nq;
+            }
+            g_mb_batches += 1;
+            g_mb_requests += (int64_t)batch.size();
+        });
+        if (status != HB_OK) err = t_err;
+    }
+    for (PendingSearch *r : batch) {
+        r->status = status;
+        r->err = err;
+    }
+}
+
+static int search_combined(PendingSearch &me) {
+    std::unique_lock<std::mutex> lk(q_mu);
+    q_pending.push_back(&me);
+    while (!me.done) {
+        if (q_leader) {
+            q_cv.wait(lk);
+            continue;
+        }
+        q_leader = true;
+        // everything queued that can share a launch with the oldest request
+        std::vector<PendingSearch *> batch, rest;
+        PendingSearch &f = *q_pending.front();
+        int64_t total = 0;
+        for (PendingSearch *r : q_pending) {
+            const bool same = r->index == f.index && r->k == f.k && r->param == f.param && r->qdtype == f.qdtype;
+            if (same && (batch.empty() || total + r->nq <= g_micro_batch)) {
+                batch.push_back(r);
+                total += r->nq;
+            } else {
+                rest.push_back(r);
+            }
+        }
+        q_pending.swap(rest);
+        lk.unlock();
+        run_batch(batch);
+        lk.lock();
+        for (PendingSearch *r : batch) r->done = true;
+        q_leader = false;
+        q_cv.notify_all();
+    }
+    if (me.status != HB_OK) t_err = me.err;
+    return me.status;
+}
+
 HB_API int hb_search(hb_index *index, const void *queries, int qdtype, int64_t nq, int32_t k, int32_t param,
                      int64_t *out_ids, double *out_dist) {
+    // small calls on host buffers go through the combiner; everything else straight to the device
+    if (g_micro_batch > 0 && index && queries && out_ids && out_dist && nq >= 1 && nq <= kSmallScanQ && k >= 1 && k <= 1024 &&
+        (qdtype == HB_F32 || qdtype == HB_F64)) {
+        bool host = false;
+        const int st = guarded([&] {
+            ensure_init();
+            host = !is_device_ptr(queries) && !is_device_ptr(out_ids) && !is_device_ptr(out_dist);
+        });
+        if (st != HB_OK) return st;
+        if (host) {
+            PendingSearch me{index, queries, qdtype, nq, k, param, out_ids, out_dist};
+            return search_combined(me);
+        }
+    }
+    return guarded([&] { search_call(index, queries, qdtype, nq, k, param, out_ids, out_dist); });
+}
+
+// ---- multi-GPU: one process per GPU (hb_comm.cu) -------------------------------------------------------------------------
+
+HB_API int hb_comm_unique_id(void *out_id) {
+    return guarded([&] {
+        HB_REQUIRE(out_id, "null buffer");
+        comm_unique_id(out_id);
+    });
+}
+HB_API int hb_comm_init(const void *id, int32_t nranks, int32_t rank) {
     return guarded([&] {
         ensure_init();
-        HB_REQUIRE(index, "null index");
-        HB_REQUIRE(qdtype == HB_F32 || qdtype == HB_F64, "queries must be fp32 or fp64");
-        HB_REQUIRE(nq >= 0 && k >= 0, "bad arguments");
-        if (nq == 0 || k == 0) return;
-        HB_REQUIRE(queries && out_ids && out_dist, "null buffer");
-        HB_REQUIRE(k <= 1024, "k > 1024 is not supported");
-        HostFeed feed;
-        const void *q = nullptr;
-        const size_t qrow = (size_t)index->d * dtype_size(qdtype);
-        if (index->type == HB_INDEX_IVF_FLAT && g_mode == HB_MODE_FAST && !is_device_ptr(queries) && g_host_feed_block > 0 &&
-            nq >= 2 * g_host_feed_block) {
-            // blocks of 2048 queries on a copy stream, one event each (pinned host memory makes the copies asynchronous)
-            if (!g_copy_stream) HB_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
-            char *dq = (char *)g_ws.in_b.get((size_t)nq * qrow);
-            feed.block = g_host_feed_block;
-            for (int64_t b0 = 0; b0 < nq; b0 += feed.block) {
-                const int64_t nb = std::min<int64_t>(feed.block, nq - b0);
-                HB_CUDA(cudaMemcpyAsync(dq + (size_t)b0 * qrow, (const char *)queries + (size_t)b0 * qrow, (size_t)nb * qrow,
-                                        cudaMemcpyHostToDevice, g_copy_stream));
-                cudaEvent_t e;
-                HB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                HB_CUDA(cudaEventRecord(e, g_copy_stream));
-                feed.ready.push_back(e);
-            }
-            q = dq;
+        HB_REQUIRE(id, "null id");
+        comm_init(id, nranks, rank, g_device);
+    });
+}
+HB_API int hb_comm_info(int32_t *out_nranks, int32_t *out_rank, int32_t *out_p2p) {
+    return guarded([&] {
+        const CommInfo &c = comm_info();
+        if (out_nranks) *out_nranks = c.inited ? c.nranks : 0;
+        if (out_rank) *out_rank = c.inited ? c.rank : 0;
+        if (out_p2p) *out_p2p = c.p2p ? 1 : 0;
+    });
+}
+HB_API int hb_comm_shutdown(void) {
+    return guarded([&] { comm_shutdown(); });
+}
+HB_API int hb_comm_broadcast(void *buf, int64_t bytes, int32_t root) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(bytes >= 0 && (bytes == 0 || buf), "bad arguments");
+        if (bytes == 0) return;
+        if (is_device_ptr(buf)) {
+            comm_broadcast_bytes(buf, bytes, root);
         } else {
-            q = stage_in(queries, (size_t)nq * qrow, g_ws.in_b);
+            void *d = g_ws.in_a.get((size_t)bytes);
+            if (comm_info().rank == root) HB_CUDA(cudaMemcpyAsync(d, buf, (size_t)bytes, cudaMemcpyHostToDevice, g_stream));
+            comm_broadcast_bytes(d, bytes, root);
+            HB_CUDA(cudaMemcpyAsync(buf, d, (size_t)bytes, cudaMemcpyDeviceToHost, g_stream));
         }
-        struct FeedGuard {
-            HostFeed &f;
-            ~FeedGuard() {
-                for (cudaEvent_t e : f.ready) cudaEventDestroy(e);
-            }
-        } feed_guard{feed};
+        sync_stream();
+    });
+}
+HB_API int hb_comm_allreduce_f64(double *buf, int64_t count, int32_t op) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(count >= 0 && (count == 0 || buf) && (op == 0 || op == 1), "bad arguments (op: 0 = sum, 1 = max)");
+        if (count == 0) return;
+        const bool dev = is_device_ptr(buf);
+        double *d = dev ? buf : g_ws.in_a.as<double>((size_t)count);
+        if (!dev) HB_CUDA(cudaMemcpyAsync(d, buf, (size_t)count * 8, cudaMemcpyHostToDevice, g_stream));
+        if (op == 0) comm_allreduce_sum_f64(d, count);
+        else comm_allreduce_max_f64(d, count);
+        if (!dev) HB_CUDA(cudaMemcpyAsync(buf, d, (size_t)count * 8, cudaMemcpyDeviceToHost, g_stream));
+        sync_stream();
+    });
+}
+
+HB_API int hb_index_set_id_base(hb_index *index, int64_t first_global_row) {
+    return guarded([&] {
+        HB_REQUIRE(index && first_global_row >= 0, "bad arguments");
+        index->id_base = first_global_row;
+    });
+}
+HB_API int hb_index_set_mode(hb_index *index, int mode) {
+    return guarded([&] {
+        HB_REQUIRE(index && (mode == -1 || mode == HB_MODE_EXACT || mode == HB_MODE_FAST), "bad arguments");
+        index->mode = mode;
+    });
+}
+
+// Global top-k over the row shards of all ranks: local search (any index type) -> exchange of the local top-k ->
+// merge, all on the library's stream.  partitioned_hnsw.clj:149-196 (search every partition, concat, sort-by :distance, take k).
+HB_API int hb_sharded_search(hb_index *index, const void *queries, int qdtype, int64_t nq, int32_t k, int32_t param,
+                             int64_t *out_ids, double *out_dist) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(comm_info().inited, "hb_sharded_search before hb_comm_init");
+        check_search_args(index, queries, qdtype, nq, k, out_ids, out_dist);
+        if (nq == 0 || k == 0) return;
         OutStage oi = stage_out(out_ids, (size_t)nq * k * 8, g_ws.out_a);
         OutStage od = stage_out(out_dist, (size_t)nq * k * 8, g_ws.out_b);
-        if (index->type == HB_INDEX_FLAT) {
-            if (g_mode == HB_MODE_FAST) flat_search_fast(index, q, qdtype, nq, k, (int64_t *)oi.dev, (double *)od.dev);
-            else
-                flat_search_exact(index->rows.p, index->dtype, (const double *)index->norms.p, index->n, index->d, index->metric, q,
-                                  qdtype, nq, k, (int64_t *)oi.dev, (double *)od.dev);
-        } else if (index->type == HB_INDEX_IVF_FLAT) {
-            HB_REQUIRE(param >= 1, "num-probes must be >= 1");
-            if (g_mode == HB_MODE_FAST)
-                ivf_search_fast(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev, feed.block ? &feed : nullptr);
-            else ivf_search_exact(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev, nullptr);
-        } else if (index->type == HB_INDEX_HNSW) {
-            HB_REQUIRE(param >= 0, "ef must be >= 0");
-            hnsw_search(index, q, qdtype, nq, k, param, (int64_t *)oi.dev, (double *)od.dev);
-        } else {
-            throw Error(HB_ERR_UNSUPPORTED, "search on this index type is not implemented");
+        int64_t *lid = g_ws.sh_ids.as<int64_t>((size_t)nq * k);
+        double *ldist = g_ws.sh_dist.as<double>((size_t)nq * k);
+        search_core(index, queries, qdtype, nq, k, param, lid, ldist);
+        ExchangeStats st;
+        if (g_profile) {
+            cudaEventCreate(&st.e0);
+            cudaEventCreate(&st.e1);
+            cudaEventCreate(&st.e2);
         }
+        comm_topk_exchange_merge(ldist, lid, index->id_base, nq, k, (double *)od.dev, (int64_t *)oi.dev, g_comm_p2p, &st);
         finish_out(oi);
         finish_out(od);
         sync_stream();
+        if (g_profile) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, st.e0, st.e1);
+            cudaEventElapsedTime(&b, st.e1, st.e2);
+            g_prof_ms[PROF_EXCHANGE] += a, g_prof_n[PROF_EXCHANGE] += 1;
+            g_prof_ms[PROF_MERGE] += b, g_prof_n[PROF_MERGE] += 1;
+            cudaEventDestroy(st.e0);
+            cudaEventDestroy(st.e1);
+            cudaEventDestroy(st.e2);
+        }
+        comm_check_exchange();
     });
 }
 
@@ -2145,6 +2478,11 @@ HB_API int hb_kmeans_update(const void *rows, int64_t n, int32_t d, int dtype, c
         HB_REQUIRE(assign && (centroids || out_sums), "null buffer");
         const void *r = stage_in(rows, (size_t)n * d * dtype_size(dtype), g_ws.in_a);
         const int32_t *a = (const int32_t *)stage_in(assign, (size_t)n * 4, g_ws.in_c);
+        {
+            Validator v;
+            v.range_i32(a, n, 0, nlist);
+            v.require("hb_kmeans_update: assignment out of range");
+        }
         int64_t *list_off = g_ws.lq_off.as<int64_t>(nlist + 1);
         int64_t *list_rows = g_ws.cand_id.as<int64_t>(n);
         build_lists(a, n, nlist, list_off, list_rows, g_ws.tmp);
@@ -2177,12 +2515,89 @@ HB_API int hb_kmeans(const void *rows, int64_t n, int32_t d, int dtype, int metr
         HB_REQUIRE(out_centroids && out_assign, "null buffer");
         const void *r = stage_in(rows, (size_t)n * d * dtype_size(dtype), g_ws.in_a);
         const int64_t *sr = seed_rows ? (const int64_t *)stage_in(seed_rows, (size_t)nlist * 8, g_ws.in_c) : nullptr;
+        if (sr) {
+            Validator v;
+            v.range_i64(sr, nlist, 0, n);
+            v.require("hb_kmeans: seed row out of range");
+        }
         OutStage oc = stage_out(out_centroids, (size_t)nlist * d * 8, g_ws.out_a);
         OutStage oa = stage_out(out_assign, (size_t)n * 4, g_ws.out_b);
         kmeans_exact(r, dtype, n, d, metric, nlist, iters, seed, sr, (double *)oc.dev, (int32_t *)oa.dev, nullptr);
         finish_out(oc);
         finish_out(oa);
         sync_stream();
+    });
+}
+
+// global seed rows on the device, checked against the global row count
+static const int64_t *stage_global_seeds(const int64_t *seed_rows, int nlist, int64_t n_total) {
+    HB_REQUIRE(seed_rows, "sharded k-means: seed_rows (global row ids) are required");
+    const int64_t *sr = (const int64_t *)stage_in(seed_rows, (size_t)nlist * 8, g_ws.in_c);
+    Validator v;
+    v.range_i64(sr, nlist, 0, n_total);
+    v.require("sharded k-means: seed row out of range");
+    return sr;
+}
+static int64_t global_row_count(int64_t n_local, int64_t first_row) {
+    // every rank passes its block [first_row, first_row + n_local): the total is the largest end
+    double *x = g_ws.sh_small.as<double>(8);
+    const double end = (double)(first_row + n_local);
+    HB_CUDA(cudaMemcpyAsync(x, &end, 8, cudaMemcpyHostToDevice, g_stream));
+    comm_allreduce_max_f64(x, 1);
+    double tot = 0;
+    HB_CUDA(cudaMemcpyAsync(&tot, x, 8, cudaMemcpyDeviceToHost, g_stream));
+    sync_stream();
+    return (int64_t)tot;
+}
+
+HB_API int hb_sharded_kmeans(const void *rows, int64_t n_local, int32_t d, int dtype, int metric, int32_t nlist, int32_t iters,
+                             const int64_t *seed_rows, int64_t first_global_row, double *out_centroids, int32_t *out_assign) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(comm_info().inited, "hb_sharded_kmeans before hb_comm_init");
+        ivf_common_checks(rows, n_local, d, dtype, metric, nlist);
+        HB_REQUIRE(iters >= 0 && first_global_row >= 0, "bad arguments");
+        HB_REQUIRE(out_centroids && out_assign, "null buffer");
+        const void *r = stage_in(rows, (size_t)n_local * d * dtype_size(dtype), g_ws.in_a);
+        const int64_t *sr = stage_global_seeds(seed_rows, nlist, global_row_count(n_local, first_global_row));
+        OutStage oc = stage_out(out_centroids, (size_t)nlist * d * 8, g_ws.out_a);
+        OutStage oa = stage_out(out_assign, (size_t)n_local * 4, g_ws.out_b);
+        kmeans_sharded(r, dtype, n_local, d, metric, nlist, iters, sr, first_global_row, (double *)oc.dev, (int32_t *)oa.dev);
+        finish_out(oc);
+        finish_out(oa);
+        sync_stream();
+    });
+}
+
+HB_API int hb_sharded_ivf_build(const void *rows, int64_t n_local, int32_t d, int dtype, int metric, int32_t nlist, int32_t iters,
+                                const int64_t *seed_rows, int64_t first_global_row, hb_index **out) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(comm_info().inited, "hb_sharded_ivf_build before hb_comm_init");
+        HB_REQUIRE(out, "null out");
+        ivf_common_checks(rows, n_local, d, dtype, metric, nlist);
+        HB_REQUIRE(iters >= 0 && first_global_row >= 0, "bad arguments");
+        hb_index *ix = new hb_index();
+        try {
+            ix->type = HB_INDEX_IVF_FLAT;
+            ix->dtype = dtype;
+            ix->metric = metric;
+            ix->d = d;
+            ix->n = n_local;
+            ix->nlist = nlist;
+            ix->id_base = first_global_row;
+            const void *r = stage_in(rows, (size_t)n_local * d * dtype_size(dtype), g_ws.in_a);
+            const int64_t *sr = stage_global_seeds(seed_rows, nlist, global_row_count(n_local, first_global_row));
+            double *cents = ix->cents.as<double>((size_t)nlist * d);
+            int32_t *assign = ix->assign.as<int32_t>(n_local);
+            kmeans_sharded(r, dtype, n_local, d, metric, nlist, iters, sr, first_global_row, cents, assign);
+            ivf_finalize(ix, r, (const double *)g_ws.misc.p);
+        } catch (...) {
+            ix->release();
+            delete ix;
+            throw;
+        }
+        *out = ix;
     });
 }
 
@@ -2213,6 +2628,9 @@ HB_API int hb_hnsw_create(const void *rows, int64_t n, int32_t d, int dtype, int
             if (n) {
                 int32_t *lv = ix->levels.as<int32_t>(n);
                 HB_CUDA(cudaMemcpyAsync(lv, levels, (size_t)n * 4, cudaMemcpyDefault, g_stream));
+                Validator val;
+                val.range_i32(lv, n, 0, (int64_t)max_level + 1);
+                val.require("hb_hnsw_create: node level out of range");
                 ix->adj_off.resize((size_t)max_level + 1);
                 ix->adj_ids.resize((size_t)max_level + 1);
                 for (int l = 0; l <= max_level; ++l) {
@@ -2226,8 +2644,13 @@ HB_API int hb_hnsw_create(const void *rows, int64_t n, int32_t d, int dtype, int
                     } else {
                         tot = level_offsets[l][n];
                     }
+                    HB_REQUIRE(tot >= 0 && tot <= n * (int64_t)4096, "hb_hnsw_create: bad adjacency size");
+                    val.offsets(o, n + 1, tot);
+                    val.require("hb_hnsw_create: adjacency offsets must start at 0 and not decrease");
                     int32_t *a = ix->adj_ids[l].as<int32_t>(std::max<int64_t>(tot, 1));
                     if (tot) HB_CUDA(cudaMemcpyAsync(a, level_ids[l], (size_t)tot * 4, cudaMemcpyDefault, g_stream));
+                    val.csr(o, a, n);
+                    val.require("hb_hnsw_create: neighbour id out of range");
                 }
                 std::vector<const void *> po((size_t)max_level + 1), pi((size_t)max_level + 1);
                 for (int l = 0; l <= max_level; ++l) po[l] = ix->adj_off[l].p, pi[l] = ix->adj_ids[l].p;
@@ -2262,6 +2685,12 @@ HB_API int hb_gather_score(hb_index *index, const void *queries, int qdtype, int
         const int32_t *pq = (const int32_t *)stage_in(pair_query, (size_t)npairs * 4, g_ws.in_c);
         const int32_t *pr = (const int32_t *)stage_in(pair_row, (size_t)npairs * 4, g_ws.in_d);
         OutStage o = stage_out(out_scores, (size_t)npairs * 8, g_ws.out_a);
+        {  // an unknown id is an exception in the reference (ultra_fast.clj:189-192), never an out-of-bounds read here
+            Validator v;
+            v.range_i32(pq, npairs, 0, nq);
+            v.range_i32(pr, npairs, 0, index->n);
+            v.require("hb_gather_score: pair_query / pair_row out of range");
+        }
         bool l2;
         int epi;
         metric_to_epi(index->metric, true, l2, epi);
@@ -2415,6 +2844,14 @@ struct File {
     File(const char *path, const char *mode) : f(fopen(path, mode)) {
         if (!f) throw Error(HB_ERR_INVALID, std::string("cannot open ") + path + ": " + strerror(errno));
     }
+    // flush + fsync + close with every result checked: only then may the temporary file replace the target
+    void commit() {
+        FILE *g = f;
+        f = nullptr;
+        const bool ok = fflush(g) == 0 && fsync(fileno(g)) == 0;
+        const bool closed = fclose(g) == 0;
+        if (!ok || !closed) throw Error(HB_ERR_INVALID, std::string("write failed: ") + strerror(errno));
+    }
     ~File() {
         if (f) fclose(f);
     }
@@ -2481,10 +2918,18 @@ HB_API int hb_index_save(const hb_index *index, const char *path) {
             File f(tmp.c_str(), "wb");
             PinnedChunk pin;
             if (fwrite(&h, sizeof(h), 1, f.f) != 1) throw Error(HB_ERR_INVALID, "write failed");
-            for (const Sec &s : secs) write_section(f.f, s.tag, s.p, s.bytes, pin);
-            if (fflush(f.f) != 0) throw Error(HB_ERR_INVALID, "write failed");
+            try {
+                for (const Sec &s : secs) write_section(f.f, s.tag, s.p, s.bytes, pin);
+                f.commit();
+            } catch (...) {
+                remove(tmp.c_str());
+                throw;
+            }
         }
-        if (rename(tmp.c_str(), path) != 0) throw Error(HB_ERR_INVALID, std::string("cannot rename to ") + path);
+        if (rename(tmp.c_str(), path) != 0) {
+            remove(tmp.c_str());
+            throw Error(HB_ERR_INVALID, std::string("cannot rename to ") + path);
+        }
     });
 }
 
@@ -2500,6 +2945,8 @@ HB_API int hb_index_load(const char *path, hb_index **out) {
                        h.max_level < 64 && h.nsections >= 0 && h.nsections < 1024,
                    "corrupt index file header");
         check_dtype(h.dtype);
+        HB_REQUIRE(h.metric == HB_COSINE || h.metric == HB_L2 || h.metric == HB_IP, "corrupt index file header (metric)");
+        HB_REQUIRE(h.n < (1ll << 40) && h.d <= (1 << 20), "corrupt index file header (size)");
         hb_index *ix = new hb_index();
         try {
             ix->type = h.type, ix->dtype = h.dtype, ix->metric = h.metric, ix->d = h.d;
@@ -2512,6 +2959,7 @@ HB_API int hb_index_load(const char *path, hb_index **out) {
             PinnedChunk pin;
             uint64_t seen = 0;  // bit per fixed tag
             std::vector<char> seen_off((size_t)h.max_level + 1, 0), seen_ids((size_t)h.max_level + 1, 0);
+            std::vector<int64_t> adj_count((size_t)h.max_level + 1, 0);
             for (int s = 0; s < h.nsections; ++s) {
                 SectionHeader sh{};
                 if (fread(&sh, sizeof(sh), 1, f.f) != 1) throw Error(HB_ERR_INVALID, "index file is truncated");
@@ -2530,7 +2978,11 @@ HB_API int hb_index_load(const char *path, hb_index **out) {
                         const uint32_t l = sh.tag & 0xff;
                         HB_REQUIRE(ix->type == HB_INDEX_HNSW && n > 0 && l <= (uint32_t)h.max_level, "unknown section in index file");
                         if ((sh.tag & ~0xffu) == SEC_ADJ_OFF) dst = &ix->adj_off[l], want = ((size_t)n + 1) * 8, seen_off[l] = 1;
-                        else if ((sh.tag & ~0xffu) == SEC_ADJ_IDS) dst = &ix->adj_ids[l], want = sh.bytes, seen_ids[l] = 1;
+                        else if ((sh.tag & ~0xffu) == SEC_ADJ_IDS) {
+                            HB_REQUIRE(sh.bytes % 4 == 0 && sh.bytes <= (uint64_t)n * 4096 * 4, "corrupt adjacency section");
+                            dst = &ix->adj_ids[l], want = sh.bytes, seen_ids[l] = 1;
+                            adj_count[l] = (int64_t)(sh.bytes / 4);
+                        }
                         else throw Error(HB_ERR_INVALID, "unknown section in index file");
                     }
                 }
@@ -2544,15 +2996,34 @@ HB_API int hb_index_load(const char *path, hb_index **out) {
             if (ix->type == HB_INDEX_IVF_FLAT) {
                 HB_REQUIRE(n >= 1 && h.nlist >= 1, "corrupt index file header");
                 need(SEC_CENTS), need(SEC_CENT_NORM), need(SEC_LIST_OFF), need(SEC_LIST_ROWS), need(SEC_ASSIGN);
+                // the contents drive device addressing (slab offsets, row ids, scratch and grid sizes): check them, and take
+                // max_list from the offsets rather than from the header
+                Validator val;
+                val.offsets((const int64_t *)ix->list_off.p, (int64_t)h.nlist + 1, n);
+                val.range_i64((const int64_t *)ix->list_rows.p, n, 0, n);
+                val.range_i32((const int32_t *)ix->assign.p, n, 0, h.nlist);
+                val.require("corrupt index file (list offsets / row ids / assignments out of range)");
+                std::vector<int64_t> off((size_t)h.nlist + 1);
+                HB_CUDA(cudaMemcpyAsync(off.data(), ix->list_off.p, off.size() * 8, cudaMemcpyDeviceToHost, g_stream));
+                sync_stream();
+                ix->max_list = 0;
+                for (int l = 0; l < h.nlist; ++l) ix->max_list = std::max(ix->max_list, off[(size_t)l + 1] - off[(size_t)l]);
             }
             if (ix->type == HB_INDEX_HNSW && n > 0) {
                 need(SEC_LEVELS);
                 HB_REQUIRE(h.entry >= 0 && h.entry < n, "corrupt index file header");
                 std::vector<const void *> po((size_t)h.max_level + 1), pi((size_t)h.max_level + 1);
+                Validator val;
+                val.range_i32((const int32_t *)ix->levels.p, n, 0, (int64_t)h.max_level + 1);
                 for (int l = 0; l <= h.max_level; ++l) {
                     HB_REQUIRE(seen_off[l] && seen_ids[l], "index file lacks an adjacency level");
                     po[l] = ix->adj_off[l].p, pi[l] = ix->adj_ids[l].p;
+                    // offsets must be a CSR over exactly the ids stored for the level, the ids must be nodes
+                    val.offsets((const int64_t *)ix->adj_off[l].p, n + 1, adj_count[l]);
+                    val.require("corrupt index file (adjacency offsets / levels)");
+                    val.csr((const int64_t *)ix->adj_off[l].p, (const int32_t *)ix->adj_ids[l].p, n);
                 }
+                val.require("corrupt index file (neighbour id out of range)");
                 HB_CUDA(cudaMemcpyAsync(ix->adj_off_ptrs.as<const void *>(po.size()), po.data(), po.size() * sizeof(void *),
                                         cudaMemcpyHostToDevice, g_stream));
                 HB_CUDA(cudaMemcpyAsync(ix->adj_ids_ptrs.as<const void *>(pi.size()), pi.data(), pi.size() * sizeof(void *),

@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _lib as hb
 from .flat import FlatIndex
-from .index import results_to_maps, split_data
+from .index import metric_code, results_to_maps, split_data
 from .simd_optimized import _pairwise
 
 NUM_HASH_TABLES = 8   # :12
@@ -88,7 +88,10 @@ def build_index(data, distance_fn="cosine", show_progress=False, num_threads=8) 
     ids, rows = split_data(data)
     if rows.shape[0] == 0:
         raise hb.HbInvalid(hb.ERR_INVALID, "cannot build an LSH index from no vectors")
-    flat = FlatIndex(rows, distance_fn)
+    # search-bucket-brute-force always scores 1 - dot / (qnorm * vnorm) whatever :distance-fn is (query-norm is always
+    # truthy, hybrid_lsh.clj:159-167,199): the backing flat index is cosine, distance_fn stays as metadata only
+    metric_code(distance_fn)  # still rejects an unknown :distance-fn like the reference's dispatch
+    flat = FlatIndex(rows, "cosine")
     matrices = projection_matrices(rows.shape[1])
     return HybridIndex(flat, ids, matrices, bucket_ids(rows, matrices), distance_fn)
 

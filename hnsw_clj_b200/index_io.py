@@ -32,6 +32,11 @@ def save_index(index: DeviceIndex, filepath: str) -> DeviceIndex:
         os.replace(side + ".tmp", side)
     elif os.path.exists(side):
         os.remove(side)
+    # the index flavour is a property of the host mirror (a Lightning index is an IVF-FLAT layout probed by other tables)
+    meta = filepath + ".meta.json"
+    with open(meta + ".tmp", "w") as f:
+        json.dump({"class": type(index).__name__, "distance_fn": getattr(index, "distance_fn", None)}, f)
+    os.replace(meta + ".tmp", meta)
     return index
 
 
@@ -52,12 +57,22 @@ def load_index(filepath: str, distance_fn=None):
     info = base.info()
     metric = _METRIC_NAMES[info["metric"]]
     cls = {hb.INDEX_FLAT: FlatIndex, hb.INDEX_IVF_FLAT: IVFFlatIndex, hb.INDEX_HNSW: HnswIndex}[info["type"]]
+    meta = filepath + ".meta.json"
+    if os.path.exists(meta):
+        with open(meta) as f:
+            m = json.load(f)
+        if cls is IVFFlatIndex and m.get("class") == "LightningIndex":
+            from .lightning import LightningIndex
+
+            cls = LightningIndex
+        if m.get("distance_fn"):
+            metric = m["distance_fn"]
     ix = cls.__new__(cls)
     DeviceIndex.__init__(ix, h.value, ids)
     base._h = None  # ownership moved to ix
     if cls is FlatIndex:
         ix.metric = info["metric"]
-    elif cls is IVFFlatIndex:
+    elif issubclass(cls, IVFFlatIndex):
         ix.num_partitions = info["nlist"]
         ix.distance_fn = metric
     return ix

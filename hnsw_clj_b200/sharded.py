@@ -1,20 +1,150 @@
-"""Row-sharded multi-GPU search: one process per GPU (torch.distributed), each rank holds the rows of the
-IVF lists it owns (list l lives on rank l mod G) next to the replicated centroids, produces a local top-k,
-and a small all-gather plus the merge kernel (hb_topk_merge) gives the global top-k on every rank.
+"""Row-sharded multi-GPU search: one process per GPU, every rank holds a contiguous block of the global rows.
 
-This is the reference's own scale-out model — independent sub-indexes searched in parallel and merged by
-(sort-by :distance) + (take k) (src/hnsw/ann/partition/partitioned_hnsw.clj:149-196) — applied to the lists
-of ONE global IVF-FLAT index, so results are identical to the single-GPU results.
-torch.distributed is plumbing only: the collective carries G*nq*k (distance, id) pairs.
+This is the reference's own scale-out model — independent sub-indexes over row ranges searched in parallel and merged
+by (apply concat) + (sort-by :distance) + (take k) (src/hnsw/ann/partition/partitioned_hnsw.clj:86-196) — applied to
+ONE global index, so results are identical to the single-GPU results.
+
+The data plane lives in the library (include/hnswb200.h, "multi-GPU"): `comm_init` hands every rank the communicator
+id, `RowShardedIVFFlat` / `RowShardedFlat` build the local shard (data-parallel k-means with one all-reduce per Lloyd
+round) and `search_raw` is ONE C-ABI call per rank: local search -> exchange of the local top-k over NVLink peer
+windows (or ncclAllGather) -> merge kernel, no host synchronisation in between.  torch.distributed only carries the
+128-byte id.
+
+`ShardedIVFFlat` / `ShardedFlat` / `all_gather_merge` below are the earlier host-orchestrated form (torch collectives +
+hb_topk_merge); the gloo tests use them to cover the host logic on CPU.
 """
 from __future__ import annotations
 
 import numpy as np
 
+import ctypes as C
+
 from . import _lib as hb
 from . import ivf_flat
+from .index import DeviceIndex, metric_code, new_handle
 
 
+# ---- the library's data plane ---------------------------------------------------------------------------------------
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    hb.check(hb.lib().hb_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(rank: int | None = None, world: int | None = None, id_bytes: bytes | None = None, group=None):
+    """hb_comm_init for this process (after hb_init(LOCAL_RANK)).  Without `id_bytes` rank 0 draws the id and
+    torch.distributed (any backend) broadcasts it."""
+    if id_bytes is None:
+        import torch.distributed as dist_
+
+        rank = dist_.get_rank(group) if rank is None else rank
+        world = dist_.get_world_size(group) if world is None else world
+        box = [comm_unique_id() if rank == 0 else None]
+        dist_.broadcast_object_list(box, src=0, group=group)
+        id_bytes = box[0]
+    hb.check(hb.lib().hb_comm_init(id_bytes, int(world), int(rank)))
+    return comm_info()
+
+
+def comm_info() -> dict:
+    a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+    hb.check(hb.lib().hb_comm_info(C.byref(a), C.byref(b), C.byref(c)))
+    return {"nranks": a.value, "rank": b.value, "p2p": bool(c.value)}
+
+
+def comm_shutdown():
+    hb.check(hb.lib().hb_comm_shutdown())
+
+
+def comm_allreduce(values, op="sum") -> np.ndarray:
+    """Small host-side reduction through the library's communicator (timings, counters)."""
+    x = np.ascontiguousarray(np.atleast_1d(values), dtype=np.float64).copy()
+    hb.check(hb.lib().hb_comm_allreduce_f64(hb.ptr(x), x.size, 0 if op == "sum" else 1))
+    return x
+
+
+def comm_broadcast(arr: np.ndarray, root: int = 0) -> np.ndarray:
+    hb.check(hb.lib().hb_comm_broadcast(hb.ptr(arr), arr.nbytes, root))
+    return arr
+
+
+class _ShardedSearch(DeviceIndex):
+    def search_raw(self, queries, k: int, param: int = 0, out_ids=None, out_dist=None):
+        """Global top-k on every rank (ids = global rows): one hb_sharded_search call.  Collective."""
+        q = hb.as_matrix(queries, allow=(hb.F32, hb.F64))
+        nq = q.shape[0]
+        if out_ids is None:
+            out_ids = np.empty((nq, k), dtype=np.int64)
+        if out_dist is None:
+            out_dist = np.empty((nq, k), dtype=np.float64)
+        hb.check(hb.lib().hb_sharded_search(self._h, hb.ptr(q), hb.dtype_code(q), nq, k, param, hb.ptr(out_ids), hb.ptr(out_dist)))
+        return out_ids, out_dist
+
+    def local_search_raw(self, queries, k: int, param: int = 0, out_ids=None, out_dist=None):
+        """This shard only (local row ids): plain hb_search."""
+        return DeviceIndex.search_raw(self, queries, k, param, out_ids, out_dist)
+
+
+class RowShardedIVFFlat(_ShardedSearch):
+    """This rank's rows [first_row, first_row + n_local) of a global IVF-FLAT index (hb_sharded_ivf_build): the k-means
+    runs over all ranks' rows, the centroids are replicated, the local slabs hold this rank's part of every list."""
+
+    def __init__(self, local_rows, first_row: int, num_partitions: int, seed_rows, max_iterations=10, distance_fn="cosine"):
+        rows = hb.as_matrix(local_rows)
+        sr = np.ascontiguousarray(seed_rows, dtype=np.int64)
+        if sr.shape != (num_partitions,):
+            raise hb.HbInvalid(hb.ERR_INVALID, "seed_rows must hold num_partitions global row ids")
+        h = new_handle()
+        hb.check(hb.lib().hb_sharded_ivf_build(hb.ptr(rows), rows.shape[0], rows.shape[1], hb.dtype_code(rows),
+                                               metric_code(distance_fn), int(num_partitions), int(max_iterations), hb.ptr(sr),
+                                               int(first_row), C.byref(h)))
+        super().__init__(h.value, None)
+        self.first_row, self.num_partitions = int(first_row), int(num_partitions)
+
+    def export(self):
+        i = self.info()
+        cents = np.empty((i["nlist"], i["dim"]), dtype=np.float64)
+        asg = np.empty(i["n"], dtype=np.int32)
+        hb.check(hb.lib().hb_ivf_export(self._h, hb.ptr(cents), hb.ptr(asg)))
+        return cents, asg
+
+
+class RowShardedFlat(_ShardedSearch):
+    """This rank's rows [first_row, first_row + n_local) of an exact flat index (BASELINE configs[2])."""
+
+    def __init__(self, local_rows, first_row: int, distance_fn="cosine"):
+        rows = hb.as_matrix(local_rows)
+        h = new_handle()
+        hb.check(hb.lib().hb_flat_create(hb.ptr(rows), rows.shape[0], rows.shape[1], hb.dtype_code(rows), metric_code(distance_fn),
+                                         C.byref(h)))
+        super().__init__(h.value, None)
+        hb.check(hb.lib().hb_index_set_id_base(self._h, int(first_row)))
+        self.first_row = int(first_row)
+
+
+def import_row_shard(local_rows, first_row: int, centroids, local_assignments, distance_fn="cosine") -> _ShardedSearch:
+    """A row shard of a global IVF-FLAT index from given centroids + this shard's assignments (parity: oracle-built
+    partitions split by rows)."""
+    ix = ivf_flat.import_index(local_rows, centroids, local_assignments, distance_fn)
+    sh = _ShardedSearch(ix.__dict__.pop("_h").value, None)
+    ix._h = None
+    hb.check(hb.lib().hb_index_set_id_base(sh._h, int(first_row)))
+    return sh
+
+
+def sharded_kmeans(local_rows, first_row: int, num_partitions: int, seed_rows, max_iterations=10, distance_fn="cosine"):
+    """hb_sharded_kmeans -> (centroids fp64 [nlist, d] — identical on every rank, assignments int32 of this shard)."""
+    rows = hb.as_matrix(local_rows)
+    sr = np.ascontiguousarray(seed_rows, dtype=np.int64)
+    cents = np.empty((num_partitions, rows.shape[1]), dtype=np.float64)
+    asg = np.empty(rows.shape[0], dtype=np.int32)
+    hb.check(hb.lib().hb_sharded_kmeans(hb.ptr(rows), rows.shape[0], rows.shape[1], hb.dtype_code(rows), metric_code(distance_fn),
+                                        int(num_partitions), int(max_iterations), hb.ptr(sr), int(first_row), hb.ptr(cents),
+                                        hb.ptr(asg)))
+    return cents, asg
+
+
+# ---- the earlier host-orchestrated form (torch collectives + hb_topk_merge) ------------------------------------------
 def list_owner(nlist: int, world: int) -> np.ndarray:
     return (np.arange(nlist) % world).astype(np.int32)
 

@@ -76,7 +76,7 @@ HB_API int hb_shutdown(void);
 HB_API const char *hb_last_error(void);
 HB_API int hb_version(void);
 HB_API int hb_set_stream(void *cuda_stream); /* launch on this stream (default: legacy stream 0) */
-HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches (default EXACT) */
+HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches and builds (default EXACT); per index: hb_index_set_mode */
 /* knobs: "scratch_mb" = budget for the transient distance scratch (default 8192); "profile" = 1 records
  * CUDA events around the main kernels (and resets the counters); "fast_digits" = 2 | 3 signed 8-bit digits per
  * element in the HB_MODE_FAST candidate pass (16- or 24-bit block-fixed-point mantissas); "fast_sample_tiles" = row
@@ -84,7 +84,10 @@ HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches 
  * "fast_prune" = 0 scans every probed list in HB_MODE_FAST (default 1: lists that provably hold no top-k row of a query are
  * dropped, same results); "rowstream" = 0 keeps small batches (<= 8 queries) on the register-buffered scan instead of
  * the bulk-copy ring, "stream_seg" (256 | 384 | 512 bytes per row and stage), "stream_stages" (2..4), "stream_warps"
- * (0 = as many as fit) shape that ring.  Results never depend on a knob. */
+ * (0 = as many as fit) shape that ring; "micro_batch" = n combines concurrent hb_search calls of <= 8 queries on host buffers
+ * into batches of up to n queries (default 64, 0 = off: parallel-search-futures, src/hnsw/helper/parallel_search.clj:15-49,
+ * without a thread per query); "comm_p2p" = 0 exchanges the local top-k of hb_sharded_search by ncclAllGather instead of
+ * the peer-window kernel.  Results never depend on a knob. */
 HB_API int hb_set_option(const char *name, int64_t value);
 /* measurements: "scan_ms"/"scan_count" (list/flat scan kernel), "coarse_ms", "select_ms", "plan_ms", "assign_ms",
  * "tc_ms" (tensor-core candidate pass over all probed lists), "tc_sample_ms" (its threshold-seeding pass), "pack_ms",
@@ -204,6 +207,48 @@ HB_API int hb_fast_scores(hb_index *index, const void *queries, int qdtype, int6
  * partitioned_hnsw.clj:187-196, ties by (part, position). */
 HB_API int hb_topk_merge(const double *dist, const int64_t *ids, int32_t nparts, int64_t nq, int32_t k,
                          int64_t *out_ids, double *out_dist);
+
+/* ---- multi-GPU: one process per GPU, rows sharded ------------------------------------------------------------------
+ * The reference scales out by building independent sub-indexes over row ranges, searching all of them in parallel and
+ * merging: (apply concat) + (sort-by :distance) + (take k), src/hnsw/ann/partition/partitioned_hnsw.clj:86-196.  Here rank g
+ * of G (one process per GPU of an NVSwitch box) holds the global rows [first_global_row, first_global_row + n_local) of ONE
+ * index: an exact flat shard, or the rows of that range inside every list of a global IVF-FLAT index whose centroids are
+ * replicated.  hb_sharded_search = local search -> exchange of the G local top-k lists -> merge by (distance, rank,
+ * position), i.e. the stable sort of the concatenation in rank order; with contiguous row blocks that is the single-GPU
+ * (distance, row) order.  The exchange is ONE kernel launch per search: every rank writes its block into its peers' windows
+ * over NVLink (cudaIpc-mapped memory), signals, waits and merges; hb_set_option("comm_p2p", 0) — or a box without peer
+ * access — uses ncclAllGather + the same merge instead.  NCCL (libnccl.so.2, resolved with dlopen at hb_comm_init)
+ * carries the bulk collectives of the build.  All collectives run on the library's stream; no host synchronisation
+ * between the local search and the merge.  Every rank must make the same calls in the same order. */
+#define HB_COMM_ID_BYTES 128
+/* rank 0: an opaque id to hand to every rank by any means (file, environment, socket, torch.distributed) */
+HB_API int hb_comm_unique_id(void *out_id /* HB_COMM_ID_BYTES */);
+/* collective; after hb_init(device).  nranks <= 8 */
+HB_API int hb_comm_init(const void *id, int32_t nranks, int32_t rank);
+/* out_p2p: 1 once the peer windows are mapped (the first hb_sharded_search decides) */
+HB_API int hb_comm_info(int32_t *out_nranks, int32_t *out_rank, int32_t *out_p2p);
+HB_API int hb_comm_shutdown(void);
+/* plumbing for the host side (seeds, centroids, timings): in place, host or device buffers */
+HB_API int hb_comm_broadcast(void *buf, int64_t bytes, int32_t root);
+HB_API int hb_comm_allreduce_f64(double *buf, int64_t count, int32_t op /* 0 = sum, 1 = max */);
+/* the global row of this index's local row 0; hb_sharded_search adds it to every id */
+HB_API int hb_index_set_id_base(hb_index *index, int64_t first_global_row);
+/* search mode of THIS index: HB_MODE_EXACT / HB_MODE_FAST, or -1 to follow hb_set_mode (threads that want different
+ * modes on different indexes do not race on the process default) */
+HB_API int hb_index_set_mode(hb_index *index, int mode);
+/* search-knn over all shards: same arguments and result layout as hb_search, ids are GLOBAL rows, identical results on
+ * every rank.  Collective. */
+HB_API int hb_sharded_search(hb_index *index, const void *queries, int qdtype, int64_t nq, int32_t k, int32_t param,
+                             int64_t *out_ids, double *out_dist);
+/* partition-vectors-kmeans (ivf_flat.clj:92-131) data-parallel: every rank assigns its rows and sums its members per
+ * cluster, one all-reduce(sum) of the fp64 sums + counts per Lloyd round, centroids replicated.  seed_rows = nlist GLOBAL
+ * row ids (the k-means++ result, the same array on every rank).  out_assign: this rank's rows.  Collective. */
+HB_API int hb_sharded_kmeans(const void *rows, int64_t n_local, int32_t d, int dtype, int metric, int32_t nlist, int32_t iters,
+                             const int64_t *seed_rows, int64_t first_global_row, double *out_centroids, int32_t *out_assign);
+/* build-ivf-flat-index (ivf_flat.clj:137-211) over the row shards: hb_sharded_kmeans, then this rank's rows laid out as the
+ * list-major slabs of the global partitioning (id base = first_global_row).  Collective. */
+HB_API int hb_sharded_ivf_build(const void *rows, int64_t n_local, int32_t d, int dtype, int metric, int32_t nlist, int32_t iters,
+                                const int64_t *seed_rows, int64_t first_global_row, hb_index **out);
 
 /* ---- persistence ------------------------------------------------------------------------------- */
 /* save-index / load-index (src/hnsw/api.clj:40-50, src/hnsw/helper/index_io.clj:10-80: EDN text of the HNSW graph

@@ -77,6 +77,10 @@ SIGNATURES = {
     "hb_sharded_search": (_int, [_p, _p, _int, _i64, _i32, _i32, _p, _p]),
     "hb_sharded_kmeans": (_int, [_p, _i64, _i32, _int, _int, _i32, _i32, _p, _i64, _p, _p]),
     "hb_sharded_ivf_build": (_int, [_p, _i64, _i32, _int, _int, _i32, _i32, _p, _i64, _pp]),
+    "hb_pairwise_f32lanes": (_int, [_p, _i64, _p, _i64, _i32, _int, _i32, _p]),
+    "hb_pcaf_matrix": (_int, [_i32, _i32, _i64, _p]),
+    "hb_pcaf_project": (_int, [_p, _i32, _i32, _p, _i64, _i32, _p]),
+    "hb_pcaf_search": (_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p]),
     "hb_index_save": (_int, [_p, C.c_char_p]),
     "hb_index_load": (_int, [C.c_char_p, _pp]),
     "hb_index_info": (_int, [_p, C.POINTER(HbInfo)]),

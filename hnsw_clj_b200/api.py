@@ -2,7 +2,7 @@
 (src/hnsw/api/protocol.clj:9-28,58-67) for the device-resident index types."""
 from __future__ import annotations
 
-from . import flat, hybrid_lsh, ivf_flat, lightning, ultra_fast
+from . import flat, hybrid_lsh, ivf_flat, lightning, pcaf, ultra_fast
 from .index import DeviceIndex
 
 INDEX_TYPES = {0: "FLAT", 1: "IVF-FLAT", 2: "HNSW"}
@@ -19,6 +19,8 @@ def index(data, index_type="ivf-flat", metric="cosine", **opts) -> DeviceIndex:
         return lightning.build_index(data, distance_fn=metric, **opts)
     if t in ("hybrid-lsh", "lsh"):
         return hybrid_lsh.build_index(data, distance_fn=metric, **opts)
+    if t in ("pcaf", "p-hnsw"):
+        return pcaf.build_index(data, **opts)
     raise ValueError(f"unknown index type {index_type!r}")
 
 
@@ -36,6 +38,8 @@ def search_knn_(idx: DeviceIndex, query, k, mode="balanced", **opts):
         return lightning.search_knn(idx, query, k, opts.get("search_percent"), mode=mode)
     if isinstance(idx, hybrid_lsh.HybridIndex):
         return hybrid_lsh.search_knn(idx, query, k, mode)
+    if isinstance(idx, pcaf.PCAFIndex):
+        return pcaf.search_knn(idx, query, k, mode)
     if isinstance(idx, ivf_flat.IVFFlatIndex):
         return ivf_flat.search_knn(idx, query, k, mode, opts.get("num_probes"))
     if isinstance(idx, ultra_fast.HnswIndex):
@@ -48,6 +52,8 @@ def index_info_(idx: DeviceIndex) -> dict:
         return lightning.index_info(idx)
     if isinstance(idx, hybrid_lsh.HybridIndex):
         return hybrid_lsh.index_info(idx)
+    if isinstance(idx, pcaf.PCAFIndex):
+        return pcaf.index_info(idx)
     if isinstance(idx, ivf_flat.IVFFlatIndex):
         return ivf_flat.index_info(idx)
     i = idx.info()
@@ -59,6 +65,8 @@ def index_type_(idx: DeviceIndex) -> str:
         return "LIGHTNING"
     if isinstance(idx, hybrid_lsh.HybridIndex):
         return "HYBRID-LSH"
+    if isinstance(idx, pcaf.PCAFIndex):
+        return "PCAF"
     return INDEX_TYPES[idx.info()["type"]]
 
 
@@ -70,6 +78,8 @@ def search_batch_(idx: DeviceIndex, queries, k, mode="balanced", **opts):
         return lightning.search_batch(idx, queries, k, opts.get("search_percent"), mode=mode)
     if isinstance(idx, hybrid_lsh.HybridIndex):
         return hybrid_lsh.search_batch(idx, queries, k, mode)
+    if isinstance(idx, pcaf.PCAFIndex):
+        return pcaf.search_batch(idx, queries, k, mode)
     if isinstance(idx, ivf_flat.IVFFlatIndex):
         return ivf_flat.search_batch(idx, queries, k, mode, opts.get("num_probes"))
     if isinstance(idx, ultra_fast.HnswIndex):

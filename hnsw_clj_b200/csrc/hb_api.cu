@@ -20,6 +20,7 @@
 #include "hb_fast.cuh"
 #include "hb_hnsw.cuh"
 #include "hb_kernels.cuh"
+#include "hb_lanes.cuh"
 #include "hb_validate.cuh"
 
 namespace hb {
@@ -2749,6 +2750,120 @@ HB_API int hb_lsh_matrices(int32_t d, int32_t ntables, int32_t proj_dim, int64_t
         JavaGaussian g(seed);  // host arithmetic only: no device is needed
         const int64_t count = (int64_t)ntables * proj_dim * d;
         for (int64_t i = 0; i < count; ++i) out[i] = g.next();
+    });
+}
+
+// ---- a4: the float[] Vector-API variants (src/hnsw/simd.clj:18-115) and PCAF (src/hnsw/ann/dimreduct/pcaf.clj) ------------
+HB_API int hb_pairwise_f32lanes(const float *a, int64_t na, const float *b, int64_t nb, int32_t d, int metric, int32_t lanes,
+                                double *out) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(na >= 0 && nb >= 0 && d >= 1 && lanes >= 1 && lanes <= 64, "bad arguments");
+        HB_REQUIRE(metric == HB_COSINE || metric == HB_L2 || metric == HB_IP, "unknown metric");
+        if (na == 0 || nb == 0) return;
+        HB_REQUIRE(a && b && out, "null buffer");
+        const float *da = (const float *)stage_in(a, (size_t)na * d * 4, g_ws.in_a);
+        const float *db = (const float *)stage_in(b, (size_t)nb * d * 4, g_ws.in_b);
+        OutStage o = stage_out(out, (size_t)na * nb * 8, g_ws.out_a);
+        launch_lanes_pairwise(da, na, db, nb, d, metric, lanes, (double *)o.dev, nb);
+        finish_out(o);
+        sync_stream();
+    });
+}
+
+HB_API int hb_pcaf_matrix(int32_t original_dim, int32_t target_dim, int64_t seed, float *out) {
+    return guarded([&] {
+        HB_REQUIRE(original_dim >= 1 && target_dim >= 1 && out, "bad arguments");
+        // create-random-projection (pcaf.clj:33-46): scale = (float)(1 / sqrt(target)); two floats multiply in double in Clojure
+        // and aset narrows the product
+        JavaGaussian g(seed);
+        const float scale = (float)(1.0 / std::sqrt((double)target_dim));
+        const int64_t count = (int64_t)original_dim * target_dim;
+        for (int64_t i = 0; i < count; ++i) {
+            const float x = (float)g.next();
+            out[i] = (float)((double)scale * (double)x);
+        }
+    });
+}
+
+HB_API int hb_pcaf_project(const float *matrix, int32_t original_dim, int32_t target_dim, const float *rows, int64_t n,
+                           int32_t lanes, float *out) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(original_dim >= 1 && target_dim >= 1 && n >= 0 && lanes >= 1 && lanes <= 64, "bad arguments");
+        if (n == 0) return;
+        HB_REQUIRE(matrix && rows && out, "null buffer");
+        const float *dm = (const float *)stage_in(matrix, (size_t)original_dim * target_dim * 4, g_ws.in_a);
+        const float *dr = (const float *)stage_in(rows, (size_t)n * original_dim * 4, g_ws.in_b);
+        OutStage o = stage_out(out, (size_t)n * target_dim * 4, g_ws.out_a);
+        launch_lanes_project(dm, target_dim, dr, n, original_dim, lanes, (float *)o.dev);
+        finish_out(o);
+        sync_stream();
+    });
+}
+
+// search-pcaf-parallel (pcaf.clj:195-253) for a batch: low-dimensional scan of every row, stable top min(k_filter, 3k),
+// full-dimension re-rank of those, stable sort in candidate order, take k.
+HB_API int hb_pcaf_search(hb_index *high, hb_index *low, const float *queries, const float *low_queries, int64_t nq, int32_t k,
+                          int32_t k_filter, int32_t lanes, int64_t *out_ids, double *out_dist) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(high && low && high->type == HB_INDEX_FLAT && low->type == HB_INDEX_FLAT, "PCAF needs two flat indexes");
+        HB_REQUIRE(high->dtype == HB_F32 && low->dtype == HB_F32 && high->n == low->n, "PCAF stores float[] rows (doubles-to-floats, pcaf.clj:83-90)");
+        HB_REQUIRE(nq >= 0 && k >= 0 && k_filter >= 1 && lanes >= 1 && lanes <= 64, "bad arguments");
+        if (nq == 0 || k == 0) return;
+        HB_REQUIRE(queries && low_queries && out_ids && out_dist, "null buffer");
+        HB_REQUIRE(k <= 1024 && k_filter <= 1024, "k / k-filter > 1024 is not supported");
+        const int64_t n = high->n;
+        const int d = high->d, t = low->d;
+        OutStage oi = stage_out(out_ids, (size_t)nq * k * 8, g_ws.out_a);
+        OutStage od = stage_out(out_dist, (size_t)nq * k * 8, g_ws.out_b);
+        if (n == 0) {
+            fill_empty_results((int64_t *)oi.dev, (double *)od.dev, nq * k);
+            finish_out(oi);
+            finish_out(od);
+            sync_stream();
+            return;
+        }
+        const float *q = (const float *)stage_in(queries, (size_t)nq * d * 4, g_ws.in_b);
+        const float *lq = (const float *)stage_in(low_queries, (size_t)nq * t * 4, g_ws.in_c);
+        const int c = (int)std::min<int64_t>(std::min<int64_t>(k_filter, 3ll * k), n);  // (take (min k-filter (* 3 k)) ...), :229-230
+        int64_t qc = (int64_t)(scratch_budget() / 8 / (size_t)n);
+        qc = std::max<int64_t>(1, std::min(qc, nq));
+        double *scratch = g_ws.scratch.as<double>((size_t)qc * n);
+        double *cval = g_ws.cand_val.as<double>((size_t)qc * c);
+        int64_t *cpos = g_ws.cand_id.as<int64_t>((size_t)qc * c);
+        double *exact = g_ws.sel_val.as<double>((size_t)qc * c);
+        int64_t *pos2 = g_ws.sel_pos.as<int64_t>((size_t)qc * k);
+        for (int64_t q0 = 0; q0 < nq; q0 += qc) {
+            const int64_t nqc = std::min(qc, nq - q0);
+            // phase 1 (:214-230): cosine-distance-simd of the projected query against every projected row
+            launch_lanes_pairwise(lq + q0 * t, nqc, (const float *)low->rows.p, n, t, HB_COSINE, lanes, scratch, n);
+            SelectParams L;
+            L.vals = scratch;
+            L.nseg = nqc;
+            L.seg_stride = n;
+            L.seg_len_const = n;
+            L.k = c;
+            L.out_val = cval;
+            L.out_pos = cpos;
+            launch_select(L);
+            // phase 2 (:236-243): exact distance in the full dimension, candidates in phase-1 order
+            launch_lanes_gather(q + q0 * d, (const float *)high->rows.p, d, lanes, cpos, nqc, c, exact);
+            SelectParams M;  // stable sort of the candidate list + take k (:246-252): ties keep the phase-1 order
+            M.vals = exact;
+            M.nseg = nqc;
+            M.seg_stride = c;
+            M.seg_len_const = c;
+            M.k = k;
+            M.out_val = (double *)od.dev + q0 * k;
+            M.out_pos = pos2;
+            launch_select(M);
+            launch_lookup_ids(pos2, nqc, k, cpos, c, (int64_t *)oi.dev + q0 * k);
+        }
+        finish_out(oi);
+        finish_out(od);
+        sync_stream();
     });
 }
 

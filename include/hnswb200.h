@@ -183,6 +183,27 @@ HB_API int hb_gather_score(hb_index *index, const void *queries, int qdtype, int
                            const int32_t *pair_query, const int32_t *pair_row, int64_t npairs,
                            double *out_scores);
 
+/* ---- fp32 Vector-API variants + PCAF ---------------------------------------------------------------------------------
+ * cosine-distance-simd-optimized / euclidean-distance-simd-optimized / dot-product-simd-optimized on float[]
+ * (src/hnsw/simd.clj:18-115): per chunk of `lanes` floats (= FloatVector/SPECIES_PREFERRED .length of the reference's
+ * machine: 4, 8 or 16) fp32 lane products reduced in fp32, chunk sums accumulated in fp64, scalar tail in fp64.  The JDK
+ * leaves the lane order of reduceLanes(ADD) unspecified; the device uses left-to-right (its scalar fallback / HotSpot's
+ * ordered reduction), so results are within the north star's 1e-5 relative bound of any JVM and bit-identical to the
+ * oracle's restatement.  out[i*nb + j] = metric(a_i, b_j); HB_IP = the dot product. */
+HB_API int hb_pairwise_f32lanes(const float *a, int64_t na, const float *b, int64_t nb, int32_t d, int metric, int32_t lanes,
+                                double *out);
+/* create-random-projection (src/hnsw/ann/dimreduct/pcaf.clj:33-46): [target_dim][original_dim] floats,
+ * (float)(1/sqrt(target)) * (float) Random(seed).nextGaussian(), on the HOST */
+HB_API int hb_pcaf_matrix(int32_t original_dim, int32_t target_dim, int64_t seed, float *out);
+/* project-vector-simd (pcaf.clj:48-81) for n rows: out [n][target_dim] floats */
+HB_API int hb_pcaf_project(const float *matrix, int32_t original_dim, int32_t target_dim, const float *rows, int64_t n,
+                           int32_t lanes, float *out);
+/* search-pcaf-parallel (pcaf.clj:195-253), batched: `high` / `low` are flat indexes (hb_flat_create, HB_F32) over the
+ * float rows and their projections; phase 1 scans every projected row (cosine-distance-simd), keeps the
+ * min(k_filter, 3k) best in stable order, phase 2 re-ranks them in the full dimension; ties keep phase-1 order. */
+HB_API int hb_pcaf_search(hb_index *high, hb_index *low, const float *queries, const float *low_queries, int64_t nq, int32_t k,
+                          int32_t k_filter, int32_t lanes, int64_t *out_ids, double *out_dist);
+
 /* ---- LSH projections ------------------------------------------------------------------------------ */
 /* generate-random-matrix x NUM-HASH-TABLES (src/hnsw/ann/hash/hybrid_lsh.clj:24-31, :77-81): ntables matrices of
  * proj_dim x d doubles drawn in order from ONE java.util.Random(seed).nextGaussian stream (polar method over

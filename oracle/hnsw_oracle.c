@@ -1214,3 +1214,151 @@ ORC_EXPORT void orc_lsh_search(const float *rows, int64_t n, int64_t d, const do
     free(tmp);
     free(seen);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * a4: the float[] Vector-API variants (src/hnsw/simd.clj:18-115) and their only consumer, PCAF
+ * (src/hnsw/ann/dimreduct/pcaf.clj).
+ *
+ * Per SPECIES-LENGTH chunk the reference multiplies fp32 lanes (FloatVector.mul), reduces them with
+ * reduceLanes(VectorOperators/ADD) and adds the (float) chunk sum into a double accumulator
+ * ((+ sum (double (.reduceLanes ...))), simd.clj:33, :56, :96-98); the tail (len mod lanes) is scalar in
+ * double (:37-43, :100-110).  The JDK leaves the lane order of a floating-point ADD reduction unspecified;
+ * restated here is the order of its scalar fallback and of HotSpot's ordered AddReductionVF: fp32 adds
+ * left to right starting from 0.0f.  `lanes` = SPECIES_PREFERRED.length() of the machine the reference ran on
+ * (4 / 8 / 16; 8 = AVX2 is the default of the tests).  Another lane order or width moves the result by
+ * a few fp32 ulps of a chunk sum: the north star's 1e-5 relative bound for fp32 covers it
+ * (tests/test_oracle.py::test_simd_lane_order_is_within_the_fp32_bound).
+ * ---------------------------------------------------------------------------------------- */
+static inline float lane_sum_mul(const float *a, const float *b, int lanes) {
+    float s = 0.0f;
+    for (int i = 0; i < lanes; ++i) {
+        float p = a[i] * b[i];
+        s = s + p;
+    }
+    return s;
+}
+/* dot-product-simd-optimized, simd.clj:18-43 */
+ORC_EXPORT double orc_simd_dot(const float *a, const float *b, int64_t d, int32_t lanes) {
+    const int64_t ub = d - d % lanes;
+    double sum = 0.0;
+    for (int64_t i = 0; i < ub; i += lanes) sum = sum + (double)lane_sum_mul(a + i, b + i, lanes);
+    for (int64_t j = ub; j < d; ++j) sum = sum + (double)a[j] * (double)b[j];
+    return sum;
+}
+/* euclidean-distance-simd-optimized, simd.clj:45-71: diff and square in fp32 lanes */
+ORC_EXPORT double orc_simd_euclidean(const float *a, const float *b, int64_t d, int32_t lanes) {
+    const int64_t ub = d - d % lanes;
+    double sum = 0.0;
+    for (int64_t i = 0; i < ub; i += lanes) {
+        float s = 0.0f;
+        for (int l = 0; l < lanes; ++l) {
+            float df = a[i + l] - b[i + l];
+            float sq = df * df;
+            s = s + sq;
+        }
+        sum = sum + (double)s;
+    }
+    for (int64_t j = ub; j < d; ++j) {
+        double df = (double)a[j] - (double)b[j];
+        sum = sum + df * df;
+    }
+    return sqrt(sum);
+}
+/* cosine-distance-simd-optimized, simd.clj:73-115: three accumulators, (zero? magnitude) -> 1.0 */
+ORC_EXPORT double orc_simd_cosine(const float *a, const float *b, int64_t d, int32_t lanes) {
+    const int64_t ub = d - d % lanes;
+    double dot = 0.0, na = 0.0, nb = 0.0;
+    for (int64_t i = 0; i < ub; i += lanes) {
+        dot = dot + (double)lane_sum_mul(a + i, b + i, lanes);
+        na = na + (double)lane_sum_mul(a + i, a + i, lanes);
+        nb = nb + (double)lane_sum_mul(b + i, b + i, lanes);
+    }
+    for (int64_t j = ub; j < d; ++j) {
+        double x = (double)a[j], y = (double)b[j];
+        dot = dot + x * y;
+        na = na + x * x;
+        nb = nb + y * y;
+    }
+    double mag = sqrt(na) * sqrt(nb);
+    if (mag == 0.0) return 1.0;
+    return 1.0 - dot / mag;
+}
+/* the same three with another lane order (pairwise tree): used only to show the sensitivity to the unspecified order */
+ORC_EXPORT double orc_simd_cosine_tree(const float *a, const float *b, int64_t d, int32_t lanes) {
+    const int64_t ub = d - d % lanes;
+    double acc[3] = {0.0, 0.0, 0.0};
+    float t[3][16];
+    for (int64_t i = 0; i < ub; i += lanes) {
+        for (int l = 0; l < lanes; ++l) {
+            t[0][l] = a[i + l] * b[i + l];
+            t[1][l] = a[i + l] * a[i + l];
+            t[2][l] = b[i + l] * b[i + l];
+        }
+        for (int w = lanes / 2; w >= 1; w /= 2)
+            for (int v = 0; v < 3; ++v)
+                for (int l = 0; l < w; ++l) t[v][l] = t[v][l] + t[v][l + w];
+        for (int v = 0; v < 3; ++v) acc[v] = acc[v] + (double)t[v][0];
+    }
+    for (int64_t j = ub; j < d; ++j) {
+        double x = (double)a[j], y = (double)b[j];
+        acc[0] = acc[0] + x * y;
+        acc[1] = acc[1] + x * x;
+        acc[2] = acc[2] + y * y;
+    }
+    double mag = sqrt(acc[1]) * sqrt(acc[2]);
+    if (mag == 0.0) return 1.0;
+    return 1.0 - acc[0] / mag;
+}
+
+/* create-random-projection, pcaf.clj:33-46: Random(42), scale = (float)(1 / sqrt(target)), matrix[i] =
+ * scale * (float) nextGaussian — Clojure multiplies two floats in double and aset narrows the product to float.
+ * out: [target][original] fp32. */
+ORC_EXPORT void orc_pcaf_matrix(int64_t original_dim, int64_t target_dim, int64_t seed, float *out) {
+    orc_rng r;
+    orc_rng_init(&r, seed);
+    const float scale = (float)(1.0 / sqrt((double)target_dim));
+    for (int64_t i = 0; i < target_dim * original_dim; ++i) {
+        const float g = (float)orc_rng_next_gaussian(&r);
+        out[i] = (float)((double)scale * (double)g);
+    }
+}
+/* project-vector-simd, pcaf.clj:48-81: result[i] = (float) of the chunked dot of matrix row i and the vector (the loop
+ * local `sum` is initialised with (float 0.0), which Clojure widens to a double loop local; the tail multiplies two
+ * floats in double). */
+ORC_EXPORT void orc_pcaf_project(const float *matrix, int64_t original_dim, int64_t target_dim, const float *rows, int64_t n,
+                                 int32_t lanes, float *out) {
+    for (int64_t r = 0; r < n; ++r)
+        for (int64_t t = 0; t < target_dim; ++t)
+            out[r * target_dim + t] = (float)orc_simd_dot(matrix + t * original_dim, rows + r * original_dim, original_dim, lanes);
+}
+/* search-pcaf-parallel, pcaf.clj:195-253, for a batch: phase 1 = simd cosine of the projected query against every
+ * projected row, stable sort, take min(k-filter, 3k) (:229-230); phase 2 = simd cosine in the full dimension for those
+ * (:236-243), stable sort of the candidates in phase-1 order (:246-250), take k.  The reference iterates a hash map
+ * in phase 1, so exact low-dim distance ties fall in hash order there; rows in data order here. */
+ORC_EXPORT void orc_pcaf_search(const float *rows, const float *low_rows, int64_t n, int64_t d, int64_t t, const float *matrix,
+                                const float *queries, int64_t nq, int64_t k, int64_t k_filter, int32_t lanes,
+                                int64_t *out_ids, double *out_dist) {
+    orc_hit *h = (orc_hit *)malloc(sizeof(orc_hit) * (size_t)(n + 1));
+    orc_hit *tmp = (orc_hit *)malloc(sizeof(orc_hit) * (size_t)(n + 1));
+    float *lq = (float *)malloc(sizeof(float) * (size_t)t);
+    for (int64_t qi = 0; qi < nq; ++qi) {
+        const float *q = queries + qi * d;
+        orc_pcaf_project(matrix, d, t, q, 1, lanes, lq);
+        for (int64_t r = 0; r < n; ++r) {
+            h[r].dist = orc_simd_cosine(lq, low_rows + r * t, t, lanes);
+            h[r].id = r;
+        }
+        stable_sort_hits(h, n, tmp);
+        int64_t c = k_filter < 3 * k ? k_filter : 3 * k;
+        if (c > n) c = n;
+        for (int64_t i = 0; i < c; ++i) h[i].dist = orc_simd_cosine(q, rows + h[i].id * d, d, lanes);
+        stable_sort_hits(h, c, tmp);
+        for (int64_t j = 0; j < k; ++j) {
+            out_ids[qi * k + j] = j < c ? h[j].id : -1;
+            out_dist[qi * k + j] = j < c ? h[j].dist : INFINITY;
+        }
+    }
+    free(h);
+    free(tmp);
+    free(lq);
+}

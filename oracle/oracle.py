@@ -89,6 +89,13 @@ def _declare(L):
     L.orc_hnsw_dist_evals.restype, L.orc_hnsw_dist_evals.argtypes = _i64, [_p]
     L.orc_gather_score.restype = None
     L.orc_gather_score.argtypes = [_p, _i64, _p, _p, _p, _i64, _int, _p]
+    for name in ("orc_simd_dot", "orc_simd_euclidean", "orc_simd_cosine", "orc_simd_cosine_tree"):
+        f = getattr(L, name)
+        f.restype, f.argtypes = _f64, [_p, _p, _i64, _i32]
+    L.orc_pcaf_matrix.restype, L.orc_pcaf_matrix.argtypes = None, [_i64, _i64, _i64, _p]
+    L.orc_pcaf_project.restype, L.orc_pcaf_project.argtypes = None, [_p, _i64, _i64, _p, _i64, _i32, _p]
+    L.orc_pcaf_search.restype = None
+    L.orc_pcaf_search.argtypes = [_p, _p, _i64, _i64, _i64, _p, _p, _i64, _i64, _i64, _i32, _p, _p]
 
 
 def _ptr(a: np.ndarray):
@@ -386,3 +393,50 @@ def gather_score(rows, queries, pair_query, pair_row, metric=COSINE) -> np.ndarr
     lib().orc_gather_score(_ptr(rows), rows.shape[1], _ptr(queries), _ptr(pq), _ptr(pr), pq.shape[0], metric,
                            _ptr(out))
     return out
+
+
+# ---- a4: float[] Vector-API variants (src/hnsw/simd.clj:18-115) and PCAF (src/hnsw/ann/dimreduct/pcaf.clj) ----------------
+def simd_cosine(a, b, lanes=8, tree=False) -> float:
+    a, b = _f32(a), _f32(b)
+    f = lib().orc_simd_cosine_tree if tree else lib().orc_simd_cosine
+    return float(f(_ptr(a), _ptr(b), a.shape[0], lanes))
+
+
+def simd_dot(a, b, lanes=8) -> float:
+    a, b = _f32(a), _f32(b)
+    return float(lib().orc_simd_dot(_ptr(a), _ptr(b), a.shape[0], lanes))
+
+
+def simd_euclidean(a, b, lanes=8) -> float:
+    a, b = _f32(a), _f32(b)
+    return float(lib().orc_simd_euclidean(_ptr(a), _ptr(b), a.shape[0], lanes))
+
+
+def simd_pairwise(A, B, metric=COSINE, lanes=8) -> np.ndarray:
+    A, B = _f32(A), _f32(B)
+    fn = {COSINE: simd_cosine, L2: simd_euclidean, IP: simd_dot}[metric]
+    return np.array([[fn(a, b, lanes) for b in B] for a in A], dtype=np.float64)
+
+
+def pcaf_matrix(original_dim, target_dim=100, seed=42) -> np.ndarray:
+    out = np.empty((target_dim, original_dim), dtype=np.float32)
+    lib().orc_pcaf_matrix(original_dim, target_dim, seed, _ptr(out))
+    return out
+
+
+def pcaf_project(matrix, rows, lanes=8) -> np.ndarray:
+    matrix, rows = _f32(matrix), _f32(np.atleast_2d(rows))
+    out = np.empty((rows.shape[0], matrix.shape[0]), dtype=np.float32)
+    lib().orc_pcaf_project(_ptr(matrix), matrix.shape[1], matrix.shape[0], _ptr(rows), rows.shape[0], lanes, _ptr(out))
+    return out
+
+
+def pcaf_search(rows, queries, k, n_components=100, k_filter=32, lanes=8, seed=42):
+    rows, queries = _f32(rows), _f32(np.atleast_2d(queries))
+    m = pcaf_matrix(rows.shape[1], n_components, seed)
+    low = pcaf_project(m, rows, lanes)
+    ids = np.empty((queries.shape[0], k), dtype=np.int64)
+    dist = np.empty((queries.shape[0], k), dtype=np.float64)
+    lib().orc_pcaf_search(_ptr(rows), _ptr(low), rows.shape[0], rows.shape[1], n_components, _ptr(m), _ptr(queries),
+                          queries.shape[0], k, k_filter, lanes, _ptr(ids), _ptr(dist))
+    return ids, dist

@@ -266,3 +266,37 @@ def test_topk_merge(hb):
         order = np.argsort(cd, kind="stable")[:k]  # stable: ties by (part, position)
         assert out_d[qi].tolist() == cd[order].tolist()
         assert out_i[qi].tolist() == ci[order].tolist()
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_ivf_bf16_slabs_equal_oracle_on_the_rounded_values(mode):
+    """north_star: "contiguous per-list fp32/bf16 slabs".  bf16 storage holds fp32-representable values, so the reference's
+    arithmetic on the bf16-rounded rows (widened to double[]) is what the device must return: build (k-means++ seeds, 3 Lloyd
+    rounds, final assignment) and search, ids and fp64 distance bits, in both modes."""
+    import torch
+
+    from hnsw_clj_b200 import _lib, ivf_flat
+
+    _lib.check(_lib.lib().hb_init(0))
+    r = np.random.default_rng(23)
+    c = r.standard_normal((40, 128))
+    rows32 = (c[r.integers(0, 40, 6000)] + 0.2 * r.standard_normal((6000, 128))).astype(np.float32)
+    rows_bf = torch.from_numpy(rows32).to(torch.bfloat16)
+    rows = rows_bf.to(torch.float32).numpy()  # the values the slab holds
+    q = (c[r.integers(0, 40, 300)] + 0.2 * r.standard_normal((300, 128))).astype(np.float32)
+    oc, oa = orc.kmeans(rows, 32, iters=3, seed=42)
+    want_i, want_d = orc.ivf_search(rows, oc, oa, q, 10, 6)
+    _lib.set_mode(_lib.MODE_FAST if mode == "fast" else _lib.MODE_EXACT)
+    try:
+        for data in (rows_bf, rows_bf.cuda()):  # host and device bf16 buffers
+            with ivf_flat.build_index(data, num_partitions=32, max_iterations=3) as ix:
+                assert ix.info()["dtype"] == _lib.BF16
+                cents, asg = ix.export()
+                assert (asg == oa).all() and (cents.view(np.int64) == oc.view(np.int64)).all()
+                ids, d = ix.search_raw(q, 10, 6)
+                assert ids.tolist() == want_i.tolist()
+                assert (d.view(np.int64) == want_d.view(np.int64)).all()
+                ids1, d1 = ix.search_raw(q[:1], 10, 6)  # small-batch path on a bf16 slab
+                assert ids1.tolist() == want_i[:1].tolist() and (d1.view(np.int64) == want_d[:1].view(np.int64)).all()
+    finally:
+        _lib.set_mode(_lib.MODE_EXACT)

@@ -218,3 +218,47 @@ def test_lightning_seeding_matches_a_literal_python_walk():
         for v in members:
             acc = acc + v
         assert (cents[c] == (acc / len(members) if len(members) else acc)).all()
+
+
+def test_simd_lane_order_is_within_the_fp32_bound():
+    """a4 (src/hnsw/simd.clj:73-115): the float[] cosine restated with 4 / 8 / 16 lanes, left-to-right or pairwise-tree lane
+    sums, and the double[] cosine-distance-direct all agree within the north star's 1e-5 relative for fp32; the KATs of
+    test/hnsw/core_test.clj:22-31 hold for it."""
+    r = np.random.default_rng(11)
+    for _ in range(20):
+        a = r.standard_normal(768).astype(np.float32)
+        b = (a + 0.5 * r.standard_normal(768)).astype(np.float32)
+        ref = orc.cosine_distance_direct(a.astype(np.float64), b.astype(np.float64))
+        for lanes in (4, 8, 16):
+            for tree in (False, True):
+                assert abs(orc.simd_cosine(a, b, lanes, tree) - ref) <= 1e-5 * abs(ref)
+    assert abs(orc.simd_cosine([1, 2, 3], [4, 5, 6], 8) - 0.025368153802923787) < 1e-7   # scalar tail only (d < lanes)
+    assert orc.simd_cosine([1, 0], [-1, 0], 4) == 2.0 and orc.simd_cosine([0, 0], [1, 2], 4) == 1.0
+    assert orc.simd_euclidean([0, 0], [3, 4], 8) == 5.0
+    # d a multiple of the lane count: no tail; the chunk sums are fp32
+    a = np.full(16, 0.1, np.float32)
+    assert orc.simd_dot(a, a, 8) == float(np.float32(8 * 0).item()) + 2 * float(sum_f32([np.float32(0.1) * np.float32(0.1)] * 8))
+
+
+def sum_f32(xs):
+    s = np.float32(0.0)
+    for x in xs:
+        s = np.float32(s + x)
+    return s
+
+
+def test_pcaf_matrix_is_the_java_gaussian_stream_and_matches_the_library():
+    """create-random-projection (src/hnsw/ann/dimreduct/pcaf.clj:33-46): (float)(1/sqrt(t)) * (float) Random(42).nextGaussian();
+    hb_pcaf_matrix is host arithmetic (no device needed) and must equal the oracle bit for bit."""
+    m = orc.pcaf_matrix(768, 100)
+    g = orc.JavaRandom(42)
+    scale = np.float32(1.0 / np.sqrt(100.0))
+    first = [np.float32(float(scale) * float(np.float32(g.next_gaussian()))) for _ in range(5)]
+    assert m.reshape(-1)[:5].tolist() == [float(x) for x in first]
+    assert abs(float(m[0, 0]) - 0.11419053) < 1e-7  # 1.1419053154730547 / 10
+    from hnsw_clj_b200 import pcaf
+
+    lib_m = pcaf.create_random_projection(768, 100)
+    assert (lib_m.view(np.int32) == m.view(np.int32)).all()
+    low = orc.pcaf_project(m, np.ones((1, 768), np.float32))
+    assert low.shape == (1, 100) and np.isfinite(low).all()

@@ -349,7 +349,7 @@ def run_ours(args, w, key, ctx, replicas_only=False):
     pruned_pairs = hb.get_stat("fast_pruned_pairs") / args.steps
     pruned_rows = hb.get_stat("fast_pruned_rows") / args.steps
     probe_pairs = hb.get_stat("fast_probe_pairs") / args.steps
-    hb_stats = {n: hb.get_stat(n) for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units")}
+    hb_stats = {n: hb.get_stat(n) for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units", "tc_narrow_units", "tc_narrow_items")}
     hb.set_option("profile", 0)
     if world > 1:
         t = torch.tensor([ms], device=device)
@@ -450,12 +450,14 @@ def run_ours(args, w, key, ctx, replicas_only=False):
         pairs = pairs - pruned_rows
         flops = 2.0 * pairs * w["d"]
         tc_units, tc_items, tc_tiles, tc_half = (hb_stats[n] / args.steps for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units"))
+        tc_narrow, tc_narrow_items = hb_stats["tc_narrow_units"] / args.steps, hb_stats["tc_narrow_items"] / args.steps
         if tc_items > 0:
             items = tc_items
         int8_ops = 2.0 * items * 128 * 128 * dpad * nprod if items else None
         # digit images read once: the row tiles some unit scans + the units' query images (128 slots each, 64 for the
-        # units that run with M = 64)
-        img_bytes = (tc_tiles * 128.0 * dpad * args.digits + (tc_units - 0.5 * tc_half) * 128.0 * dpad * args.digits) if tc_items > 0 else (
+        # units that run with M = 64, 32 for the narrow units of tc_narrow_kernel)
+        slots = 128.0 * (tc_units - tc_half) + 64.0 * (tc_half - tc_narrow) + 32.0 * tc_narrow
+        img_bytes = (tc_tiles * 128.0 * dpad * args.digits + slots * dpad * args.digits) if tc_items > 0 else (
             float(w["n"]) * dpad * args.digits + nq * nprobe * dpad * args.digits)
         hbm_peak = peaks.get("hbm_gbs", 7700.0)
         t_flops, t_bytes = flops / (bf16_peak * 1e12), img_bytes / (hbm_peak * 1e9)
@@ -465,7 +467,8 @@ def run_ours(args, w, key, ctx, replicas_only=False):
         hbm = {"achieved_gbs": img_bytes / t_tc / 1e9 if single else None, "peak_gbs": hbm_peak,
                "frac": (img_bytes / t_tc / 1e9 / hbm_peak) if single else None}
         roofline = {
-            "kernel": f"tc_pass_kernel<{args.digits},EMIT> (tcgen05.mma kind::i8, IVF list scan candidate pass)",
+            "kernel": (f"tc_narrow_kernel<{args.digits}> (tcgen05.mma kind::i8, rows on M, <= 32 queries on N: {tc_narrow_items:.0f} of "
+                       f"{items or 0:.0f} items) + tc_pass_kernel<{args.digits},EMIT> (the rest): IVF list scan candidate pass"),
             "bound": "hbm" if hbm_bound else "tensor",
             "achieved": (hbm["achieved_gbs"] if hbm_bound else tensor["achieved_tflops"]),
             "peak": hbm_peak if hbm_bound else bf16_peak, "unit": "GB/s" if hbm_bound else "TFLOP/s",
@@ -479,7 +482,8 @@ def run_ours(args, w, key, ctx, replicas_only=False):
             "launch_ms": t_tc * 1e3, "launches_per_step": tc_n / args.steps,
             "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": img_bytes,
             "tensor": tensor, "hbm": hbm,
-            "units_per_launch": tc_units, "m64_units_per_launch": tc_half, "items_per_launch": items,
+            "units_per_launch": tc_units, "m64_units_per_launch": tc_half, "narrow_units_per_launch": tc_narrow,
+            "narrow_items_per_launch": tc_narrow_items, "items_per_launch": items,
             "row_tiles_read_per_launch": tc_tiles,
             "scored_pairs_per_launch": pairs, "algorithmic_pairs_per_step": algorithmic_pairs,
             "probe_pruning": {"probe_pairs": probe_pairs, "pruned_probe_pairs": pruned_pairs, "pruned_rows": pruned_rows,
@@ -666,7 +670,7 @@ def run_sharded(args, S, ctx):
     pruned_pairs = hb.get_stat("fast_pruned_pairs") / args.steps
     pruned_rows = hb.get_stat("fast_pruned_rows") / args.steps
     probe_pairs = hb.get_stat("fast_probe_pairs") / args.steps
-    tc = {n: hb.get_stat(n) / args.steps for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units")}
+    tc = {n: hb.get_stat(n) / args.steps for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units", "tc_narrow_units", "tc_narrow_items")}
     hb.set_option("profile", 0)
     # the slowest rank's share of the step spent in the exchange + merge (what the collective costs)
     comm_ms = max_over_ranks(stats["exchange_ms"] + stats["merge_ms"])
@@ -729,8 +733,9 @@ def run_sharded(args, S, ctx):
     roofline = None
     if fast and tc["tc_items"] > 0:
         t_tc = (tc_ms / tc_n) * 1e-3
-        img_bytes = tc["tc_tiles"] * 128.0 * dpad * args.digits + (tc["tc_units"] - 0.5 * tc["tc_half_units"]) * 128.0 * dpad * args.digits
-        roofline = {"kernel": f"tc_pass_kernel<{args.digits},EMIT> (rank 0's shard)", "bound": "hbm",
+        slots = 128.0 * (tc["tc_units"] - tc["tc_half_units"]) + 64.0 * (tc["tc_half_units"] - tc["tc_narrow_units"]) + 32.0 * tc["tc_narrow_units"]
+        img_bytes = tc["tc_tiles"] * 128.0 * dpad * args.digits + slots * dpad * args.digits
+        roofline = {"kernel": f"tc_narrow_kernel<{args.digits}> ({tc['tc_narrow_items']:.0f} of {tc['tc_items']:.0f} items) + tc_pass_kernel<{args.digits},EMIT> (rank 0's shard)", "bound": "hbm",
                     "achieved": img_bytes / t_tc / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": img_bytes / t_tc / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s", "traffic": None,
                     "launch_ms": t_tc * 1e3, "launches_per_step": tc_n / args.steps, "algorithmic_bytes_per_launch": img_bytes,

@@ -320,11 +320,13 @@ static bool g_tc_interleave = true;
 static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
 static int g_hnsw_prefetch = -1;     // hb_set_option("hnsw_prefetch", lines): -1 = sized to the L2 (hnsw_search)
 static bool g_tc_half_m = true;      // EMIT passes: units with <= 64 selections run with M = 64 (hb_tc.cu)
+static bool g_tc_narrow = true;      // IVF list scans: units with <= 32 selections run with the rows on the M side (tc_narrow_kernel)
 static bool g_fast_prune = true;     // IVF scan: drop (query, probed list) pairs that cannot reach the query's threshold
 static int64_t g_fast_probe_pairs = 0;
 // profiling counters that live on the device (a search makes no host round trip for them): [pruned (query, list) pairs,
 // rows they held, units / items / row tiles of the IVF main candidate pass]
-enum { DS_PRUNED_PAIRS = 0, DS_PRUNED_ROWS = 1, DS_TC_UNITS = 2, DS_TC_ITEMS = 3, DS_TC_TILES = 4, DS_TC_HALF_UNITS = 5, DS_COUNT = 8 };
+enum { DS_PRUNED_PAIRS = 0, DS_PRUNED_ROWS = 1, DS_TC_UNITS = 2, DS_TC_ITEMS = 3, DS_TC_TILES = 4, DS_TC_HALF_UNITS = 5,
+       DS_TC_NARROW_UNITS = 6, DS_TC_NARROW_ITEMS = 7, DS_COUNT = 8 };
 static DevBuf g_dev_stats;
 static unsigned long long *dev_stats() {
     const bool fresh = g_dev_stats.p == nullptr;
@@ -832,15 +834,15 @@ static void ivf_finalize(hb_index *ix, const void *rows_dev, const double *row_n
 // =================================================================================================
 struct FastWs {
     DevBuf dig, q64, pslot, srow, ptotal, qu, ql1, qscale, qeps, qmargin, thr, cnt, cnegv, crel, cpos, selval, selpos, pq, pr, exact;
-    DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_slotq, u_slotrel;
-    DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_slotq, t_slotrel;
+    DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_item0n, u_slotq, u_slotrel;
+    DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_item0n, t_slotq, t_slotrel;
     DevBuf a_ids, a_dist, a_norm, a_tmp, dump, timing, simub, pruned;
     DevBuf ppos, ppos0, ok_a, ok_b, relk, probes0, pair_out0, qsel0, lq_off0, uprefix0, uprefix, flat_plan, idx, gq, gids, gdist,
         tmp2;
     void release() {
         DevBuf *all[] = {&dig, &q64, &pslot, &srow, &ptotal, &qu, &ql1, &qscale, &qeps, &qmargin, &thr, &cnt, &cnegv, &crel, &cpos, &selval, &selpos, &pq, &pr, &exact,
-                         &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_slotq, &u_slotrel,
-                         &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_slotq, &t_slotrel,
+                         &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_item0n, &u_slotq, &u_slotrel,
+                         &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_item0n, &t_slotq, &t_slotrel,
                          &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
                          &idx, &gq, &gids, &gdist, &tmp2, &a_ids, &a_dist, &a_norm, &a_tmp, &dump, &timing, &simub, &pruned};
         for (DevBuf *b : all) b->release();
@@ -980,9 +982,10 @@ struct FastJob {
 };
 
 static UnitPlan make_units(const FastPlan &F, DevBuf &b_list, DevBuf &b_sel0, DevBuf &b_nsel, DevBuf &b_ntile, DevBuf &b_item0,
-                           DevBuf &b_slotq, DevBuf &b_slotrel, const int64_t *tile_off) {
+                           DevBuf &b_slotq, DevBuf &b_slotrel, const int64_t *tile_off, DevBuf *b_item0n = nullptr) {
     UnitPlan U;
     const size_t nu = (size_t)std::max(F.nunits, 1);
+    if (b_item0n) U.unit_item0n = b_item0n->as<int32_t>(nu + 1);
     U.unit_list = b_list.as<int32_t>(nu);
     U.unit_sel0 = b_sel0.as<int32_t>(nu);
     U.unit_nsel = b_nsel.as<int32_t>(nu);
@@ -1008,6 +1011,8 @@ static void fast_topk(const FastJob &J) {
     const int ns = S.ns, kbn = S.kbn, kk = fast_kk(J.k), cap = fast_cap(J.k);
     const int64_t nq = J.nq;
     const bool do_sample = J.phase != 2, do_main = J.phase != 1;
+    // IVF list scans (their own threshold plan, EMIT passes, thresholds seeded by the sample): sparse units on tc_narrow_kernel
+    const bool narrow = g_tc_narrow && !J.shared_units && ns == 2;
     HB_REQUIRE(J.phase == 0 || !J.shared_units, "phased jobs need their own threshold plan");
     double *qscale = W.qscale.as<double>(nq), *qeps = W.qeps.as<double>(nq);
     float *qmargin = W.qmargin.as<float>(nq);
@@ -1028,11 +1033,13 @@ static void fast_topk(const FastJob &J) {
     {
         Prof pr(J.profile ? PROF_PACK : -1);
         if (do_main) {
-            U = make_units(J.emit, W.u_list, W.u_sel0, W.u_nsel, W.u_ntile, W.u_item0, W.u_slotq, W.u_slotrel, (const int64_t *)S.tile_off.p);
+            U = make_units(J.emit, W.u_list, W.u_sel0, W.u_nsel, W.u_ntile, W.u_item0, W.u_slotq, W.u_slotrel, (const int64_t *)S.tile_off.p,
+                           narrow ? &W.u_item0n : nullptr);
             aimg = W.aimg.as<int8_t>((size_t)std::max(J.emit.nunits, 1) * kbn * ns * kFastImg);
-            // an IVF list scan runs EMIT passes only: its M = 64 units (<= 64 selections) need half an image
+            // an IVF list scan runs EMIT passes only: its M = 64 units (<= 64 selections) need half an image, its narrow
+            // units (<= 32) a quarter
             launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.emit.nunits, U.slot_query, aimg,
-                              (g_tc_half_m && !J.shared_units) ? U.unit_nsel : nullptr);
+                              ((g_tc_half_m || narrow) && !J.shared_units) ? U.unit_nsel : nullptr, narrow);
         }
         if (!do_sample) {
         } else if (J.shared_units) {
@@ -1045,10 +1052,10 @@ static void fast_topk(const FastJob &J) {
             aimg0 = aimg;
         } else {
             T = make_units(J.thresh, W.t_list, W.t_sel0, W.t_nsel, W.t_ntile, W.t_item0, W.t_slotq, W.t_slotrel,
-                           (const int64_t *)S.tile_off.p);
+                           (const int64_t *)S.tile_off.p, narrow ? &W.t_item0n : nullptr);
             aimg0 = W.aimg0.as<int8_t>((size_t)std::max(J.thresh.nunits, 1) * kbn * ns * kFastImg);
             launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.thresh.nunits, T.slot_query, aimg0,
-                              g_tc_half_m ? T.unit_nsel : nullptr);
+                              (g_tc_half_m || narrow) ? T.unit_nsel : nullptr, narrow);
         }
     }
     TcParams P;
@@ -1064,8 +1071,8 @@ static void fast_topk(const FastJob &J) {
     P.kk = kk;
     P.cap = cap;
     if (g_fast_debug) {
-        P.timing = (long long *)W.timing.get((size_t)g_num_sms * 8 * 8);
-        HB_CUDA(cudaMemsetAsync(P.timing, 0, (size_t)g_num_sms * 8 * 8, g_stream));
+        P.timing = (long long *)W.timing.get((size_t)g_num_sms * 8 * 8 * 2);  // [dense kernel | narrow kernel]
+        HB_CUDA(cudaMemsetAsync(P.timing, 0, (size_t)g_num_sms * 8 * 8 * 2, g_stream));
     }
     P.cnt = cnt;
     P.cand_negv = cnegv;
@@ -1134,6 +1141,8 @@ static void fast_topk(const FastJob &J) {
         P.unit_list = T.unit_list;
         P.unit_nsel = g_tc_half_m ? T.unit_nsel : nullptr;
         P.unit_item0 = T.unit_item0;
+        P.unit_item0n = T.unit_item0n;
+        P.unit_nsel_all = T.unit_nsel;
         P.slot_query = T.slot_query;
         P.slot_rel0 = T.slot_rel0;
         P.tile_stride = J.thresh.tile_div > 1 ? J.thresh.tile_div : 1;
@@ -1152,6 +1161,8 @@ static void fast_topk(const FastJob &J) {
         P.unit_list = U.unit_list;
         P.unit_nsel = g_tc_half_m ? U.unit_nsel : nullptr;
         P.unit_item0 = U.unit_item0;
+        P.unit_item0n = U.unit_item0n;
+        P.unit_nsel_all = U.unit_nsel;
         P.slot_query = U.slot_query;
         P.slot_rel0 = U.slot_rel0;
         launch_tc_pass(P, ns, FAST_EMIT);
@@ -1198,6 +1209,16 @@ static void fast_topk(const FastJob &J) {
             for (int j = 0; j < 6; ++j) a[j] += (double)ht[(size_t)c * 8 + j] / g_num_sms;
         fprintf(stderr, "[hb fast] last tc pass, mean per CTA: items %.1f, mma warp %.0f clk (wait accumulators free %.0f, wait operands %.0f), "
                         "epilogue: wait accumulators %.0f, phase A %.0f\n", a[3], a[0], a[1], a[2], a[4], a[5]);
+        if (narrow) {
+            std::vector<long long> hn((size_t)g_num_sms * 8);
+            HB_CUDA(cudaMemcpy(hn.data(), P.timing + (size_t)g_num_sms * 8, hn.size() * 8, cudaMemcpyDeviceToHost));
+            double b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int c = 0; c < g_num_sms; ++c)
+                for (int j = 0; j < 8; ++j) b[j] += (double)hn[(size_t)c * 8 + j] / g_num_sms;
+            fprintf(stderr, "[hb fast] last narrow pass, mean per CTA: items %.1f, mma warp %.0f clk (wait accumulators free %.0f, wait operands %.0f), "
+                            "epilogue: wait accumulators %.0f, per-item setup %.0f, scores + emission %.0f; producer waits for a free stage %.0f\n",
+                    b[3], b[0], b[1], b[2], b[4], b[5], b[6], b[7]);
+        }
     }
     if (g_fast_debug) {
         std::vector<int32_t> hc((size_t)nq), hok((size_t)nq);
@@ -1636,7 +1657,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
             fast_topk(J);
         }
         // what the main candidate pass covered: units, items (unit x row tile), distinct row tiles
-        if (g_profile) launch_tc_cover(uprefix, (const int64_t *)S.tile_off.p, g_tc_half_m ? lq_off : nullptr, nlist, dev_stats() + DS_TC_UNITS);
+        if (g_profile) launch_tc_cover(uprefix, (const int64_t *)S.tile_off.p, (g_tc_half_m || g_tc_narrow) ? lq_off : nullptr, nlist, dev_stats() + DS_TC_UNITS);
         launch_ivf_resolve(relk, nqc, k, np_eff, probes, pair_out, (const int64_t *)ix->list_off.p, (const int64_t *)ix->list_rows.p,
                            ids + (size_t)q0 * k);
         launch_and_flags(ok_all + q0, ok_c, nqc);
@@ -1818,6 +1839,8 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             g_hnsw_prefetch = (int)value;
         } else if (!strcmp(name, "tc_half_m")) {
             g_tc_half_m = value != 0;
+        } else if (!strcmp(name, "tc_narrow")) {
+            g_tc_narrow = value != 0;
         } else if (!strcmp(name, "rowstream")) {
             g_use_rowstream = value != 0;
         } else if (!strncmp(name, "stream_", 7)) {
@@ -1862,6 +1885,8 @@ HB_API int hb_get_stat(const char *name, double *out) {
         if (!strcmp(name, "tc_items")) { *out = dev_stat(DS_TC_ITEMS); return; }
         if (!strcmp(name, "tc_tiles")) { *out = dev_stat(DS_TC_TILES); return; }
         if (!strcmp(name, "tc_half_units")) { *out = dev_stat(DS_TC_HALF_UNITS); return; }
+        if (!strcmp(name, "tc_narrow_units")) { *out = dev_stat(DS_TC_NARROW_UNITS); return; }
+        if (!strcmp(name, "tc_narrow_items")) { *out = dev_stat(DS_TC_NARROW_ITEMS); return; }
         if (!strcmp(name, "fast_pruned_rows")) { *out = dev_stat(DS_PRUNED_ROWS); return; }
         if (!strcmp(name, "fast_probe_pairs")) { *out = (double)g_fast_probe_pairs; return; }
         if (!strcmp(name, "hnsw_scored")) { *out = (double)g_hnsw_scored; return; }

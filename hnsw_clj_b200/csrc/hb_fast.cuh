@@ -26,6 +26,7 @@ namespace hb {
 constexpr int kFastTile = 128;          // rows per B tile = query slots per unit = UMMA M = UMMA N
 constexpr int kFastKB = 128;            // dimensions per k-block (one 128-byte swizzle row of int8)
 constexpr int kFastImg = kFastTile * kFastKB;  // bytes of one (tile, kb, slice) image
+constexpr int kNarrowSlots = 32;        // a unit with at most this many selections runs with the rows on the M side (tc_narrow_kernel)
 
 // quantisation range: |m| <= qmax so that every digit fits int8 after the balanced split
 __host__ __device__ constexpr double fast_qmax(int ns) { return ns == 2 ? 32000.0 : 8000000.0; }
@@ -63,6 +64,8 @@ struct UnitPlan {
     int32_t *unit_nsel = nullptr;   // [nunits] selections (<= 128)
     int32_t *unit_ntile = nullptr;  // [nunits+1] scratch: row tiles per unit
     int32_t *unit_item0 = nullptr;  // [nunits+1]
+    int32_t *unit_item0n = nullptr; // optional [nunits+1]: when set, the units with <= kNarrowSlots selections are counted
+                                    // here (tc_narrow_kernel) and unit_item0 covers only the others
     int32_t *slot_query = nullptr;  // [nunits*128] query index or -1
     int32_t *slot_rel0 = nullptr;   // [nunits*128] position of the (query, list) segment inside the query's concatenation
 };
@@ -73,8 +76,9 @@ void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_pref
                       const int64_t *pair_out, int pair_div, const int32_t *pair_query, UnitPlan U);
 // gathers the digits of each unit's queries into A images [nunits][kbn][ns][kFastImg]
 // unit_nsel (optional): units with <= 64 selections get only slots 0..63 packed (the M = 64 candidate pass reads no more)
+// narrow: units with <= kNarrowSlots selections get only slots 0..31 (tc_narrow_kernel's B operand)
 void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int32_t *slot_query, int8_t *aimg,
-                       const int32_t *unit_nsel = nullptr);
+                       const int32_t *unit_nsel = nullptr, bool narrow = false);
 
 // ---- the tensor-core pass (hb_tc.cu) -------------------------------------------------------------------
 enum FastMode { FAST_EMIT = 1, FAST_DUMP = 2 };
@@ -85,6 +89,8 @@ struct TcParams {
     int nunits = 0;
     const int32_t *unit_list = nullptr;
     const int32_t *unit_item0 = nullptr;
+    const int32_t *unit_item0n = nullptr;  // non-NULL: item prefix of the narrow units (see UnitPlan); EMIT only
+    const int32_t *unit_nsel_all = nullptr;  // [nunits] selections per unit (always set with unit_item0n)
     const int64_t *tile_off = nullptr;  // first B tile of each list
     const int64_t *list_off = nullptr;  // first slab row of each list
     const int32_t *slot_query = nullptr;

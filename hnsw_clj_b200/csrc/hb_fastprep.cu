@@ -220,15 +220,24 @@ __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, 
     U.unit_ntile[slot_u] = nt;
 }
 
-// exclusive prefix of ntile -> item0 (single block)
-__global__ void __launch_bounds__(1024) unit_scan_kernel(const int32_t *__restrict__ ntile, int count, int32_t *__restrict__ item0) {
+// exclusive prefix of ntile -> item0 (single block).  With item0n: the units of at most kNarrowSlots selections are counted in
+// item0n (tc_narrow_kernel's items), the others in item0 (tc_pass_kernel's).
+__global__ void __launch_bounds__(1024) unit_scan_kernel(const int32_t *__restrict__ ntile, int count, int32_t *__restrict__ item0_all,
+                                                         const int32_t *__restrict__ nsel, int32_t *__restrict__ item0n) {
     __shared__ int s_part[1024];
     __shared__ int s_run;
+    for (int pass = 0; pass < (item0n ? 2 : 1); ++pass) {
+    int32_t *item0 = pass == 0 ? item0_all : item0n;
+    __syncthreads();
     if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
     for (int base = 0; base < count; base += 1024) {
         const int i = base + threadIdx.x;
-        const int v = i < count ? ntile[i] : 0;
+        int v = i < count ? ntile[i] : 0;
+        if (item0n && i < count - 1) {
+            const bool narrow = nsel[i] <= kNarrowSlots;
+            if (narrow != (pass == 1)) v = 0;
+        }
         s_part[threadIdx.x] = v;
         __syncthreads();
         for (int off = 1; off < 1024; off <<= 1) {
@@ -241,6 +250,7 @@ __global__ void __launch_bounds__(1024) unit_scan_kernel(const int32_t *__restri
         __syncthreads();
         if (threadIdx.x == 1023) s_run += s_part[1023];
         __syncthreads();
+    }
     }
 }
 
@@ -266,11 +276,13 @@ __global__ void unit_slots_kernel(int nunits, const int32_t *__restrict__ unit_s
 template <int NS>
 __global__ void __launch_bounds__(256) pack_units_kernel(const int8_t *__restrict__ dig, int kbn,
                                                          const int32_t *__restrict__ slot_query, int8_t *__restrict__ aimg,
-                                                         const int32_t *__restrict__ unit_nsel) {
+                                                         const int32_t *__restrict__ unit_nsel, bool narrow) {
     const int u = blockIdx.x, kb = blockIdx.y;
     const int dpad = kbn * kFastKB;
     if (slot_query[(int64_t)u * kFastTile] < 0) return;  // slots fill from 0: an empty unit (padding / bound) has no items
-    const int nslots = (unit_nsel != nullptr && unit_nsel[u] <= 64) ? 64 : kFastTile;  // M = 64 units: first 8 row groups
+    // M = 64 units: the first 8 row groups of each image; narrow units: the first 4
+    const int ns_u = unit_nsel != nullptr ? unit_nsel[u] : kFastTile;
+    const int nslots = (narrow && ns_u <= kNarrowSlots) ? kNarrowSlots : (ns_u <= 64 ? 64 : kFastTile);
     int8_t *dst = aimg + ((int64_t)u * kbn + kb) * NS * kFastImg;
     for (int i = threadIdx.x; i < NS * nslots * 8; i += blockDim.x) {
         const int ch = i & 7, slot = (i >> 3) % nslots, s = i / (8 * nslots);
@@ -919,26 +931,34 @@ __global__ void accumulate_u64_kernel(unsigned long long *__restrict__ acc, cons
 // acc[3] += units whose selections fit 64 slots (run with M = 64: half of the query image is staged), counted if lq_off
 __global__ void tc_cover_kernel(const int64_t *__restrict__ unit_prefix, const int64_t *__restrict__ tile_off,
                                 const int64_t *__restrict__ lq_off, int nlist, unsigned long long *__restrict__ acc) {
-    unsigned long long u = 0, it = 0, t = 0, h = 0;
+    unsigned long long u = 0, it = 0, t = 0, h = 0, nw = 0, nwi = 0;
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < nlist; l += gridDim.x * blockDim.x) {
         const unsigned long long units = (unsigned long long)(unit_prefix[l + 1] - unit_prefix[l]);
         const unsigned long long tiles = (unsigned long long)(tile_off[l + 1] - tile_off[l]);
         u += units;
         it += units * tiles;
         if (units > 0) t += tiles;
-        if (lq_off != nullptr && units > 0 && (lq_off[l + 1] - lq_off[l]) - (int64_t)(units - 1) * kFastTile <= 64) h += 1;
+        if (lq_off != nullptr && units > 0) {
+            const int64_t last = (lq_off[l + 1] - lq_off[l]) - (int64_t)(units - 1) * kFastTile;  // selections of the list's last unit
+            if (last <= 64) h += 1;
+            if (last <= kNarrowSlots) nw += 1, nwi += tiles;  // acc[4], acc[5]: narrow units and their items
+        }
     }
     for (int o = 16; o > 0; o >>= 1) {
         u += __shfl_xor_sync(0xffffffffu, u, o);
         it += __shfl_xor_sync(0xffffffffu, it, o);
         t += __shfl_xor_sync(0xffffffffu, t, o);
         h += __shfl_xor_sync(0xffffffffu, h, o);
+        nw += __shfl_xor_sync(0xffffffffu, nw, o);
+        nwi += __shfl_xor_sync(0xffffffffu, nwi, o);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(acc, u);
         atomicAdd(acc + 1, it);
         atomicAdd(acc + 2, t);
         atomicAdd(acc + 3, h);
+        atomicAdd(acc + 4, nw);
+        atomicAdd(acc + 5, nwi);
     }
 }
 __global__ void set_i64x4_kernel(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d) {
@@ -1158,7 +1178,7 @@ void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_pref
     unit_plan_kernel<<<blocks_for(nunits + 1, 256), 256, 0, g_stream>>>(nlist, lq_off, unit_prefix, tile_off, nunits, nunits_real,
                                                                         interleave, tile_limit, tile_div, tile_start, U);
     HB_LAUNCH_CHECK();
-    unit_scan_kernel<<<1, 1024, 0, g_stream>>>(U.unit_ntile, nunits + 1, U.unit_item0);
+    unit_scan_kernel<<<1, 1024, 0, g_stream>>>(U.unit_ntile, nunits + 1, U.unit_item0, U.unit_nsel, U.unit_item0n);
     HB_LAUNCH_CHECK();
     unit_slots_kernel<<<blocks_for((int64_t)nunits * kFastTile, 256), 256, 0, g_stream>>>(
         nunits, U.unit_sel0, U.unit_nsel, qsel, pair_out, pair_div, pair_query, U.slot_query, U.slot_rel0);
@@ -1166,11 +1186,11 @@ void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_pref
 }
 
 void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int32_t *slot_query, int8_t *aimg,
-                       const int32_t *unit_nsel) {
+                       const int32_t *unit_nsel, bool narrow) {
     if (nunits == 0) return;
     dim3 grid((unsigned)nunits, (unsigned)kbn);
-    if (ns == 2) pack_units_kernel<2><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg, unit_nsel);
-    else pack_units_kernel<3><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg, unit_nsel);
+    if (ns == 2) pack_units_kernel<2><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg, unit_nsel, narrow);
+    else pack_units_kernel<3><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg, unit_nsel, narrow);
     HB_LAUNCH_CHECK();
 }
 

@@ -494,6 +494,335 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
     }
 }
 
+// =====================================================================================================================
+// Narrow units: rows on the M side.
+//
+// An IVF scan after probe pruning (and the threshold sample of every scan) is made of units that hold a handful of
+// queries: a 128 x 128 item then costs its 96 MMAs at the N = 128 floor (64 clocks each, ~12 k clocks with the hand-off)
+// while HBM needs 8.4 k clocks to deliver the 196 KB of row digits — the tensor pipe, 90 % of it padding, is the bound.
+// tc_narrow_kernel swaps the operands: A = the row tile (M = 128 rows), B = the unit's first 32 query slots (N = 32), so
+// an MMA takes 16 clocks (1.5 k per item), the accumulators are 3 x 32 TMEM columns (two sets: the epilogue of item i
+// overlaps the MMAs of item i + 1) and the only cost left is the bulk copy of the row digits: the pass is HBM-bound.
+// Epilogue: thread = row (TMEM lane), columns = queries.  Thresholds are read, not raised, here (they come from the
+// sample pass; a query without one takes every real row of the tile, slots reserved with one atomic per (query, tile));
+// a row at or above a query's threshold is appended with one warp-aggregated atomic.  Correctness does not depend on the
+// threshold's value: the proof in fast_final_kernel bounds whatever was not emitted by it.
+// =====================================================================================================================
+constexpr int NARROW_EPI_THREADS = 256;
+constexpr int NARROW_THREADS = 64 + NARROW_EPI_THREADS;
+template <int NS>
+struct NarrowCfg {
+    static constexpr int A_BYTES = NS * kFastImg;                  // one k-block of the row tile, every digit
+    static constexpr int B_SLICE = kNarrowSlots * kFastKB;         // one k-block of 32 query slots, one digit (4 KB)
+    static constexpr int B_BYTES = NS * B_SLICE;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int NSTAGE = NS == 2 ? 5 : 3;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024;
+    static constexpr int ACC_COLS = 32;    // TMEM columns of one digit-product accumulator: [hi.hi | hi.lo | lo.hi | lo.lo] (row digit . query digit)
+    static constexpr int SET_COLS = 128;   // columns of one accumulator set
+    static constexpr int TMEM_COLS = 256;  // two sets
+};
+// D = S32, A = B = signed int8, K-major, M = 128, N = 64: the B operand is the unit's 32 query slots TWICE — their high
+// digits (rows 0-31 of the tile) stacked on their low digits (rows 32-63) — so one MMA per row digit yields both digit
+// products and every row image is read from shared memory once per k-step instead of twice (NS = 2 only).
+constexpr uint32_t kIdescI8Narrow = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * kNarrowSlots) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+template <int NS>
+__global__ void __launch_bounds__(NARROW_THREADS, 1) tc_narrow_kernel(const TcParams P) {
+    using Cfg = NarrowCfg<NS>;
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t s_full[Cfg::NSTAGE];
+    __shared__ __align__(8) uint64_t s_empty[Cfg::NSTAGE];
+    __shared__ __align__(8) uint64_t s_tmem_full[2];
+    __shared__ __align__(8) uint64_t s_tmem_empty[2];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int32_t s_q[2][kNarrowSlots];     // per item parity: query of each slot (-1: unused)
+    __shared__ int32_t s_rel0[2][kNarrowSlots];  // position of the (query, list) segment in the query's concatenation
+    __shared__ float s_thr[2][kNarrowSlots];
+    __shared__ int32_t s_base[2][kNarrowSlots];  // >= 0: every real row of the tile is a candidate, its slots start here
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t stage0 = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const int kbn = P.kbn;
+    const int32_t *item0 = P.unit_item0n;
+    const int total_items = item0[P.nunits];
+    const int item_begin = (int)((int64_t)total_items * blockIdx.x / gridDim.x);
+    const int item_end = (int)((int64_t)total_items * (blockIdx.x + 1) / gridDim.x);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::NSTAGE; ++s) {
+            mbar_init(smem_u32(&s_full[s]), 1);
+            mbar_init(smem_u32(&s_empty[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&s_tmem_full[s]), 1);
+            mbar_init(smem_u32(&s_tmem_empty[s]), NARROW_EPI_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                     "n"(Cfg::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        // ===== producer: per k-block the row tile's digit images (NS x 16 KB, from HBM) + the unit's 32 query slots (NS x 4 KB, L2).
+        // One lane, large copies: splitting a stage into 96 pieces of <= 1 KB issued by the whole warp was measured 2.3x slower
+        // (the copy engine takes ~60 clocks per operation). =====
+        if (lane == 0 && item_begin < item_end) {
+            int stage = 0;
+            uint32_t phase = 0;
+            long long t_wait = 0;
+            int u = find_unit(item0, P.nunits, item_begin);
+            for (int item = item_begin; item < item_end; ++item) {
+                while (item >= item0[u + 1]) ++u;
+                const int t = P.tile_start + (item - item0[u]) * P.tile_stride;
+                const int64_t btile = P.tile_off[P.unit_list[u]] + t;
+                const int8_t *qsrc = P.aimg + (int64_t)u * kbn * NS * kFastImg;
+                const int8_t *rsrc = P.bimg + btile * kbn * NS * kFastImg;
+                for (int kb = 0; kb < kbn; ++kb) {
+                    const long long c0 = P.timing ? clock64() : 0;
+                    mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
+                    if (P.timing) t_wait += clock64() - c0;
+                    const uint32_t full = smem_u32(&s_full[stage]);
+                    const uint32_t dst = stage0 + (uint32_t)stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(full, Cfg::STAGE_BYTES);
+                    bulk_g2s(dst, rsrc + (int64_t)kb * NS * kFastImg, Cfg::A_BYTES, full);
+#pragma unroll
+                    for (int sl = 0; sl < NS; ++sl)
+                        bulk_g2s(dst + Cfg::A_BYTES + sl * Cfg::B_SLICE, qsrc + ((int64_t)kb * NS + sl) * kFastImg, Cfg::B_SLICE, full);
+                    if (++stage == Cfg::NSTAGE) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+            if (P.timing) P.timing[(gridDim.x + blockIdx.x) * 8 + 7] = t_wait;
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: D[rows x queries] (+)= A[rows] * B[queries]^T, accumulator sets alternate per item =====
+        if (lane == 0 && item_begin < item_end) {
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t tphase[2] = {0, 0};
+            int it = 0;
+            long long t_tmem = 0, t_full = 0;
+            const long long t_all0 = clock64();
+            for (int item = item_begin; item < item_end; ++item, ++it) {
+                const int set = it & 1;
+                long long c0 = P.timing ? clock64() : 0;
+                mbar_wait(smem_u32(&s_tmem_empty[set]), tphase[set] ^ 1u);
+                if (P.timing) t_tmem += clock64() - c0;
+                tphase[set] ^= 1u;
+                tc_fence_after();
+                const uint32_t dbase = tmem_base + (uint32_t)set * Cfg::SET_COLS;
+                for (int kb = 0; kb < kbn; ++kb) {
+                    c0 = P.timing ? clock64() : 0;
+                    mbar_wait(smem_u32(&s_full[stage]), phase);
+                    if (P.timing) t_full += clock64() - c0;
+                    tc_fence_after();
+                    const uint32_t abase = stage0 + (uint32_t)stage * Cfg::STAGE_BYTES;
+                    const uint32_t bbase = abase + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < kFastKB / 32; ++k4) {
+                        const uint64_t bd = smem_desc(bbase + k4 * 32);  // 64 rows: the slots' high digits, then their low digits
+#pragma unroll
+                        for (int sr = 0; sr < 2; ++sr) {  // digit of the row
+                            const uint64_t ad = smem_desc(abase + sr * kFastImg + k4 * 32);
+                            umma_i8(dbase + (uint32_t)sr * 2 * Cfg::ACC_COLS, ad, bd, kIdescI8Narrow, (kb == 0 && k4 == 0) ? 0u : 1u);
+                        }
+                    }
+                    umma_commit(smem_u32(&s_empty[stage]));
+                    if (++stage == Cfg::NSTAGE) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(smem_u32(&s_tmem_full[set]));
+            }
+            if (P.timing) {  // debug (narrow entries live behind the dense kernel's)
+                long long *T = P.timing + (gridDim.x + blockIdx.x) * 8;
+                T[0] = clock64() - t_all0;
+                T[1] = t_tmem;
+                T[2] = t_full;
+                T[3] = item_end - item_begin;
+            }
+        }
+    } else {
+        // ===== epilogue: 8 warps; thread = (row of the tile = TMEM lane, every other group of 8 query columns) =====
+        // A lone warp per scheduler issues a dependent instruction every ~5 clocks, so the work per item is kept short: only
+        // the column groups the unit really uses are read and scored, the unit's slot data is fetched once per unit (not per
+        // item), one compare per column decides (thr_eff: +inf unused, -inf take every real row).
+        const int quarter = warp & 3;
+        const int chalf = (warp - 2) >> 2;      // column groups chalf, chalf + 2
+        const int et = (warp - 2) * 32 + lane;  // 0..255; threads 0..31 stage the unit's slots
+        const int row = quarter * 32 + lane;    // row of the tile = accumulator lane
+        uint32_t tphase[2] = {0, 0};
+        int u = item_begin < item_end ? find_unit(item0, P.nunits, item_begin) : 0;
+        int it = 0;
+        long long t_meta = 0, t_wait = 0, t_proc = 0;
+        // per-unit state, refreshed when the unit changes
+        int cur_u = -1, u_end = 0, u_item0 = 0, nsel = 0, list_len = 0, my_q = -1, my_rel0 = 0;
+        int64_t tile0 = 0, list_row0 = 0;
+        float my_thr = INFINITY;
+        for (int item = item_begin; item < item_end; ++item, ++it) {
+            const long long e0 = (P.timing && et == 0) ? clock64() : 0;
+            if (cur_u < 0 || item >= u_end) {
+                while (item >= item0[u + 1]) ++u;
+                cur_u = u;
+                u_item0 = item0[u];
+                u_end = item0[u + 1];
+                const int l = P.unit_list[u];
+                nsel = P.unit_nsel_all[u];
+                tile0 = P.tile_off[l];
+                list_row0 = P.list_off[l];
+                list_len = (int)(P.list_off[l + 1] - list_row0);
+                if (et < kNarrowSlots) {
+                    my_q = P.slot_query[(int64_t)u * kFastTile + et];
+                    my_rel0 = my_q >= 0 ? P.slot_rel0[(int64_t)u * kFastTile + et] : 0;
+                    my_thr = my_q >= 0 ? P.thr[my_q] : INFINITY;
+                }
+            }
+            const int t = P.tile_start + (item - u_item0) * P.tile_stride;
+            const int64_t btile = tile0 + t;
+            const int par = it & 1, set = it & 1;
+            const int nvalid = min(max(list_len - t * kFastTile, 0), kFastTile);
+            if (et < kNarrowSlots) {
+                int base = -1;
+                // no bound yet: every real row of the tile is a candidate of this query, its slots reserved with one atomic
+                if (my_q >= 0 && my_thr == -INFINITY && nvalid > 0) base = atomicAdd(&P.cnt[my_q], nvalid);
+                s_q[par][et] = my_q;
+                s_rel0[par][et] = my_rel0;
+                s_thr[par][et] = my_thr;
+                s_base[par][et] = base;
+            }
+            const float rs = P.rs[btile * kFastTile + row] * 256.0f;
+            const bool valid = row < nvalid;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const long long e1 = (P.timing && et == 0) ? clock64() : 0;
+            mbar_wait(smem_u32(&s_tmem_full[set]), tphase[set]);
+            const long long e2 = (P.timing && et == 0) ? clock64() : 0;
+            tphase[set] ^= 1u;
+            tc_fence_after();
+            const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)set * Cfg::SET_COLS;
+            // this thread's columns: group g0 = chalf (columns 8 g0 ..) and g1 = chalf + 2, where the unit reaches them
+            const bool use0 = chalf * 8 < nsel, use1 = (chalf + 2) * 8 < nsel;
+            uint32_t c0[16], c1[16], c1b[16], c2[16];  // hi.hi, hi.lo, lo.hi, lo.lo
+            if (use0) {
+                tmem_ld8(tl + chalf * 8, &c0[0]);
+                tmem_ld8(tl + Cfg::ACC_COLS + chalf * 8, &c1[0]);
+                tmem_ld8(tl + 2 * Cfg::ACC_COLS + chalf * 8, &c1b[0]);
+                tmem_ld8(tl + 3 * Cfg::ACC_COLS + chalf * 8, &c2[0]);
+            }
+            if (use1) {
+                tmem_ld8(tl + (chalf + 2) * 8, &c0[8]);
+                tmem_ld8(tl + Cfg::ACC_COLS + (chalf + 2) * 8, &c1[8]);
+                tmem_ld8(tl + 2 * Cfg::ACC_COLS + (chalf + 2) * 8, &c1b[8]);
+                tmem_ld8(tl + 3 * Cfg::ACC_COLS + (chalf + 2) * 8, &c2[8]);
+            }
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_tmem_empty[set]));
+            if (use0) {
+                const int pos_in_list = t * kFastTile + row;
+                // column c (0..15) of this thread is slot col_of(c) of the unit
+                float sc[16];
+                uint32_t passbits = 0;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c >= 8 && !use1) break;
+                    const int slot = (chalf + (c >> 3) * 2) * 8 + (c & 7);
+                    const int lo = (int)c1[c] + (int)c1b[c] + ((int)c2[c] >> 8);
+                    sc[c] = fmaf((float)(int)c0[c], 256.0f, (float)lo) * rs;
+                    // +inf: unused slot, -inf: every real row is taken (s_base >= 0)
+                    const float th = s_base[par][slot] >= 0 ? -INFINITY : (s_q[par][slot] >= 0 ? s_thr[par][slot] : INFINITY);
+                    passbits |= ((valid && sc[c] >= th) ? 1u : 0u) << c;
+                }
+                // lane c of the warp reserves the slots of column c with ONE atomic for the warp's 32 rows: all columns' atomics
+                // are in flight together
+                uint32_t mymask = 0;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c >= 8 && !use1) break;
+                    const uint32_t m = __ballot_sync(0xffffffffu, (passbits >> c) & 1u);
+                    if (lane == c) mymask = m;
+                }
+                const int myslot = (chalf + ((lane & 15) >> 3) * 2) * 8 + (lane & 7);
+                int mybase = 0;
+                if (lane < 16 && mymask != 0 && s_base[par][myslot] < 0) mybase = atomicAdd(&P.cnt[s_q[par][myslot]], __popc(mymask));
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (c >= 8 && !use1) break;
+                    const uint32_t m = __shfl_sync(0xffffffffu, mymask, c);
+                    if (m == 0) continue;  // uniform over the warp
+                    const int b = __shfl_sync(0xffffffffu, mybase, c);
+                    if ((passbits >> c) & 1u) {
+                        const int slot = (chalf + (c >> 3) * 2) * 8 + (c & 7);
+                        const int fb = s_base[par][slot];
+                        const int idx = fb >= 0 ? fb + row : b + __popc(m & ((1u << lane) - 1u));
+                        if (idx < P.cap) {
+                            const int64_t o = (int64_t)s_q[par][slot] * P.cap + idx;
+                            P.cand_negv[o] = -(double)sc[c];
+                            P.cand_rel[o] = s_rel0[par][slot] + pos_in_list;
+                            P.cand_pos[o] = (int32_t)(list_row0 + pos_in_list);
+                        }
+                    }
+                }
+            }
+            if (P.timing && et == 0) {
+                t_meta += e1 - e0;
+                t_wait += e2 - e1;
+                t_proc += clock64() - e2;
+            }
+        }
+        if (P.timing && et == 0) {
+            long long *T = P.timing + (gridDim.x + blockIdx.x) * 8;
+            T[4] = t_wait;
+            T[5] = t_meta;
+            T[6] = t_proc;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+template <int NS>
+void narrow_launch(const TcParams &P) {
+    auto kernel = tc_narrow_kernel<NS>;
+    HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NarrowCfg<NS>::SMEM_BYTES));
+    const int grid = std::max(1, std::min(g_num_sms, P.nunits * 8));
+    kernel<<<grid, NARROW_THREADS, NarrowCfg<NS>::SMEM_BYTES, g_stream>>>(P);
+    HB_LAUNCH_CHECK();
+}
+
 template <int NS, int MODE, int NB>
 void tc_launch(const TcParams &P, int total_items) {
     auto kernel = tc_pass_kernel<NS, MODE, NB>;
@@ -509,6 +838,10 @@ void tc_launch(const TcParams &P, int total_items) {
 void launch_tc_pass(const TcParams &P, int ns, int mode) {
     if (P.nunits == 0) return;
     HB_REQUIRE(ns == 2 || ns == 3, "digit count must be 2 or 3");
+    if (P.unit_item0n != nullptr) {  // the units with <= kNarrowSlots selections (unit_item0 then covers the others only)
+        HB_REQUIRE(mode == FAST_EMIT && ns == 2, "narrow units serve 2-digit EMIT passes only");
+        narrow_launch<2>(P);
+    }
     HB_REQUIRE(P.kk == 64 || P.kk == 128 || mode == FAST_DUMP, "candidates re-scored per query must be 64 or 128");
     const int hint = P.nunits * 8;
 #define HB_TC(NS_)                                                          \

@@ -476,8 +476,8 @@ def run_ours(args, w, key, ctx, replicas_only=False):
             "peak_source": ("MEASURED_PEAKS.json " + ("hbm_gbs" if hbm_bound else "bf16_tflops (burst)")) if peaks else "fallback",
             "why_this_bound": f"lower bounds on the launch: unique digit-image bytes / HBM peak = {t_bytes * 1e3:.3f} ms, "
                               f"algorithmic flops / bf16 peak = {t_flops * 1e3:.3f} ms",
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel's launch, ncu --set full capture of this very
-            # command (see TRAFFIC below)
+            # dram__bytes_read.sum + dram__bytes_write.sum of the candidate-pass launch: measured by an ncu pass of this very
+            # command (measure_traffic, below); the constant is the last committed capture, used when ncu is unavailable
             "traffic": TRAFFIC.get((key, args.digits, pruned_rows > 0)),
             "launch_ms": t_tc * 1e3, "launches_per_step": tc_n / args.steps,
             "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": img_bytes,
@@ -517,6 +517,26 @@ def run_ours(args, w, key, ctx, replicas_only=False):
             "step_breakdown_ms": stats,
         }
 
+    # ---- the same index without probe pruning, and a second data distribution on which pruning finds nothing ----------
+    unpruned = hard = None
+    if fast and world == 1 and not args.no_extras:
+        hb.set_mode(hb.MODE_FAST)  # (the recall / fast_vs_exact legs above left the process in EXACT mode)
+        unpruned = measure_variant(args, hb, lambda q: gix.search_raw(q, k, nprobe, out_ids=out_ids, out_dist=out_dist), queries, nq,
+                                   opts={"fast_prune": 0})
+        unpruned["ids_equal_pruned_run"] = bool((out_ids.cpu().numpy() == ids_np).all())
+        flops_all = 2.0 * float(np.bincount(asg, minlength=w["nlist"])[probes.reshape(-1)].sum()) * w["d"]
+        unpruned["roofline"] = {"bound": "tensor", "achieved": flops_all / (unpruned["tc_ms"] * 1e-3) / 1e12, "peak": bf16_peak,
+                                "unit": "TFLOP/s", "frac": flops_all / (unpruned["tc_ms"] * 1e-3) / 1e12 / bf16_peak,
+                                "note": "every probed list scanned: the candidate pass is bound by the tensor pipe / its operand traffic"}
+        hard = measure_hard_distribution(args, hb, w, device)
+        hb.set_mode(hb.MODE_EXACT)
+    traffic = None
+    if fast and world == 1 and not args.no_traffic:
+        traffic = measure_traffic(args)
+        if traffic.get("bytes") is not None:
+            roofline["traffic"] = traffic["bytes"]
+        roofline["traffic_source"] = traffic
+
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample + parity on that sample ---------
     cpu = None
     parity = None
@@ -541,12 +561,120 @@ def run_ours(args, w, key, ctx, replicas_only=False):
                                 if replicas else "lists of one global index, l mod N; one batch; all-gather + merge"),
                    "build_s": build_s, "e2e_results_equal_device_results": e2e_same},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-        "fast_vs_exact": fast_vs_exact,
+        "fast_vs_exact": fast_vs_exact, "unpruned": unpruned, "hard_distribution": hard,
     }
     gix.close() if (world == 1 or replicas) else shard.close()
     if world > 1:
         dist.barrier()
     return line
+
+
+# ---------------------------------------------------------------------------------------------------------
+# secondary measurements of the N = 1 line
+# ---------------------------------------------------------------------------------------------------------
+def measure_variant(args, hb, search, queries, nq, opts):
+    """The timed region again (device-resident inputs, CUDA events) with library knobs changed; knobs restored afterwards."""
+    import torch
+
+    for name, val in opts.items():
+        hb.set_option(name, val)
+    try:
+        for _ in range(3):
+            search(queries)
+        torch.cuda.synchronize()
+        hb.set_option("profile", 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            search(queries)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out = {"value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "opts": opts,
+               "tc_ms": hb.get_stat("tc_ms") / args.steps, "exact_fallbacks_per_step": hb.get_stat("fast_fallbacks") / args.steps,
+               "pruned_probe_pairs_per_step": hb.get_stat("fast_pruned_pairs") / args.steps,
+               "probe_pairs_per_step": hb.get_stat("fast_probe_pairs") / args.steps}
+        hb.set_option("profile", 0)
+        return out
+    finally:
+        for name in opts:
+            hb.set_option(name, 1)
+
+
+def measure_hard_distribution(args, hb, w, device):
+    """configs[1]'s shape on data where IVF is not trivially right: the same 2048 Gaussian centres, per-dimension noise 1.0
+    instead of 0.1 (a row sits 45 degrees from its centre, clusters overlap), so recall@10 at nprobe = 32 is below 1 and the
+    exact probe pruning can drop next to nothing.  Same index build, same search call, results checked against EXACT mode."""
+    import torch
+
+    from hnsw_clj_b200 import ivf_flat
+    from hnsw_clj_b200.flat import FlatIndex, recall_at_k
+
+    wh = dict(w, noise=1.0)
+    rows, queries = gen_gpu(wh, device)
+    k, nprobe, nq = wh["k"], wh["nprobe"], wh["nq"]
+    t0 = time.perf_counter()
+    ix = ivf_flat.build_index(rows, num_partitions=wh["nlist"], max_iterations=wh["iters"])
+    build_s = time.perf_counter() - t0
+    ids = torch.empty((nq, k), dtype=torch.int64, device=device)
+    dist = torch.empty((nq, k), dtype=torch.float64, device=device)
+    out = measure_variant(args, hb, lambda q: ix.search_raw(q, k, nprobe, out_ids=ids, out_dist=dist), queries, nq, opts={})
+    f_ids, f_d = ids.cpu().numpy().copy(), dist.cpu().numpy().copy()
+    hb.set_mode(hb.MODE_EXACT)
+    s = min(nq, 2048)
+    x_ids, x_d = ix.search_raw(queries[:s].contiguous(), k, nprobe)
+    with FlatIndex(rows) as fx:
+        exact_ids, _ = fx.search_raw(queries, k)
+    hb.set_mode(hb.MODE_FAST)
+    ix.close()
+    out.update({"workload": f"ivf-flat {wh['n']}x{wh['d']} fp32 cosine nlist={wh['nlist']} nprobe={nprobe} nq={nq} k={k}, "
+                            f"{wh['centres']} Gaussian centres + noise 1.0 per dimension",
+                "recall_at_10": recall_at_k(f_ids, exact_ids), "build_s": build_s,
+                "fast_equals_exact_mode": {"queries": s, "ids_equal": bool((f_ids[:s] == x_ids).all()),
+                                           "dist_bits_equal": bool((f_d[:s].view(np.int64) == x_d.view(np.int64)).all())}})
+    del rows
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from an ncu pass over a child run of
+    this very command (one profiled step, the kernel replayed by ncu; nothing from that run is reported as a timing)."""
+    import shutil
+
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return {"bytes": None, "why": "ncu not found"}
+    kernel = "tc_narrow_kernel" if not any(o.startswith("tc_narrow=0") for o in args.opt) else "tc_pass_kernel"
+    cmd = [ncu, "--profile-from-start", "off", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum",
+           "--clock-control", "none", "-k", f"regex:{kernel}", "--csv", sys.executable, os.path.abspath(__file__), "--steps", "1",
+           "--warmup", "3", "--no-cpu", "--no-extras", "--no-traffic", "--ncu-region", "--workload", args.workload,
+           "--digits", str(args.digits)] + [x for o in args.opt for x in ("--opt", o)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    except Exception as e:  # noqa: BLE001
+        return {"bytes": None, "why": repr(e)[:200]}
+    best = None  # the largest launch of the kernel inside the profiled step = the list scan's main pass
+    rows = {}
+    for line in r.stdout.splitlines():
+        parts = [p.strip('"') for p in line.split('","')]
+        if len(parts) < 5 or not parts[0].lstrip('"').isdigit():
+            continue
+        lid, metric, unit, val = parts[0].lstrip('"'), parts[-3], parts[-2], parts[-1].rstrip('"').replace(",", "")
+        try:
+            v = float(val)
+        except ValueError:
+            continue
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6}.get(unit, 1.0)
+        rows.setdefault(lid, {})[metric] = v * scale
+    for lid, m in rows.items():
+        if "dram__bytes_read.sum" in m and "dram__bytes_write.sum" in m:
+            tot = m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]
+            if best is None or tot > best["bytes"]:
+                best = {"bytes": tot, "read": m["dram__bytes_read.sum"], "write": m["dram__bytes_write.sum"],
+                        "kernel": kernel, "launches_profiled": len(rows),
+                        "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over a child run of this command (1 step)"}
+    return best or {"bytes": None, "why": ("no kernel matched; ncu said: " + (r.stderr or r.stdout)[-300:])}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -777,6 +905,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the unpruned / hard-distribution secondary measurements")
+    ap.add_argument("--no-traffic", action="store_true", help="N = 1: skip the ncu child run that measures roofline.traffic")
     ap.add_argument("--shard", default="rows", choices=["rows", "replicas", "lists"],
                     help="N > 1: rows (ONE global index of N x 12.5M rows, contiguous row blocks, data plane inside the library: "
                          "hb_sharded_ivf_build / hb_sharded_search; weak scaling), replicas (whole configs[1] index per GPU, one "

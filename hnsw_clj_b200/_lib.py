@@ -74,6 +74,7 @@ SIGNATURES = {
     "hb_comm_allreduce_f64": (_int, [_p, _i64, _i32]),
     "hb_index_set_id_base": (_int, [_p, _i64]),
     "hb_index_set_mode": (_int, [_p, _int]),
+    "hb_index_set_coarse_sharded": (_int, [_p, _int]),
     "hb_sharded_search": (_int, [_p, _p, _int, _i64, _i32, _i32, _p, _p]),
     "hb_sharded_kmeans": (_int, [_p, _i64, _i32, _int, _int, _i32, _i32, _p, _i64, _p, _p]),
     "hb_sharded_ivf_build": (_int, [_p, _i64, _i32, _int, _int, _i32, _i32, _p, _i64, _pp]),
@@ -81,6 +82,7 @@ SIGNATURES = {
     "hb_pcaf_matrix": (_int, [_i32, _i32, _i64, _p]),
     "hb_pcaf_project": (_int, [_p, _i32, _i32, _p, _i64, _i32, _p]),
     "hb_pcaf_search": (_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p]),
+    "hb_kpp_sum_pick": (_int, [_p, _i64, C.c_double, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "hb_index_save": (_int, [_p, C.c_char_p]),
     "hb_index_load": (_int, [C.c_char_p, _pp]),
     "hb_index_info": (_int, [_p, C.POINTER(HbInfo)]),

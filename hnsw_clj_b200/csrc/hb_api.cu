@@ -346,6 +346,7 @@ static int g_fast_level_min = 33;     // flat scans of at least this many row ti
 static int g_fast_sample_tiles = 2;  // IVF: row tiles of the nearest list scored by the threshold-seeding pass
 static int64_t g_fast_queries = 0;   // queries answered in FAST mode ...
 static int64_t g_fast_fallbacks = 0; // ... of which recomputed by the exact path (proof failed)
+static int64_t g_coarse_fallbacks = 0;  // sharded coarse routing: (query, rank) pairs whose slice ranking took the exact kernels
 static int64_t g_hnsw_scored = 0;    // (query, row) pairs scored by the HNSW search since "profile" was set
 static int64_t g_hnsw_overflows = 0; // queries re-run with their candidate queue in global memory
 static int g_hnsw_cand_cap = 0;      // shared-memory candidate queue slots (0: 4 * ef, at least 256)
@@ -362,6 +363,11 @@ struct hb_index {
     int64_t n = 0;
     int mode = -1;        // hb_index_set_mode: HB_MODE_EXACT / HB_MODE_FAST for searches of this index, -1 = the process default
     int64_t id_base = 0;  // multi-GPU: global row of local row 0 (hb_sharded_search returns id_base + local row)
+    // multi-GPU row shard of a global IVF-FLAT index (hb_sharded_ivf_build / hb_index_set_coarse_sharded): the coarse routing
+    // of hb_sharded_search is split over the ranks too — rank r ranks the centroids [r nlist/G, (r+1) nlist/G) exactly and the
+    // per-rank top-nprobe lists are exchanged and merged like the final results
+    bool coarse_sharded = false;
+    int cents_slice0 = 0, cents_slice1 = 0;  // the slice fast_cents was built over (0, 0: all centroids)
     // rows as given (flat / hnsw) or list-major slab (ivf)
     DevBuf rows, norms;
     // ivf
@@ -703,12 +709,78 @@ static void assign_rows(const void *rows, int dtype, const double *row_norm, int
 
 // kmeans-plus-plus-init (ivf_flat.clj:32-60; linear: Lightning's d_i-weighted walk, lightning.clj:86-109): `seeds` receives
 // the nlist chosen rows (device int64).  norm = fp64 row norms (device).
+static bool g_kpp_scale = true;  // hb_set_option("kpp_scale", 0): the one-thread prefix walk + exhaustive distance pass (same seeds)
+static int64_t g_kpp_scored = 0, g_kpp_walked = 0, g_kpp_steps = 0;
+static DevBuf g_kpp_buf;
 static void kpp_seeds(const void *rows, int dtype, int64_t n, int d, const double *norm, bool l2, int nlist, int64_t seed, bool linear,
                       int64_t *seeds) {
     JavaRandom rng(seed);
     std::vector<double> u((size_t)nlist);
     const int64_t first = rng.next_int((int32_t)n);
     for (int t = 1; t < nlist; ++t) u[t] = rng.next_double();
+    if (g_kpp_scale) {
+        // hb_kpp.cu: the same picks, with the distance pass pruned by the triangle inequality and the ordered fp64 sum done
+        // as integer adds per chunk
+        const int64_t nchunks = ceil_div(n, kKppChunk);
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        size_t off = 0;
+        auto take = [&](size_t bytes) {
+            const size_t o = off;
+            off += al(bytes);
+            return o;
+        };
+        const size_t o_u = take((size_t)nlist * 8), o_mind = take((size_t)n * 8), o_near = take((size_t)n * 4), o_theta = take((size_t)n * 4),
+                     o_bound = take((size_t)nlist * 8), o_ap = take((size_t)nchunks * 8), o_pf = take((size_t)nchunks * 8),
+                     o_st = take((size_t)(nchunks + 1) * 8), o_ex = take((size_t)nchunks * 4), o_q = take((size_t)nchunks * 8),
+                     o_misc = take(64);
+        char *base = (char *)g_kpp_buf.get(off);
+        KppScaleParams K;
+        K.rows = rows;
+        K.dtype = dtype;
+        K.n = n;
+        K.d = d;
+        K.row_norm = norm;
+        K.l2 = l2;
+        K.linear = linear;
+        K.mind = (double *)(base + o_mind);
+        K.near = (int32_t *)(base + o_near);
+        K.theta = (float *)(base + o_theta);
+        K.seeds = seeds;
+        K.seeds_rw = seeds;
+        K.bound = (double *)(base + o_bound);
+        K.c_approx = (double *)(base + o_ap);
+        K.c_prefix = (double *)(base + o_pf);
+        K.c_start = (double *)(base + o_st);
+        K.c_exp = (int *)(base + o_ex);
+        K.c_q = (long long *)(base + o_q);
+        K.total = (double *)(base + o_misc);
+        K.pick = (int64_t *)(base + o_misc + 8);
+        unsigned long long *counters = (unsigned long long *)(base + o_misc + 16);
+        if (g_profile) {
+            HB_CUDA(cudaMemsetAsync(counters, 0, 16, g_stream));
+            K.n_scored = counters;
+            K.n_walked = counters + 1;
+        }
+        double *ud = (double *)(base + o_u);
+        HB_CUDA(cudaMemcpyAsync(ud, u.data(), (size_t)nlist * 8, cudaMemcpyHostToDevice, g_stream));
+        HB_CUDA(cudaMemcpyAsync(seeds, &first, 8, cudaMemcpyHostToDevice, g_stream));
+        launch_kpp_init_state(n, K.mind, K.near, K.theta);
+        for (int t = 1; t < nlist; ++t) {
+            K.t = t;
+            K.u = ud + t;
+            launch_kpp_scale_step(K);
+        }
+        if (g_profile) {
+            unsigned long long h[2];
+            HB_CUDA(cudaMemcpyAsync(h, counters, 16, cudaMemcpyDeviceToHost, g_stream));
+            sync_stream();
+            g_kpp_scored += (int64_t)h[0];
+            g_kpp_walked += (int64_t)h[1];
+            g_kpp_steps += nlist - 1;
+        }
+        sync_stream();  // u / first (host) were sources of async copies
+        return;
+    }
     double *ud = g_ws.misc3.as<double>((size_t)nlist + 2 + 2 * (size_t)n);
     double *total = ud + nlist;
     double *mind = ud + nlist + 2;
@@ -837,13 +909,14 @@ struct FastWs {
     DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_item0n, u_slotq, u_slotrel;
     DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_item0n, t_slotq, t_slotrel;
     DevBuf a_ids, a_dist, a_norm, a_tmp, dump, timing, simub, pruned;
+    DevBuf sc_pos, sc_dist, sc_gdist, ok_c;
     DevBuf ppos, ppos0, ok_a, ok_b, relk, probes0, pair_out0, qsel0, lq_off0, uprefix0, uprefix, flat_plan, idx, gq, gids, gdist,
         tmp2;
     void release() {
         DevBuf *all[] = {&dig, &q64, &pslot, &srow, &ptotal, &qu, &ql1, &qscale, &qeps, &qmargin, &thr, &cnt, &cnegv, &crel, &cpos, &selval, &selpos, &pq, &pr, &exact,
                          &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_item0n, &u_slotq, &u_slotrel,
                          &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_item0n, &t_slotq, &t_slotrel,
-                         &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
+                         &sc_pos, &sc_dist, &sc_gdist, &ok_c, &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
                          &idx, &gq, &gids, &gdist, &tmp2, &a_ids, &a_dist, &a_norm, &a_tmp, &dump, &timing, &simub, &pruned};
         for (DevBuf *b : all) b->release();
     }
@@ -901,15 +974,20 @@ static FastSideBufs &fast_rows_side(hb_index *ix, bool cosine) {
     }
     return S;
 }
-static FastSideBufs &fast_cents_side(hb_index *ix) {
+// digit images of the centroids [c0, c1) (default: all of them)
+static FastSideBufs &fast_cents_side(hb_index *ix, int c0 = 0, int c1 = -1) {
+    if (c1 < 0) c1 = ix->nlist;
     FastSideBufs &S = ix->fast_cents;
-    if (S.built && S.ns == g_fast_ns) return S;
+    if (S.built && S.ns == g_fast_ns && ix->cents_slice0 == c0 && ix->cents_slice1 == c1) return S;
     S.release();
-    int64_t h[2] = {0, ix->nlist};
+    int64_t h[2] = {0, c1 - c0};
     int64_t *lo = S.list_off.as<int64_t>(2);
     HB_CUDA(cudaMemcpyAsync(lo, h, 16, cudaMemcpyHostToDevice, g_stream));
     sync_stream();
-    build_fast_side(S, ix->cents.p, HB_F64, ix->d, 1, lo, (const double *)ix->cent_norm.p, g_fast_ns);
+    build_fast_side(S, (const double *)ix->cents.p + (size_t)c0 * ix->d, HB_F64, ix->d, 1, lo, (const double *)ix->cent_norm.p + c0,
+                    g_fast_ns);
+    ix->cents_slice0 = c0;
+    ix->cents_slice1 = c1;
     return S;
 }
 
@@ -1441,6 +1519,102 @@ static cudaStream_t g_copy_stream = nullptr;
 // stage costs more than the hidden copy saves (e2e 3.52 ms with one copy, 3.80 ms in blocks of 2048, 4.67 ms in blocks of 1024).
 static int64_t g_host_feed_block = 0;
 
+// ---- coarse routing split over the ranks (row shards of ONE global IVF-FLAT index) -------------------------------------------
+// Every rank holds all centroids, but ranking nlist = 65,536 centroids for every query on every rank is replicated work that
+// grows with the number of GPUs.  Rank r therefore ranks only its slice [r nlist/G, (r+1) nlist/G) — EXACTLY: candidate pass,
+// fp64 re-score of the nprobe best, proof, exact fallback for the queries that fail it — and the G local top-nprobe lists
+// are merged by the same exchange + merge step as the final results (distance, then centroid index: the stable sort of
+// ivf_flat.clj:263-269).  The probe ORDER is then exact as well, so no cross-list tie needs the exact path.
+static bool sharded_coarse_on(const hb_index *ix, int np_eff) {
+    const CommInfo &c = comm_info();
+    return c.inited && c.nranks > 1 && ix->coarse_sharded && ix->metric == HB_COSINE && np_eff <= kFastMaxK &&
+           ix->nlist / c.nranks >= 2 * kFastTile && ix->nlist / c.nranks >= np_eff;
+}
+// exact top-np of the centroid slice for nb queries (device): the reference's arithmetic, ids = position inside the slice
+static void coarse_slice_exact(hb_index *ix, int c0, int c1, const void *q, int qdtype, const double *qn, int64_t nb, int np,
+                               int64_t *out_pos, double *out_dist) {
+    const int d = ix->d, ns = c1 - c0;
+    int64_t *plan = g_ws.plan.as<int64_t>(6);
+    double *coarse = g_ws.cand_val.as<double>((size_t)nb * ns);
+    int64_t h[6] = {0, ns, 0, nb, 0, ceil_div(ns, kTileRows) * ceil_div(nb, kTileQ)};
+    HB_CUDA(cudaMemcpyAsync(plan, h, sizeof(h), cudaMemcpyHostToDevice, g_stream));
+    sync_stream();
+    ScanParams Sc;
+    Sc.rows = (const double *)ix->cents.p + (size_t)c0 * d;
+    Sc.row_norm = (const double *)ix->cent_norm.p + c0;
+    Sc.queries = q;
+    Sc.q_norm = qn;
+    Sc.d = d;
+    Sc.nlist = 1;
+    Sc.list_off = plan;
+    Sc.lq_off = plan + 2;
+    Sc.tile_prefix = plan + 4;
+    Sc.out_stride = ns;
+    Sc.out = coarse;
+    Sc.epi = EPI_COS_GUARD;
+    launch_pairscan(Sc, HB_F64, qdtype, false);
+    SelectParams L;
+    L.vals = coarse;
+    L.nseg = nb;
+    L.seg_stride = ns;
+    L.seg_len_const = ns;
+    L.k = np;
+    L.out_val = out_dist;
+    L.out_pos = out_pos;
+    launch_select(L);
+}
+// Per query the global top-np_eff centroids in exact (distance, index) order -> ppos (list ids), simub (upper bound of the
+// cosine similarity to each probed centroid).  Collective: every rank calls it with the same queries.
+static void sharded_coarse(hb_index *ix, const void *qptr, int qdtype, const double *q64, const double *qn, int64_t nqc, int np_eff,
+                           int64_t *ppos, double *simub) {
+    const CommInfo &c = comm_info();
+    const int nlist = ix->nlist, d = ix->d;
+    const int c0 = (int)((int64_t)nlist * c.rank / c.nranks), c1 = (int)((int64_t)nlist * (c.rank + 1) / c.nranks);
+    FastWs &W = g_fw;
+    int64_t *lpos = W.sc_pos.as<int64_t>((size_t)nqc * np_eff);
+    double *ldist = W.sc_dist.as<double>((size_t)nqc * np_eff);
+    double *gdist = W.sc_gdist.as<double>((size_t)nqc * np_eff);
+    FastSideBufs &C = fast_cents_side(ix, c0, c1);
+    if (C.usable) {
+        int32_t *ok = W.ok_b.as<int32_t>(nqc);
+        FastJob J;
+        J.side = &C;
+        J.list_off = (const int64_t *)C.list_off.p;
+        J.rows_exact = (const double *)ix->cents.p + (size_t)c0 * d;
+        J.rdtype = HB_F64;
+        J.row_norm = (const double *)ix->cent_norm.p + c0;
+        J.queries = qptr;
+        J.qdtype = qdtype;
+        J.q64 = q64;
+        J.nq = nqc;
+        J.qn = qn;
+        J.d = d;
+        J.metric = HB_COSINE;
+        J.epi = EPI_COS_GUARD;
+        J.profile = false;
+        J.k = np_eff;
+        flat_fast_plan(nqc, J.emit, J.thresh, W.flat_plan);
+        J.shared_units = true;
+        J.out_rel = lpos;
+        J.out_dist = ldist;
+        J.out_ok = ok;
+        fast_topk(J);
+        const int64_t served0 = g_fast_queries, fell0 = g_fast_fallbacks;
+        fast_fallback(ok, qptr, qdtype, nqc, d, np_eff, lpos, ldist, [&](const void *gq, int64_t nb, int64_t *gids, double *gd) {
+            double *gn = g_fw.a_norm.as<double>(nb);
+            launch_row_norms(gq, qdtype, nb, d, gn);
+            coarse_slice_exact(ix, c0, c1, gq, qdtype, gn, nb, np_eff, gids, gd);
+        });
+        g_coarse_fallbacks += g_fast_fallbacks - fell0;  // "fast_queries" / "fast_fallbacks" count whole searches, not this stage
+        g_fast_queries = served0;
+        g_fast_fallbacks = fell0;
+    } else {
+        coarse_slice_exact(ix, c0, c1, qptr, qdtype, qn, nqc, np_eff, lpos, ldist);
+    }
+    comm_topk_exchange_merge(ldist, lpos, c0, nqc, np_eff, gdist, ppos, g_comm_p2p, nullptr);
+    launch_sim_from_dist(gdist, nqc * np_eff, simub);
+}
+
 // search-ivf-flat in FAST mode: coarse routing and the probed-list scan both run the candidate pass
 static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64_t nq, int k, int nprobe, int64_t *ids,
                             double *dist, const HostFeed *feed = nullptr) {
@@ -1457,17 +1631,32 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         return;
     }
     FastSideBufs &S = fast_rows_side(ix, true);
-    if (!S.usable) {
-        wait_all();
-        ivf_search_exact(ix, queries, qdtype, nq, k, nprobe, ids, dist, nullptr);
-        return;
-    }
-    const bool fast_coarse = ix->metric == HB_COSINE && np_eff <= kFastMaxK && nlist >= 2 * kFastTile;
-    FastSideBufs *C = fast_coarse ? &fast_cents_side(ix) : nullptr;
-    const bool coarse_tc = C && C->usable;
+    const bool shard_coarse = sharded_coarse_on(ix, np_eff);  // the same on every rank
     const size_t qsz = dtype_size(qdtype);
     int64_t qc = std::max<int64_t>(kFastTile, (1ll << 20) / np_eff);
     qc = std::min(qc, nq);
+    if (!S.usable) {
+        wait_all();
+        if (shard_coarse) {
+            // this shard's rows cannot take the candidate pass (a zero / non-finite norm), but the other ranks wait for its
+            // part of the coarse exchange: contribute it, then answer from the exact path (which ranks all centroids itself)
+            for (int64_t q0 = 0; q0 < nq; q0 += qc) {
+                const int64_t nqc = std::min(qc, nq - q0);
+                const void *qptr = (const char *)queries + (size_t)q0 * d * qsz;
+                double *qn = g_ws.qnorm.as<double>(nqc);
+                launch_row_norms(qptr, qdtype, nqc, d, qn);
+                fast_quant_queries(qptr, qdtype, nqc, d);
+                const double *q64 = launch_widen_queries(qptr, qdtype, nqc * d, g_fw.q64.as<double>((size_t)nqc * d));
+                sharded_coarse(ix, qptr, qdtype, q64, qn, nqc, np_eff, g_fw.ppos.as<int64_t>((size_t)nqc * np_eff),
+                               g_fw.simub.as<double>((size_t)nqc * np_eff));
+            }
+        }
+        ivf_search_exact(ix, queries, qdtype, nq, k, nprobe, ids, dist, nullptr);
+        return;
+    }
+    const bool fast_coarse = !shard_coarse && ix->metric == HB_COSINE && np_eff <= kFastMaxK && nlist >= 2 * kFastTile;
+    FastSideBufs *C = fast_coarse ? &fast_cents_side(ix) : nullptr;
+    const bool coarse_tc = shard_coarse || (C && C->usable);
     if (feed) {  // query chunks must start on a block boundary of the feed
         if (qc >= feed->block && qc < nq) qc -= qc % feed->block;
         else if (qc < feed->block) {
@@ -1485,8 +1674,21 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         const double *q64 = qdtype == HB_F64 ? (const double *)qptr : q64buf;
         int64_t *ppos = W.ppos.as<int64_t>((size_t)nqc * np_eff);
         double *simub = W.simub.as<double>((size_t)nqc * np_eff);
-        int32_t *ok_c = W.ok_b.as<int32_t>(nqc);
-        if (coarse_tc) {
+        int32_t *ok_c = W.ok_c.as<int32_t>(nqc);
+        if (shard_coarse) {
+            Prof pr(PROF_COARSE);
+            wait_all();
+            launch_row_norms(qptr, qdtype, nqc, d, qn);
+            fast_quant_queries(qptr, qdtype, nqc, d);
+            launch_widen_queries(qptr, qdtype, nqc * d, q64buf);
+            sharded_coarse(ix, qptr, qdtype, q64, qn, nqc, np_eff, ppos, simub);
+            {
+                float one_bits;
+                const int32_t one = 1;
+                memcpy(&one_bits, &one, 4);
+                launch_fill_f32((float *)ok_c, nqc, one_bits);  // every probe list is exact: int32 1 in every slot
+            }
+        } else if (coarse_tc) {
             Prof pr(PROF_COARSE);
             // per-query stages in blocks (the blocks of a host batch as they arrive; a device batch is one block)
             const int64_t blk = (feed && feed->block > 0) ? feed->block : nqc;
@@ -1630,7 +1832,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         J.out_rel = relk;
         J.out_dist = dist + (size_t)q0 * k;
         J.out_ok = ok_all + q0;
-        if (coarse_tc && g_fast_set_only) {  // probe order is approximate: cross-list distance ties go to the exact path
+        if (coarse_tc && g_fast_set_only && !shard_coarse) {  // probe order is approximate: cross-list distance ties go to the exact path
             J.tie_list_off = (const int64_t *)ix->list_off.p;
             J.tie_nlist = nlist;
         }
@@ -1787,6 +1989,7 @@ HB_API int hb_shutdown(void) {
         g_fw.release();
         g_dev_stats.release();
         g_assign_side.release();
+        g_kpp_buf.release();
     });
 }
 HB_API const char *hb_last_error(void) { return t_err.c_str(); }
@@ -1830,7 +2033,8 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             prof_collect();
             g_profile = value != 0;
             for (int i = 0; i < PROF_NTAGS; ++i) g_prof_ms[i] = 0, g_prof_n[i] = 0;
-            g_fast_queries = g_fast_fallbacks = 0;
+            g_fast_queries = g_fast_fallbacks = g_coarse_fallbacks = 0;
+            g_kpp_scored = g_kpp_walked = g_kpp_steps = 0;
             g_fast_probe_pairs = 0;
             HB_CUDA(cudaMemsetAsync(dev_stats(), 0, DS_COUNT * 8, g_stream));
             g_hnsw_scored = g_hnsw_overflows = 0;
@@ -1839,6 +2043,8 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             g_hnsw_prefetch = (int)value;
         } else if (!strcmp(name, "tc_half_m")) {
             g_tc_half_m = value != 0;
+        } else if (!strcmp(name, "kpp_scale")) {
+            g_kpp_scale = value != 0;
         } else if (!strcmp(name, "tc_narrow")) {
             g_tc_narrow = value != 0;
         } else if (!strcmp(name, "rowstream")) {
@@ -1880,6 +2086,10 @@ HB_API int hb_get_stat(const char *name, double *out) {
         }
         if (!strcmp(name, "fast_queries")) { *out = (double)g_fast_queries; return; }
         if (!strcmp(name, "fast_fallbacks")) { *out = (double)g_fast_fallbacks; return; }
+        if (!strcmp(name, "coarse_fallbacks")) { *out = (double)g_coarse_fallbacks; return; }
+        if (!strcmp(name, "kpp_rows_scored")) { *out = (double)g_kpp_scored; return; }
+        if (!strcmp(name, "kpp_chunks_walked")) { *out = (double)g_kpp_walked; return; }
+        if (!strcmp(name, "kpp_steps")) { *out = (double)g_kpp_steps; return; }
         if (!strcmp(name, "fast_pruned_pairs")) { *out = dev_stat(DS_PRUNED_PAIRS); return; }
         if (!strcmp(name, "tc_units")) { *out = dev_stat(DS_TC_UNITS); return; }
         if (!strcmp(name, "tc_items")) { *out = dev_stat(DS_TC_ITEMS); return; }
@@ -2395,6 +2605,12 @@ HB_API int hb_index_set_id_base(hb_index *index, int64_t first_global_row) {
         index->id_base = first_global_row;
     });
 }
+HB_API int hb_index_set_coarse_sharded(hb_index *index, int on) {
+    return guarded([&] {
+        HB_REQUIRE(index && index->type == HB_INDEX_IVF_FLAT, "not an IVF-FLAT index");
+        index->coarse_sharded = on != 0;
+    });
+}
 HB_API int hb_index_set_mode(hb_index *index, int mode) {
     return guarded([&] {
         HB_REQUIRE(index && (mode == -1 || mode == HB_MODE_EXACT || mode == HB_MODE_FAST), "bad arguments");
@@ -2612,6 +2828,7 @@ HB_API int hb_sharded_ivf_build(const void *rows, int64_t n_local, int32_t d, in
             ix->n = n_local;
             ix->nlist = nlist;
             ix->id_base = first_global_row;
+            ix->coarse_sharded = true;
             const void *r = stage_in(rows, (size_t)n_local * d * dtype_size(dtype), g_ws.in_a);
             const int64_t *sr = stage_global_seeds(seed_rows, nlist, global_row_count(n_local, first_global_row));
             double *cents = ix->cents.as<double>((size_t)nlist * d);
@@ -2888,6 +3105,36 @@ HB_API int hb_pcaf_search(hb_index *high, hb_index *low, const float *queries, c
         }
         finish_out(oi);
         finish_out(od);
+        sync_stream();
+    });
+}
+
+// The ordered fp64 sum + pick of one k-means++ step on given weights (hb_kpp.cu), for the parity tests:
+// total = w_0 + w_1 + ... added left to right in fp64 (ivf_flat.clj:51-52), pick = first i with running sum >= u * total (:53-58).
+HB_API int hb_kpp_sum_pick(const double *weights, int64_t n, double u, double *out_total, int64_t *out_pick) {
+    return guarded([&] {
+        ensure_init();
+        HB_REQUIRE(weights && n >= 1 && out_total && out_pick, "bad arguments");
+        const int64_t nchunks = ceil_div(n, kKppChunk);
+        const double *w = (const double *)stage_in(weights, (size_t)n * 8, g_ws.in_a);
+        char *base = (char *)g_kpp_buf.get((size_t)(5 * nchunks + 16) * 8 + 1024);
+        KppScaleParams K;
+        K.n = n;
+        K.linear = true;  // the weights as they are
+        K.mind = const_cast<double *>(w);
+        K.c_approx = (double *)base;
+        K.c_prefix = K.c_approx + nchunks;
+        K.c_start = K.c_prefix + nchunks;
+        K.c_q = (long long *)(K.c_start + nchunks + 1);
+        K.c_exp = (int *)(K.c_q + nchunks);
+        double *misc = (double *)(base + (size_t)(5 * nchunks + 8) * 8);
+        HB_CUDA(cudaMemcpyAsync(misc, &u, 8, cudaMemcpyHostToDevice, g_stream));
+        K.u = misc;
+        K.total = misc + 1;
+        K.pick = (int64_t *)(misc + 2);
+        launch_kpp_sum_pick(K);
+        HB_CUDA(cudaMemcpyAsync(out_total, K.total, 8, cudaMemcpyDeviceToHost, g_stream));
+        HB_CUDA(cudaMemcpyAsync(out_pick, K.pick, 8, cudaMemcpyDeviceToHost, g_stream));
         sync_stream();
     });
 }

@@ -33,6 +33,37 @@ struct KppParams {
 };
 void launch_kpp_step(const KppParams &P);
 
+// The same step at scale and bit-identical (hb_kpp.cu): rows the triangle inequality excludes are skipped, the ordered
+// sum runs as integer adds per chunk of kKppChunk rows.  State per row: mind, near (pick order of the seed that gave mind),
+// theta (the row's bound towards that seed); per chunk: the scratch of the ordered sum.
+constexpr int kKppChunk = 512;
+struct KppScaleParams {
+    const void *rows = nullptr;
+    int dtype = HB_F32;
+    int64_t n = 0;
+    int d = 0;
+    const double *row_norm = nullptr;
+    bool l2 = false, linear = false;
+    double *mind = nullptr;    // [n]
+    int32_t *near = nullptr;   // [n]
+    float *theta = nullptr;    // [n]
+    const int64_t *seeds = nullptr;  // [nlist] rows picked so far (device); seeds[t - 1] is the newest
+    int64_t *seeds_rw = nullptr;     // the same array: the new pick goes to seeds_rw[t]
+    int t = 0;                       // seeds picked so far
+    double *bound = nullptr;         // [nlist] scratch
+    double *c_approx = nullptr, *c_prefix = nullptr, *c_start = nullptr;  // [nchunks], [nchunks], [nchunks + 1]
+    int *c_exp = nullptr;            // [nchunks]
+    long long *c_q = nullptr;        // [nchunks]
+    const double *u = nullptr;       // [1] the nextDouble() of this step (device)
+    double *total = nullptr;         // [1]
+    int64_t *pick = nullptr;         // [1]
+    unsigned long long *n_scored = nullptr, *n_walked = nullptr;  // optional counters: rows scored / chunks walked with fp64 adds
+};
+void launch_kpp_init_state(int64_t n, double *mind, int32_t *near, float *theta);
+void launch_kpp_scale_step(const KppScaleParams &P);
+// S, r = u * S and the pick for the weights already in P.mind (the second half of a step on its own)
+void launch_kpp_sum_pick(const KppScaleParams &P);
+
 // slab[j][:] = rows[list_rows[j]][:], slab_norm[j] = norm[list_rows[j]]
 void launch_gather_rows(const void *rows, int dtype, int d, const int64_t *list_rows, int64_t n, void *slab,
                         const double *norm, double *slab_norm);

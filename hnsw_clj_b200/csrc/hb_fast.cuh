@@ -192,6 +192,8 @@ void launch_accumulate_u64(unsigned long long *acc, const unsigned long long *sr
 void launch_tc_cover(const int64_t *unit_prefix, const int64_t *tile_off, const int64_t *lq_off /*NULL: M = 64 units off*/,
                      int nlist, unsigned long long *acc /*[4]: units, items, row tiles, M = 64 units*/);
 void launch_set_i64x4(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d);
+// sim[i] = 1 - dist[i] (+ a rounding allowance): the similarity bound of an exactly ranked probe list
+void launch_sim_from_dist(const double *dist, int64_t n, double *sim);
 // ok[q] &= other[q]
 void launch_and_flags(int32_t *ok, const int32_t *other, int64_t nq);
 

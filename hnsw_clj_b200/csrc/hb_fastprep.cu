@@ -961,6 +961,11 @@ __global__ void tc_cover_kernel(const int64_t *__restrict__ unit_prefix, const i
         atomicAdd(acc + 5, nwi);
     }
 }
+// upper bound of the cosine similarity from an exact cosine distance (probe pruning needs sim(q, centroid) from above)
+__global__ void sim_from_dist_kernel(const double *__restrict__ dist, int64_t n, double *__restrict__ sim) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sim[i] = (1.0 - dist[i]) + 1e-12;
+}
 __global__ void set_i64x4_kernel(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d) {
     p[0] = a, p[1] = b, p[2] = c, p[3] = d;
 }
@@ -1110,6 +1115,11 @@ void launch_tc_cover(const int64_t *unit_prefix, const int64_t *tile_off, const 
                      unsigned long long *acc) {
     if (nlist == 0) return;
     tc_cover_kernel<<<blocks_for(nlist, 256), 256, 0, g_stream>>>(unit_prefix, tile_off, lq_off, nlist, acc);
+    HB_LAUNCH_CHECK();
+}
+void launch_sim_from_dist(const double *dist, int64_t n, double *sim) {
+    if (n == 0) return;
+    sim_from_dist_kernel<<<blocks_for(n, 256), 256, 0, g_stream>>>(dist, n, sim);
     HB_LAUNCH_CHECK();
 }
 void launch_set_i64x4(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d) {

@@ -87,7 +87,9 @@ HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches 
  * (0 = as many as fit) shape that ring; "micro_batch" = n combines concurrent hb_search calls of <= 8 queries on host buffers
  * into batches of up to n queries (default 64, 0 = off: parallel-search-futures, src/hnsw/helper/parallel_search.clj:15-49,
  * without a thread per query); "comm_p2p" = 0 exchanges the local top-k of hb_sharded_search by ncclAllGather instead of
- * the peer-window kernel.  Results never depend on a knob. */
+ * the peer-window kernel; "kpp_scale" = 0 runs k-means++ as the one-thread prefix walk with an exhaustive distance pass
+ * (default 1: pruned distance pass + chunked ordered sum, hb_kpp.cu); "tc_narrow" = 0 keeps sparse IVF units on the
+ * 128 x 128 candidate kernel.  Results never depend on a knob. */
 HB_API int hb_set_option(const char *name, int64_t value);
 /* measurements: "scan_ms"/"scan_count" (list/flat scan kernel), "coarse_ms", "select_ms", "plan_ms", "assign_ms",
  * "tc_ms" (tensor-core candidate pass over all probed lists), "tc_sample_ms" (its threshold-seeding pass), "pack_ms",
@@ -212,6 +214,13 @@ HB_API int hb_pcaf_search(hb_index *high, hb_index *low, const float *queries, c
  * (search-bucket-brute-force, :147-193) is hb_gather_score, the final sort + take k is hb_topk_merge. */
 HB_API int hb_lsh_matrices(int32_t d, int32_t ntables, int32_t proj_dim, int64_t seed, double *out);
 
+/* ---- k-means++ diagnostics ----------------------------------------------------------------------------------------
+ * One k-means++ pick on given non-negative weights: out_total = the weights added left to right in fp64
+ * (ivf_flat.clj:51-52), out_pick = the first i whose running sum reaches u * total (:53-58).  The device computes the
+ * ordered sum with integer adds per chunk (hb_kpp.cu) and must return the bits of the sequential loop; used by the
+ * parity tests to pin that machinery on adversarial inputs (ties, power-of-two crossings, huge dynamic range). */
+HB_API int hb_kpp_sum_pick(const double *weights, int64_t n, double u, double *out_total, int64_t *out_pick);
+
 /* ---- FAST-mode diagnostics ----------------------------------------------------------------------- */
 /* The candidate pass of HB_MODE_FAST on a flat index, unfiltered: for every (query, row) the tensor-core score
  * (exact integer dot product of the quantised digits times the row scale).  Batched form of
@@ -254,6 +263,10 @@ HB_API int hb_comm_broadcast(void *buf, int64_t bytes, int32_t root);
 HB_API int hb_comm_allreduce_f64(double *buf, int64_t count, int32_t op /* 0 = sum, 1 = max */);
 /* the global row of this index's local row 0; hb_sharded_search adds it to every id */
 HB_API int hb_index_set_id_base(hb_index *index, int64_t first_global_row);
+/* IVF-FLAT row shards: split the coarse routing of hb_sharded_search over the ranks as well (rank r ranks the centroids
+ * [r nlist/G, (r+1) nlist/G) exactly, the G top-nprobe lists are exchanged and merged like the results).  On by default for
+ * indexes built by hb_sharded_ivf_build; every rank must use the same setting.  Same results either way. */
+HB_API int hb_index_set_coarse_sharded(hb_index *index, int on);
 /* search mode of THIS index: HB_MODE_EXACT / HB_MODE_FAST, or -1 to follow hb_set_mode (threads that want different
  * modes on different indexes do not race on the process default) */
 HB_API int hb_index_set_mode(hb_index *index, int mode);

@@ -170,6 +170,22 @@ def _rank_main(rank, world, id_path, ret):
             ids, d = sh.search_raw(q, 10, 4)
             res[f"ivf_p2p{p2p}"] = ids.tolist() == wi.tolist() and bool((d.view(np.int64) == wd.view(np.int64)).all())
         res[f"info_p2p{p2p}"] = sharded.comm_info()["p2p"]
+    # coarse routing split over the ranks (needs >= 256 centroids per rank): rank r ranks its half of the 512 centroids exactly,
+    # the top-nprobe lists are exchanged and merged; results must still be the oracle's, with and without the split
+    rows2, q2 = _data(n=20000, d=64, nq=300, seed=29)
+    lo2, hi2 = sharded.row_range(rows2.shape[0], rank, world)
+    oc2, oa2 = orc.kmeans(rows2, 512, iters=1, seed=42)
+    wi2, wd2, wp2 = orc.ivf_search(rows2, oc2, oa2, q2, 10, 8, return_probes=True)
+    for split in (1, 0):
+        for p2p in (1, 0):
+            _lib.set_option("comm_p2p", p2p)
+            with sharded.import_row_shard(rows2[lo2:hi2], lo2, oc2, oa2[lo2:hi2]) as sh:
+                _lib.check(_lib.lib().hb_index_set_coarse_sharded(sh._h, split))
+                _lib.check(_lib.lib().hb_index_set_mode(sh._h, _lib.MODE_FAST))
+                for rep in range(2):
+                    ids, d = sh.search_raw(q2, 10, 8)
+                res[f"coarse_split{split}_p2p{p2p}"] = ids.tolist() == wi2.tolist() and bool((d.view(np.int64) == wd2.view(np.int64)).all())
+    _lib.set_option("comm_p2p", 1)
     # data-parallel k-means: same seeds as the single-GPU build; assignments equal, centroids to the last ulps
     seeds = orc.kmeanspp_init(rows, 16, seed=42)
     cents, asg = sharded.sharded_kmeans(rows[lo:hi], lo, 16, seeds, max_iterations=2)

@@ -1,0 +1,11 @@
+set -x
+timeout 600 python -m pytest tests/test_gpu_multi.py -x -q > gpurun_out/r2h_pytest_multi.log 2>&1; tail -12 gpurun_out/r2h_pytest_multi.log
+timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 2 --steps 5 --warmup 3 --no-replicas > gpurun_out/r2h_bench_2gpu.json 2> gpurun_out/r2h_bench_2gpu.err; tail -c 800 gpurun_out/r2h_bench_2gpu.err
+python - <<'PY'
+import json
+try:
+    l=json.loads(open('gpurun_out/r2h_bench_2gpu.json').read().strip().splitlines()[-1])
+    print('value',l['value'],'ms',l['ms_per_step'],'e2e',l['e2e']['value'],'recall',l['config']['recall_at_10'], l['config']['collective']['kind'])
+    print(l['roofline']['frac'], l['roofline']['step_breakdown_ms']); print(l['fast_vs_exact'], l['parity'])
+except Exception as e: print('ERR',e)
+PY

@@ -117,9 +117,15 @@ def gen_gpu(w, device, query_seed=43):
 
     g = torch.Generator(device=device)
     g.manual_seed(42)
-    centres = torch.randn((w["centres"], w["d"]), generator=g, device=device)
     rows = torch.empty((w["n"], w["d"]), dtype=torch.float32, device=device)
     step = 131072
+    if w.get("structureless"):  # i.i.d. Gaussian rows and queries: no cluster structure for IVF (or the pruning) to exploit
+        for i in range(0, w["n"], step):
+            m = min(step, w["n"] - i)
+            rows[i:i + m] = torch.randn((m, w["d"]), generator=g, device=device)
+        g.manual_seed(query_seed)
+        return rows, torch.randn((w["nq"], w["d"]), generator=g, device=device).contiguous()
+    centres = torch.randn((w["centres"], w["d"]), generator=g, device=device)
     for i in range(0, w["n"], step):
         m = min(step, w["n"] - i)
         idx = torch.randint(0, w["centres"], (m,), generator=g, device=device)
@@ -602,15 +608,16 @@ def measure_variant(args, hb, search, queries, nq, opts):
 
 
 def measure_hard_distribution(args, hb, w, device):
-    """configs[1]'s shape on data where IVF is not trivially right: the same 2048 Gaussian centres, per-dimension noise 1.0
-    instead of 0.1 (a row sits 45 degrees from its centre, clusters overlap), so recall@10 at nprobe = 32 is below 1 and the
-    exact probe pruning can drop next to nothing.  Same index build, same search call, results checked against EXACT mode."""
+    """configs[1]'s shape on data where IVF is not trivially right: i.i.d. Gaussian rows and queries (no clusters at all), so
+    recall@10 at nprobe = 32 of 1024 is far below 1, the exact probe pruning can drop next to nothing and the candidate pass
+    has no score gap to exploit (queries whose proof fails are recomputed by the exact kernels: `exact_fallbacks_per_step`).
+    Same index build, same search call, results checked against EXACT mode."""
     import torch
 
     from hnsw_clj_b200 import ivf_flat
     from hnsw_clj_b200.flat import FlatIndex, recall_at_k
 
-    wh = dict(w, noise=1.0)
+    wh = dict(w, structureless=True)
     rows, queries = gen_gpu(wh, device)
     k, nprobe, nq = wh["k"], wh["nprobe"], wh["nq"]
     t0 = time.perf_counter()
@@ -628,7 +635,7 @@ def measure_hard_distribution(args, hb, w, device):
     hb.set_mode(hb.MODE_FAST)
     ix.close()
     out.update({"workload": f"ivf-flat {wh['n']}x{wh['d']} fp32 cosine nlist={wh['nlist']} nprobe={nprobe} nq={nq} k={k}, "
-                            f"{wh['centres']} Gaussian centres + noise 1.0 per dimension",
+                            f"i.i.d. Gaussian rows and queries (structureless)",
                 "recall_at_10": recall_at_k(f_ids, exact_ids), "build_s": build_s,
                 "fast_equals_exact_mode": {"queries": s, "ids_equal": bool((f_ids[:s] == x_ids).all()),
                                            "dist_bits_equal": bool((f_d[:s].view(np.int64) == x_d.view(np.int64)).all())}})
@@ -755,17 +762,32 @@ def run_sharded(args, S, ctx):
     truth_ids = truth_ids.copy()
 
     # ---- build (untimed setup; reported): data-parallel k-means + local slabs, inside the library ----------------------
-    seeds = draw_seed_rows(n_total, nlist)
+    # seeds: the reference's k-means++ (ivf_flat.clj:32-60, bit-exact device implementation: hb_kmeanspp_init) over the first
+    # 8 * nlist rows of rank 0's shard (the data are i.i.d. over the ranks, rank 0 holds global rows 0..n_per), broadcast
+    # through the library's communicator.  k-means++ over all N * 12.5M rows would walk every row once per seed.
     hb.set_option("profile", 1)
     barrier()
     t0 = time.perf_counter()
+    sample = min(n_per, 8 * nlist)
+    seeds = np.zeros(nlist, dtype=np.int64)
+    if args.seeding == "random":
+        seeds = draw_seed_rows(n_total, nlist)
+    elif rank == 0:
+        from hnsw_clj_b200 import ivf_flat
+
+        seeds = np.ascontiguousarray(ivf_flat.kmeanspp_init(rows[:sample], nlist), dtype=np.int64)
+    if args.seeding != "random":
+        sharded.comm_broadcast(seeds, 0)
+    seed_s = time.perf_counter() - t0
     ix = sharded.RowShardedIVFFlat(rows, first_row, nlist, seeds, max_iterations=S["iters"])
     barrier()
     build_s = time.perf_counter() - t0
     build = {"build_s": build_s, "lloyd_rounds": S["iters"], "assign_ms": hb.get_stat("assign_ms"), "update_ms": hb.get_stat("update_ms"),
              "allreduce_ms": hb.get_stat("allreduce_ms"), "allreduce_bytes_per_round": nlist * d * 8 + nlist * 8,
-             "seeding": "nlist distinct random global rows (numpy default_rng(42)); the reference's k-means++ "
-                        "(ivf_flat.clj:32-60) walks all rows once per seed"}
+             "seeding_s": seed_s, "kpp_rows_scored": hb.get_stat("kpp_rows_scored"), "kpp_chunks_walked": hb.get_stat("kpp_chunks_walked"),
+             "seeding": ("nlist distinct random global rows (numpy default_rng(42))" if args.seeding == "random" else
+                         f"k-means++ (ivf_flat.clj:32-60: java.util.Random(42), exact) over the first {sample} rows of rank 0's shard "
+                         "(an i.i.d. sample of the data), seeds broadcast; Lloyd rounds over all rows of all ranks")}
     hb.set_option("profile", 0)
 
     out_ids = torch.empty((nq, k), dtype=torch.int64, device=device)
@@ -914,6 +936,8 @@ def main():
     ap.add_argument("--shard-workload", default="c100m", choices=["c100m", "small"],
                     help="--shard rows: c100m = 12.5M rows per GPU (100M x 768 at N = 8), small = 0.5M rows per GPU (smoke runs)")
     ap.add_argument("--no-replicas", action="store_true", help="--shard rows: skip the secondary replicas measurement")
+    ap.add_argument("--seeding", default="kpp-sample", choices=["kpp-sample", "random"],
+                    help="--shard rows: seeds of the sharded k-means (k-means++ over a sample held by rank 0, or random rows)")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"],
                     help="fast: tensor-core candidate pass + fp64 re-score + proof (same results); exact: fp64 for every pair")
     ap.add_argument("--opt", action="append", default=[], help="library knob name=value (hb_set_option), repeatable")

@@ -200,8 +200,10 @@ __global__ void __launch_bounds__(128) kpp_chunk_exact_kernel(const double *__re
     }
 }
 
-// Composition over the chunks (thread 0; chunk records staged through shared memory by the block), S, r = u * S and the pick:
-// the first i with fl(cum_i + x_i) >= r (ivf_flat.clj:54-58), clamped to n - 1.
+// Composition over the chunks, S, r = u * S and the pick: the first i with fl(cum_i + x_i) >= r (ivf_flat.clj:54-58), clamped
+// to n - 1.  Thread 0 composes (one integer add per chunk; the chunk records are staged through shared memory by the block);
+// a chunk that needs real fp64 adds is first copied into shared memory by the whole block (one coalesced read instead of 512
+// dependent global loads), then walked by thread 0.
 template <bool SQ>
 __global__ void __launch_bounds__(256) kpp_compose_pick_kernel(const double *__restrict__ mind, int64_t n, int nchunks,
                                                                const int *__restrict__ c_exp, const long long *__restrict__ c_q,
@@ -211,8 +213,9 @@ __global__ void __launch_bounds__(256) kpp_compose_pick_kernel(const double *__r
     constexpr int TILE = 2048;
     __shared__ int s_e[TILE];
     __shared__ long long s_qq[TILE];
+    __shared__ double s_w[KC];
     __shared__ double s_cum, s_r;
-    __shared__ int s_k;
+    __shared__ int s_k, s_next, s_need;
     __shared__ unsigned long long s_walk;
     if (threadIdx.x == 0) {
         s_cum = 0.0;
@@ -225,28 +228,44 @@ __global__ void __launch_bounds__(256) kpp_compose_pick_kernel(const double *__r
             s_e[j] = c_exp[base + j];
             s_qq[j] = c_q[base + j];
         }
+        if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            double cum = s_cum;
-            for (int j = 0; j < m; ++j) {
-                const int k = base + j;
-                c_start[k] = cum;
-                const int e = s_e[j];
-                bool done = false;
-                if (e != INT_MIN && cum > 0.0 && ilogb(cum) == e) {
-                    const long long mm = (long long)scalbn(cum, 52 - e) + s_qq[j];  // cum / ulp is an integer in [2^52, 2^53)
-                    if (mm < 9007199254740992ll) {
-                        cum = scalbn((double)mm, e - 52);
-                        done = true;
+        while (true) {
+            if (threadIdx.x == 0) {
+                double cum = s_cum;
+                int j = s_next;
+                s_need = -1;
+                for (; j < m; ++j) {
+                    const int e = s_e[j];
+                    c_start[base + j] = cum;
+                    if (e != INT_MIN && cum > 0.0 && ilogb(cum) == e) {
+                        const long long mm = (long long)scalbn(cum, 52 - e) + s_qq[j];  // cum / ulp is an integer in [2^52, 2^53)
+                        if (mm < 9007199254740992ll) {
+                            cum = scalbn((double)mm, e - 52);
+                            continue;
+                        }
                     }
+                    s_need = base + j;  // real fp64 adds in row order
+                    break;
                 }
-                if (!done) {  // real fp64 adds in row order
-                    const int64_t b = (int64_t)k * KC, eend = min(n, b + KC);
-                    for (int64_t i = b; i < eend; ++i) cum = __dadd_rn(cum, weight_of<SQ>(mind[i]));
-                    ++s_walk;
-                }
+                s_cum = cum;
+                s_next = j + 1;
             }
-            s_cum = cum;
+            __syncthreads();
+            const int need = s_need;
+            if (need < 0) break;
+            const int64_t b = (int64_t)need * KC;
+            const int cnt = (int)min((int64_t)KC, n - b);
+            for (int j = threadIdx.x; j < cnt; j += blockDim.x) s_w[j] = weight_of<SQ>(mind[b + j]);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double cum = s_cum;
+#pragma unroll 8
+                for (int j = 0; j < cnt; ++j) cum = __dadd_rn(cum, s_w[j]);
+                s_cum = cum;
+                ++s_walk;
+            }
+            __syncthreads();
         }
     }
     __syncthreads();
@@ -265,22 +284,28 @@ __global__ void __launch_bounds__(256) kpp_compose_pick_kernel(const double *__r
             break;
         }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int64_t p = n - 1;
-        if (s_k < nchunks) {
-            double cum = c_start[s_k];
-            const int64_t b = (int64_t)s_k * KC, eend = min(n, b + KC);
-            for (int64_t i = b; i < eend; ++i) {
-                cum = __dadd_rn(cum, weight_of<SQ>(mind[i]));
+    const int kp = s_k;
+    if (kp < nchunks) {
+        const int64_t b = (int64_t)kp * KC;
+        const int cnt = (int)min((int64_t)KC, n - b);
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x) s_w[j] = weight_of<SQ>(mind[b + j]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int64_t p = n - 1;
+            double cum = c_start[kp];
+            for (int j = 0; j < cnt; ++j) {
+                cum = __dadd_rn(cum, s_w[j]);
                 if (cum >= r) {
-                    p = i;
+                    p = b + j;
                     break;
                 }
             }
+            *pick = p;
         }
-        *pick = p;
-        if (n_walked) atomicAdd(n_walked, s_walk);
+    } else if (threadIdx.x == 0) {
+        *pick = n - 1;
     }
+    if (threadIdx.x == 0 && n_walked) atomicAdd(n_walked, s_walk);
 }
 
 __global__ void kpp_record_pick_kernel(const int64_t *pick, int64_t *out_seed) { *out_seed = *pick; }

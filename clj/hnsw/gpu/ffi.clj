@@ -48,6 +48,32 @@
 (defonce hb-index-load (handle "hb_index_load" I P P))
 ;; int hb_index_free(hb_index*)
 (defonce hb-index-free (handle "hb_index_free" I P))
+;; int hb_index_set_mode(hb_index*, int mode): HB_MODE_EXACT 0 / HB_MODE_FAST 1 / -1 = process default
+(defonce hb-index-set-mode (handle "hb_index_set_mode" I P I))
+
+;; ---- multi-GPU: one JVM per GPU (include/hnswb200.h, "multi-GPU") ----
+;; int hb_comm_unique_id(void* out128); int hb_comm_init(const void* id128, int32 nranks, int32 rank)
+(defonce hb-comm-unique-id (handle "hb_comm_unique_id" I P))
+(defonce hb-comm-init (handle "hb_comm_init" I P I I))
+(defonce hb-comm-shutdown (handle "hb_comm_shutdown" I))
+;; int hb_comm_broadcast(void* buf, int64 bytes, int32 root)
+(defonce hb-comm-broadcast (handle "hb_comm_broadcast" I P J I))
+;; int hb_sharded_ivf_build(rows, n_local, d, dtype, metric, nlist, iters, const int64* seed_rows, int64 first_global_row, hb_index** out)
+(defonce hb-sharded-ivf-build (handle "hb_sharded_ivf_build" I P J I I I I I P J P))
+;; int hb_index_set_id_base(hb_index*, int64 first_global_row)
+(defonce hb-index-set-id-base (handle "hb_index_set_id_base" I P J))
+;; int hb_sharded_search(index, queries, qdtype, nq, k, param, int64* out_ids, double* out_dist): ids are global rows
+(defonce hb-sharded-search (handle "hb_sharded_search" I P P I J I I P P))
+
+;; ---- float[] Vector-API variants + PCAF (src/hnsw/simd.clj:18-115, src/hnsw/ann/dimreduct/pcaf.clj) ----
+;; int hb_pairwise_f32lanes(const float* a, int64 na, const float* b, int64 nb, int32 d, int metric, int32 lanes, double* out)
+(defonce hb-pairwise-f32lanes (handle "hb_pairwise_f32lanes" I P J P J I I I P))
+;; int hb_pcaf_matrix(int32 original_dim, int32 target_dim, int64 seed, float* out)
+(defonce hb-pcaf-matrix (handle "hb_pcaf_matrix" I I I J P))
+;; int hb_pcaf_project(matrix, original_dim, target_dim, rows, n, lanes, float* out)
+(defonce hb-pcaf-project (handle "hb_pcaf_project" I P I I P J I P))
+;; int hb_pcaf_search(high, low, queries, low_queries, nq, k, k_filter, lanes, int64* out_ids, double* out_dist)
+(defonce hb-pcaf-search (handle "hb_pcaf_search" I P P P P J I I I P P))
 
 (defn last-error ^String []
   (let [^MemorySegment p (.invokeWithArguments ^MethodHandle hb-last-error (object-array 0))]

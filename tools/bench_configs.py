@@ -383,8 +383,25 @@ def run_c5(args):
 
     dev = torch.device("cuda", 0)
     n, d, nq, k, ef = args.n or 20000, 768, 16384, 10, 128
-    rows = unit_rows(n, d, 42, dev)
     g = torch.Generator(device=dev)
+    if args.data == "gaussian":
+        # structureless: i.i.d. Gaussian directions.  Every graph index struggles here (the reference's own insert-built graph
+        # reaches the same recall as the bulk graph, profiles/r01c_config4_hnsw_20k.json.log)
+        rows = unit_rows(n, d, 42, dev)
+        data_desc = "unit-norm i.i.d. Gaussian (structureless)"
+    else:
+        # unit-norm rows with cluster structure (cf. :clustered, test/data_generator.clj:74-79): n / 500 centres, per-dimension
+        # noise args.noise, then normalised — embeddings-like data on which a navigable graph is meaningful
+        g.manual_seed(42)
+        ncent = max(8, n // 500)
+        centres = torch.randn((ncent, d), generator=g, device=dev)
+        rows = torch.empty((n, d), dtype=torch.float32, device=dev)
+        for i in range(0, n, 1 << 18):
+            m = min(1 << 18, n - i)
+            idx = torch.randint(0, ncent, (m,), generator=g, device=dev)
+            rows[i:i + m] = centres[idx] + args.noise * torch.randn((m, d), generator=g, device=dev)
+        rows = rows / rows.norm(dim=1, keepdim=True)
+        data_desc = f"unit-norm clustered ({ncent} Gaussian centres, noise {args.noise} per dimension)"
     g.manual_seed(43)
     queries = (rows[torch.randint(0, n, (nq,), generator=g, device=dev)] +
                0.3 / d ** 0.5 * torch.randn((nq, d), generator=g, device=dev)).contiguous()
@@ -428,7 +445,7 @@ def run_c5(args):
     pk = peaks()
     bytes_scored = scored * (d * 4 + 4)
     line = {
-        "config": f"BASELINE configs[4]{'' if n >= 1000000 else ' on a reduced graph'}: HNSW M=16 efSearch={ef}, {n}x{d} fp32 unit-norm, {nq} concurrent queries, top-{k} "
+        "config": f"BASELINE configs[4]{'' if n >= 1000000 else ' on a reduced graph'}: HNSW M=16 efSearch={ef}, {n}x{d} fp32 {data_desc}, {nq} concurrent queries, top-{k} "
                   f"({how}, {build_s:.0f} s)",
         "metric": "queries/s", "value": nq / ms * 1e3, "ms_per_batch": ms, "recall_at_10": recall_at_k(ids, ex_ids),
         "pairs_scored_per_batch": scored,
@@ -512,6 +529,8 @@ def main():
     ap.add_argument("--nlist", type=int, default=65536)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--graph", choices=["oracle", "bulk"], default="bulk")
+    ap.add_argument("--data", choices=["gaussian", "clustered"], default="clustered", help="c5: row distribution")
+    ap.add_argument("--noise", type=float, default=0.5, help="c5 --data clustered: per-dimension noise around the centres")
     ap.add_argument("--opt", action="append", default=[], help="library knob name=value (hb_set_option), repeatable")
     ap.add_argument("--sweep", default="", help="c5: name=v1,v2,... re-times the search for each value of a library knob")
     args = ap.parse_args()

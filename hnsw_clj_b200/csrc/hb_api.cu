@@ -320,6 +320,7 @@ static bool g_tc_interleave = true;
 static int g_fast_ns = 2;            // digits per element in FAST mode (2: 16-bit mantissas, 3: 24-bit)
 static int g_hnsw_prefetch = -1;     // hb_set_option("hnsw_prefetch", lines): -1 = sized to the L2 (hnsw_search)
 static bool g_tc_half_m = true;      // EMIT passes: units with <= 64 selections run with M = 64 (hb_tc.cu)
+static bool g_fast_carry = true;     // IVF list scans: the sample pass's candidates are kept, its tiles are not scanned twice
 static bool g_tc_narrow = true;      // IVF list scans: units with <= 32 selections run with the rows on the M side (tc_narrow_kernel)
 static bool g_fast_prune = true;     // IVF scan: drop (query, probed list) pairs that cannot reach the query's threshold
 static int64_t g_fast_probe_pairs = 0;
@@ -906,7 +907,7 @@ static void ivf_finalize(hb_index *ix, const void *rows_dev, const double *row_n
 // =================================================================================================
 struct FastWs {
     DevBuf dig, q64, pslot, srow, ptotal, qu, ql1, qscale, qeps, qmargin, thr, cnt, cnegv, crel, cpos, selval, selpos, pq, pr, exact;
-    DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_item0n, u_slotq, u_slotrel;
+    DevBuf aimg, aimg0, u_list, u_sel0, u_nsel, u_ntile, u_item0, u_item0n, u_tile0, u_slotq, u_slotrel;
     DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_item0n, t_slotq, t_slotrel;
     DevBuf a_ids, a_dist, a_norm, a_tmp, dump, timing, simub, pruned;
     DevBuf sc_pos, sc_dist, sc_gdist, ok_c;
@@ -914,7 +915,7 @@ struct FastWs {
         tmp2;
     void release() {
         DevBuf *all[] = {&dig, &q64, &pslot, &srow, &ptotal, &qu, &ql1, &qscale, &qeps, &qmargin, &thr, &cnt, &cnegv, &crel, &cpos, &selval, &selpos, &pq, &pr, &exact,
-                         &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_item0n, &u_slotq, &u_slotrel,
+                         &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_item0n, &u_tile0, &u_slotq, &u_slotrel,
                          &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_item0n, &t_slotq, &t_slotrel,
                          &sc_pos, &sc_dist, &sc_gdist, &ok_c, &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
                          &idx, &gq, &gids, &gdist, &tmp2, &a_ids, &a_dist, &a_norm, &a_tmp, &dump, &timing, &simub, &pruned};
@@ -1045,6 +1046,7 @@ struct FastJob {
     FastPlan emit, thresh;
     bool shared_units = false;  // thresh covers the same units as emit (fewer tiles)
     bool profile = true;        // record the per-stage events (the coarse job is timed as a whole by its caller)
+    bool cover_stats = false;   // count what the main candidate pass covers ("tc_units" ... stats; the IVF list scan)
     // The caller needs the exact top-k SET only (IVF coarse routing: which lists to probe): candidates that are in it by
     // their bounds alone are not re-scored, out_rel lists them first, out_dist is not meaningful.
     bool set_only = false;
@@ -1060,10 +1062,12 @@ struct FastJob {
 };
 
 static UnitPlan make_units(const FastPlan &F, DevBuf &b_list, DevBuf &b_sel0, DevBuf &b_nsel, DevBuf &b_ntile, DevBuf &b_item0,
-                           DevBuf &b_slotq, DevBuf &b_slotrel, const int64_t *tile_off, DevBuf *b_item0n = nullptr) {
+                           DevBuf &b_slotq, DevBuf &b_slotrel, const int64_t *tile_off, DevBuf *b_item0n = nullptr,
+                           DevBuf *b_tile0 = nullptr, int skip_tiles = 0, unsigned long long *stats = nullptr) {
     UnitPlan U;
     const size_t nu = (size_t)std::max(F.nunits, 1);
     if (b_item0n) U.unit_item0n = b_item0n->as<int32_t>(nu + 1);
+    if (b_tile0) U.unit_tile0 = b_tile0->as<int32_t>(nu);
     U.unit_list = b_list.as<int32_t>(nu);
     U.unit_sel0 = b_sel0.as<int32_t>(nu);
     U.unit_nsel = b_nsel.as<int32_t>(nu);
@@ -1072,7 +1076,7 @@ static UnitPlan make_units(const FastPlan &F, DevBuf &b_list, DevBuf &b_sel0, De
     U.slot_query = b_slotq.as<int32_t>(nu * kFastTile);
     U.slot_rel0 = b_slotrel.as<int32_t>(nu * kFastTile);
     launch_unit_plan(F.nlist, F.lq_off, F.unit_prefix, tile_off, F.nunits, F.nunits_real, F.interleave, F.tile_limit, F.tile_div,
-                     F.tile_start, F.qsel, F.pair_out, F.pair_div, nullptr, U);
+                     F.tile_start, F.qsel, F.pair_out, F.pair_div, nullptr, U, skip_tiles, stats);
     return U;
 }
 
@@ -1091,6 +1095,10 @@ static void fast_topk(const FastJob &J) {
     const bool do_sample = J.phase != 2, do_main = J.phase != 1;
     // IVF list scans (their own threshold plan, EMIT passes, thresholds seeded by the sample): sparse units on tc_narrow_kernel
     const bool narrow = g_tc_narrow && !J.shared_units && ns == 2;
+    // IVF list scans: the sample pass scores the first tiles of every query's nearest list; its kk best candidates are KEPT
+    // (compacted in place) and the main pass does not read those tiles again for the units that only hold nearest-list queries
+    const bool carry = g_fast_carry && !J.shared_units && J.thresh.tile_limit > 0 && J.thresh.tile_div <= 1;
+    const int skip_tiles = carry ? J.thresh.tile_limit : 0;
     HB_REQUIRE(J.phase == 0 || !J.shared_units, "phased jobs need their own threshold plan");
     double *qscale = W.qscale.as<double>(nq), *qeps = W.qeps.as<double>(nq);
     float *qmargin = W.qmargin.as<float>(nq);
@@ -1112,7 +1120,8 @@ static void fast_topk(const FastJob &J) {
         Prof pr(J.profile ? PROF_PACK : -1);
         if (do_main) {
             U = make_units(J.emit, W.u_list, W.u_sel0, W.u_nsel, W.u_ntile, W.u_item0, W.u_slotq, W.u_slotrel, (const int64_t *)S.tile_off.p,
-                           narrow ? &W.u_item0n : nullptr);
+                           narrow ? &W.u_item0n : nullptr, carry ? &W.u_tile0 : nullptr, skip_tiles,
+                           (g_profile && J.cover_stats) ? dev_stats() + DS_TC_UNITS : nullptr);
             aimg = W.aimg.as<int8_t>((size_t)std::max(J.emit.nunits, 1) * kbn * ns * kFastImg);
             // an IVF list scan runs EMIT passes only: its M = 64 units (<= 64 selections) need half an image, its narrow
             // units (<= 32) a quarter
@@ -1226,9 +1235,16 @@ static void fast_topk(const FastJob &J) {
         P.tile_stride = J.thresh.tile_div > 1 ? J.thresh.tile_div : 1;
         launch_tc_pass(P, ns, FAST_EMIT);
     }
-    select_candidates();
-    launch_thr_from_sample(selval, cnt, nq, kk, cap, J.k, qmargin, thr);
-    HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
+    if (carry) {
+        // keep the kk best sample candidates in place (cnt = their number) and raise the thresholds to the kk-th best / the
+        // k-th best - margin: what thr_from_sample did, without throwing the candidates away
+        Prof pr(J.profile ? PROF_SELECT : -1);
+        launch_cand_compact(cnegv, crel, cpos, cnt, nq, kk, cap, J.k, qmargin, thr, selval, selpos);
+    } else {
+        select_candidates();
+        launch_thr_from_sample(selval, cnt, nq, kk, cap, J.k, qmargin, thr);
+        HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
+    }
     }
     if (!do_main) return;
     {
@@ -1241,9 +1257,13 @@ static void fast_topk(const FastJob &J) {
         P.unit_item0 = U.unit_item0;
         P.unit_item0n = U.unit_item0n;
         P.unit_nsel_all = U.unit_nsel;
+        P.unit_tile0 = U.unit_tile0;
+        P.skip_tiles = skip_tiles;
         P.slot_query = U.slot_query;
         P.slot_rel0 = U.slot_rel0;
         launch_tc_pass(P, ns, FAST_EMIT);
+        P.unit_tile0 = nullptr;
+        P.skip_tiles = 0;
     }
     select_candidates();
     }
@@ -1832,6 +1852,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         J.out_rel = relk;
         J.out_dist = dist + (size_t)q0 * k;
         J.out_ok = ok_all + q0;
+        J.cover_stats = true;
         if (coarse_tc && g_fast_set_only && !shard_coarse) {  // probe order is approximate: cross-list distance ties go to the exact path
             J.tie_list_off = (const int64_t *)ix->list_off.p;
             J.tie_nlist = nlist;
@@ -1859,7 +1880,6 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
             fast_topk(J);
         }
         // what the main candidate pass covered: units, items (unit x row tile), distinct row tiles
-        if (g_profile) launch_tc_cover(uprefix, (const int64_t *)S.tile_off.p, (g_tc_half_m || g_tc_narrow) ? lq_off : nullptr, nlist, dev_stats() + DS_TC_UNITS);
         launch_ivf_resolve(relk, nqc, k, np_eff, probes, pair_out, (const int64_t *)ix->list_off.p, (const int64_t *)ix->list_rows.p,
                            ids + (size_t)q0 * k);
         launch_and_flags(ok_all + q0, ok_c, nqc);
@@ -2043,6 +2063,8 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             g_hnsw_prefetch = (int)value;
         } else if (!strcmp(name, "tc_half_m")) {
             g_tc_half_m = value != 0;
+        } else if (!strcmp(name, "fast_carry")) {
+            g_fast_carry = value != 0;
         } else if (!strcmp(name, "kpp_scale")) {
             g_kpp_scale = value != 0;
         } else if (!strcmp(name, "tc_narrow")) {

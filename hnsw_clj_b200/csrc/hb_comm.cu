@@ -125,6 +125,7 @@ struct ExchangeParams {
     double *out_dist;
     int64_t *out_ids;
     int32_t *err;
+    int stage_doubles;  // shared-memory doubles per warp for the merge (nranks * k), 0: search in global memory
 };
 
 // elements of a sorted list whose key precedes `key` (or_equal: or equals it)
@@ -141,19 +142,42 @@ __device__ __forceinline__ int count_before(const double *lst, int k, uint64_t k
 
 // Merge of the nranks sorted (distance, id) lists of query q: the k smallest by (distance, rank, position) — the stable
 // sort of the concatenation in rank order, then take k (partitioned_hnsw.clj:187-196, ivf_flat.clj:291-294).
-__device__ __forceinline__ void merge_query(const ExchangeParams &P, const char *base, int64_t q, int lane) {
+// `stage` (optional): nranks * k doubles of shared memory owned by this warp — the query's lists are copied there once and
+// the binary searches run on shared memory (a search step from L2 is ~300 clocks, and a candidate makes nranks * log2 k of them)
+__device__ __forceinline__ void merge_query(const ExchangeParams &P, const char *base, int64_t q, int lane, double *stage) {
     const int k = P.k, total = P.nranks * k;
     const size_t ids_off = (size_t)P.nq * k * 8;
+    if (stage) {
+        __syncwarp();
+        for (int c = lane; c < total; c += 32) {
+            const int r = c / k, j = c - r * k;
+            stage[c] = __ldcg((const double *)(base + (size_t)r * P.slot_bytes) + q * k + j);
+        }
+        __syncwarp();
+    }
     for (int c = lane; c < total; c += 32) {
         const int r = c / k, j = c - r * k;
         const double *lr = (const double *)(base + (size_t)r * P.slot_bytes) + q * k;
-        const double dv = __ldcg(lr + j);
+        const double dv = stage ? stage[c] : __ldcg(lr + j);
         const uint64_t key = dist_key(dv);
         int pos = j;
         for (int r2 = 0; r2 < P.nranks; ++r2) {
             if (r2 == r) continue;
-            const double *l2 = (const double *)(base + (size_t)r2 * P.slot_bytes) + q * k;
-            pos += count_before(l2, k, key, r2 < r);
+            if (stage) {
+                const double *l2 = stage + r2 * k;
+                int lo = 0, hi = k;
+                const bool or_equal = r2 < r;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const uint64_t km = dist_key(l2[mid]);
+                    if (or_equal ? km <= key : km < key) lo = mid + 1;
+                    else hi = mid;
+                }
+                pos += lo;
+            } else {
+                const double *l2 = (const double *)(base + (size_t)r2 * P.slot_bytes) + q * k;
+                pos += count_before(l2, k, key, r2 < r);
+            }
         }
         if (pos < k) {
             const int64_t *ir = (const int64_t *)(base + (size_t)r * P.slot_bytes + ids_off) + q * k;
@@ -209,7 +233,9 @@ __global__ void __launch_bounds__(kExchangeThreads) exchange_merge_kernel(const 
         if (s_fail) return;
     }
     const char *base = P.win[P.rank] + P.parity_off;
-    for (int64_t q = cta + (int64_t)warp * grid; q < P.nq; q += (int64_t)grid * (kExchangeThreads / 32)) merge_query(P, base, q, lane);
+    extern __shared__ double s_stage[];
+    double *stage = P.stage_doubles > 0 ? s_stage + (size_t)warp * P.stage_doubles : nullptr;
+    for (int64_t q = cta + (int64_t)warp * grid; q < P.nq; q += (int64_t)grid * (kExchangeThreads / 32)) merge_query(P, base, q, lane, stage);
 }
 
 // NCCL path: [dist nq*k][ids nq*k] block to all-gather
@@ -414,6 +440,13 @@ void comm_topk_exchange_merge(const double *loc_dist, const int64_t *loc_ids, in
     P.out_ids = out_ids;
     P.err = C.err_dev;
     const int grid = (int)std::min<int64_t>(nq, kExchangeGrid);
+    size_t smem = (size_t)nr * k * 8 * (kExchangeThreads / 32);
+    if (smem > 96 * 1024) smem = 0;
+    P.stage_doubles = smem ? nr * k : 0;
+    if (smem > 48 * 1024) {
+        HB_CUDA(cudaFuncSetAttribute(exchange_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HB_CUDA(cudaFuncSetAttribute(exchange_merge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const bool want_p2p = use_p2p && C.p2p_ok && (nr > 1 || use_p2p == 2);  // 2: also with one rank (single-GPU tests of the kernel)
     if (want_p2p) ensure_windows(block);  // may turn p2p_ok off (IPC not available)
     if (st && st->e0) HB_CUDA(cudaEventRecord(st->e0, g_stream));
@@ -426,7 +459,7 @@ void comm_topk_exchange_merge(const double *loc_dist, const int64_t *loc_ids, in
         P.flag_off = 2 * (size_t)nr * C.slot_bytes + (size_t)parity * nr * kFlagCtas * 4;
         P.epoch = C.epoch;
         if (st && st->e1) HB_CUDA(cudaEventRecord(st->e1, g_stream));
-        exchange_merge_kernel<true><<<grid, kExchangeThreads, 0, g_stream>>>(P);
+        exchange_merge_kernel<true><<<grid, kExchangeThreads, smem, g_stream>>>(P);
         HB_LAUNCH_CHECK();
     } else {
         char *pack = (char *)C.pack.get(block);
@@ -441,7 +474,7 @@ void comm_topk_exchange_merge(const double *loc_dist, const int64_t *loc_ids, in
         P.win[P.rank] = gath;
         P.slot_bytes = block;
         P.parity_off = 0;
-        exchange_merge_kernel<false><<<grid, kExchangeThreads, 0, g_stream>>>(P);
+        exchange_merge_kernel<false><<<grid, kExchangeThreads, smem, g_stream>>>(P);
         HB_LAUNCH_CHECK();
     }
     if (st && st->e2) HB_CUDA(cudaEventRecord(st->e2, g_stream));

@@ -64,6 +64,7 @@ struct UnitPlan {
     int32_t *unit_nsel = nullptr;   // [nunits] selections (<= 128)
     int32_t *unit_ntile = nullptr;  // [nunits+1] scratch: row tiles per unit
     int32_t *unit_item0 = nullptr;  // [nunits+1]
+    int32_t *unit_tile0 = nullptr;  // [nunits] first row tile of the unit's items (units whose tiles [0, skip) were already scored start at skip)
     int32_t *unit_item0n = nullptr; // optional [nunits+1]: when set, the units with <= kNarrowSlots selections are counted
                                     // here (tc_narrow_kernel) and unit_item0 covers only the others
     int32_t *slot_query = nullptr;  // [nunits*128] query index or -1
@@ -71,9 +72,12 @@ struct UnitPlan {
 };
 // nunits = unit slots (>= nunits_real; a multiple of `interleave` when interleave > 0, see unit_plan_kernel);
 // nunits_real < 0: read the real count from unit_prefix[nlist] on the device (nunits is then an upper bound)
+// skip_tiles > 0 (IVF main pass after a sample of the first skip_tiles tiles of every query's nearest list, whose candidates
+// were kept): a unit all of whose selections are probe rank 0 (pair % pair_div == 0) starts at tile skip_tiles.
 void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_prefix, const int64_t *tile_off, int nunits,
                       int nunits_real, int interleave, int tile_limit, int tile_div, int tile_start, const int32_t *qsel,
-                      const int64_t *pair_out, int pair_div, const int32_t *pair_query, UnitPlan U);
+                      const int64_t *pair_out, int pair_div, const int32_t *pair_query, UnitPlan U, int skip_tiles = 0,
+                      unsigned long long *stats = nullptr /* optional [6] counters of what the pass covers */);
 // gathers the digits of each unit's queries into A images [nunits][kbn][ns][kFastImg]
 // unit_nsel (optional): units with <= 64 selections get only slots 0..63 packed (the M = 64 candidate pass reads no more)
 // narrow: units with <= kNarrowSlots selections get only slots 0..31 (tc_narrow_kernel's B operand)
@@ -91,6 +95,10 @@ struct TcParams {
     const int32_t *unit_item0 = nullptr;
     const int32_t *unit_item0n = nullptr;  // non-NULL: item prefix of the narrow units (see UnitPlan); EMIT only
     const int32_t *unit_nsel_all = nullptr;  // [nunits] selections per unit (always set with unit_item0n)
+    const int32_t *unit_tile0 = nullptr;     // [nunits] first row tile of each unit's items (NULL: tile_start)
+    // > 0: the first skip_tiles tiles of every query's NEAREST list (slots with rel0 == 0) were scored by the sample pass and
+    // their candidates kept: such slots emit nothing for tiles below skip_tiles
+    int skip_tiles = 0;
     const int64_t *tile_off = nullptr;  // first B tile of each list
     const int64_t *list_off = nullptr;  // first slab row of each list
     const int32_t *slot_query = nullptr;

@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(256) quant_queries_kernel(const T *__restrict_
 
 __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, const int64_t *__restrict__ unit_prefix,
                                  const int64_t *__restrict__ tile_off, int nunits, int nunits_real, int interleave,
-                                 int tile_limit, int tile_div, int tile_start, UnitPlan U) {
+                                 int tile_limit, int tile_div, int tile_start, UnitPlan U, int skip_tiles,
+                                 const int32_t *__restrict__ qsel, int pair_div, unsigned long long *__restrict__ stats) {
     const int slot_u = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot_u > nunits) return;
     if (slot_u == nunits) {
@@ -198,6 +199,7 @@ __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, 
         U.unit_sel0[slot_u] = 0;
         U.unit_nsel[slot_u] = 0;
         U.unit_ntile[slot_u] = 0;
+        if (U.unit_tile0) U.unit_tile0[slot_u] = 0;
         return;
     }
     int lo = 0, hi = nlist;  // last l with unit_prefix[l] <= u (lists without selections share a prefix value:
@@ -212,8 +214,35 @@ __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, 
     const int nsel = (int)min((int64_t)kFastTile, lq_off[l + 1] - sel0);
     int nt = (int)(tile_off[l + 1] - tile_off[l]);
     if (tile_div > 1) nt = (nt + tile_div - 1) / tile_div;  // tiles 0, tile_div, 2*tile_div, ...
-    nt = max(nt - tile_start, 0);                           // tiles tile_start .. (tile_div == 1 only)
+    int t0 = tile_start;
+    if (skip_tiles > 0 && pair_div > 0) {
+        // every selection of the unit is its query's nearest list (probe rank 0): the sample pass has scored the first tiles
+        bool all0 = true;
+        for (int s2 = 0; s2 < nsel && all0; ++s2) {
+            const int64_t pr = qsel ? (int64_t)qsel[sel0 + s2] : sel0 + s2;
+            all0 = pr % pair_div == 0;
+        }
+        if (all0) t0 = skip_tiles;
+    }
+    nt = max(nt - t0, 0);                                   // tiles t0 .. (tile_div == 1 only)
     if (tile_limit > 0) nt = min(nt, tile_limit);
+    if (U.unit_tile0) U.unit_tile0[slot_u] = t0;
+    if (stats && nsel > 0) {
+        // what the pass covers: [0] units, [1] items (unit x row tile), [2] distinct row tiles read (a list with several units:
+        // at least its tiles beyond the skipped ones), [3] units of <= 64 selections, [4] narrow units, [5] their items
+        atomicAdd(stats + 0, 1ull);
+        atomicAdd(stats + 1, (unsigned long long)nt);
+        if (j == 0) {
+            const int units_l = (int)(unit_prefix[l + 1] - unit_prefix[l]);
+            const int all_t = (int)(tile_off[l + 1] - tile_off[l]);
+            atomicAdd(stats + 2, (unsigned long long)(units_l == 1 ? nt : max(all_t - skip_tiles, 0)));
+        }
+        if (nsel <= 64) atomicAdd(stats + 3, 1ull);
+        if (nsel <= kNarrowSlots) {
+            atomicAdd(stats + 4, 1ull);
+            atomicAdd(stats + 5, (unsigned long long)nt);
+        }
+    }
     U.unit_list[slot_u] = l;
     U.unit_sel0[slot_u] = (int32_t)sel0;
     U.unit_nsel[slot_u] = nsel;
@@ -1183,10 +1212,12 @@ void launch_quant_queries(const void *queries, int qdtype, int64_t nq, int d, in
 
 void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_prefix, const int64_t *tile_off, int nunits,
                       int nunits_real, int interleave, int tile_limit, int tile_div, int tile_start, const int32_t *qsel,
-                      const int64_t *pair_out, int pair_div, const int32_t *pair_query, UnitPlan U) {
+                      const int64_t *pair_out, int pair_div, const int32_t *pair_query, UnitPlan U, int skip_tiles,
+                      unsigned long long *stats) {
     if (nunits == 0) return;
     unit_plan_kernel<<<blocks_for(nunits + 1, 256), 256, 0, g_stream>>>(nlist, lq_off, unit_prefix, tile_off, nunits, nunits_real,
-                                                                        interleave, tile_limit, tile_div, tile_start, U);
+                                                                        interleave, tile_limit, tile_div, tile_start, U, skip_tiles, qsel,
+                                                                        pair_div, stats);
     HB_LAUNCH_CHECK();
     unit_scan_kernel<<<1, 1024, 0, g_stream>>>(U.unit_ntile, nunits + 1, U.unit_item0, U.unit_nsel, U.unit_item0n);
     HB_LAUNCH_CHECK();

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
             int u = find_unit(P.unit_item0, P.nunits, item_begin);
             for (int item = item_begin; item < item_end; ++item) {
                 while (item >= P.unit_item0[u + 1]) ++u;
-                const int t = P.tile_start + (item - P.unit_item0[u]) * P.tile_stride;
+                const int t = (P.unit_tile0 ? P.unit_tile0[u] : P.tile_start) + (item - P.unit_item0[u]) * P.tile_stride;
                 const int64_t btile = P.tile_off[P.unit_list[u]] + t;
                 const int8_t *asrc = P.aimg + (int64_t)u * kbn * NS * kFastImg;
                 const int8_t *bsrc = P.bimg + btile * kbn * NS * kFastImg;
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
         int it = 0;
         for (int item = item_begin; item < item_end; ++item, ++it) {
             while (item >= P.unit_item0[u + 1]) ++u;
-            const int t = P.tile_start + (item - P.unit_item0[u]) * P.tile_stride;
+            const int t = (P.unit_tile0 ? P.unit_tile0[u] : P.tile_start) + (item - P.unit_item0[u]) * P.tile_stride;
             const bool new_unit = item == item_begin || item == P.unit_item0[u];
             const int l = P.unit_list[u];
             const int64_t btile = P.tile_off[l] + t;
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
                 }
                 // no bound yet: every real row of this tile will be a candidate -- reserve their slots now, so that the
                 // round trip of the atomic overlaps the wait for the accumulators
-                flood = qi >= 0 && thr == -INFINITY;
+                flood = qi >= 0 && thr == -INFINITY && !(rel0 == 0 && t < P.skip_tiles);
                 if (flood) {
                     if (nst > 0) flush_stash(C, qi, rel0, list_row0, nst, -1, my_stash);
                     nst = 0;
@@ -407,7 +407,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_pass_kernel(const TcParams P
             }
             // phase B: thresholds and candidates
             if (MODE == FAST_EMIT) {
-                const float cut = fmaxf(thr, -FLT_MAX);  // padding rows score -inf: never candidates
+                // padding rows score -inf: never candidates; a nearest-list slot emits nothing for the tiles the sample pass took
+                const float cut = (rel0 == 0 && t < P.skip_tiles) ? INFINITY : fmaxf(thr, -FLT_MAX);
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
                     uint32_t mask = 0;
@@ -600,7 +601,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, 1) tc_narrow_kernel(const TcPa
             int u = find_unit(item0, P.nunits, item_begin);
             for (int item = item_begin; item < item_end; ++item) {
                 while (item >= item0[u + 1]) ++u;
-                const int t = P.tile_start + (item - item0[u]) * P.tile_stride;
+                const int t = (P.unit_tile0 ? P.unit_tile0[u] : P.tile_start) + (item - item0[u]) * P.tile_stride;
                 const int64_t btile = P.tile_off[P.unit_list[u]] + t;
                 const int8_t *qsrc = P.aimg + (int64_t)u * kbn * NS * kFastImg;
                 const int8_t *rsrc = P.bimg + btile * kbn * NS * kFastImg;
@@ -686,7 +687,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, 1) tc_narrow_kernel(const TcPa
         int it = 0;
         long long t_meta = 0, t_wait = 0, t_proc = 0;
         // per-unit state, refreshed when the unit changes
-        int cur_u = -1, u_end = 0, u_item0 = 0, nsel = 0, list_len = 0, my_q = -1, my_rel0 = 0;
+        int cur_u = -1, u_end = 0, u_item0 = 0, u_tile0 = 0, nsel = 0, list_len = 0, my_q = -1, my_rel0 = 0;
         int64_t tile0 = 0, list_row0 = 0;
         float my_thr = INFINITY;
         for (int item = item_begin; item < item_end; ++item, ++it) {
@@ -696,6 +697,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, 1) tc_narrow_kernel(const TcPa
                 cur_u = u;
                 u_item0 = item0[u];
                 u_end = item0[u + 1];
+                u_tile0 = P.unit_tile0 ? P.unit_tile0[u] : P.tile_start;
                 const int l = P.unit_list[u];
                 nsel = P.unit_nsel_all[u];
                 tile0 = P.tile_off[l];
@@ -707,17 +709,19 @@ __global__ void __launch_bounds__(NARROW_THREADS, 1) tc_narrow_kernel(const TcPa
                     my_thr = my_q >= 0 ? P.thr[my_q] : INFINITY;
                 }
             }
-            const int t = P.tile_start + (item - u_item0) * P.tile_stride;
+            const int t = u_tile0 + (item - u_item0) * P.tile_stride;
             const int64_t btile = tile0 + t;
             const int par = it & 1, set = it & 1;
             const int nvalid = min(max(list_len - t * kFastTile, 0), kFastTile);
             if (et < kNarrowSlots) {
                 int base = -1;
+                // a nearest-list slot emits nothing for the tiles the sample pass already took (its candidates were kept)
+                const bool sampled = my_rel0 == 0 && t < P.skip_tiles;
                 // no bound yet: every real row of the tile is a candidate of this query, its slots reserved with one atomic
-                if (my_q >= 0 && my_thr == -INFINITY && nvalid > 0) base = atomicAdd(&P.cnt[my_q], nvalid);
+                if (my_q >= 0 && my_thr == -INFINITY && nvalid > 0 && !sampled) base = atomicAdd(&P.cnt[my_q], nvalid);
                 s_q[par][et] = my_q;
                 s_rel0[par][et] = my_rel0;
-                s_thr[par][et] = my_thr;
+                s_thr[par][et] = sampled ? INFINITY : my_thr;
                 s_base[par][et] = base;
             }
             const float rs = P.rs[btile * kFastTile + row] * 256.0f;

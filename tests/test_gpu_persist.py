@@ -127,3 +127,69 @@ def test_missing_truncated_and_foreign_files(hb, tmp_path):
     with pytest.raises(HbInvalid):  # unwritable destination
         with FlatIndex(clustered(10, 8, 7)) as fx:
             index_io.save_index(fx, str(tmp_path / "no_such_dir" / "x.hbix"))
+
+
+def test_corrupt_contents_are_rejected_not_dereferenced(hb, tmp_path):
+    """hb_index_load must validate what later drives device addressing (list offsets, row ids, assignments,
+    adjacency ids) and answer HB_ERR_INVALID — never an out-of-bounds read on the device.  Lightning flavour survives a
+    save / load round trip (index_io keeps the host-side class)."""
+    import struct
+
+    from hnsw_clj_b200 import _lib, index_io, ivf_flat, lightning
+
+    rows = clustered(3000, 32, 4)
+    n = len(rows)
+    path = str(tmp_path / "ivf.hbix")
+    with ivf_flat.build_index(rows, num_partitions=8, max_iterations=2) as ix:
+        index_io.save_index(ix, path)
+    blob = bytearray(open(path, "rb").read())
+    # layout tail of an IVF-FLAT file: ... [hdr16][list_rows n x int64][hdr16][assign n x int32]
+    off_assign = len(blob) - n * 4
+    off_rows = off_assign - 16 - n * 8
+    for name, (off, fmt, bad) in {"assignment": (off_assign + 40, "<i", 10 ** 6), "row id": (off_rows + 80, "<q", -5),
+                                  "row id high": (off_rows + 8, "<q", n)}.items():
+        b2 = bytearray(blob)
+        struct.pack_into(fmt, b2, off, bad)
+        p2 = str(tmp_path / "bad.hbix")
+        open(p2, "wb").write(b2)
+        with pytest.raises(ValueError):
+            index_io.load_index(p2)
+    ok = index_io.load_index(path)  # the untouched file still loads, and the device is healthy after the rejections
+    assert ok.search_raw(rows[:4], 3, 2)[0][:, 0].tolist() == [0, 1, 2, 3]
+    ok.close()
+    with lightning.build_index(rows, num_partitions=16, smart_partition=True) as lx:
+        want = lightning.search_knn(lx, rows[5], 5, mode="balanced")
+        index_io.save_index(lx, path)
+    back = index_io.load_index(path)
+    assert isinstance(back, lightning.LightningIndex) and lightning.search_knn(back, rows[5], 5, mode="balanced") == want
+    back.close()
+
+
+def test_out_of_range_indices_are_invalid_arguments(hb):
+    """caller-supplied indices are range-checked (the reference throws on an unknown id)."""
+    import ctypes as C
+
+    from hnsw_clj_b200 import _lib, ivf_flat, ultra_fast
+    from hnsw_clj_b200.flat import FlatIndex
+
+    rows = clustered(500, 16, 5)
+    with FlatIndex(rows) as fx:
+        good = ultra_fast.gather_score(fx, rows[:2], np.array([0, 1], np.int32), np.array([3, 4], np.int32))
+        assert good.shape == (2,)
+        for pq, pr in (([0, 2], [3, 4]), ([0, 1], [3, 500]), ([0, -1], [3, 4])):
+            with pytest.raises(ValueError):
+                ultra_fast.gather_score(fx, rows[:2], np.array(pq, np.int32), np.array(pr, np.int32))
+        assert ultra_fast.gather_score(fx, rows[:2], np.array([0, 1], np.int32), np.array([3, 4], np.int32)).tolist() == good.tolist()
+    cents = np.zeros((4, 16))
+    asg = np.zeros(500, np.int32)
+    asg[7] = 4
+    with pytest.raises(ValueError):
+        ivf_flat.import_index(rows, cents, asg)
+    with pytest.raises(ValueError):
+        ivf_flat.partition_vectors_kmeans(rows, 4, seed_rows=[0, 1, 2, 500])
+    levels = np.zeros(500, np.int32)
+    off = np.arange(501, dtype=np.int64)
+    nbr = np.arange(500, dtype=np.int32)[::-1].copy()
+    nbr[9] = 777
+    with pytest.raises(ValueError):
+        ultra_fast.HnswIndex(rows, levels, 0, [(off, nbr)])

@@ -1094,7 +1094,10 @@ static void fast_topk(const FastJob &J) {
     const int64_t nq = J.nq;
     const bool do_sample = J.phase != 2, do_main = J.phase != 1;
     // IVF list scans (their own threshold plan, EMIT passes, thresholds seeded by the sample): sparse units on tc_narrow_kernel
-    const bool narrow = g_tc_narrow && !J.shared_units && ns == 2;
+    // ... and a levelled flat scan of at most 32 queries (one narrow unit): 9..32 queries over a long list then cost one pass
+    // over the digit images at HBM speed instead of the fp64 tiles (thresholds rise between the levels, not inside them)
+    const bool leveled_flat = J.phase == 0 && J.shared_units && J.emit.nlist == 1 && S.ntiles >= g_fast_level_min;
+    const bool narrow = g_tc_narrow && ns == 2 && (!J.shared_units || (leveled_flat && J.nq <= kNarrowSlots));
     // IVF list scans: the sample pass scores the first tiles of every query's nearest list; its kk best candidates are KEPT
     // (compacted in place) and the main pass does not read those tiles again for the units that only hold nearest-list queries
     const bool carry = g_fast_carry && !J.shared_units && J.thresh.tile_limit > 0 && J.thresh.tile_div <= 1;
@@ -1174,7 +1177,7 @@ static void fast_topk(const FastJob &J) {
     // A long flat scan (one list, many row tiles) runs in levels over growing tile ranges [0,2), [2,32), [32,512), ...:
     // after each level the candidate lists are cut back to their kk best and the thresholds rise to the exact kk-th best
     // (k-th best - margin) so far, so a level emits about kk * 15 rows per query however long the scan is.
-    const bool leveled = J.phase == 0 && J.shared_units && J.emit.nlist == 1 && S.ntiles >= g_fast_level_min;
+    const bool leveled = leveled_flat;
     // A short flat scan (coarse routing, k-means assignment over <= 2048 centroids) dumps its whole score matrix and lets
     // one warp per query pick the candidates from it: no thresholds, no sample pass, no sort.
     const int64_t flat_rows = J.emit.nlist == 1 ? S.nrows : 0;
@@ -1189,8 +1192,10 @@ static void fast_topk(const FastJob &J) {
         P.slot_query = U.slot_query;
         P.slot_rel0 = U.slot_rel0;
         P.tile_stride = 1;
+        P.items_hint = (int64_t)J.emit.nunits * S.ntiles;
         P.dump = W.dump.as<float>((size_t)J.emit.nunits * S.ntiles * kFastTile * kFastTile);
         launch_tc_pass(P, ns, FAST_DUMP);
+        P.items_hint = 0;
         launch_dense_select(P.dump, (int)S.ntiles, nq, (int)flat_rows, J.k, kk, cap, qmargin, cnegv, crel, cpos, cnt, thr, selval,
                             selpos);
     } else if (leveled) {
@@ -1205,18 +1210,24 @@ static void fast_topk(const FastJob &J) {
         UnitPlan Lp = U;
         Lp.unit_ntile = W.t_ntile.as<int32_t>((size_t)J.emit.nunits + 1);
         Lp.unit_item0 = W.t_item0.as<int32_t>((size_t)J.emit.nunits + 1);
+        if (narrow) Lp.unit_item0n = W.t_item0n.as<int32_t>((size_t)J.emit.nunits + 1);
+        P.unit_nsel_all = U.unit_nsel;
         for (int64_t t0 = 0; t0 < S.ntiles;) {
             const int64_t t1 = t0 == 0 ? 2 : std::min<int64_t>(S.ntiles, t0 * 16);
             launch_unit_plan(J.emit.nlist, J.emit.lq_off, J.emit.unit_prefix, (const int64_t *)S.tile_off.p, J.emit.nunits,
                              J.emit.nunits_real, J.emit.interleave, (int)(t1 - t0), 1, (int)t0, J.emit.qsel, J.emit.pair_out,
                              J.emit.pair_div, nullptr, Lp);
             P.unit_item0 = Lp.unit_item0;
+            P.unit_item0n = Lp.unit_item0n;
             P.tile_start = (int)t0;
+            P.items_hint = (int64_t)J.emit.nunits * (t1 - t0);
             launch_tc_pass(P, ns, FAST_EMIT);
             launch_cand_compact(cnegv, crel, cpos, cnt, nq, kk, cap, J.k, qmargin, thr, selval, selpos);
             t0 = t1;
         }
         P.tile_start = 0;
+        P.unit_item0n = nullptr;
+        P.items_hint = 0;
     } else {
     if (do_sample) {
     {
@@ -1233,7 +1244,9 @@ static void fast_topk(const FastJob &J) {
         P.slot_query = T.slot_query;
         P.slot_rel0 = T.slot_rel0;
         P.tile_stride = J.thresh.tile_div > 1 ? J.thresh.tile_div : 1;
+        if (J.shared_units && J.emit.nlist == 1) P.items_hint = (int64_t)J.thresh.nunits * ceil_div(S.ntiles, P.tile_stride);
         launch_tc_pass(P, ns, FAST_EMIT);
+        P.items_hint = 0;
     }
     if (carry) {
         // keep the kk best sample candidates in place (cnt = their number) and raise the thresholds to the kk-th best / the
@@ -1261,7 +1274,9 @@ static void fast_topk(const FastJob &J) {
         P.skip_tiles = skip_tiles;
         P.slot_query = U.slot_query;
         P.slot_rel0 = U.slot_rel0;
+        if (J.shared_units && J.emit.nlist == 1) P.items_hint = (int64_t)J.emit.nunits * S.ntiles;
         launch_tc_pass(P, ns, FAST_EMIT);
+        P.items_hint = 0;
         P.unit_tile0 = nullptr;
         P.skip_tiles = 0;
     }
@@ -1402,8 +1417,11 @@ static bool fast_metric_ok(int metric) { return metric == HB_COSINE || metric ==
 static void flat_search_fast(hb_index *ix, const void *queries, int qdtype, int64_t nq, int k, int64_t *ids, double *dist) {
     const bool cosine = ix->metric == HB_COSINE;
     if (nq == 0 || k == 0) return;
-    // a small batch fills at most 8 of a unit's 128 query slots: the HBM-bound exact scan (smallscan_kernel) is the faster path
-    if (ix->n == 0 || k > kFastMaxK || !fast_metric_ok(ix->metric) || ix->n >= (1ll << 31) || nq <= kSmallScanQ) {
+    // One query, or a few over rows that fit a couple of hundred MB: the HBM-bound exact scan (rowstream_kernel) is the faster
+    // path.  2..8 queries over a long list read half the bytes as digit images on the levelled narrow scan (1M x 768: 8
+    // queries 1.34 ms exact, 0.56 ms here).
+    const bool long_list = (size_t)ix->n * ix->d * dtype_size(ix->dtype) >= ((size_t)1 << 30) && ceil_div(ix->n, kFastTile) >= g_fast_level_min;
+    if (ix->n == 0 || k > kFastMaxK || !fast_metric_ok(ix->metric) || ix->n >= (1ll << 31) || nq < 2 || (nq <= kSmallScanQ && !long_list)) {
         flat_search_exact(ix->rows.p, ix->dtype, (const double *)ix->norms.p, ix->n, ix->d, ix->metric, queries, qdtype, nq, k, ids, dist);
         return;
     }

@@ -99,6 +99,9 @@ struct TcParams {
     // > 0: the first skip_tiles tiles of every query's NEAREST list (slots with rel0 == 0) were scored by the sample pass and
     // their candidates kept: such slots emit nothing for tiles below skip_tiles
     int skip_tiles = 0;
+    // upper bound of the pass's items (unit x row tile) when the host knows it (flat scans: units x tiles of the level); sizes
+    // the grid.  0: units x 8 (IVF plans live on the device)
+    int64_t items_hint = 0;
     const int64_t *tile_off = nullptr;  // first B tile of each list
     const int64_t *list_off = nullptr;  // first slab row of each list
     const int32_t *slot_query = nullptr;

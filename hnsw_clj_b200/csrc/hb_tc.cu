@@ -824,7 +824,7 @@ template <int NS>
 void narrow_launch(const TcParams &P) {
     auto kernel = tc_narrow_kernel<NS>;
     HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NarrowCfg<NS>::SMEM_BYTES));
-    const int grid = std::max(1, std::min(g_num_sms, P.nunits * 8));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(g_num_sms, P.items_hint > 0 ? P.items_hint : (int64_t)P.nunits * 8));
     kernel<<<grid, NARROW_THREADS, NarrowCfg<NS>::SMEM_BYTES, g_stream>>>(P);
     HB_LAUNCH_CHECK();
 }
@@ -849,7 +849,8 @@ void launch_tc_pass(const TcParams &P, int ns, int mode) {
         narrow_launch<2>(P);
     }
     HB_REQUIRE(P.kk == 64 || P.kk == 128 || mode == FAST_DUMP, "candidates re-scored per query must be 64 or 128");
-    const int hint = P.nunits * 8;
+    // a flat scan of a few units still has thousands of items: size the grid by the items when the host knows them
+    const int hint = (int)std::min<int64_t>(1 << 30, P.items_hint > 0 ? P.items_hint : (int64_t)P.nunits * 8);
 #define HB_TC(NS_)                                                          \
     do {                                                                    \
         if (mode == FAST_DUMP) tc_launch<NS_, FAST_DUMP, 16>(P, hint);      \

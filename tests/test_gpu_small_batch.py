@@ -194,3 +194,69 @@ def test_more_lists_than_queries_and_full_units(hb):
                 _lib.set_mode(_lib.MODE_EXACT)
         assert got[0].tolist() == want[0].tolist() and same_bits(got[1], want[1]), (nlist, nprobe)
         assert got9[0].tolist() == want[0][:9].tolist() and same_bits(got9[1], want[1][:9]), (nlist, nprobe)
+
+
+@pytest.mark.parametrize("metric", ["cosine", "ip"])
+def test_flat_fast_9_to_33_queries_levelled_narrow_scan(metric):
+    """9..32 queries over a long flat list run the levelled candidate scan on tc_narrow_kernel (one narrow unit, thresholds
+    raised between the levels); 33 queries take the 128 x 128 kernel.  Same ids and fp64 distance bits as the exact mode and
+    the oracle, on clustered and on structureless rows (where a failed proof falls back to the exact kernels)."""
+    from hnsw_clj_b200 import _lib
+    from hnsw_clj_b200.flat import FlatIndex
+
+    _lib.check(_lib.lib().hb_init(0))
+    r = np.random.default_rng(77)
+    c = r.standard_normal((50, 64))
+    clustered = (c[r.integers(0, 50, 70000)] + 0.2 * r.standard_normal((70000, 64))).astype(np.float32)
+    gauss = r.standard_normal((70000, 64)).astype(np.float32)
+    code = orc.COSINE if metric == "cosine" else orc.IP
+    for rows in (clustered, gauss):
+        q = (rows[r.integers(0, len(rows), 33)] + 0.1 * r.standard_normal((33, 64))).astype(np.float32)
+        want_i, want_d = orc.exact_knn(rows, q, 10, code)
+        with FlatIndex(rows, metric) as fx:
+            _lib.set_mode(_lib.MODE_FAST)
+            try:
+                for nq in (9, 20, 32, 33):
+                    ids, d = fx.search_raw(q[:nq], 10)
+                    assert ids.tolist() == want_i[:nq].tolist(), (metric, nq)
+                    assert (d.view(np.int64) == want_d[:nq].view(np.int64)).all(), (metric, nq)
+                ids, d = fx.search_raw(q[:20], 100)  # k = 100: kk = 128 candidates per query
+                wi, wd = orc.exact_knn(rows, q[:20], 100, code)
+                assert ids.tolist() == wi.tolist() and (d.view(np.int64) == wd.view(np.int64)).all()
+            finally:
+                _lib.set_mode(_lib.MODE_EXACT)
+
+
+def test_flat_fast_2_to_8_queries_over_a_long_list():
+    """In FAST mode 2..8 queries over a list of >= 1 GB take the levelled narrow scan over the digit images (half the bytes of
+    the fp32 rows); one query stays on the exact row stream.  Same bits either way."""
+    import torch
+
+    from hnsw_clj_b200 import _lib
+    from hnsw_clj_b200.flat import FlatIndex
+
+    _lib.check(_lib.lib().hb_init(0))
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    n, d = 400_000, 768  # 1.23 GB of fp32 rows
+    c = torch.randn((800, d), generator=g, device=dev)
+    rows = (c[torch.randint(0, 800, (n,), generator=g, device=dev)] + 0.1 * torch.randn((n, d), generator=g, device=dev)).contiguous()
+    q = (c[torch.randint(0, 800, (8,), generator=g, device=dev)] + 0.1 * torch.randn((8, d), generator=g, device=dev)).contiguous()
+    with FlatIndex(rows) as fx:
+        want_i, want_d = fx.search_raw(q, 10)  # exact mode
+        _lib.set_mode(_lib.MODE_FAST)
+        _lib.set_option("profile", 1)
+        try:
+            for nq in (1, 2, 5, 8):
+                ids, dist = fx.search_raw(q[:nq].contiguous(), 10)
+                assert (ids == want_i[:nq]).all() and (dist.view(np.int64) == want_d[:nq].view(np.int64)).all(), nq
+            assert _lib.get_stat("fast_queries") == 2 + 5 + 8  # the one-query call stayed on the exact path
+        finally:
+            _lib.set_option("profile", 0)
+            _lib.set_mode(_lib.MODE_EXACT)
+    s = 3
+    oi, od = orc.exact_knn(rows.cpu().numpy(), q[:s].cpu().numpy(), 10)
+    assert want_i[:s].tolist() == oi.tolist() and (want_d[:s].view(np.int64) == od.view(np.int64)).all()
+    del rows
+    torch.cuda.empty_cache()

@@ -26,8 +26,8 @@ def main():
     ap.add_argument("--n-ivf", type=int, default=1000000)
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--opt", action="append", default=[])
-    ap.add_argument("--batches", default="1,8,64")
-    ap.add_argument("--indexes", default="flat31k,flat1m,ivf")
+    ap.add_argument("--batches", default="1,8,16,32,64")
+    ap.add_argument("--indexes", default="flat31k,flat1m,flat1mc,ivf")
     ap.add_argument("--modes", default="exact,fast")
     ap.add_argument("--grid", default="", help="name=v1,v2;name2=... : repeat every sweep for each combination of library knobs")
     ap.add_argument("--ncu-region", action="store_true", help="cudaProfilerStart/Stop around ONE call per (index, mode, batch)")
@@ -86,10 +86,12 @@ def main():
                 for _ in range(calls):
                     ix.search_raw(qd, k, nprobe) if nprobe else ix.search_raw(qd, k)
                 scan_ms, sel_ms = hb.get_stat("scan_ms"), hb.get_stat("select_ms")
+                served, fell = hb.get_stat("fast_queries"), hb.get_stat("fast_fallbacks")
                 hb.set_option("profile", 0)
                 same = bool((ids == want_ids[:nq]).all() and (dist.view(np.int64) == want_d[:nq].view(np.int64)).all())
                 print(json.dumps({"index": name, "mode": mode, "knobs": dict(combo), "queries_per_call": nq, "median_us": med, "best_us": best,
                                   "qps": nq / med * 1e6, "equals_large_batch_exact": same,
+                                  "fast_served_per_call": served / calls, "exact_fallbacks_per_call": fell / calls,
                                   "hbm_floor_us": unique_bytes(nq) / 6562.6e3,
                                                                     "scan_us_per_call": scan_ms / calls * 1e3, "select_us_per_call": sel_ms / calls * 1e3,
                                   "scan_hbm_gbs": unique_bytes(nq) / (scan_ms / calls * 1e-3) / 1e9 if scan_ms > 0 else None,
@@ -114,6 +116,14 @@ def main():
         with FlatIndex(rows) as fx:
             sweep(f"flat {n}x768 fp32 cosine top-10", fx, q.cpu().numpy(), 0, lambda nq: n * d * 4.0)
         del rows
+    if "flat1mc" in args.indexes:
+        # the same size with cluster structure (configs[1]'s rows as a flat index): what embeddings look like
+        c = torch.randn((2048, d), generator=g, device=dev)
+        rows = (c[torch.randint(0, 2048, (n,), generator=g, device=dev)] + 0.1 * torch.randn((n, d), generator=g, device=dev)).contiguous()
+        q = (c[torch.randint(0, 2048, (64,), generator=g, device=dev)] + 0.1 * torch.randn((64, d), generator=g, device=dev)).contiguous()
+        with FlatIndex(rows) as fx:
+            sweep(f"flat {n}x768 fp32 cosine top-10, clustered rows", fx, q.cpu().numpy(), 0, lambda nq: n * d * 4.0)
+        del rows, c
     if "ivf" not in args.indexes:
         return
     # configs[1]: IVF-FLAT, nlist 1024, nprobe 32

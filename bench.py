@@ -768,7 +768,7 @@ def run_sharded(args, S, ctx):
     hb.set_option("profile", 1)
     barrier()
     t0 = time.perf_counter()
-    sample = min(n_per, 8 * nlist)
+    sample = min(n_per, max(4 * nlist, min(8 * nlist, 262144)))  # seeding cost grows with sample x nlist
     seeds = np.zeros(nlist, dtype=np.int64)
     if args.seeding == "random":
         seeds = draw_seed_rows(n_total, nlist)

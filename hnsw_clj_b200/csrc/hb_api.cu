@@ -344,6 +344,8 @@ static double dev_stat(int i) {
 static bool g_fast_set_only = true;  // IVF coarse routing proves the probed set only (FastJob::set_only)
 static bool g_fast_dense = true;     // short flat scans (<= 2048 rows) select from the dumped score matrix
 static int g_fast_level_min = 33;     // flat scans of at least this many row tiles run in levels (fast_topk)
+static int g_fast_level_dense = 8;    // ... whose first level dumps the scores of this many row tiles (<= 16) instead of emitting them; 0: off
+static int g_fast_level_ratio = 16;   // each level covers (ratio - 1) x the tiles before it: it emits about kk x (ratio - 1) rows per query
 static int g_fast_sample_tiles = 2;  // IVF: row tiles of the nearest list scored by the threshold-seeding pass
 static int64_t g_fast_queries = 0;   // queries answered in FAST mode ...
 static int64_t g_fast_fallbacks = 0; // ... of which recomputed by the exact path (proof failed)
@@ -1199,7 +1201,6 @@ static void fast_topk(const FastJob &J) {
         launch_dense_select(P.dump, (int)S.ntiles, nq, (int)flat_rows, J.k, kk, cap, qmargin, cnegv, crel, cpos, cnt, thr, selval,
                             selpos);
     } else if (leveled) {
-        Prof pr(J.profile ? PROF_TC : -1);
         P.aimg = aimg;
         P.nunits = J.emit.nunits;
         P.unit_list = U.unit_list;
@@ -1212,17 +1213,49 @@ static void fast_topk(const FastJob &J) {
         Lp.unit_item0 = W.t_item0.as<int32_t>((size_t)J.emit.nunits + 1);
         if (narrow) Lp.unit_item0n = W.t_item0n.as<int32_t>((size_t)J.emit.nunits + 1);
         P.unit_nsel_all = U.unit_nsel;
-        for (int64_t t0 = 0; t0 < S.ntiles;) {
-            const int64_t t1 = t0 == 0 ? 2 : std::min<int64_t>(S.ntiles, t0 * 16);
-            launch_unit_plan(J.emit.nlist, J.emit.lq_off, J.emit.unit_prefix, (const int64_t *)S.tile_off.p, J.emit.nunits,
-                             J.emit.nunits_real, J.emit.interleave, (int)(t1 - t0), 1, (int)t0, J.emit.qsel, J.emit.pair_out,
-                             J.emit.pair_div, nullptr, Lp);
+        int64_t t0 = 0;
+        if (!narrow && g_fast_level_dense > 0) {
+            // level 0 without thresholds would push every score of its tiles through the candidate lists (atomics, then a sort
+            // of all of them per query): dump the scores of the first tiles instead and let one warp per query pick from the
+            // matrix, as the short flat scans do — 8 tiles cost less than the 2 emitted ones did, and the next level starts
+            // from the k-th best of 1024 rows instead of 256
+            const int64_t t1 = std::min<int64_t>(S.ntiles, g_fast_level_dense);
+            {
+                Prof pr(J.profile ? PROF_PLAN : -1);
+                launch_unit_plan(J.emit.nlist, J.emit.lq_off, J.emit.unit_prefix, (const int64_t *)S.tile_off.p, J.emit.nunits,
+                                 J.emit.nunits_real, J.emit.interleave, (int)t1, 1, 0, J.emit.qsel, J.emit.pair_out, J.emit.pair_div,
+                                 nullptr, Lp);
+            }
+            Prof pr(J.profile ? PROF_TC_SAMPLE : -1);
+            P.unit_item0 = Lp.unit_item0;
+            P.tile_start = 0;
+            P.items_hint = (int64_t)J.emit.nunits * t1;
+            P.dump = W.dump.as<float>((size_t)J.emit.nunits * t1 * kFastTile * kFastTile);
+            launch_tc_pass(P, ns, FAST_DUMP);
+            launch_dense_select(P.dump, (int)t1, nq, (int)std::min<int64_t>(S.nrows, t1 * kFastTile), J.k, kk, cap, qmargin, cnegv, crel,
+                                cpos, cnt, thr, selval, selpos);
+            t0 = t1;
+        }
+        while (t0 < S.ntiles) {
+            const int64_t t1 = t0 == 0 ? 2 : std::min<int64_t>(S.ntiles, t0 * g_fast_level_ratio);
+            {
+                Prof pr(J.profile ? PROF_PLAN : -1);
+                launch_unit_plan(J.emit.nlist, J.emit.lq_off, J.emit.unit_prefix, (const int64_t *)S.tile_off.p, J.emit.nunits,
+                                 J.emit.nunits_real, J.emit.interleave, (int)(t1 - t0), 1, (int)t0, J.emit.qsel, J.emit.pair_out,
+                                 J.emit.pair_div, nullptr, Lp);
+            }
             P.unit_item0 = Lp.unit_item0;
             P.unit_item0n = Lp.unit_item0n;
             P.tile_start = (int)t0;
             P.items_hint = (int64_t)J.emit.nunits * (t1 - t0);
-            launch_tc_pass(P, ns, FAST_EMIT);
-            launch_cand_compact(cnegv, crel, cpos, cnt, nq, kk, cap, J.k, qmargin, thr, selval, selpos);
+            {
+                Prof pr(J.profile ? (t0 == 0 ? PROF_TC_SAMPLE : PROF_TC) : -1);
+                launch_tc_pass(P, ns, FAST_EMIT);
+            }
+            {
+                Prof pr(J.profile ? PROF_SELECT : -1);
+                launch_cand_compact(cnegv, crel, cpos, cnt, nq, kk, cap, J.k, qmargin, thr, selval, selpos);
+            }
             t0 = t1;
         }
         P.tile_start = 0;
@@ -2056,6 +2089,12 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             g_fast_ns = (int)value;
         } else if (!strcmp(name, "fast_dense")) {
             g_fast_dense = value != 0;
+        } else if (!strcmp(name, "fast_level_dense")) {
+            HB_REQUIRE(value >= 0 && value <= 16, "fast_level_dense must be 0..16 row tiles");
+            g_fast_level_dense = (int)value;
+        } else if (!strcmp(name, "fast_level_ratio")) {
+            HB_REQUIRE(value >= 2 && value <= 64, "fast_level_ratio must be 2..64");
+            g_fast_level_ratio = (int)value;
         } else if (!strcmp(name, "fast_level_min")) {
             HB_REQUIRE(value >= 3, "fast_level_min must be >= 3");
             g_fast_level_min = (int)value;

@@ -5,10 +5,14 @@
 //      | q.r - u_q*u_r*sum(mq_i*mr_i) |  <=  kFastRound * (u_q*||r||_1 + u_r*||q||_1) + kFastRound^2 * d * u_q*u_r
 // which, divided by the norms (cosine), is the eps_q of launch_query_bounds once the per-row factors are
 // replaced by their maxima over the index (stats[0], stats[1]).
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
 #include <float.h>
 #include <math.h>
 
 #include "hb_fast.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace hb {
 namespace {
@@ -230,17 +234,22 @@ __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, 
     if (stats && nsel > 0) {
         // what the pass covers: [0] units, [1] items (unit x row tile), [2] distinct row tiles read (a list with several units:
         // at least its tiles beyond the skipped ones), [3] units of <= 64 selections, [4] narrow units, [5] their items
-        atomicAdd(stats + 0, 1ull);
-        atomicAdd(stats + 1, (unsigned long long)nt);
+        // (one atomic per counter and warp: thousands of units adding to the same six words serialise in L2)
+        unsigned long long c[6] = {1ull, (unsigned long long)nt, 0ull, nsel <= 64 ? 1ull : 0ull, 0ull, 0ull};
         if (j == 0) {
             const int units_l = (int)(unit_prefix[l + 1] - unit_prefix[l]);
             const int all_t = (int)(tile_off[l + 1] - tile_off[l]);
-            atomicAdd(stats + 2, (unsigned long long)(units_l == 1 ? nt : max(all_t - skip_tiles, 0)));
+            c[2] = (unsigned long long)(units_l == 1 ? nt : max(all_t - skip_tiles, 0));
         }
-        if (nsel <= 64) atomicAdd(stats + 3, 1ull);
         if (nsel <= kNarrowSlots) {
-            atomicAdd(stats + 4, 1ull);
-            atomicAdd(stats + 5, (unsigned long long)nt);
+            c[4] = 1ull;
+            c[5] = (unsigned long long)nt;
+        }
+        const cg::coalesced_group g = cg::coalesced_threads();
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+            const unsigned long long sum = cg::reduce(g, c[m], cg::plus<unsigned long long>());
+            if (g.thread_rank() == 0 && sum != 0) atomicAdd(stats + m, sum);
         }
     }
     U.unit_list[slot_u] = l;
@@ -250,36 +259,50 @@ __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, 
 }
 
 // exclusive prefix of ntile -> item0 (single block).  With item0n: the units of at most kNarrowSlots selections are counted in
-// item0n (tc_narrow_kernel's items), the others in item0 (tc_pass_kernel's).
+// item0n (tc_narrow_kernel's items), the others in item0 (tc_pass_kernel's).  Both counts ride in one 64-bit value through
+// one shuffle scan per 1024 entries (the plan of a 65,536-list shard has 68 k unit slots: the earlier shared-memory
+// Hillis-Steele scan, two passes, took 0.3 ms there).
 __global__ void __launch_bounds__(1024) unit_scan_kernel(const int32_t *__restrict__ ntile, int count, int32_t *__restrict__ item0_all,
                                                          const int32_t *__restrict__ nsel, int32_t *__restrict__ item0n) {
-    __shared__ int s_part[1024];
-    __shared__ int s_run;
-    for (int pass = 0; pass < (item0n ? 2 : 1); ++pass) {
-    int32_t *item0 = pass == 0 ? item0_all : item0n;
-    __syncthreads();
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
     for (int base = 0; base < count; base += 1024) {
         const int i = base + threadIdx.x;
-        int v = i < count ? ntile[i] : 0;
-        if (item0n && i < count - 1) {
-            const bool narrow = nsel[i] <= kNarrowSlots;
-            if (narrow != (pass == 1)) v = 0;
+        unsigned long long v = 0;
+        if (i < count) {
+            const unsigned long long nt = (unsigned long long)(uint32_t)ntile[i];
+            const bool narrow = item0n != nullptr && i < count - 1 && nsel[i] <= kNarrowSlots;
+            v = narrow ? nt << 32 : nt;
         }
-        s_part[threadIdx.x] = v;
-        __syncthreads();
-        for (int off = 1; off < 1024; off <<= 1) {
-            const int t = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0;
-            __syncthreads();
-            s_part[threadIdx.x] += t;
-            __syncthreads();
+        unsigned long long x = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += t;
         }
-        if (i < count) item0[i] = s_run + s_part[threadIdx.x] - v;
+        if (lane == 31) s_w[warp] = x;
         __syncthreads();
-        if (threadIdx.x == 1023) s_run += s_part[1023];
+        if (warp == 0) {
+            unsigned long long y = s_w[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, y, off);
+                if (lane >= off) y += t;
+            }
+            s_w[lane] = y;
+        }
         __syncthreads();
-    }
+        const unsigned long long pre = s_run + (warp > 0 ? s_w[warp - 1] : 0ull) + x - v;
+        if (i < count) {
+            item0_all[i] = (int32_t)(uint32_t)(pre & 0xffffffffull);
+            if (item0n) item0n[i] = (int32_t)(uint32_t)(pre >> 32);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += s_w[31];
+        __syncthreads();
     }
 }
 
@@ -301,14 +324,17 @@ __global__ void unit_slots_kernel(int nunits, const int32_t *__restrict__ unit_s
     slot_rel0[i] = rel0;
 }
 
-// grid (nunits, kbn): copies the 16-byte chunks of the unit's query digits into swizzled images
+// copies the 16-byte chunks of the units' query digits into swizzled images; a block walks (unit, k-block) pairs with a
+// grid stride: the unit slots of an IVF plan are an upper bound (ceil(pairs / 128) + nlist) and mostly empty — 68 k slots
+// for ~9 k units on a 65,536-list shard — and one block per slot spent 0.3 ms per plan on blocks that only returned
 template <int NS>
-__global__ void __launch_bounds__(256) pack_units_kernel(const int8_t *__restrict__ dig, int kbn,
+__global__ void __launch_bounds__(256) pack_units_kernel(const int8_t *__restrict__ dig, int kbn, int nunits,
                                                          const int32_t *__restrict__ slot_query, int8_t *__restrict__ aimg,
                                                          const int32_t *__restrict__ unit_nsel, bool narrow) {
-    const int u = blockIdx.x, kb = blockIdx.y;
     const int dpad = kbn * kFastKB;
-    if (slot_query[(int64_t)u * kFastTile] < 0) return;  // slots fill from 0: an empty unit (padding / bound) has no items
+    for (int64_t w = blockIdx.x; w < (int64_t)nunits * kbn; w += gridDim.x) {
+    const int u = (int)(w / kbn), kb = (int)(w % kbn);
+    if (slot_query[(int64_t)u * kFastTile] < 0) continue;  // slots fill from 0: an empty unit (padding / bound) has no items
     // M = 64 units: the first 8 row groups of each image; narrow units: the first 4
     const int ns_u = unit_nsel != nullptr ? unit_nsel[u] : kFastTile;
     const int nslots = (narrow && ns_u <= kNarrowSlots) ? kNarrowSlots : (ns_u <= 64 ? 64 : kFastTile);
@@ -319,6 +345,7 @@ __global__ void __launch_bounds__(256) pack_units_kernel(const int8_t *__restric
         uint4 v = make_uint4(0, 0, 0, 0);
         if (q >= 0) v = *reinterpret_cast<const uint4 *>(dig + ((int64_t)q * NS + s) * dpad + kb * kFastKB + ch * 16);
         *reinterpret_cast<uint4 *>(dst + (int64_t)s * kFastImg + img_offset(slot, ch * 16)) = v;
+    }
     }
 }
 
@@ -525,11 +552,12 @@ struct CompactParams {  // non-null cand_rel: keep only the kk best candidates, 
 };
 __global__ void __launch_bounds__(256) cand_select_kernel(const double *__restrict__ cand_negv, const int32_t *__restrict__ cnt,
                                                           int kk, int cap, double *__restrict__ sel_negv,
-                                                          int64_t *__restrict__ sel_pos, const CompactParams CP) {
+                                                          int64_t *__restrict__ sel_pos, const CompactParams CP, int skip_upto) {
     extern __shared__ uint64_t s_keys[];
     const int64_t q = blockIdx.x;
     const int craw = cnt[q];
     const int n = min(craw, cap);
+    if (craw <= cap && n <= skip_upto) return;  // cand_select_warp_kernel has served this query
     int m = kk > 64 ? 128 : 64;
     while (m < n) m <<= 1;
     const double *v = cand_negv + q * cap;
@@ -590,6 +618,94 @@ __global__ void __launch_bounds__(256) cand_select_kernel(const double *__restri
         const float sk = (float)(-nv);
         const float t = sk - CP.margin[q] - 4e-6f * fabsf(sk);
         if (t > CP.thr[q]) CP.thr[q] = t;
+    }
+}
+
+// The same selection for the queries with at most kWarpSelMax candidates — nearly all of them once thresholds are in place —
+// by one WARP per query (four queries per block, __syncwarp instead of __syncthreads, 4 KB of shared memory per query): the
+// block-per-query kernel above holds eight queries per SM in flight and spends most of its time in load latency and barriers
+// (0.11 ms per call for 10,000 queries whatever their length); this one holds 64.  Keys are unique (the slot index is the low
+// word), so both kernels produce the same order.  Longer lists are left to cand_select_kernel(skip_upto = kWarpSelMax).
+constexpr int kWarpSelMax = 512;
+__global__ void __launch_bounds__(128) cand_select_warp_kernel(const double *__restrict__ cand_negv, const int32_t *__restrict__ cnt,
+                                                               int64_t nq, int kk, int cap, double *__restrict__ sel_negv,
+                                                               int64_t *__restrict__ sel_pos, const CompactParams CP) {
+    __shared__ uint64_t s_all[4][kWarpSelMax];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 4 + warp;
+    if (q >= nq) return;
+    const int craw = cnt[q];
+    const int n = min(craw, cap);
+    if (craw > cap || n > kWarpSelMax) return;  // overflowed or long: the block kernel
+    uint64_t *keys = s_all[warp];
+    int m = kk > 64 ? 128 : 64;
+    while (m < n) m <<= 1;
+    const double *v = cand_negv + q * cap;
+    for (int i = lane; i < m; i += 32) keys[i] = i < n ? ((uint64_t)f32_desc_key((float)(-v[i])) << 32) | (uint32_t)i : ~0ull;
+    for (int size = 2; size <= m; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncwarp();
+            for (int i = lane; i < m / 2; i += 32) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const uint64_t a = keys[lo], b = keys[hi];
+                if ((a > b) == asc) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (CP.cand_rel == nullptr) {
+        for (int j = lane; j < kk; j += 32) {
+            const bool ok = j < n;
+            const int slot = ok ? (int)(uint32_t)keys[j] : -1;
+            sel_pos[q * kk + j] = slot;
+            sel_negv[q * kk + j] = ok ? v[slot] : INFINITY;
+        }
+        return;
+    }
+    // compaction: read the kk best (kk <= 128: four per lane), then write them to the front of the list, best first
+    double nv[4];
+    int32_t rel[4], pos[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int j = u * 32 + lane;
+        const bool ok = j < kk && j < n;
+        const int slot = ok ? (int)(uint32_t)keys[j] : 0;
+        nv[u] = ok ? v[slot] : INFINITY;
+        rel[u] = ok ? CP.cand_rel[q * cap + slot] : 0;
+        pos[u] = ok ? CP.cand_pos[q * cap + slot] : 0;
+    }
+    __syncwarp();
+    double *s_nv = reinterpret_cast<double *>(keys);  // the sorted values, for the two threshold reads below
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int j = u * 32 + lane;
+        if (j >= kk) continue;
+        const bool ok = j < n;
+        if (ok) {  // (n <= kWarpSelMax <= cap: no overflow here)
+            CP.cand_negv[q * cap + j] = nv[u];
+            CP.cand_rel[q * cap + j] = rel[u];
+            CP.cand_pos[q * cap + j] = pos[u];
+        }
+        sel_pos[q * kk + j] = ok ? j : -1;
+        sel_negv[q * kk + j] = nv[u];
+        s_nv[j] = nv[u];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        CP.cnt_rw[q] = min(n, kk);
+        float t = CP.thr[q];
+        if (n >= kk) t = fmaxf(t, (float)(-s_nv[kk - 1]));
+        if (CP.k <= kk && n >= CP.k) {
+            const float sk = (float)(-s_nv[CP.k - 1]);
+            const float t2 = sk - CP.margin[q] - 4e-6f * fabsf(sk);
+            if (t2 > t) t = t2;
+        }
+        CP.thr[q] = t;
     }
 }
 
@@ -1009,7 +1125,10 @@ void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq,
                         int64_t *sel_pos) {
     if (nq == 0) return;
     HB_REQUIRE(cap <= 4096 && kk <= 128, "candidate select: cap <= 4096, kk <= 128");
-    cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos, CompactParams{});
+    cand_select_warp_kernel<<<blocks_for(nq, 4), 128, 0, g_stream>>>(cand_negv, cnt, nq, kk, cap, sel_negv, sel_pos, CompactParams{});
+    HB_LAUNCH_CHECK();
+    cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos, CompactParams{},
+                                                                         kWarpSelMax);
     HB_LAUNCH_CHECK();
 }
 void launch_dense_select(const float *dump, int ntiles, int64_t nq, int nrows, int k, int kk, int cap, const float *margin,
@@ -1037,7 +1156,10 @@ void launch_cand_compact(double *cand_negv, int32_t *cand_rel, int32_t *cand_pos
     CP.thr = thr;
     CP.margin = margin;
     CP.k = k;
-    cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos, CP);
+    // the warp kernel first: it lowers cnt to <= kk for the queries it compacts, so the block kernel skips them
+    cand_select_warp_kernel<<<blocks_for(nq, 4), 128, 0, g_stream>>>(cand_negv, cnt, nq, kk, cap, sel_negv, sel_pos, CP);
+    HB_LAUNCH_CHECK();
+    cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos, CP, kWarpSelMax);
     HB_LAUNCH_CHECK();
 }
 
@@ -1229,9 +1351,9 @@ void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_pref
 void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int32_t *slot_query, int8_t *aimg,
                        const int32_t *unit_nsel, bool narrow) {
     if (nunits == 0) return;
-    dim3 grid((unsigned)nunits, (unsigned)kbn);
-    if (ns == 2) pack_units_kernel<2><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg, unit_nsel, narrow);
-    else pack_units_kernel<3><<<grid, 256, 0, g_stream>>>(dig, kbn, slot_query, aimg, unit_nsel, narrow);
+    const int grid = (int)std::min<int64_t>((int64_t)nunits * kbn, (int64_t)g_num_sms * 32);
+    if (ns == 2) pack_units_kernel<2><<<grid, 256, 0, g_stream>>>(dig, kbn, nunits, slot_query, aimg, unit_nsel, narrow);
+    else pack_units_kernel<3><<<grid, 256, 0, g_stream>>>(dig, kbn, nunits, slot_query, aimg, unit_nsel, narrow);
     HB_LAUNCH_CHECK();
 }
 

@@ -1592,16 +1592,18 @@ static int64_t g_host_feed_block = 0;
 
 // ---- coarse routing split over the ranks (row shards of ONE global IVF-FLAT index) -------------------------------------------
 // Every rank holds all centroids, but ranking nlist = 65,536 centroids for every query on every rank is replicated work that
-// grows with the number of GPUs.  Rank r therefore ranks only its slice [r nlist/G, (r+1) nlist/G) — EXACTLY: candidate pass,
-// fp64 re-score of the nprobe best, proof, exact fallback for the queries that fail it — and the G local top-nprobe lists
-// are merged by the same exchange + merge step as the final results (distance, then centroid index: the stable sort of
-// ivf_flat.clj:263-269).  The probe ORDER is then exact as well, so no cross-list tie needs the exact path.
+// grows with the number of GPUs.  The QUERIES are split instead: rank r ranks all centroids for the queries
+// [r per, (r + 1) per), per = ceil(nq / G) — EXACTLY: candidate pass, fp64 re-score, proof, exact fallback for the queries that
+// fail it, in (distance, centroid index) order, the stable sort of ivf_flat.clj:263-269 — and one all-gather replicates the probe
+// lists.  The probe ORDER is then exact as well, so no cross-list tie needs the exact path.  (The first version split the
+// CENTROIDS: every rank ranked its slice for all queries and the G local top-nprobe lists were merged.  That repeats the per-query
+// stages — selection, 35 fp64 re-scores, proof — on every rank: 1.9 ms per 10,000 queries on 8 GPUs, most of it those stages.)
 static bool sharded_coarse_on(const hb_index *ix, int np_eff) {
     const CommInfo &c = comm_info();
     return c.inited && c.nranks > 1 && ix->coarse_sharded && ix->metric == HB_COSINE && np_eff <= kFastMaxK &&
-           ix->nlist / c.nranks >= 2 * kFastTile && ix->nlist / c.nranks >= np_eff;
+           ix->nlist >= 2 * kFastTile && ix->nlist >= np_eff;
 }
-// exact top-np of the centroid slice for nb queries (device): the reference's arithmetic, ids = position inside the slice
+// exact top-np of the centroids [c0, c1) for nb queries (device): the reference's arithmetic, ids = position inside the range
 static void coarse_slice_exact(hb_index *ix, int c0, int c1, const void *q, int qdtype, const double *qn, int64_t nb, int np,
                                int64_t *out_pos, double *out_dist) {
     const int d = ix->d, ns = c1 - c0;
@@ -1635,55 +1637,67 @@ static void coarse_slice_exact(hb_index *ix, int c0, int c1, const void *q, int 
     launch_select(L);
 }
 // Per query the global top-np_eff centroids in exact (distance, index) order -> ppos (list ids), simub (upper bound of the
-// cosine similarity to each probed centroid).  Collective: every rank calls it with the same queries.
+// cosine similarity to each probed centroid).  Collective: every rank calls it with the same queries; qn / q64 hold the norms
+// and the widened copy of all nqc queries.  Leaves the digit images of this rank's query block in the workspace: the caller
+// quantises the whole batch again before the list scan.
 static void sharded_coarse(hb_index *ix, const void *qptr, int qdtype, const double *q64, const double *qn, int64_t nqc, int np_eff,
                            int64_t *ppos, double *simub) {
     const CommInfo &c = comm_info();
     const int nlist = ix->nlist, d = ix->d;
-    const int c0 = (int)((int64_t)nlist * c.rank / c.nranks), c1 = (int)((int64_t)nlist * (c.rank + 1) / c.nranks);
+    const int64_t per = ceil_div(nqc, (int64_t)c.nranks);
+    const int64_t q_lo = std::min(nqc, per * c.rank), nb = std::min(nqc, q_lo + per) - q_lo;
+    const size_t blk = (size_t)per * np_eff;
     FastWs &W = g_fw;
-    int64_t *lpos = W.sc_pos.as<int64_t>((size_t)nqc * np_eff);
-    double *ldist = W.sc_dist.as<double>((size_t)nqc * np_eff);
-    double *gdist = W.sc_gdist.as<double>((size_t)nqc * np_eff);
-    FastSideBufs &C = fast_cents_side(ix, c0, c1);
-    if (C.usable) {
-        int32_t *ok = W.ok_b.as<int32_t>(nqc);
-        FastJob J;
-        J.side = &C;
-        J.list_off = (const int64_t *)C.list_off.p;
-        J.rows_exact = (const double *)ix->cents.p + (size_t)c0 * d;
-        J.rdtype = HB_F64;
-        J.row_norm = (const double *)ix->cent_norm.p + c0;
-        J.queries = qptr;
-        J.qdtype = qdtype;
-        J.q64 = q64;
-        J.nq = nqc;
-        J.qn = qn;
-        J.d = d;
-        J.metric = HB_COSINE;
-        J.epi = EPI_COS_GUARD;
-        J.profile = false;
-        J.k = np_eff;
-        flat_fast_plan(nqc, J.emit, J.thresh, W.flat_plan);
-        J.shared_units = true;
-        J.out_rel = lpos;
-        J.out_dist = ldist;
-        J.out_ok = ok;
-        fast_topk(J);
-        const int64_t served0 = g_fast_queries, fell0 = g_fast_fallbacks;
-        fast_fallback(ok, qptr, qdtype, nqc, d, np_eff, lpos, ldist, [&](const void *gq, int64_t nb, int64_t *gids, double *gd) {
-            double *gn = g_fw.a_norm.as<double>(nb);
-            launch_row_norms(gq, qdtype, nb, d, gn);
-            coarse_slice_exact(ix, c0, c1, gq, qdtype, gn, nb, np_eff, gids, gd);
-        });
-        g_coarse_fallbacks += g_fast_fallbacks - fell0;  // "fast_queries" / "fast_fallbacks" count whole searches, not this stage
-        g_fast_queries = served0;
-        g_fast_fallbacks = fell0;
-    } else {
-        coarse_slice_exact(ix, c0, c1, qptr, qdtype, qn, nqc, np_eff, lpos, ldist);
+    // [pos | dist] of this rank's block, then the gathered blocks of every rank
+    char *mine = (char *)W.sc_pos.get(blk * 16);
+    char *all = (char *)W.sc_dist.get(blk * 16 * c.nranks);
+    int64_t *lpos = (int64_t *)mine;
+    double *ldist = (double *)(mine + blk * 8);
+    if (nb < per) HB_CUDA(cudaMemsetAsync(mine, 0, blk * 16, g_stream));  // the padding rows travel too
+    if (nb > 0) {
+        const size_t qsz = dtype_size(qdtype);
+        const void *bptr = (const char *)qptr + (size_t)q_lo * d * qsz;
+        FastSideBufs &C = fast_cents_side(ix);
+        if (C.usable) {
+            fast_quant_queries(bptr, qdtype, nb, d);
+            int32_t *ok = W.ok_b.as<int32_t>(nb);
+            FastJob J;
+            J.side = &C;
+            J.list_off = (const int64_t *)C.list_off.p;
+            J.rows_exact = ix->cents.p;
+            J.rdtype = HB_F64;
+            J.row_norm = (const double *)ix->cent_norm.p;
+            J.queries = bptr;
+            J.qdtype = qdtype;
+            J.q64 = q64 + (size_t)q_lo * d;
+            J.nq = nb;
+            J.qn = qn + q_lo;
+            J.d = d;
+            J.metric = HB_COSINE;
+            J.epi = EPI_COS_GUARD;
+            J.profile = false;
+            J.k = np_eff;
+            flat_fast_plan(nb, J.emit, J.thresh, W.flat_plan);
+            J.shared_units = true;
+            J.out_rel = lpos;
+            J.out_dist = ldist;
+            J.out_ok = ok;
+            fast_topk(J);
+            const int64_t served0 = g_fast_queries, fell0 = g_fast_fallbacks;
+            fast_fallback(ok, bptr, qdtype, nb, d, np_eff, lpos, ldist, [&](const void *gq, int64_t ng, int64_t *gids, double *gd) {
+                double *gn = g_fw.a_norm.as<double>(ng);
+                launch_row_norms(gq, qdtype, ng, d, gn);
+                coarse_slice_exact(ix, 0, nlist, gq, qdtype, gn, ng, np_eff, gids, gd);
+            });
+            g_coarse_fallbacks += g_fast_fallbacks - fell0;  // "fast_queries" / "fast_fallbacks" count whole searches, not this stage
+            g_fast_queries = served0;
+            g_fast_fallbacks = fell0;
+        } else {
+            coarse_slice_exact(ix, 0, nlist, bptr, qdtype, qn + q_lo, nb, np_eff, lpos, ldist);
+        }
     }
-    comm_topk_exchange_merge(ldist, lpos, c0, nqc, np_eff, gdist, ppos, g_comm_p2p, nullptr);
-    launch_sim_from_dist(gdist, nqc * np_eff, simub);
+    comm_allgather_bytes(mine, all, (int64_t)(blk * 16));
+    launch_unpack_probe_blocks(all, c.nranks, per, nqc, np_eff, ppos, simub);
 }
 
 // search-ivf-flat in FAST mode: coarse routing and the probed-list scan both run the candidate pass
@@ -1716,7 +1730,6 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
                 const void *qptr = (const char *)queries + (size_t)q0 * d * qsz;
                 double *qn = g_ws.qnorm.as<double>(nqc);
                 launch_row_norms(qptr, qdtype, nqc, d, qn);
-                fast_quant_queries(qptr, qdtype, nqc, d);
                 const double *q64 = launch_widen_queries(qptr, qdtype, nqc * d, g_fw.q64.as<double>((size_t)nqc * d));
                 sharded_coarse(ix, qptr, qdtype, q64, qn, nqc, np_eff, g_fw.ppos.as<int64_t>((size_t)nqc * np_eff),
                                g_fw.simub.as<double>((size_t)nqc * np_eff));
@@ -1750,9 +1763,9 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
             Prof pr(PROF_COARSE);
             wait_all();
             launch_row_norms(qptr, qdtype, nqc, d, qn);
-            fast_quant_queries(qptr, qdtype, nqc, d);
             launch_widen_queries(qptr, qdtype, nqc * d, q64buf);
-            sharded_coarse(ix, qptr, qdtype, q64, qn, nqc, np_eff, ppos, simub);
+            sharded_coarse(ix, qptr, qdtype, q64, qn, nqc, np_eff, ppos, simub);  // (quantises this rank's query block)
+            fast_quant_queries(qptr, qdtype, nqc, d);  // the list scan packs its units from the whole batch's digits
             {
                 float one_bits;
                 const int32_t one = 1;
@@ -2443,7 +2456,7 @@ static void search_core(hb_index *index, const void *queries, int qdtype, int64_
     const void *q = nullptr;
     const size_t qrow = (size_t)index->d * dtype_size(qdtype);
     if (index->type == HB_INDEX_IVF_FLAT && mode == HB_MODE_FAST && !is_device_ptr(queries) && g_host_feed_block > 0 &&
-        nq >= 2 * g_host_feed_block) {
+        nq > g_host_feed_block) {
         // blocks of 2048 queries on a copy stream, one event each (pinned host memory makes the copies asynchronous)
         if (!g_copy_stream) HB_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
         char *dq = (char *)g_ws.in_b.get((size_t)nq * qrow);

@@ -205,6 +205,8 @@ void launch_tc_cover(const int64_t *unit_prefix, const int64_t *tile_off, const 
 void launch_set_i64x4(int64_t *p, int64_t a, int64_t b, int64_t c, int64_t d);
 // sim[i] = 1 - dist[i] (+ a rounding allowance): the similarity bound of an exactly ranked probe list
 void launch_sim_from_dist(const double *dist, int64_t n, double *sim);
+// the all-gathered probe lists of the query-split coarse routing (hb_api.cu: sharded_coarse) -> ppos, simub = 1 - dist (+ allowance)
+void launch_unpack_probe_blocks(const void *gathered, int nranks, int64_t per, int64_t nq, int np, int64_t *ppos, double *simub);
 // ok[q] &= other[q]
 void launch_and_flags(int32_t *ok, const int32_t *other, int64_t nq);
 

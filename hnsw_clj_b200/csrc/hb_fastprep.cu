@@ -1268,6 +1268,22 @@ void launch_tc_cover(const int64_t *unit_prefix, const int64_t *tile_off, const 
     tc_cover_kernel<<<blocks_for(nlist, 256), 256, 0, g_stream>>>(unit_prefix, tile_off, lq_off, nlist, acc);
     HB_LAUNCH_CHECK();
 }
+// gathered[g] = [per x np positions (int64) | per x np distances (fp64)] of rank g's query block -> ppos / simub of all nq queries
+__global__ void unpack_probe_blocks_kernel(const char *__restrict__ gathered, int64_t per, int64_t nq, int np,
+                                           int64_t *__restrict__ ppos, double *__restrict__ simub) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * np) return;
+    const int64_t q = i / np, g = q / per, o = (q - g * per) * np + i % np;
+    const char *blk = gathered + (size_t)g * (size_t)per * np * 16;
+    ppos[i] = reinterpret_cast<const int64_t *>(blk)[o];
+    simub[i] = (1.0 - reinterpret_cast<const double *>(blk + (size_t)per * np * 8)[o]) + 1e-12;
+}
+void launch_unpack_probe_blocks(const void *gathered, int nranks, int64_t per, int64_t nq, int np, int64_t *ppos, double *simub) {
+    if (nq * np == 0) return;
+    (void)nranks;
+    unpack_probe_blocks_kernel<<<blocks_for(nq * np, 256), 256, 0, g_stream>>>((const char *)gathered, per, nq, np, ppos, simub);
+    HB_LAUNCH_CHECK();
+}
 void launch_sim_from_dist(const double *dist, int64_t n, double *sim) {
     if (n == 0) return;
     sim_from_dist_kernel<<<blocks_for(n, 256), 256, 0, g_stream>>>(dist, n, sim);

@@ -913,13 +913,13 @@ struct FastWs {
     DevBuf t_list, t_sel0, t_nsel, t_ntile, t_item0, t_item0n, t_slotq, t_slotrel;
     DevBuf a_ids, a_dist, a_norm, a_tmp, dump, timing, simub, pruned;
     DevBuf sc_pos, sc_dist, sc_gdist, ok_c;
-    DevBuf ppos, ppos0, ok_a, ok_b, relk, probes0, pair_out0, qsel0, lq_off0, uprefix0, uprefix, flat_plan, idx, gq, gids, gdist,
+    DevBuf ppos, ppos0, ok_a, ok_b, relk, probes0, qsel0, lq_off0, uprefix0, uprefix, flat_plan, idx, gq, gids, gdist,
         tmp2;
     void release() {
         DevBuf *all[] = {&dig, &q64, &pslot, &srow, &ptotal, &qu, &ql1, &qscale, &qeps, &qmargin, &thr, &cnt, &cnegv, &crel, &cpos, &selval, &selpos, &pq, &pr, &exact,
                          &aimg, &aimg0, &u_list, &u_sel0, &u_nsel, &u_ntile, &u_item0, &u_item0n, &u_tile0, &u_slotq, &u_slotrel,
                          &t_list, &t_sel0, &t_nsel, &t_ntile, &t_item0, &t_item0n, &t_slotq, &t_slotrel,
-                         &sc_pos, &sc_dist, &sc_gdist, &ok_c, &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &pair_out0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
+                         &sc_pos, &sc_dist, &sc_gdist, &ok_c, &ppos, &ppos0, &ok_a, &ok_b, &relk, &probes0, &qsel0, &lq_off0, &uprefix0, &uprefix, &flat_plan,
                          &idx, &gq, &gids, &gdist, &tmp2, &a_ids, &a_dist, &a_norm, &a_tmp, &dump, &timing, &simub, &pruned};
         for (DevBuf *b : all) b->release();
     }
@@ -1421,19 +1421,17 @@ static void flat_fast_plan(int64_t nq, FastPlan &E, FastPlan &T, DevBuf &buf) {
 template <typename F>
 static void fast_fallback(const int32_t *ok_dev, const void *queries, int qdtype, int64_t nq, int d, int k, int64_t *ids,
                           double *dist, F &&exact_fn) {
-    std::vector<int32_t> ok((size_t)nq);
-    HB_CUDA(cudaMemcpyAsync(ok.data(), ok_dev, (size_t)nq * 4, cudaMemcpyDeviceToHost, g_stream));
+    // the failed queries are compacted on the device; the host reads one word (how many) to size the exact call
+    int32_t *idx = g_fw.idx.as<int32_t>((size_t)nq + 1);
+    launch_compact_failed(ok_dev, nq, idx);
+    int32_t nbad = 0;
+    HB_CUDA(cudaMemcpyAsync(&nbad, idx + nq, 4, cudaMemcpyDeviceToHost, g_stream));
     sync_stream();
-    std::vector<int32_t> bad;
-    for (int64_t q = 0; q < nq; ++q)
-        if (!ok[(size_t)q]) bad.push_back((int32_t)q);
     g_fast_queries += nq;
-    g_fast_fallbacks += (int64_t)bad.size();
-    if (bad.empty()) return;
-    const int64_t nb = (int64_t)bad.size();
+    g_fast_fallbacks += nbad;
+    if (nbad == 0) return;
+    const int64_t nb = nbad;
     const size_t qsz = dtype_size(qdtype);
-    int32_t *idx = g_fw.idx.as<int32_t>(nb);
-    HB_CUDA(cudaMemcpyAsync(idx, bad.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, g_stream));
     void *gq = g_fw.gq.get((size_t)nb * d * qsz);
     launch_gather_bytes(queries, idx, nb, (int64_t)d * qsz, gq);
     int64_t *gids = g_fw.gids.as<int64_t>((size_t)nb * k);
@@ -1441,7 +1439,6 @@ static void fast_fallback(const int32_t *ok_dev, const void *queries, int qdtype
     exact_fn(gq, nb, gids, gdist);
     launch_scatter_rows64(gids, idx, nb, k, ids);
     launch_scatter_rows64(gdist, idx, nb, k, dist);
-    sync_stream();  // `bad` (host) was the source of an async copy
 }
 
 static bool fast_metric_ok(int metric) { return metric == HB_COSINE || metric == HB_IP; }
@@ -1863,7 +1860,6 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         int64_t *uprefix = W.uprefix.as<int64_t>(nlist + 1);
         int64_t *ppos0 = W.ppos0.as<int64_t>(nqc);
         int32_t *probes0 = W.probes0.as<int32_t>(nqc);
-        int64_t *pair_out0 = W.pair_out0.as<int64_t>(nqc + 1);
         int32_t *qsel0 = W.qsel0.as<int32_t>(nqc);
         int64_t *lq_off0 = W.lq_off0.as<int64_t>(nlist + 1);
         int64_t *uprefix0 = W.uprefix0.as<int64_t>(nlist + 1);
@@ -1871,15 +1867,15 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         // (query, probed list) pair whose rows cannot reach the query's threshold, and plan the scan over the rest.
         const bool prune = coarse_tc && g_fast_prune && np_eff > 1;
         auto plan_emit = [&] {
-            ivf_plan(ppos, np, nlist, (const int64_t *)ix->list_off.p, probes, pair_out, qsel, lq_off, uprefix, 1 << 30, kFastTile,
-                     g_ws.tmp);
+            ivf_plan_fast(ppos, nqc, np_eff, nlist, (const int64_t *)ix->list_off.p, probes, pair_out, qsel, lq_off, uprefix, kFastTile,
+                          g_ws.tmp);
         };
         {
             Prof prp(PROF_PLAN);
             if (!prune) plan_emit();
             launch_first_column(ppos, nqc, np_eff, ppos0);
-            ivf_plan(ppos0, nqc, nlist, (const int64_t *)ix->list_off.p, probes0, pair_out0, qsel0, lq_off0, uprefix0, 1 << 30,
-                     kFastTile, g_ws.tmp);
+            ivf_plan_fast(ppos0, nqc, 1, nlist, (const int64_t *)ix->list_off.p, probes0, nullptr, qsel0, lq_off0, uprefix0, kFastTile,
+                          g_ws.tmp);
         }
         // no host round trip: unit counts stay on the device, the host sizes buffers and grids by their bounds
         int64_t *relk = W.relk.as<int64_t>((size_t)nqc * k);

@@ -374,6 +374,103 @@ void ivf_plan(const int64_t *probe_pos, int64_t np, int nlist, const int64_t *li
     HB_LAUNCH_CHECK();
 }
 
+// ---- the same bookkeeping for the FAST list scan: three small kernels instead of two scans and a radix sort ----------------
+// The candidate pass needs the pairs grouped by list, not sorted: a counting pass (atomics), one scan over the lists and a
+// scatter.  pair_out holds the offsets of a query's probed lists inside THAT query's concatenation (its first entry is 0):
+// every consumer takes differences within a query (unit_slots_kernel, ivf_resolve_kernel).  The order of the pairs inside a
+// list is whatever the atomics give; no result depends on it (candidates are ranked by score, then position in the
+// query's concatenation).
+__global__ void planf_count_kernel(const int64_t *__restrict__ probe_pos, int64_t nq, int npq, int nlist,
+                                   const int64_t *__restrict__ list_off, int32_t *__restrict__ probes, int64_t *__restrict__ pair_out,
+                                   int32_t *__restrict__ cnt) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int64_t run = 0;
+    for (int j = 0; j < npq; ++j) {
+        const int64_t p = q * npq + j;
+        const int64_t l = probe_pos[p];
+        const bool ok = l >= 0 && l < nlist;
+        probes[p] = ok ? (int32_t)l : -1;
+        if (pair_out) pair_out[p] = run;
+        if (ok) {
+            run += list_off[l + 1] - list_off[l];
+            atomicAdd(&cnt[l], 1);
+        }
+    }
+}
+// lq_off = exclusive prefix of the pairs per list, unit_prefix = exclusive prefix of ceil(pairs / tile_q) for the lists that
+// hold rows; cursor[l] = lq_off[l] (the scatter's write positions).  One block; both counts ride in one 64-bit shuffle scan.
+__global__ void __launch_bounds__(1024) planf_scan_kernel(const int32_t *__restrict__ cnt, int nlist, const int64_t *__restrict__ list_off,
+                                                          int tile_q, int64_t *__restrict__ lq_off, int64_t *__restrict__ unit_prefix,
+                                                          int32_t *__restrict__ cursor) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base <= nlist; base += 1024) {
+        const int l = base + threadIdx.x;
+        unsigned long long v = 0;
+        if (l < nlist) {
+            const unsigned long long c = (unsigned long long)(uint32_t)cnt[l];
+            const unsigned long long units = list_off[l + 1] > list_off[l] ? (c + tile_q - 1) / tile_q : 0ull;
+            v = (units << 32) | c;
+        }
+        unsigned long long x = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += t;
+        }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long y = s_w[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, y, off);
+                if (lane >= off) y += t;
+            }
+            s_w[lane] = y;
+        }
+        __syncthreads();
+        const unsigned long long pre = s_run + (warp > 0 ? s_w[warp - 1] : 0ull) + x - v;
+        if (l <= nlist) {
+            lq_off[l] = (int64_t)(pre & 0xffffffffull);
+            unit_prefix[l] = (int64_t)(pre >> 32);
+            if (l < nlist) cursor[l] = (int32_t)(pre & 0xffffffffull);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += s_w[31];
+        __syncthreads();
+    }
+}
+__global__ void planf_scatter_kernel(const int32_t *__restrict__ probes, int64_t np, int32_t *__restrict__ cursor,
+                                     int32_t *__restrict__ qsel) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    const int l = probes[p];
+    if (l >= 0) qsel[atomicAdd(&cursor[l], 1)] = (int32_t)p;
+}
+void ivf_plan_fast(const int64_t *probe_pos, int64_t nq, int npq, int nlist, const int64_t *list_off, int32_t *probes,
+                   int64_t *pair_out, int32_t *qsel, int64_t *lq_off, int64_t *unit_prefix, int tile_q, DevBuf &tmp) {
+    const int64_t np = nq * npq;
+    HB_REQUIRE(np < (1ll << 31), "too many (query, probe) pairs for one plan");
+    int32_t *cnt = (int32_t *)tmp.get((size_t)(nlist + 1) * 8);
+    int32_t *cursor = cnt + nlist + 1;
+    HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(nlist + 1) * 4, g_stream));
+    if (nq > 0) {
+        planf_count_kernel<<<blocks_for(nq, 128), 128, 0, g_stream>>>(probe_pos, nq, npq, nlist, list_off, probes, pair_out, cnt);
+        HB_LAUNCH_CHECK();
+    }
+    planf_scan_kernel<<<1, 1024, 0, g_stream>>>(cnt, nlist, list_off, tile_q, lq_off, unit_prefix, cursor);
+    HB_LAUNCH_CHECK();
+    if (np > 0) {
+        planf_scatter_kernel<<<blocks_for(np, 256), 256, 0, g_stream>>>(probes, np, cursor, qsel);
+        HB_LAUNCH_CHECK();
+    }
+}
+
 void launch_ivf_resolve(const int64_t *pos, int64_t nq, int k, int nprobe, const int32_t *probes,
                         const int64_t *pair_out, const int64_t *list_off, const int64_t *list_rows, int64_t *out_ids) {
     if (nq * k == 0) return;

@@ -81,6 +81,13 @@ void ivf_plan(const int64_t *probe_pos /*[np] from select, -1 padded*/, int64_t 
               const int64_t *list_off, int32_t *probes, int64_t *pair_out, int32_t *qsel, int64_t *lq_off,
               int64_t *tile_prefix, int tile_rows, int tile_q, DevBuf &tmp);
 
+// The FAST list scan's variant (three small kernels, no sort): pairs grouped by list in no particular order inside a list;
+// pair_out (optional) [nq x npq]: offset of each probed list inside ITS query's concatenation; unit_prefix = exclusive
+// prefix of ceil(pairs of the list / tile_q) over the lists that hold rows.
+void ivf_plan_fast(const int64_t *probe_pos, int64_t nq, int npq, int nlist, const int64_t *list_off, int32_t *probes,
+                   int64_t *pair_out /*NULL: not wanted*/, int32_t *qsel, int64_t *lq_off, int64_t *unit_prefix, int tile_q,
+                   DevBuf &tmp);
+
 // pos (within the query's concatenated probed lists) -> row id
 void launch_ivf_resolve(const int64_t *pos, int64_t nq, int k, int nprobe, const int32_t *probes,
                         const int64_t *pair_out, const int64_t *list_off, const int64_t *list_rows,

@@ -185,6 +185,8 @@ void launch_rescore(const void *rows, int rdtype, const double *row_norm, const 
 const double *launch_widen_queries(const void *queries, int qdtype, int64_t count, double *buf);
 // fallback plumbing: dst[i] = src[idx[i]] (rows of row_bytes, multiple of 4) and dst[idx[i]] = src[i] (rows of k 8-byte words)
 void launch_gather_bytes(const void *src, const int32_t *idx, int64_t n, int64_t row_bytes, void *dst);
+// idx[0 .. count) = the queries whose proof failed (ok[q] == 0), ascending; idx[nq] = count.  idx holds nq + 1 entries.
+void launch_compact_failed(const int32_t *ok, int64_t nq, int32_t *idx);
 void launch_scatter_rows64(const void *src, const int32_t *idx, int64_t n, int k, void *dst);
 void launch_i32_to_i64(const int32_t *in, int64_t n, int64_t *out);
 // first[q] = pos[q*stride]  (probe rank 0 of every query)

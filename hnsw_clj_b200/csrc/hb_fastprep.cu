@@ -429,92 +429,121 @@ __global__ void __launch_bounds__(256) rescore_pairs_kernel(const int64_t *__res
 }
 
 // One CTA (128 threads) per query.  Entry j < kk: exact distance + rel; rank by (distance key, rel).
+// One WARP per query (four queries per block): the kernel is a chain of dependent loads per query — selection -> pair -> exact
+// distance / candidate record, then the proof's scalars — and a block per query kept 16 of those chains in flight per SM;
+// this keeps 64.  Lane l owns the selections l, l + 32, ... (kk <= 128: at most four).
 __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
-    __shared__ uint64_t s_key[128];
-    __shared__ int32_t s_rel[128];
-    __shared__ double s_kth;
-    __shared__ int s_skipped;
-    __shared__ uint64_t s_okey[129];  // the k + 1 best in rank order: ties across lists (tie_list_off)
-    __shared__ int32_t s_orow[129];
-    __shared__ int s_tie;
-    const int64_t q = blockIdx.x;
-    const int j = threadIdx.x;
+    __shared__ uint64_t s_key_all[4][128];
+    __shared__ int32_t s_rel_all[4][128];
+    __shared__ uint64_t s_okey_all[4][129];  // the k + 1 best in rank order: ties across lists (tie_list_off)
+    __shared__ int32_t s_orow_all[4][129];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t q = (int64_t)blockIdx.x * 4 + warp;
+    if (q >= P.nq) return;
+    uint64_t *s_key = s_key_all[warp], *s_okey = s_okey_all[warp];
+    int32_t *s_rel = s_rel_all[warp], *s_orow = s_orow_all[warp];
     const int kk = P.kk, k = P.k;
     const int cnt = P.cnt[q];
-    uint64_t key = kKeyEmpty;
-    int32_t rel = INT_MAX;
-    double dist = INFINITY;
-    if (j == 0) {
-        s_kth = INFINITY;
-        s_skipped = INT_MAX;
-        s_tie = 0;
-    }
-    int32_t prow = -1;
-    __syncthreads();
-    if (j < kk) {
-        const int64_t p = P.sel_pos[q * kk + j];
-        if (p >= 0 && P.sel_negv[q * kk + j] < INFINITY) {
-            prow = P.pair_row[q * kk + j];
-            if (prow >= 0 || prow == -2) {  // re-scored, or (set_only) certainly in the top-k: exact reads -inf
-                dist = P.exact[q * kk + j];
-                // a certain candidate keeps its approximate rank j (the selection is best-first), ahead of every re-scored one:
-                // column 0 stays the (approximately) nearest row, which seeds the IVF scan's thresholds
-                key = prow == -2 ? (uint64_t)j : dist_key(dist);
-                rel = P.cand_rel[q * P.cap + p];
-            } else {
-                atomicMin(&s_skipped, j);  // selected but not re-scored: the best of them bounds the others
+    constexpr int U = 4;
+    uint64_t key[U];
+    int32_t rel[U], prow[U];
+    double dist[U];
+    int skipped = INT_MAX;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int j = u * 32 + lane;
+        key[u] = kKeyEmpty;
+        rel[u] = INT_MAX;
+        dist[u] = INFINITY;
+        prow[u] = -1;
+        if (j < kk) {
+            const int64_t p = P.sel_pos[q * kk + j];
+            if (p >= 0 && P.sel_negv[q * kk + j] < INFINITY) {
+                prow[u] = P.pair_row[q * kk + j];
+                if (prow[u] >= 0 || prow[u] == -2) {  // re-scored, or (set_only) certainly in the top-k: exact reads -inf
+                    dist[u] = P.exact[q * kk + j];
+                    // a certain candidate keeps its approximate rank j (the selection is best-first), ahead of every re-scored one:
+                    // column 0 stays the (approximately) nearest row, which seeds the IVF scan's thresholds
+                    key[u] = prow[u] == -2 ? (uint64_t)j : dist_key(dist[u]);
+                    rel[u] = P.cand_rel[q * P.cap + p];
+                } else {
+                    skipped = min(skipped, j);  // selected but not re-scored: the best of them bounds the others
+                }
             }
+            s_key[j] = key[u];
+            s_rel[j] = rel[u];
         }
     }
-    s_key[j] = key;
-    s_rel[j] = rel;
-    __syncthreads();
-    int rank = 0, nvalid = 0;
+    skipped = __reduce_min_sync(0xffffffffu, skipped);
+    __syncwarp();
+    int nvalid = 0;
+    int rank[U] = {0, 0, 0, 0};
     for (int i = 0; i < kk; ++i) {
         const uint64_t ki = s_key[i];
         const int32_t ri = s_rel[i];
         nvalid += ki != kKeyEmpty;
-        if (i != j && (ki < key || (ki == key && (ri < rel || (ri == rel && i < j))))) ++rank;
-    }
-    if (j < kk && key != kKeyEmpty && rank < k) {
-        P.out_rel[q * k + rank] = rel;
-        P.out_dist[q * k + rank] = dist;
-        if (rank == min(k, nvalid) - 1) s_kth = dist;
-        if (P.out_simub) {  // upper bound of the winner's similarity: exact if re-scored, approximate score + eps_q if certain
-            const double sim = prow == -2 ? -P.sel_negv[q * kk + j] * P.q_scale[q] + P.q_eps[q] : (P.metric == HB_COSINE ? 1.0 - dist : -dist);
-            P.out_simub[q * k + rank] = sim + 1e-9 * (1.0 + fabs(sim));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (u * 32 >= kk) break;  // (uniform: kk = 64 uses two of the four)
+            const int j = u * 32 + lane;
+            if (i != j && (ki < key[u] || (ki == key[u] && (ri < rel[u] || (ri == rel[u] && i < j))))) ++rank[u];
         }
     }
+    double kth = INFINITY;  // exact k-th best distance among the selected (the lane that holds it)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int j = u * 32 + lane;
+        if (j < kk && key[u] != kKeyEmpty && rank[u] < k) {
+            P.out_rel[q * k + rank[u]] = rel[u];
+            P.out_dist[q * k + rank[u]] = dist[u];
+            if (rank[u] == min(k, nvalid) - 1) kth = dist[u];
+            if (P.out_simub) {  // upper bound of the winner's similarity: exact if re-scored, approximate score + eps_q if certain
+                const double sim = prow[u] == -2 ? -P.sel_negv[q * kk + j] * P.q_scale[q] + P.q_eps[q]
+                                                 : (P.metric == HB_COSINE ? 1.0 - dist[u] : -dist[u]);
+                P.out_simub[q * k + rank[u]] = sim + 1e-9 * (1.0 + fabs(sim));
+            }
+        }
+    }
+    {   // one lane at most holds a finite kth (ranks are distinct); +inf otherwise, as before
+        const unsigned has = __ballot_sync(0xffffffffu, kth != INFINITY);
+        kth = __shfl_sync(0xffffffffu, kth, has ? __ffs(has) - 1 : 0);
+    }
+    int tie = 0;
     if (P.tie_list_off) {
         // The caller's `rel` order across lists is not the reference's (approximate probe order, see set_only): equal
         // distances inside a list still fall in row order, but a tie between rows of different lists among the k + 1 best
         // would be broken by probe rank in the reference (ivf_flat.clj:281-294) -- such a query goes to the exact path.
-        if (j < kk && key != kKeyEmpty && rank <= k) s_okey[rank] = key, s_orow[rank] = prow;
-        __syncthreads();
-        if (j < k && j + 1 < nvalid && s_okey[j] == s_okey[j + 1]) {
-            auto list_of = [&](int32_t row) {
-                int lo = 0, hi = P.tie_nlist;  // last l with list_off[l] <= row
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (P.tie_list_off[mid] <= row) lo = mid; else hi = mid;
-                }
-                return lo;
-            };
-            if (list_of(s_orow[j]) != list_of(s_orow[j + 1])) s_tie = 1;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = u * 32 + lane;
+            if (j < kk && key[u] != kKeyEmpty && rank[u] <= k) s_okey[rank[u]] = key[u], s_orow[rank[u]] = prow[u];
         }
+        __syncwarp();
+        for (int j = lane; j < k; j += 32) {
+            if (j + 1 < nvalid && s_okey[j] == s_okey[j + 1]) {
+                auto list_of = [&](int32_t row) {
+                    int lo = 0, hi = P.tie_nlist;  // last l with list_off[l] <= row
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (P.tie_list_off[mid] <= row) lo = mid; else hi = mid;
+                    }
+                    return lo;
+                };
+                if (list_of(s_orow[j]) != list_of(s_orow[j + 1])) tie = 1;
+            }
+        }
+        tie = __any_sync(0xffffffffu, tie);
     }
-    for (int r = nvalid + j; r < k; r += blockDim.x) {
+    for (int r = nvalid + lane; r < k; r += 32) {
         P.out_rel[q * k + r] = -1;
         P.out_dist[q * k + r] = INFINITY;
         if (P.out_simub) P.out_simub[q * k + r] = INFINITY;
     }
-    __syncthreads();
-    if (j == 0) {
+    if (lane == 0) {
         // rejected rows: selected but not re-scored (score <= the best of them), emitted but not selected (score <= worst
         // selected) or never emitted (score < thr)
-        bool ok = cnt <= P.cap && !s_tie;
+        bool ok = cnt <= P.cap && !tie;
         const float thr = P.thr[q];
-        const int skipped = s_skipped;
         const bool none_rejected = cnt <= kk && thr == -INFINITY && skipped == INT_MAX;
         if (ok && !none_rejected) {
             if (nvalid < k) ok = false;  // rejected rows would be needed to fill k
@@ -524,7 +553,6 @@ __global__ void __launch_bounds__(128) fast_final_kernel(const FinalParams P) {
                 if (skipped != INT_MAX) t_v = fmax(t_v, -P.sel_negv[q * kk + skipped]);
                 const double t_sim = t_v * P.q_scale[q];
                 const double t_up = t_sim + P.q_eps[q] + 1e-6 * fabs(t_sim);
-                const double kth = s_kth;  // exact k-th best distance among the selected
                 const double sim_k = P.metric == HB_COSINE ? 1.0 - kth : -kth;
                 ok = (sim_k - t_up) > 1e-12 && isfinite(t_up);
             }
@@ -1284,6 +1312,36 @@ void launch_unpack_probe_blocks(const void *gathered, int nranks, int64_t per, i
     unpack_probe_blocks_kernel<<<blocks_for(nq * np, 256), 256, 0, g_stream>>>((const char *)gathered, per, nq, np, ppos, simub);
     HB_LAUNCH_CHECK();
 }
+// idx[0 .. count) = the queries with ok[q] == 0, ascending; idx[nq] = count (one block: ordered, and nq is a few thousand)
+__global__ void __launch_bounds__(1024) compact_failed_kernel(const int32_t *__restrict__ ok, int64_t nq, int32_t *__restrict__ idx) {
+    __shared__ int s_w[32];
+    __shared__ int s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nq; base += 1024) {
+        const int64_t q = base + threadIdx.x;
+        const bool bad = q < nq && ok[q] == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, bad);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        int before = s_run;
+        for (int w = 0; w < warp; ++w) before += s_w[w];
+        if (bad) idx[before + __popc(m & ((1u << lane) - 1u))] = (int32_t)q;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 32; ++w) tot += s_w[w];
+            s_run += tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) idx[nq] = s_run;
+}
+void launch_compact_failed(const int32_t *ok, int64_t nq, int32_t *idx) {
+    compact_failed_kernel<<<1, 1024, 0, g_stream>>>(ok, nq, idx);
+    HB_LAUNCH_CHECK();
+}
 void launch_sim_from_dist(const double *dist, int64_t n, double *sim) {
     if (n == 0) return;
     sim_from_dist_kernel<<<blocks_for(n, 256), 256, 0, g_stream>>>(dist, n, sim);
@@ -1395,7 +1453,7 @@ void launch_rescore_pairs(const int64_t *sel_pos, const double *sel_negv, const 
 void launch_fast_final(const FinalParams &P) {
     if (P.nq == 0) return;
     HB_REQUIRE(P.kk <= 128 && P.k <= P.kk, "fast final: k <= kk <= 128");
-    fast_final_kernel<<<(unsigned)P.nq, 128, 0, g_stream>>>(P);
+    fast_final_kernel<<<blocks_for(P.nq, 4), 128, 0, g_stream>>>(P);
     HB_LAUNCH_CHECK();
 }
 

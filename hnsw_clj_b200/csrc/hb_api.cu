@@ -2185,6 +2185,7 @@ HB_API int hb_get_stat(const char *name, double *out) {
         if (!strcmp(name, "tc_half_units")) { *out = dev_stat(DS_TC_HALF_UNITS); return; }
         if (!strcmp(name, "tc_narrow_units")) { *out = dev_stat(DS_TC_NARROW_UNITS); return; }
         if (!strcmp(name, "tc_narrow_items")) { *out = dev_stat(DS_TC_NARROW_ITEMS); return; }
+        if (!strcmp(name, "tc_narrow_slots")) { *out = (double)kNarrowSlots; return; }  // query slots of a narrow unit's image
         if (!strcmp(name, "fast_pruned_rows")) { *out = dev_stat(DS_PRUNED_ROWS); return; }
         if (!strcmp(name, "fast_probe_pairs")) { *out = (double)g_fast_probe_pairs; return; }
         if (!strcmp(name, "hnsw_scored")) { *out = (double)g_hnsw_scored; return; }

@@ -27,6 +27,8 @@ constexpr int kFastTile = 128;          // rows per B tile = query slots per uni
 constexpr int kFastKB = 128;            // dimensions per k-block (one 128-byte swizzle row of int8)
 constexpr int kFastImg = kFastTile * kFastKB;  // bytes of one (tile, kb, slice) image
 constexpr int kNarrowSlots = 32;        // a unit with at most this many selections runs with the rows on the M side (tc_narrow_kernel)
+                                        // (16 or 32.  Measured at configs[1] with 16: the query images halve, but 12 % of the units — 24 % of
+                                        //  the items — fall to the dense kernel: step 1.628 vs 1.632 ms, 32 queries on flat 1M 673 vs 575 us)
 
 // quantisation range: |m| <= qmax so that every digit fits int8 after the balanced split
 __host__ __device__ constexpr double fast_qmax(int ns) { return ns == 2 ? 32000.0 : 8000000.0; }

@@ -520,9 +520,11 @@ struct NarrowCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int NSTAGE = NS == 2 ? 5 : 3;
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024;
-    static constexpr int ACC_COLS = 32;    // TMEM columns of one digit-product accumulator: [hi.hi | hi.lo | lo.hi | lo.lo] (row digit . query digit)
-    static constexpr int SET_COLS = 128;   // columns of one accumulator set
-    static constexpr int TMEM_COLS = 256;  // two sets
+    static constexpr int ACC_COLS = kNarrowSlots;       // TMEM columns of one digit-product accumulator: [hi.hi | hi.lo | lo.hi | lo.lo] (row digit . query digit)
+    static constexpr int SET_COLS = 4 * kNarrowSlots;   // columns of one accumulator set
+    static constexpr int TMEM_COLS = 8 * kNarrowSlots;  // two sets (a power of two >= 32)
+    static constexpr int GPT = kNarrowSlots / 16;       // groups of 8 query columns per epilogue thread (groups chalf, chalf + 2, ...)
+    static_assert(kNarrowSlots == 16 || kNarrowSlots == 32, "narrow units hold 16 or 32 query slots");
 };
 // D = S32, A = B = signed int8, K-major, M = 128, N = 64: the B operand is the unit's 32 query slots TWICE — their high
 // digits (rows 0-31 of the tile) stacked on their low digits (rows 32-63) — so one MMA per row digit yields both digit
@@ -734,19 +736,20 @@ __global__ void __launch_bounds__(NARROW_THREADS, 1) tc_narrow_kernel(const TcPa
             tc_fence_after();
             const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)set * Cfg::SET_COLS;
             // this thread's columns: group g0 = chalf (columns 8 g0 ..) and g1 = chalf + 2, where the unit reaches them
-            const bool use0 = chalf * 8 < nsel, use1 = (chalf + 2) * 8 < nsel;
-            uint32_t c0[16], c1[16], c1b[16], c2[16];  // hi.hi, hi.lo, lo.hi, lo.lo
+            constexpr int GPT = Cfg::GPT, NC = 8 * GPT;  // this thread's columns
+            const bool use0 = chalf * 8 < nsel, use1 = GPT > 1 && (chalf + 2) * 8 < nsel;
+            uint32_t c0[NC], c1[NC], c1b[NC], c2[NC];  // hi.hi, hi.lo, lo.hi, lo.lo
             if (use0) {
                 tmem_ld8(tl + chalf * 8, &c0[0]);
                 tmem_ld8(tl + Cfg::ACC_COLS + chalf * 8, &c1[0]);
                 tmem_ld8(tl + 2 * Cfg::ACC_COLS + chalf * 8, &c1b[0]);
                 tmem_ld8(tl + 3 * Cfg::ACC_COLS + chalf * 8, &c2[0]);
             }
-            if (use1) {
-                tmem_ld8(tl + (chalf + 2) * 8, &c0[8]);
-                tmem_ld8(tl + Cfg::ACC_COLS + (chalf + 2) * 8, &c1[8]);
-                tmem_ld8(tl + 2 * Cfg::ACC_COLS + (chalf + 2) * 8, &c1b[8]);
-                tmem_ld8(tl + 3 * Cfg::ACC_COLS + (chalf + 2) * 8, &c2[8]);
+            if (GPT > 1 && use1) {
+                tmem_ld8(tl + (chalf + 2) * 8, &c0[NC - 8]);
+                tmem_ld8(tl + Cfg::ACC_COLS + (chalf + 2) * 8, &c1[NC - 8]);
+                tmem_ld8(tl + 2 * Cfg::ACC_COLS + (chalf + 2) * 8, &c1b[NC - 8]);
+                tmem_ld8(tl + 3 * Cfg::ACC_COLS + (chalf + 2) * 8, &c2[NC - 8]);
             }
             tmem_ld_wait();
             tc_fence_before();
@@ -754,11 +757,11 @@ __global__ void __launch_bounds__(NARROW_THREADS, 1) tc_narrow_kernel(const TcPa
             if (lane == 0) mbar_arrive(smem_u32(&s_tmem_empty[set]));
             if (use0) {
                 const int pos_in_list = t * kFastTile + row;
-                // column c (0..15) of this thread is slot col_of(c) of the unit
-                float sc[16];
+                // column c (0..NC-1) of this thread is slot col_of(c) of the unit
+                float sc[NC];
                 uint32_t passbits = 0;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int c = 0; c < NC; ++c) {
                     if (c >= 8 && !use1) break;
                     const int slot = (chalf + (c >> 3) * 2) * 8 + (c & 7);
                     const int lo = (int)c1[c] + (int)c1b[c] + ((int)c2[c] >> 8);
@@ -771,16 +774,16 @@ __global__ void __launch_bounds__(NARROW_THREADS, 1) tc_narrow_kernel(const TcPa
                 // are in flight together
                 uint32_t mymask = 0;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int c = 0; c < NC; ++c) {
                     if (c >= 8 && !use1) break;
                     const uint32_t m = __ballot_sync(0xffffffffu, (passbits >> c) & 1u);
                     if (lane == c) mymask = m;
                 }
                 const int myslot = (chalf + ((lane & 15) >> 3) * 2) * 8 + (lane & 7);
                 int mybase = 0;
-                if (lane < 16 && mymask != 0 && s_base[par][myslot] < 0) mybase = atomicAdd(&P.cnt[s_q[par][myslot]], __popc(mymask));
+                if (lane < NC && mymask != 0 && s_base[par][myslot] < 0) mybase = atomicAdd(&P.cnt[s_q[par][myslot]], __popc(mymask));
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int c = 0; c < NC; ++c) {
                     if (c >= 8 && !use1) break;
                     const uint32_t m = __shfl_sync(0xffffffffu, mymask, c);
                     if (m == 0) continue;  // uniform over the warp

@@ -341,6 +341,8 @@ static double dev_stat(int i) {
     HB_CUDA(cudaStreamSynchronize(g_stream));
     return (double)h[i];
 }
+static bool g_prof_coarse = false;   // diagnostics: the stage timers (pack / tc / select / re-score) record the COARSE job of an IVF search
+                                     // instead of its list scan
 static bool g_fast_set_only = true;  // IVF coarse routing proves the probed set only (FastJob::set_only)
 static bool g_fast_dense = true;     // short flat scans (<= 2048 rows) select from the dumped score matrix
 static int g_fast_level_min = 33;     // flat scans of at least this many row tiles run in levels (fast_topk)
@@ -1323,7 +1325,7 @@ static void fast_topk(const FastJob &J) {
         int32_t *ptotal = W.ptotal.as<int32_t>(1);
         launch_rescore_pairs(selpos, selval, cpos, nq, kk, cap, J.k, qmargin, srow, exact, ptotal, pq, prow, pslot, J.set_only);
         launch_rescore(J.rows_exact, J.rdtype, J.row_norm, J.q64, J.qdtype == HB_F32, J.qn, J.d, pq, prow, pslot, ptotal, nq * kk, J.epi,
-                       exact);
+                       exact, J.set_only);
         FinalParams F;
         F.nq = nq;
         F.k = J.k;
@@ -1794,7 +1796,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
                 J.d = d;
                 J.metric = HB_COSINE;
                 J.epi = EPI_COS_GUARD;
-                J.profile = false;
+                J.profile = g_prof_coarse;
                 J.k = np_eff;
                 J.out_simub = simub + (size_t)b0 * np_eff;
                 J.set_only = g_fast_set_only;  // which lists to probe; their order only numbers the candidates (ties: tie_list_off below)
@@ -1913,6 +1915,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         J.out_dist = dist + (size_t)q0 * k;
         J.out_ok = ok_all + q0;
         J.cover_stats = true;
+        J.profile = !g_prof_coarse;
         if (coarse_tc && g_fast_set_only && !shard_coarse) {  // probe order is approximate: cross-list distance ties go to the exact path
             J.tie_list_off = (const int64_t *)ix->list_off.p;
             J.tie_nlist = nlist;
@@ -2098,6 +2101,8 @@ HB_API int hb_set_option(const char *name, int64_t value) {
             g_fast_ns = (int)value;
         } else if (!strcmp(name, "fast_dense")) {
             g_fast_dense = value != 0;
+        } else if (!strcmp(name, "prof_coarse")) {
+            g_prof_coarse = value != 0;
         } else if (!strcmp(name, "fast_level_dense")) {
             HB_REQUIRE(value >= 0 && value <= 16, "fast_level_dense must be 0..16 row tiles");
             g_fast_level_dense = (int)value;

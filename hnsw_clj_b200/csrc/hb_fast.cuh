@@ -182,7 +182,8 @@ void launch_cand_compact(double *cand_negv, int32_t *cand_rel, int32_t *cand_pos
 // exact fp64 distance of (query, row) pairs in the reference's summation order (cosine / -dot epilogues, no L2)
 void launch_rescore(const void *rows, int rdtype, const double *row_norm, const double *queries64, bool q_f32_repr,
                     const double *q_norm, int d, const int32_t *pair_query, const int32_t *pair_row, const int32_t *pair_slot,
-                    const int32_t *total, int64_t max_pairs, int epi, double *out);
+                    const int32_t *total, int64_t max_pairs, int epi, double *out, bool sparse = false);
+// (sparse: few pairs per query and fp64 rows — every lane stages its own query chunk, see rescore_kernel)
 // fp64 copy of the queries for the re-score (returns `queries` itself when they already are fp64)
 const double *launch_widen_queries(const void *queries, int qdtype, int64_t count, double *buf);
 // fallback plumbing: dst[i] = src[idx[i]] (rows of row_bytes, multiple of 4) and dst[idx[i]] = src[i] (rows of k 8-byte words)

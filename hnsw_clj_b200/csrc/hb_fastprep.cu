@@ -870,7 +870,11 @@ struct Widen<double> {
 };
 
 constexpr int RS_QSLOTS = 4;  // distinct queries per warp whose chunks are staged in shared memory (others: direct loads)
-template <typename TRow, int ARITH>
+// QLANE (fp64 rows only): every lane's query chunk is staged like its row chunk (a second 128-byte piece per lane and chunk).
+// The run slots above serve pair lists with ~35 pairs per query; the coarse stage that proves a set re-scores ~2 centroids per
+// query, a warp then holds ~18 queries, 14 of them fell to per-element global loads inside the dependent fp64 chain, and the
+// launch took 0.16 ms for 18,000 pairs.
+template <typename TRow, int ARITH, bool QLANE = false>
 __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ rows, const double *__restrict__ row_norm,
                                                       const double *__restrict__ queries, const double *__restrict__ q_norm, int d,
                                                       const int32_t *__restrict__ pair_query, const int32_t *__restrict__ pair_row,
@@ -880,8 +884,10 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
     constexpr int EPL = 16 / (int)sizeof(TRow);  // elements per lane and round (16 B)
     constexpr int PER = Widen<TRow>::PER;
     constexpr int QPL = (CH + 31) / 32;          // query elements a lane stages per chunk and slot
+    static_assert(!QLANE || sizeof(TRow) == 8, "per-lane query staging: fp64 rows (query chunk = row chunk = 128 bytes)");
     __shared__ __align__(16) unsigned char s_raw[4][32][128 + 16];
-    __shared__ __align__(16) double s_q[4][RS_QSLOTS][CH];
+    __shared__ __align__(16) double s_q[4][QLANE ? 1 : RS_QSLOTS][QLANE ? 2 : CH];
+    __shared__ __align__(16) unsigned char s_rawq[QLANE ? 4 : 1][QLANE ? 32 : 1][128 + 16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int npairs = *total;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -909,13 +915,20 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
     // cooperative loads: in round r, lanes 8*(j%4) .. +7 fetch the 128-byte chunk of the warp's row j = 4*r + lane/8
     const int part = lane & 7;
     const TRow *src[8];
+    const double *srcq[QLANE ? 8 : 1];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int rj = __shfl_sync(0xffffffffu, ri, r * 4 + (lane >> 3));
         src[r] = rj >= 0 ? rows + (int64_t)rj * d : nullptr;
+        if (QLANE) {
+            const int qj = __shfl_sync(0xffffffffu, qi, r * 4 + (lane >> 3));
+            srcq[r] = qj >= 0 ? queries + (int64_t)qj * d : nullptr;
+        }
     }
+    const bool vecq = QLANE && (((size_t)d * 8) % 16 == 0) && ((reinterpret_cast<uintptr_t>(queries) & 15) == 0);
     uint4 pre[8];
-    double preq[RS_QSLOTS][QPL];
+    uint4 preq2[QLANE ? 8 : 1];
+    double preq[QLANE ? 1 : RS_QSLOTS][QPL];
     auto fetch = [&](int c) {
         const int e0 = c * CH + part * EPL;
 #pragma unroll
@@ -930,6 +943,23 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
                 val = *reinterpret_cast<uint4 *>(tmp);
             }
             pre[r] = val;
+        }
+        if (QLANE) {
+            const int q0e = c * CH + part * 2;  // two doubles per 16-byte piece
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                uint4 val = make_uint4(0, 0, 0, 0);
+                if (srcq[r] == nullptr) {
+                } else if (vecq && q0e + 2 <= d) val = __ldg(reinterpret_cast<const uint4 *>(srcq[r] + q0e));
+                else {
+                    alignas(16) double tmp[2];
+                    tmp[0] = q0e < d ? srcq[r][q0e] : 0.0;
+                    tmp[1] = q0e + 1 < d ? srcq[r][q0e + 1] : 0.0;
+                    val = *reinterpret_cast<uint4 *>(tmp);
+                }
+                preq2[r] = val;
+            }
+            return;
         }
 #pragma unroll
         for (int sidx = 0; sidx < RS_QSLOTS; ++sidx) {
@@ -946,12 +976,17 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < 8; ++r) *reinterpret_cast<uint4 *>(&s_raw[warp][r * 4 + (lane >> 3)][part * 16]) = pre[r];
+        if (QLANE) {
 #pragma unroll
-        for (int sidx = 0; sidx < RS_QSLOTS; ++sidx) {
+            for (int r = 0; r < 8; ++r) *reinterpret_cast<uint4 *>(&s_rawq[warp][r * 4 + (lane >> 3)][part * 16]) = preq2[r];
+        } else {
 #pragma unroll
-            for (int t = 0; t < QPL; ++t) {
-                const int i = t * 32 + lane;
-                if (i < CH) s_q[warp][sidx][i] = preq[sidx][t];
+            for (int sidx = 0; sidx < RS_QSLOTS; ++sidx) {
+#pragma unroll
+                for (int t = 0; t < QPL; ++t) {
+                    const int i = t * 32 + lane;
+                    if (i < CH) s_q[warp][sidx][i] = preq[sidx][t];
+                }
             }
         }
         __syncwarp();
@@ -960,8 +995,9 @@ __global__ void __launch_bounds__(128) rescore_kernel(const TRow *__restrict__ r
         const uint4 *mine = reinterpret_cast<const uint4 *>(&s_raw[warp][lane][0]);
         const int kmax = min(CH, d - c * CH);
         if (live) {
-            const bool staged = qslot < RS_QSLOTS;
-            const double *qs = staged ? &s_q[warp][qslot][0] : qp + c * CH;
+            const bool staged = QLANE || qslot < RS_QSLOTS;
+            const double *qs = QLANE ? reinterpret_cast<const double *>(&s_rawq[warp][lane][0])
+                                     : (staged ? &s_q[warp][qslot][0] : qp + c * CH);
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
                 const uint4 bits = mine[w];
@@ -1195,8 +1231,16 @@ namespace {
 template <typename TRow>
 void rescore_arith(const void *rows, const double *row_norm, const double *queries, bool q_f32_repr, const double *q_norm, int d,
                    const int32_t *pq, const int32_t *pr, const int32_t *ps, const int32_t *total, int64_t max_pairs, int epi,
-                   double *out) {
+                   double *out, bool sparse) {
     const int grid = blocks_for(max_pairs, 128);
+    if constexpr (sizeof(TRow) == 8) {
+        if (sparse) {  // (fp64 rows are never fp32-representable products: MULADD)
+            rescore_kernel<TRow, ARITH_MULADD, true><<<grid, 128, 0, g_stream>>>((const TRow *)rows, row_norm, queries, q_norm, d, pq, pr,
+                                                                                  ps, total, epi, out);
+            HB_LAUNCH_CHECK();
+            return;
+        }
+    }
     // both factors fp32-representable: the fp64 product is exact, DFMA rounds like multiply-then-add
     if (is_f32_repr<TRow>::value && q_f32_repr)
         rescore_kernel<TRow, ARITH_FMA><<<grid, 128, 0, g_stream>>>((const TRow *)rows, row_norm, queries, q_norm, d, pq, pr, ps, total,
@@ -1213,9 +1257,9 @@ void rescore_arith(const void *rows, const double *row_norm, const double *queri
 // launch_rescore_pairs; out[pair_slot] receives the distance.
 void launch_rescore(const void *rows, int rdtype, const double *row_norm, const double *queries64, bool q_f32_repr,
                     const double *q_norm, int d, const int32_t *pair_query, const int32_t *pair_row, const int32_t *pair_slot,
-                    const int32_t *total, int64_t max_pairs, int epi, double *out) {
+                    const int32_t *total, int64_t max_pairs, int epi, double *out, bool sparse) {
     if (max_pairs == 0) return;
-#define HB_RS(T_) rescore_arith<T_>(rows, row_norm, queries64, q_f32_repr, q_norm, d, pair_query, pair_row, pair_slot, total, max_pairs, epi, out)
+#define HB_RS(T_) rescore_arith<T_>(rows, row_norm, queries64, q_f32_repr, q_norm, d, pair_query, pair_row, pair_slot, total, max_pairs, epi, out, sparse)
     if (rdtype == HB_F32) HB_RS(float);
     else if (rdtype == HB_BF16) HB_RS(__nv_bfloat16);
     else if (rdtype == HB_F64) HB_RS(double);

@@ -355,7 +355,8 @@ def run_ours(args, w, key, ctx, replicas_only=False):
     pruned_pairs = hb.get_stat("fast_pruned_pairs") / args.steps
     pruned_rows = hb.get_stat("fast_pruned_rows") / args.steps
     probe_pairs = hb.get_stat("fast_probe_pairs") / args.steps
-    hb_stats = {n: hb.get_stat(n) for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units", "tc_narrow_units", "tc_narrow_items")}
+    hb_stats = {n: hb.get_stat(n) for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units", "tc_narrow_units", "tc_narrow_items",
+                                            "tc_narrow_slots")}
     hb.set_option("profile", 0)
     if world > 1:
         t = torch.tensor([ms], device=device)
@@ -461,8 +462,8 @@ def run_ours(args, w, key, ctx, replicas_only=False):
             items = tc_items
         int8_ops = 2.0 * items * 128 * 128 * dpad * nprod if items else None
         # digit images read once: the row tiles some unit scans + the units' query images (128 slots each, 64 for the
-        # units that run with M = 64, tc_narrow_slots for the narrow units of tc_narrow_kernel)
-        slots = 128.0 * (tc_units - tc_half) + 64.0 * (tc_half - tc_narrow) + hb.get_stat("tc_narrow_slots") * tc_narrow
+        # units that run with M = 64, the 8-slot groups in use for the narrow units of tc_narrow_kernel)
+        slots = 128.0 * (tc_units - tc_half) + 64.0 * (tc_half - tc_narrow) + hb_stats["tc_narrow_slots"] / args.steps
         img_bytes = (tc_tiles * 128.0 * dpad * args.digits + slots * dpad * args.digits) if tc_items > 0 else (
             float(w["n"]) * dpad * args.digits + nq * nprobe * dpad * args.digits)
         hbm_peak = peaks.get("hbm_gbs", 7700.0)
@@ -473,7 +474,7 @@ def run_ours(args, w, key, ctx, replicas_only=False):
         hbm = {"achieved_gbs": img_bytes / t_tc / 1e9 if single else None, "peak_gbs": hbm_peak,
                "frac": (img_bytes / t_tc / 1e9 / hbm_peak) if single else None}
         roofline = {
-            "kernel": (f"tc_narrow_kernel<{args.digits}> (tcgen05.mma kind::i8, rows on M, <= {hb.get_stat('tc_narrow_slots'):.0f} queries on N: {tc_narrow_items:.0f} of "
+            "kernel": (f"tc_narrow_kernel<{args.digits}> (tcgen05.mma kind::i8, rows on M, <= 32 queries on N: {tc_narrow_items:.0f} of "
                        f"{items or 0:.0f} items) + tc_pass_kernel<{args.digits},EMIT> (the rest): IVF list scan candidate pass"),
             "bound": "hbm" if hbm_bound else "tensor",
             "achieved": (hbm["achieved_gbs"] if hbm_bound else tensor["achieved_tflops"]),
@@ -820,7 +821,8 @@ def run_sharded(args, S, ctx):
     pruned_pairs = hb.get_stat("fast_pruned_pairs") / args.steps
     pruned_rows = hb.get_stat("fast_pruned_rows") / args.steps
     probe_pairs = hb.get_stat("fast_probe_pairs") / args.steps
-    tc = {n: hb.get_stat(n) / args.steps for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units", "tc_narrow_units", "tc_narrow_items")}
+    tc = {n: hb.get_stat(n) / args.steps for n in ("tc_units", "tc_items", "tc_tiles", "tc_half_units", "tc_narrow_units", "tc_narrow_items",
+                                                   "tc_narrow_slots")}
     hb.set_option("profile", 0)
     # the slowest rank's share of the step spent in the exchange + merge (what the collective costs)
     comm_ms = max_over_ranks(stats["exchange_ms"] + stats["merge_ms"])
@@ -883,7 +885,7 @@ def run_sharded(args, S, ctx):
     roofline = None
     if fast and tc["tc_items"] > 0:
         t_tc = (tc_ms / tc_n) * 1e-3
-        slots = 128.0 * (tc["tc_units"] - tc["tc_half_units"]) + 64.0 * (tc["tc_half_units"] - tc["tc_narrow_units"]) + hb.get_stat("tc_narrow_slots") * tc["tc_narrow_units"]
+        slots = 128.0 * (tc["tc_units"] - tc["tc_half_units"]) + 64.0 * (tc["tc_half_units"] - tc["tc_narrow_units"]) + tc["tc_narrow_slots"]
         img_bytes = tc["tc_tiles"] * 128.0 * dpad * args.digits + slots * dpad * args.digits
         roofline = {"kernel": f"tc_narrow_kernel<{args.digits}> ({tc['tc_narrow_items']:.0f} of {tc['tc_items']:.0f} items) + tc_pass_kernel<{args.digits},EMIT> (rank 0's shard)", "bound": "hbm",
                     "achieved": img_bytes / t_tc / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": img_bytes / t_tc / 1e9 / hbm_peak,

@@ -327,7 +327,7 @@ static int64_t g_fast_probe_pairs = 0;
 // profiling counters that live on the device (a search makes no host round trip for them): [pruned (query, list) pairs,
 // rows they held, units / items / row tiles of the IVF main candidate pass]
 enum { DS_PRUNED_PAIRS = 0, DS_PRUNED_ROWS = 1, DS_TC_UNITS = 2, DS_TC_ITEMS = 3, DS_TC_TILES = 4, DS_TC_HALF_UNITS = 5,
-       DS_TC_NARROW_UNITS = 6, DS_TC_NARROW_ITEMS = 7, DS_COUNT = 8 };
+       DS_TC_NARROW_UNITS = 6, DS_TC_NARROW_ITEMS = 7, DS_TC_NARROW_SLOTS = 8, DS_COUNT = 9 };
 static DevBuf g_dev_stats;
 static unsigned long long *dev_stats() {
     const bool fresh = g_dev_stats.p == nullptr;
@@ -2190,7 +2190,7 @@ HB_API int hb_get_stat(const char *name, double *out) {
         if (!strcmp(name, "tc_half_units")) { *out = dev_stat(DS_TC_HALF_UNITS); return; }
         if (!strcmp(name, "tc_narrow_units")) { *out = dev_stat(DS_TC_NARROW_UNITS); return; }
         if (!strcmp(name, "tc_narrow_items")) { *out = dev_stat(DS_TC_NARROW_ITEMS); return; }
-        if (!strcmp(name, "tc_narrow_slots")) { *out = (double)kNarrowSlots; return; }  // query slots of a narrow unit's image
+        if (!strcmp(name, "tc_narrow_slots")) { *out = dev_stat(DS_TC_NARROW_SLOTS); return; }  // query slots the narrow units read (groups of 8)
         if (!strcmp(name, "fast_pruned_rows")) { *out = dev_stat(DS_PRUNED_ROWS); return; }
         if (!strcmp(name, "fast_probe_pairs")) { *out = (double)g_fast_probe_pairs; return; }
         if (!strcmp(name, "hnsw_scored")) { *out = (double)g_hnsw_scored; return; }

@@ -233,9 +233,10 @@ __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, 
     if (U.unit_tile0) U.unit_tile0[slot_u] = t0;
     if (stats && nsel > 0) {
         // what the pass covers: [0] units, [1] items (unit x row tile), [2] distinct row tiles read (a list with several units:
-        // at least its tiles beyond the skipped ones), [3] units of <= 64 selections, [4] narrow units, [5] their items
+        // at least its tiles beyond the skipped ones), [3] units of <= 64 selections, [4] narrow units, [5] their items,
+        // [6] the query slots their images hold
         // (one atomic per counter and warp: thousands of units adding to the same six words serialise in L2)
-        unsigned long long c[6] = {1ull, (unsigned long long)nt, 0ull, nsel <= 64 ? 1ull : 0ull, 0ull, 0ull};
+        unsigned long long c[7] = {1ull, (unsigned long long)nt, 0ull, nsel <= 64 ? 1ull : 0ull, 0ull, 0ull, 0ull};
         if (j == 0) {
             const int units_l = (int)(unit_prefix[l + 1] - unit_prefix[l]);
             const int all_t = (int)(tile_off[l + 1] - tile_off[l]);
@@ -244,10 +245,11 @@ __global__ void unit_plan_kernel(int nlist, const int64_t *__restrict__ lq_off, 
         if (nsel <= kNarrowSlots) {
             c[4] = 1ull;
             c[5] = (unsigned long long)nt;
+            c[6] = (unsigned long long)((nsel + 7) & ~7);  // query slots of the unit's image that are packed and read
         }
         const cg::coalesced_group g = cg::coalesced_threads();
 #pragma unroll
-        for (int m = 0; m < 6; ++m) {
+        for (int m = 0; m < 7; ++m) {
             const unsigned long long sum = cg::reduce(g, c[m], cg::plus<unsigned long long>());
             if (g.thread_rank() == 0 && sum != 0) atomicAdd(stats + m, sum);
         }
@@ -337,7 +339,8 @@ __global__ void __launch_bounds__(256) pack_units_kernel(const int8_t *__restric
     if (slot_query[(int64_t)u * kFastTile] < 0) continue;  // slots fill from 0: an empty unit (padding / bound) has no items
     // M = 64 units: the first 8 row groups of each image; narrow units: the first 4
     const int ns_u = unit_nsel != nullptr ? unit_nsel[u] : kFastTile;
-    const int nslots = (narrow && ns_u <= kNarrowSlots) ? kNarrowSlots : (ns_u <= 64 ? 64 : kFastTile);
+    // narrow units: only the 8-slot groups in use (tc_narrow_kernel copies no more than those)
+    const int nslots = (narrow && ns_u <= kNarrowSlots) ? ((ns_u + 7) & ~7) : (ns_u <= 64 ? 64 : kFastTile);
     int8_t *dst = aimg + ((int64_t)u * kbn + kb) * NS * kFastImg;
     for (int i = threadIdx.x; i < NS * nslots * 8; i += blockDim.x) {
         const int ch = i & 7, slot = (i >> 3) % nslots, s = i / (8 * nslots);
@@ -578,11 +581,9 @@ struct CompactParams {  // non-null cand_rel: keep only the kk best candidates, 
     const float *margin = nullptr;
     int k = 0;
 };
-__global__ void __launch_bounds__(256) cand_select_kernel(const double *__restrict__ cand_negv, const int32_t *__restrict__ cnt,
-                                                          int kk, int cap, double *__restrict__ sel_negv,
-                                                          int64_t *__restrict__ sel_pos, const CompactParams CP, int skip_upto) {
-    extern __shared__ uint64_t s_keys[];
-    const int64_t q = blockIdx.x;
+__device__ __forceinline__ void cand_select_block(uint64_t *s_keys, int64_t q, const double *__restrict__ cand_negv,
+                                                  const int32_t *__restrict__ cnt, int kk, int cap, double *__restrict__ sel_negv,
+                                                  int64_t *__restrict__ sel_pos, const CompactParams &CP, int skip_upto) {
     const int craw = cnt[q];
     const int n = min(craw, cap);
     if (craw <= cap && n <= skip_upto) return;  // cand_select_warp_kernel has served this query
@@ -648,6 +649,17 @@ __global__ void __launch_bounds__(256) cand_select_kernel(const double *__restri
         if (t > CP.thr[q]) CP.thr[q] = t;
     }
 }
+// the queries the warp kernel left (more than kWarpSelMax candidates, or overflowed): a small grid walks all queries — nearly
+// all of them return on the first test, and a block per query was 10,000 blocks launched to do so
+__global__ void __launch_bounds__(256) cand_select_kernel(const double *__restrict__ cand_negv, const int32_t *__restrict__ cnt,
+                                                          int64_t nq, int kk, int cap, double *__restrict__ sel_negv,
+                                                          int64_t *__restrict__ sel_pos, const CompactParams CP, int skip_upto) {
+    extern __shared__ uint64_t s_keys[];
+    for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
+        __syncthreads();  // the previous query's keys are consumed
+        cand_select_block(s_keys, q, cand_negv, cnt, kk, cap, sel_negv, sel_pos, CP, skip_upto);
+    }
+}
 
 // The same selection for the queries with at most kWarpSelMax candidates — nearly all of them once thresholds are in place —
 // by one WARP per query (four queries per block, __syncwarp instead of __syncthreads, 4 KB of shared memory per query): the
@@ -655,6 +667,54 @@ __global__ void __launch_bounds__(256) cand_select_kernel(const double *__restri
 // (0.11 ms per call for 10,000 queries whatever their length); this one holds 64.  Keys are unique (the slot index is the low
 // word), so both kernels produce the same order.  Longer lists are left to cand_select_kernel(skip_upto = kWarpSelMax).
 constexpr int kWarpSelMax = 512;
+// Bitonic sort of 32 * EPL unique 64-bit keys held in registers, lane-blocked (position i = lane * EPL + e): strides below EPL
+// are compare-exchanges between a lane's own registers, the others one __shfl_xor per key.  The same network in shared memory
+// is bound by the shared-memory pipe (64-bit keys, ~12 wavefronts per compare-exchange step of a warp): 80 us for 10,000
+// lists of 256 candidates.
+template <int EPL>
+__device__ __forceinline__ void warp_sort_regs(uint64_t (&k)[EPL], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * EPL; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride < EPL) {
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) {
+                    if ((e & stride) == 0) {
+                        const bool asc = (((lane * EPL + e) & size) == 0);
+                        const uint64_t a = k[e], b = k[e | stride];
+                        if ((a > b) == asc) {
+                            k[e] = b;
+                            k[e | stride] = a;
+                        }
+                    }
+                }
+            } else {
+                const int ld = stride / EPL;  // partner lane distance
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) {
+                    const uint64_t o = __shfl_xor_sync(0xffffffffu, k[e], ld);
+                    const int i = lane * EPL + e;
+                    const bool keep_min = (((i & size) == 0) == ((i & stride) == 0));
+                    k[e] = keep_min ? (o < k[e] ? o : k[e]) : (o > k[e] ? o : k[e]);
+                }
+            }
+        }
+    }
+}
+// loads the query's n candidate keys (candidate c = e * 32 + lane: coalesced), sorts them, writes them to keys[] in order
+template <int EPL>
+__device__ __forceinline__ void warp_sort_candidates(const double *__restrict__ v, int n, int lane, uint64_t *keys) {
+    uint64_t k[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+        const int c = e * 32 + lane;
+        k[e] = c < n ? ((uint64_t)f32_desc_key((float)(-v[c])) << 32) | (uint32_t)c : ~0ull;
+    }
+    warp_sort_regs<EPL>(k, lane);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) keys[lane * EPL + e] = k[e];
+}
 __global__ void __launch_bounds__(128) cand_select_warp_kernel(const double *__restrict__ cand_negv, const int32_t *__restrict__ cnt,
                                                                int64_t nq, int kk, int cap, double *__restrict__ sel_negv,
                                                                int64_t *__restrict__ sel_pos, const CompactParams CP) {
@@ -669,22 +729,10 @@ __global__ void __launch_bounds__(128) cand_select_warp_kernel(const double *__r
     int m = kk > 64 ? 128 : 64;
     while (m < n) m <<= 1;
     const double *v = cand_negv + q * cap;
-    for (int i = lane; i < m; i += 32) keys[i] = i < n ? ((uint64_t)f32_desc_key((float)(-v[i])) << 32) | (uint32_t)i : ~0ull;
-    for (int size = 2; size <= m; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncwarp();
-            for (int i = lane; i < m / 2; i += 32) {
-                const int lo = 2 * i - (i & (stride - 1));
-                const int hi = lo + stride;
-                const bool asc = (lo & size) == 0;
-                const uint64_t a = keys[lo], b = keys[hi];
-                if ((a > b) == asc) {
-                    keys[lo] = b;
-                    keys[hi] = a;
-                }
-            }
-        }
-    }
+    if (m == 64) warp_sort_candidates<2>(v, n, lane, keys);
+    else if (m == 128) warp_sort_candidates<4>(v, n, lane, keys);
+    else if (m == 256) warp_sort_candidates<8>(v, n, lane, keys);
+    else warp_sort_candidates<16>(v, n, lane, keys);
     __syncwarp();
     if (CP.cand_rel == nullptr) {
         for (int j = lane; j < kk; j += 32) {
@@ -1191,8 +1239,8 @@ void launch_cand_select(const double *cand_negv, const int32_t *cnt, int64_t nq,
     HB_REQUIRE(cap <= 4096 && kk <= 128, "candidate select: cap <= 4096, kk <= 128");
     cand_select_warp_kernel<<<blocks_for(nq, 4), 128, 0, g_stream>>>(cand_negv, cnt, nq, kk, cap, sel_negv, sel_pos, CompactParams{});
     HB_LAUNCH_CHECK();
-    cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos, CompactParams{},
-                                                                         kWarpSelMax);
+    cand_select_kernel<<<(unsigned)std::min<int64_t>(nq, (int64_t)g_num_sms * 8), 256, (size_t)cap * 8, g_stream>>>(
+        cand_negv, cnt, nq, kk, cap, sel_negv, sel_pos, CompactParams{}, kWarpSelMax);
     HB_LAUNCH_CHECK();
 }
 void launch_dense_select(const float *dump, int ntiles, int64_t nq, int nrows, int k, int kk, int cap, const float *margin,
@@ -1223,7 +1271,8 @@ void launch_cand_compact(double *cand_negv, int32_t *cand_rel, int32_t *cand_pos
     // the warp kernel first: it lowers cnt to <= kk for the queries it compacts, so the block kernel skips them
     cand_select_warp_kernel<<<blocks_for(nq, 4), 128, 0, g_stream>>>(cand_negv, cnt, nq, kk, cap, sel_negv, sel_pos, CP);
     HB_LAUNCH_CHECK();
-    cand_select_kernel<<<(unsigned)nq, 256, (size_t)cap * 8, g_stream>>>(cand_negv, cnt, kk, cap, sel_negv, sel_pos, CP, kWarpSelMax);
+    cand_select_kernel<<<(unsigned)std::min<int64_t>(nq, (int64_t)g_num_sms * 8), 256, (size_t)cap * 8, g_stream>>>(
+        cand_negv, cnt, nq, kk, cap, sel_negv, sel_pos, CP, kWarpSelMax);
     HB_LAUNCH_CHECK();
 }
 

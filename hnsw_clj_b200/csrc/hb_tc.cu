@@ -607,17 +607,20 @@ __global__ void __launch_bounds__(NARROW_THREADS, 1) tc_narrow_kernel(const TcPa
                 const int64_t btile = P.tile_off[P.unit_list[u]] + t;
                 const int8_t *qsrc = P.aimg + (int64_t)u * kbn * NS * kFastImg;
                 const int8_t *rsrc = P.bimg + btile * kbn * NS * kFastImg;
+                // only the 8-slot groups the unit uses are copied (and were packed): the MMA multiplies whatever the rest of the
+                // B tile holds, and the epilogue never looks at those columns
+                const uint32_t bsz = (uint32_t)((P.unit_nsel_all[u] + 7) >> 3) * 8u * kFastKB;
                 for (int kb = 0; kb < kbn; ++kb) {
                     const long long c0 = P.timing ? clock64() : 0;
                     mbar_wait(smem_u32(&s_empty[stage]), phase ^ 1u);
                     if (P.timing) t_wait += clock64() - c0;
                     const uint32_t full = smem_u32(&s_full[stage]);
                     const uint32_t dst = stage0 + (uint32_t)stage * Cfg::STAGE_BYTES;
-                    mbar_expect_tx(full, Cfg::STAGE_BYTES);
+                    mbar_expect_tx(full, Cfg::A_BYTES + NS * bsz);
                     bulk_g2s(dst, rsrc + (int64_t)kb * NS * kFastImg, Cfg::A_BYTES, full);
 #pragma unroll
                     for (int sl = 0; sl < NS; ++sl)
-                        bulk_g2s(dst + Cfg::A_BYTES + sl * Cfg::B_SLICE, qsrc + ((int64_t)kb * NS + sl) * kFastImg, Cfg::B_SLICE, full);
+                        bulk_g2s(dst + Cfg::A_BYTES + sl * Cfg::B_SLICE, qsrc + ((int64_t)kb * NS + sl) * kFastImg, bsz, full);
                     if (++stage == Cfg::NSTAGE) {
                         stage = 0;
                         phase ^= 1u;

@@ -1,4 +1,5 @@
-# The validation recipe behind profiles/r02z_* (one B200 box):  gpurun --timeout 2400 -- 'bash tools/run_r2_final.sh'
+# The validation recipe behind profiles/r02z_* (one B200 box; the HNSW / LSH legs — tools/bench_configs.py c5, lsh — were run once
+# on the earlier commit a6571f4.. and are unchanged code):  gpurun --timeout 2400 -- 'bash tools/run_r2_final.sh'
 set -x
 python __graft_entry__.py smoke > gpurun_out/r02z_smoke.log 2>&1; tail -2 gpurun_out/r02z_smoke.log
 timeout 1200 python -m pytest tests -m gpu -x -q --durations=6 > gpurun_out/r02z_pytest_gpu.log 2>&1; tail -12 gpurun_out/r02z_pytest_gpu.log
@@ -14,9 +15,6 @@ rm -f gpurun_out/r02z_tc_narrow.ncu-rep
 timeout 400 python tools/bench_small.py > gpurun_out/r02z_small_batch.json 2> gpurun_out/r02z_small.err
 timeout 300 python tools/bench_configs.py c1 > gpurun_out/r02z_config0_flat_31k.json 2> gpurun_out/r02z_cfg.err
 timeout 500 python tools/bench_configs.py c3 > gpurun_out/r02z_config2_flat_10M_bf16_top100.json 2>> gpurun_out/r02z_cfg.err
-timeout 400 python tools/bench_configs.py c5 --n 1000000 --data clustered --noise 0.5 > gpurun_out/r02z_config4_hnsw_1M_clustered.json 2>> gpurun_out/r02z_cfg.err
-timeout 400 python tools/bench_configs.py c5 --n 1000000 --data gaussian > gpurun_out/r02z_config4_hnsw_1M_gaussian.json 2>> gpurun_out/r02z_cfg.err
-timeout 300 python tools/bench_configs.py lsh > gpurun_out/r02z_hybrid_lsh_31k.json 2>> gpurun_out/r02z_cfg.err
 tail -3 gpurun_out/r02z_cfg.err
 python - <<'PY'
 import json,glob

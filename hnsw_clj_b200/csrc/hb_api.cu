@@ -1133,7 +1133,7 @@ static void fast_topk(const FastJob &J) {
             // an IVF list scan runs EMIT passes only: its M = 64 units (<= 64 selections) need half an image, its narrow
             // units (<= 32) a quarter
             launch_pack_units((const int8_t *)W.dig.p, kbn, ns, J.emit.nunits, U.slot_query, aimg,
-                              ((g_tc_half_m || narrow) && !J.shared_units) ? U.unit_nsel : nullptr, narrow);
+                              (narrow || (g_tc_half_m && !J.shared_units)) ? U.unit_nsel : nullptr, narrow);
         }
         if (!do_sample) {
         } else if (J.shared_units) {

@@ -405,18 +405,25 @@ __global__ void __launch_bounds__(1024) planf_scan_kernel(const int32_t *__restr
                                                           int32_t *__restrict__ cursor) {
     __shared__ unsigned long long s_w[32];
     __shared__ unsigned long long s_run;
+    constexpr int PT = 4;  // lists per thread and round
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
-    for (int base = 0; base <= nlist; base += 1024) {
-        const int l = base + threadIdx.x;
-        unsigned long long v = 0;
-        if (l < nlist) {
-            const unsigned long long c = (unsigned long long)(uint32_t)cnt[l];
-            const unsigned long long units = list_off[l + 1] > list_off[l] ? (c + tile_q - 1) / tile_q : 0ull;
-            v = (units << 32) | c;
+    for (int base = 0; base <= nlist; base += 1024 * PT) {
+        const int l0 = base + threadIdx.x * PT;
+        unsigned long long v[PT], x = 0;
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            const int l = l0 + j;
+            v[j] = 0;
+            if (l < nlist) {
+                const unsigned long long c = (unsigned long long)(uint32_t)cnt[l];
+                const unsigned long long units = list_off[l + 1] > list_off[l] ? (c + tile_q - 1) / tile_q : 0ull;
+                v[j] = (units << 32) | c;
+            }
+            x += v[j];
         }
-        unsigned long long x = v;
+        const unsigned long long mine = x;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
@@ -434,11 +441,16 @@ __global__ void __launch_bounds__(1024) planf_scan_kernel(const int32_t *__restr
             s_w[lane] = y;
         }
         __syncthreads();
-        const unsigned long long pre = s_run + (warp > 0 ? s_w[warp - 1] : 0ull) + x - v;
-        if (l <= nlist) {
-            lq_off[l] = (int64_t)(pre & 0xffffffffull);
-            unit_prefix[l] = (int64_t)(pre >> 32);
-            if (l < nlist) cursor[l] = (int32_t)(pre & 0xffffffffull);
+        unsigned long long pre = s_run + (warp > 0 ? s_w[warp - 1] : 0ull) + x - mine;
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            const int l = l0 + j;
+            if (l <= nlist) {
+                lq_off[l] = (int64_t)(pre & 0xffffffffull);
+                unit_prefix[l] = (int64_t)(pre >> 32);
+                if (l < nlist) cursor[l] = (int32_t)(pre & 0xffffffffull);
+            }
+            pre += v[j];
         }
         __syncthreads();
         if (threadIdx.x == 0) s_run += s_w[31];

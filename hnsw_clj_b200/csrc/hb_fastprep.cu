@@ -268,18 +268,25 @@ __global__ void __launch_bounds__(1024) unit_scan_kernel(const int32_t *__restri
                                                          const int32_t *__restrict__ nsel, int32_t *__restrict__ item0n) {
     __shared__ unsigned long long s_w[32];
     __shared__ unsigned long long s_run;
+    constexpr int PT = 4;  // entries per thread and round
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
-    for (int base = 0; base < count; base += 1024) {
-        const int i = base + threadIdx.x;
-        unsigned long long v = 0;
-        if (i < count) {
-            const unsigned long long nt = (unsigned long long)(uint32_t)ntile[i];
-            const bool narrow = item0n != nullptr && i < count - 1 && nsel[i] <= kNarrowSlots;
-            v = narrow ? nt << 32 : nt;
+    for (int base = 0; base < count; base += 1024 * PT) {
+        const int i0 = base + threadIdx.x * PT;
+        unsigned long long v[PT], x = 0;
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            const int i = i0 + j;
+            v[j] = 0;
+            if (i < count) {
+                const unsigned long long nt = (unsigned long long)(uint32_t)ntile[i];
+                const bool narrow = item0n != nullptr && i < count - 1 && nsel[i] <= kNarrowSlots;
+                v[j] = narrow ? nt << 32 : nt;
+            }
+            x += v[j];
         }
-        unsigned long long x = v;
+        const unsigned long long mine = x;  // this thread's total
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
@@ -297,10 +304,15 @@ __global__ void __launch_bounds__(1024) unit_scan_kernel(const int32_t *__restri
             s_w[lane] = y;
         }
         __syncthreads();
-        const unsigned long long pre = s_run + (warp > 0 ? s_w[warp - 1] : 0ull) + x - v;
-        if (i < count) {
-            item0_all[i] = (int32_t)(uint32_t)(pre & 0xffffffffull);
-            if (item0n) item0n[i] = (int32_t)(uint32_t)(pre >> 32);
+        unsigned long long pre = s_run + (warp > 0 ? s_w[warp - 1] : 0ull) + x - mine;
+#pragma unroll
+        for (int j = 0; j < PT; ++j) {
+            const int i = i0 + j;
+            if (i < count) {
+                item0_all[i] = (int32_t)(uint32_t)(pre & 0xffffffffull);
+                if (item0n) item0n[i] = (int32_t)(uint32_t)(pre >> 32);
+            }
+            pre += v[j];
         }
         __syncthreads();
         if (threadIdx.x == 0) s_run += s_w[31];
@@ -311,19 +323,25 @@ __global__ void __launch_bounds__(1024) unit_scan_kernel(const int32_t *__restri
 __global__ void unit_slots_kernel(int nunits, const int32_t *__restrict__ unit_sel0, const int32_t *__restrict__ unit_nsel,
                                   const int32_t *__restrict__ qsel, const int64_t *__restrict__ pair_out, int pair_div,
                                   const int32_t *__restrict__ pair_query, int32_t *__restrict__ slot_query,
-                                  int32_t *__restrict__ slot_rel0) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)nunits * kFastTile) return;
-    const int u = (int)(i / kFastTile), s = (int)(i % kFastTile);
-    int q = -1, rel0 = 0;
-    if (s < unit_nsel[u]) {
-        const int64_t sel = (int64_t)unit_sel0[u] + s;
-        const int64_t p = qsel ? (int64_t)qsel[sel] : sel;
-        q = pair_query ? pair_query[p] : (pair_div > 0 ? (int)(p / pair_div) : (int)p);
-        if (pair_out) rel0 = (int32_t)(pair_out[p] - pair_out[(int64_t)q * (pair_div > 0 ? pair_div : 1)]);
+                                  int32_t *__restrict__ slot_rel0, bool narrow) {
+    // a warp per unit slot.  The unit slots of an IVF plan are an upper bound and mostly empty: an empty one gets its first slot
+    // marked (-1, what pack_units_kernel tests), a narrow unit its first kNarrowSlots (all tc_narrow_kernel reads), the others 128
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nunits) return;
+    const int u = (int)w, ns = unit_nsel[u];
+    const int need = ns == 0 ? 1 : ((narrow && ns <= kNarrowSlots) ? kNarrowSlots : kFastTile);
+    for (int s = lane; s < need; s += 32) {
+        int q = -1, rel0 = 0;
+        if (s < ns) {
+            const int64_t sel = (int64_t)unit_sel0[u] + s;
+            const int64_t p = qsel ? (int64_t)qsel[sel] : sel;
+            q = pair_query ? pair_query[p] : (pair_div > 0 ? (int)(p / pair_div) : (int)p);
+            if (pair_out) rel0 = (int32_t)(pair_out[p] - pair_out[(int64_t)q * (pair_div > 0 ? pair_div : 1)]);
+        }
+        slot_query[(int64_t)u * kFastTile + s] = q;
+        slot_rel0[(int64_t)u * kFastTile + s] = rel0;
     }
-    slot_query[i] = q;
-    slot_rel0[i] = rel0;
 }
 
 // copies the 16-byte chunks of the units' query digits into swizzled images; a block walks (unit, k-block) pairs with a
@@ -1510,8 +1528,8 @@ void launch_unit_plan(int nlist, const int64_t *lq_off, const int64_t *unit_pref
     HB_LAUNCH_CHECK();
     unit_scan_kernel<<<1, 1024, 0, g_stream>>>(U.unit_ntile, nunits + 1, U.unit_item0, U.unit_nsel, U.unit_item0n);
     HB_LAUNCH_CHECK();
-    unit_slots_kernel<<<blocks_for((int64_t)nunits * kFastTile, 256), 256, 0, g_stream>>>(
-        nunits, U.unit_sel0, U.unit_nsel, qsel, pair_out, pair_div, pair_query, U.slot_query, U.slot_rel0);
+    unit_slots_kernel<<<blocks_for((int64_t)nunits * 32, 256), 256, 0, g_stream>>>(
+        nunits, U.unit_sel0, U.unit_nsel, qsel, pair_out, pair_div, pair_query, U.slot_query, U.slot_rel0, U.unit_item0n != nullptr);
     HB_LAUNCH_CHECK();
 }
 

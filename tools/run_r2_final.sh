@@ -13,6 +13,8 @@ timeout 500 ncu --profile-from-start off --set full --clock-control none --impor
 ncu -i gpurun_out/r02z_tc_narrow.ncu-rep --page raw --csv > gpurun_out/r02z_tc_narrow_ncu_raw.csv 2>/dev/null
 rm -f gpurun_out/r02z_tc_narrow.ncu-rep
 timeout 400 python tools/bench_small.py > gpurun_out/r02z_small_batch.json 2> gpurun_out/r02z_small.err
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/r02z_sanitizer_memcheck_smoke.log 2>&1; echo "memcheck rc=$?"
+timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/r02z_sanitizer_racecheck_smoke.log 2>&1; echo "racecheck rc=$?"
 timeout 300 python tools/bench_configs.py c1 > gpurun_out/r02z_config0_flat_31k.json 2> gpurun_out/r02z_cfg.err
 timeout 500 python tools/bench_configs.py c3 > gpurun_out/r02z_config2_flat_10M_bf16_top100.json 2>> gpurun_out/r02z_cfg.err
 tail -3 gpurun_out/r02z_cfg.err

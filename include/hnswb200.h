@@ -263,8 +263,8 @@ HB_API int hb_comm_broadcast(void *buf, int64_t bytes, int32_t root);
 HB_API int hb_comm_allreduce_f64(double *buf, int64_t count, int32_t op /* 0 = sum, 1 = max */);
 /* the global row of this index's local row 0; hb_sharded_search adds it to every id */
 HB_API int hb_index_set_id_base(hb_index *index, int64_t first_global_row);
-/* IVF-FLAT row shards: split the coarse routing of hb_sharded_search over the ranks as well (rank r ranks the centroids
- * [r nlist/G, (r+1) nlist/G) exactly, the G top-nprobe lists are exchanged and merged like the results).  On by default for
+/* IVF-FLAT row shards: split the coarse routing of hb_sharded_search over the ranks as well (rank r ranks ALL centroids,
+ * exactly, for the queries [r ceil(nq/G), (r+1) ceil(nq/G)); one all-gather replicates the probe lists).  On by default for
  * indexes built by hb_sharded_ivf_build; every rank must use the same setting.  Same results either way. */
 HB_API int hb_index_set_coarse_sharded(hb_index *index, int on);
 /* search mode of THIS index: HB_MODE_EXACT / HB_MODE_FAST, or -1 to follow hb_set_mode (threads that want different

@@ -1116,9 +1116,7 @@ static void fast_topk(const FastJob &J) {
     int32_t *cpos = W.cpos.as<int32_t>((size_t)nq * cap);
     if (do_sample) {
         launch_query_bounds((const double *)W.qu.p, (const double *)W.ql1.p, J.qn, nq, ns, J.d, J.metric, (const float *)S.stats.p, qscale,
-                            qeps, qmargin);
-        launch_fill_f32(thr, nq, -INFINITY);
-        HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, g_stream));
+                            qeps, qmargin, thr, cnt);  // also thr <- -inf, cnt <- 0
     }
 
     UnitPlan U, T;
@@ -1860,7 +1858,6 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         int32_t *qsel = g_ws.qsel.as<int32_t>((size_t)np);
         int64_t *lq_off = g_ws.lq_off.as<int64_t>(nlist + 1);
         int64_t *uprefix = W.uprefix.as<int64_t>(nlist + 1);
-        int64_t *ppos0 = W.ppos0.as<int64_t>(nqc);
         int32_t *probes0 = W.probes0.as<int32_t>(nqc);
         int32_t *qsel0 = W.qsel0.as<int32_t>(nqc);
         int64_t *lq_off0 = W.lq_off0.as<int64_t>(nlist + 1);
@@ -1869,14 +1866,13 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         // (query, probed list) pair whose rows cannot reach the query's threshold, and plan the scan over the rest.
         const bool prune = coarse_tc && g_fast_prune && np_eff > 1;
         auto plan_emit = [&] {
-            ivf_plan_fast(ppos, nqc, np_eff, nlist, (const int64_t *)ix->list_off.p, probes, pair_out, qsel, lq_off, uprefix, kFastTile,
+            ivf_plan_fast(ppos, np_eff, nqc, np_eff, nlist, (const int64_t *)ix->list_off.p, probes, pair_out, qsel, lq_off, uprefix, kFastTile,
                           g_ws.tmp);
         };
         {
             Prof prp(PROF_PLAN);
             if (!prune) plan_emit();
-            launch_first_column(ppos, nqc, np_eff, ppos0);
-            ivf_plan_fast(ppos0, nqc, 1, nlist, (const int64_t *)ix->list_off.p, probes0, nullptr, qsel0, lq_off0, uprefix0, kFastTile,
+            ivf_plan_fast(ppos, np_eff, nqc, 1, nlist, (const int64_t *)ix->list_off.p, probes0, nullptr, qsel0, lq_off0, uprefix0, kFastTile,
                           g_ws.tmp);
         }
         // no host round trip: unit counts stay on the device, the host sizes buffers and grids by their bounds
@@ -1944,8 +1940,7 @@ static void ivf_search_fast(hb_index *ix, const void *queries, int qdtype, int64
         }
         // what the main candidate pass covered: units, items (unit x row tile), distinct row tiles
         launch_ivf_resolve(relk, nqc, k, np_eff, probes, pair_out, (const int64_t *)ix->list_off.p, (const int64_t *)ix->list_rows.p,
-                           ids + (size_t)q0 * k);
-        launch_and_flags(ok_all + q0, ok_c, nqc);
+                           ids + (size_t)q0 * k, ok_all + q0, ok_c);  // and ok &= the coarse stage's flags
     }
     fast_fallback(ok_all, queries, qdtype, nq, d, k, ids, dist, [&](const void *gq, int64_t nb, int64_t *gids, double *gdist) {
         ivf_search_exact(ix, gq, qdtype, nb, k, nprobe, gids, gdist, nullptr);

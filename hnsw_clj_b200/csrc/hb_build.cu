@@ -188,10 +188,11 @@ __global__ void plan_lists_kernel(const int32_t *__restrict__ sorted_keys, int64
 __global__ void ivf_resolve_kernel(const int64_t *__restrict__ pos, int64_t nq, int k, int nprobe,
                                    const int32_t *__restrict__ probes, const int64_t *__restrict__ pair_out,
                                    const int64_t *__restrict__ list_off, const int64_t *__restrict__ list_rows,
-                                   int64_t *__restrict__ out_ids) {
+                                   int64_t *__restrict__ out_ids, int32_t *__restrict__ ok, const int32_t *__restrict__ ok_other) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nq * k) return;
     const int64_t q = t / k;
+    if (ok != nullptr && t == q * k) ok[q] &= ok_other[q];  // (the query's first thread) both stages must have proven their part
     const int64_t ps = pos[t];
     if (ps < 0) {
         out_ids[t] = -1;
@@ -380,7 +381,7 @@ void ivf_plan(const int64_t *probe_pos, int64_t np, int nlist, const int64_t *li
 // every consumer takes differences within a query (unit_slots_kernel, ivf_resolve_kernel).  The order of the pairs inside a
 // list is whatever the atomics give; no result depends on it (candidates are ranked by score, then position in the
 // query's concatenation).
-__global__ void planf_count_kernel(const int64_t *__restrict__ probe_pos, int64_t nq, int npq, int nlist,
+__global__ void planf_count_kernel(const int64_t *__restrict__ probe_pos, int pos_stride, int64_t nq, int npq, int nlist,
                                    const int64_t *__restrict__ list_off, int32_t *__restrict__ probes, int64_t *__restrict__ pair_out,
                                    int32_t *__restrict__ cnt) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -388,7 +389,7 @@ __global__ void planf_count_kernel(const int64_t *__restrict__ probe_pos, int64_
     int64_t run = 0;
     for (int j = 0; j < npq; ++j) {
         const int64_t p = q * npq + j;
-        const int64_t l = probe_pos[p];
+        const int64_t l = probe_pos[q * pos_stride + j];
         const bool ok = l >= 0 && l < nlist;
         probes[p] = ok ? (int32_t)l : -1;
         if (pair_out) pair_out[p] = run;
@@ -464,7 +465,7 @@ __global__ void planf_scatter_kernel(const int32_t *__restrict__ probes, int64_t
     const int l = probes[p];
     if (l >= 0) qsel[atomicAdd(&cursor[l], 1)] = (int32_t)p;
 }
-void ivf_plan_fast(const int64_t *probe_pos, int64_t nq, int npq, int nlist, const int64_t *list_off, int32_t *probes,
+void ivf_plan_fast(const int64_t *probe_pos, int pos_stride, int64_t nq, int npq, int nlist, const int64_t *list_off, int32_t *probes,
                    int64_t *pair_out, int32_t *qsel, int64_t *lq_off, int64_t *unit_prefix, int tile_q, DevBuf &tmp) {
     const int64_t np = nq * npq;
     HB_REQUIRE(np < (1ll << 31), "too many (query, probe) pairs for one plan");
@@ -472,7 +473,8 @@ void ivf_plan_fast(const int64_t *probe_pos, int64_t nq, int npq, int nlist, con
     int32_t *cursor = cnt + nlist + 1;
     HB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(nlist + 1) * 4, g_stream));
     if (nq > 0) {
-        planf_count_kernel<<<blocks_for(nq, 128), 128, 0, g_stream>>>(probe_pos, nq, npq, nlist, list_off, probes, pair_out, cnt);
+        planf_count_kernel<<<blocks_for(nq, 128), 128, 0, g_stream>>>(probe_pos, pos_stride, nq, npq, nlist, list_off, probes, pair_out,
+                                                                      cnt);
         HB_LAUNCH_CHECK();
     }
     planf_scan_kernel<<<1, 1024, 0, g_stream>>>(cnt, nlist, list_off, tile_q, lq_off, unit_prefix, cursor);
@@ -484,10 +486,11 @@ void ivf_plan_fast(const int64_t *probe_pos, int64_t nq, int npq, int nlist, con
 }
 
 void launch_ivf_resolve(const int64_t *pos, int64_t nq, int k, int nprobe, const int32_t *probes,
-                        const int64_t *pair_out, const int64_t *list_off, const int64_t *list_rows, int64_t *out_ids) {
+                        const int64_t *pair_out, const int64_t *list_off, const int64_t *list_rows, int64_t *out_ids, int32_t *ok,
+                        const int32_t *ok_other) {
     if (nq * k == 0) return;
     ivf_resolve_kernel<<<blocks_for(nq * k, 256), 256, 0, g_stream>>>(pos, nq, k, nprobe, probes, pair_out, list_off,
-                                                                      list_rows, out_ids);
+                                                                      list_rows, out_ids, ok, ok_other);
     HB_LAUNCH_CHECK();
 }
 void launch_offset_ids(int64_t *ids, int64_t nq, int64_t run, int64_t stride, int64_t base) {

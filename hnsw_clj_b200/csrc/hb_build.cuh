@@ -84,14 +84,16 @@ void ivf_plan(const int64_t *probe_pos /*[np] from select, -1 padded*/, int64_t 
 // The FAST list scan's variant (three small kernels, no sort): pairs grouped by list in no particular order inside a list;
 // pair_out (optional) [nq x npq]: offset of each probed list inside ITS query's concatenation; unit_prefix = exclusive
 // prefix of ceil(pairs of the list / tile_q) over the lists that hold rows.
-void ivf_plan_fast(const int64_t *probe_pos, int64_t nq, int npq, int nlist, const int64_t *list_off, int32_t *probes,
+// probe_pos: [nq x pos_stride], the first npq entries of every row are planned (npq = 1: the nearest list of every query).
+void ivf_plan_fast(const int64_t *probe_pos, int pos_stride, int64_t nq, int npq, int nlist, const int64_t *list_off, int32_t *probes,
                    int64_t *pair_out /*NULL: not wanted*/, int32_t *qsel, int64_t *lq_off, int64_t *unit_prefix, int tile_q,
                    DevBuf &tmp);
 
 // pos (within the query's concatenated probed lists) -> row id
 void launch_ivf_resolve(const int64_t *pos, int64_t nq, int k, int nprobe, const int32_t *probes,
                         const int64_t *pair_out, const int64_t *list_off, const int64_t *list_rows,
-                        int64_t *out_ids);
+                        int64_t *out_ids, int32_t *ok = nullptr /* optional: ok[q] &= ok_other[q] */,
+                        const int32_t *ok_other = nullptr);
 // flat: row id = pos + base (pos -1 stays -1) for the `run` entries at ids[q*stride ..] of every query q
 void launch_offset_ids(int64_t *ids, int64_t nq, int64_t run, int64_t stride, int64_t base);
 // [nparts][nq][k] -> [nq][nparts][k]

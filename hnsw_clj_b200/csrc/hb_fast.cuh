@@ -159,7 +159,8 @@ void launch_fast_final(const FinalParams &P);
 
 // per query: q_scale = u_q / ||q|| (cosine) or u_q (ip); q_eps from the index stats
 void launch_query_bounds(const double *qu, const double *ql1, const double *qnorm, int64_t nq, int ns, int d, int metric,
-                         const float *stats, double *q_scale, double *q_eps, float *q_margin);
+                         const float *stats, double *q_scale, double *q_eps, float *q_margin, float *thr_init = nullptr /* [nq] <- -inf */,
+                         int32_t *cnt_init = nullptr /* [nq] <- 0 */);
 // pairs for the exact re-score: per selected slot the row or -1 (slot_row), exact = +inf where not re-scored (set_only:
 // slot_row -2 and exact -inf for a candidate that is in the top-k set without a re-score), and the
 // dense list of wanted (query, row, slot) triples with its length in *total

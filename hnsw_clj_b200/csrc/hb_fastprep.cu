@@ -373,9 +373,12 @@ __global__ void __launch_bounds__(256) pack_units_kernel(const int8_t *__restric
 __global__ void query_bounds_kernel(const double *__restrict__ qu, const double *__restrict__ ql1,
                                     const double *__restrict__ qnorm, int64_t nq, int ns, int d, int metric,
                                     const float *__restrict__ stats, double *__restrict__ q_scale,
-                                    double *__restrict__ q_eps, float *__restrict__ q_margin) {
+                                    double *__restrict__ q_eps, float *__restrict__ q_margin, float *__restrict__ thr_init,
+                                    int32_t *__restrict__ cnt_init) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
+    if (thr_init) thr_init[q] = -INFINITY;  // the start of a job: no threshold, no candidates
+    if (cnt_init) cnt_init[q] = 0;
     const double w = metric == HB_COSINE ? 1.0 / qnorm[q] : 1.0;
     const double umax_r = (double)stats[0], l1max_r = (double)stats[1];
     const double us = qu[q] * w;
@@ -1543,10 +1546,10 @@ void launch_pack_units(const int8_t *dig, int kbn, int ns, int nunits, const int
 }
 
 void launch_query_bounds(const double *qu, const double *ql1, const double *qnorm, int64_t nq, int ns, int d, int metric,
-                         const float *stats, double *q_scale, double *q_eps, float *q_margin) {
+                         const float *stats, double *q_scale, double *q_eps, float *q_margin, float *thr_init, int32_t *cnt_init) {
     if (nq == 0) return;
     query_bounds_kernel<<<blocks_for(nq, 256), 256, 0, g_stream>>>(qu, ql1, qnorm, nq, ns, d, metric, stats, q_scale, q_eps,
-                                                                   q_margin);
+                                                                   q_margin, thr_init, cnt_init);
     HB_LAUNCH_CHECK();
 }
 

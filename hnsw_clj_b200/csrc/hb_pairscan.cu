@@ -430,17 +430,22 @@ __global__ void __launch_bounds__(128) row_norms_kernel(const T *__restrict__ ro
     if (r >= n) return;
     const T *p = rows + r * (int64_t)d;
     double s = 0.0;
-    constexpr int N = 16;
-    for (int k0 = 0; k0 < d; k0 += N) {
-        Run<T, N> v;
-        load_run<T, N, VEC>(p, k0, d, true, v);
-        const int kmax = min(N, d - k0);
+    constexpr int N = 16, B = 4;  // four runs of 16 elements in flight: a batch of queries is 79 CTAs, the loads are the time
+    for (int k0 = 0; k0 < d; k0 += N * B) {
+        Run<T, N> v[B];
 #pragma unroll
-        for (int i = 0; i < N; ++i)
-            if (i < kmax) {
-                const double x = to_f64(v[i]);
-                s = mac_seq<is_f32_repr<T>::value ? ARITH_FMA : ARITH_MULADD>(x, x, s);
-            }
+        for (int b = 0; b < B; ++b)
+            if (k0 + b * N < d) load_run<T, N, VEC>(p, k0 + b * N, d, true, v[b]);
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int kmax = min(N, d - (k0 + b * N));  // <= 0 past the end
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                if (i < kmax) {
+                    const double x = to_f64(v[b][i]);
+                    s = mac_seq<is_f32_repr<T>::value ? ARITH_FMA : ARITH_MULADD>(x, x, s);
+                }
+        }
     }
     out[r] = __dsqrt_rn(s);
 }

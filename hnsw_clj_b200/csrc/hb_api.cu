@@ -723,7 +723,9 @@ static void kpp_seeds(const void *rows, int dtype, int64_t n, int d, const doubl
     std::vector<double> u((size_t)nlist);
     const int64_t first = rng.next_int((int32_t)n);
     for (int t = 1; t < nlist; ++t) u[t] = rng.next_double();
-    if (g_kpp_scale) {
+    // (the staged update kernel keeps the newest seed, widened, in shared memory: rows of more than ~20,000 dimensions take
+    //  the plain path)
+    if (g_kpp_scale && (size_t)d * 8 + 40 * 1024 <= 200 * 1024) {
         // hb_kpp.cu: the same picks, with the distance pass pruned by the triangle inequality and the ordered fp64 sum done
         // as integer adds per chunk
         const int64_t nchunks = ceil_div(n, kKppChunk);

@@ -98,3 +98,22 @@ def test_large_random_mostly_integer_path():
     got, walked, _ = chunked(xs)
     assert got.hex() == sequential(xs)[-1].hex()
     assert walked <= 40  # ~log2(n / 512) binade crossings + the first chunks + the rare tie
+
+
+def test_adding_ulps_is_an_integer_add_on_the_bit_pattern():
+    """kpp_compose_pick_kernel composes a chunk as bits(cum) + Q: for a normal cum in the binade 2^e and 0 <= Q with
+    significand(cum) + Q < 2^53 that IS cum + Q * ulp(cum), exactly."""
+    import struct
+
+    rng = random.Random(5)
+    for _ in range(20000):
+        e = rng.randint(-900, 900)
+        sig = rng.randint(1 << 52, (1 << 53) - 1)
+        cum = math.ldexp(float(sig), e - 52)
+        assert math.frexp(cum)[1] - 1 == e
+        q = rng.randint(0, (1 << 53) - 1 - sig)
+        bits = struct.unpack("<q", struct.pack("<d", cum))[0]
+        assert ((bits >> 52) & 0x7FF) - 1023 == e and (bits & ((1 << 52) - 1)) | (1 << 52) == sig
+        got = struct.unpack("<d", struct.pack("<q", bits + q))[0]
+        want = math.ldexp(float(sig + q), e - 52)  # sig + q < 2^53: exact
+        assert got == want

@@ -89,7 +89,12 @@ HB_API int hb_set_mode(int mode);            /* hb_mode for subsequent searches 
  * without a thread per query); "comm_p2p" = 0 exchanges the local top-k of hb_sharded_search by ncclAllGather instead of
  * the peer-window kernel; "kpp_scale" = 0 runs k-means++ as the one-thread prefix walk with an exhaustive distance pass
  * (default 1: pruned distance pass + chunked ordered sum, hb_kpp.cu); "tc_narrow" = 0 keeps sparse IVF units on the
- * 128 x 128 candidate kernel.  Results never depend on a knob. */
+ * 128 x 128 candidate kernel; "fast_carry" = 0 discards the threshold sample's candidates instead of keeping them;
+ * "fast_level_min" (default 33 row tiles) = the length from which a flat FAST scan runs in levels, "fast_level_dense"
+ * (default 8, 0 = off) = the row tiles of its first level, scored into a matrix and selected per query,
+ * "fast_level_ratio" (default 16) = growth of the later levels; "host_feed" = B copies a host query batch in blocks of B
+ * queries on a copy stream under the coarse stage (default 0: one copy, which measures faster); "prof_coarse" = 1 points
+ * the stage timers at the coarse job of an IVF search.  Results never depend on a knob. */
 HB_API int hb_set_option(const char *name, int64_t value);
 /* measurements: "scan_ms"/"scan_count" (list/flat scan kernel), "coarse_ms", "select_ms", "plan_ms", "assign_ms",
  * "tc_ms" (tensor-core candidate pass over all probed lists), "tc_sample_ms" (its threshold-seeding pass), "pack_ms",
